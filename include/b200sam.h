@@ -1,0 +1,115 @@
+/* b200sam C ABI — B200 (sm_100a) kernels for the SAM pseudo-label refinement hot path.
+ *
+ * The reference (multimodallearning/SamCarriesTheBurden) is pure Python/PyTorch and has no FFI boundary;
+ * each entry point below names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no allocation in hot calls, no
+ *     synchronisation) except *_create, which may allocate small constant tables;
+ *   - return 0 on success; non-zero on error with a message available from b200sam_last_error()
+ *     (thread-local).  There is no CPU fallback: without a CUDA device the compute calls fail.
+ */
+#ifndef B200SAM_H
+#define B200SAM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200SAM_API __attribute__((visibility("default")))
+#else
+#define B200SAM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+B200SAM_API const char* b200sam_last_error(void);
+B200SAM_API int b200sam_abi_version(void);
+
+/* ---------------------------------------------------------------- image encoder
+ * Replaces Sam.preprocess + ImageEncoderViT.forward
+ * (segment_anything/modeling/sam.py:164-174, modeling/image_encoder.py:106-116) as called from
+ * SamPredictor.set_torch_image (segment_anything/predictor.py:62-90) and
+ * scripts/generate_img_embeddings.py:45,62. */
+typedef struct b200sam_encoder_config {
+  int embed_dim;        /* 768 | 1024 | 1280            (build_sam.py:14-44) */
+  int depth;            /* 12 | 24 | 32 */
+  int num_heads;        /* 12 | 16 | 16 */
+  int global_attn_mask; /* bit i set: block i is a global-attention block */
+  int out_chans;        /* 256 */
+} b200sam_encoder_config;
+typedef struct b200sam_encoder b200sam_encoder;
+
+B200SAM_API int b200sam_encoder_weight_count(const b200sam_encoder_config* cfg);
+/* "state_dict key|packing" of weight slot i; packing: f32 | bf16 | bf16_flat | bf16_tap | f32_tokens */
+B200SAM_API const char* b200sam_encoder_weight_name(const b200sam_encoder_config* cfg, int i);
+B200SAM_API size_t b200sam_encoder_workspace_bytes(const b200sam_encoder_config* cfg, int batch);
+B200SAM_API int b200sam_encoder_create(const b200sam_encoder_config* cfg, const void* const* weights, int n_weights,
+                           b200sam_encoder** out);
+B200SAM_API void b200sam_encoder_destroy(b200sam_encoder* enc);
+/* image: [batch,3,h,w] uint8 (is_u8=1) or float32, un-normalised, long side <= 1024;
+ * embedding_out: [batch,256,64,64] float32 == SamPredictor.features */
+B200SAM_API int b200sam_encoder_forward(const b200sam_encoder* enc, const void* image, int is_u8, int batch, int h, int w,
+                            const float* pixel_mean3_host, const float* pixel_std3_host, float* embedding_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- prompt extraction
+ * Replaces PromptExtractor._extract_seeds / _extract_box / masked_non_overlapping_label_areas
+ * (segment_anything/utils/prompt_utils.py:34-67).  masks: [n_img,C,H,W] bool bytes.
+ * seeds: [n_img,C,2] (x,y); boxes: [n_img,C,4] (xmin,ymin,xmax,ymax); has_seed/has_box: [n_img,C] (0/1). */
+B200SAM_API size_t b200sam_prompt_extract_scratch_bytes(int n_img, int n_classes);
+B200SAM_API int b200sam_prompt_extract(const uint8_t* masks, int n_img, int n_classes, int H, int W, int32_t* seeds,
+                           int32_t* boxes, uint8_t* has_seed, uint8_t* has_box, void* scratch, void* stream);
+
+/* ---------------------------------------------------------------- prompt encoder + mask decoder
+ * Replaces PromptEncoder.forward + MaskDecoder.forward (modeling/prompt_encoder.py:128-168,
+ * modeling/mask_decoder.py:71-149, modeling/transformer.py:62-240) for ALL prompts of one image at once,
+ * i.e. the per-class loop of SAMSegRefiner.refine (utils/seg_refinement.py:105-109) and
+ * SAMMaskDecoderHead.predict_mask (segment_anything/sam_mask_decoder_head.py:79-96). */
+typedef struct b200sam_decoder b200sam_decoder;
+B200SAM_API int b200sam_decoder_weight_count(void);
+/* "state_dict key[|packing]" of weight slot i (all float32); packing: cat4 | convT | repeat4 */
+B200SAM_API const char* b200sam_decoder_weight_name(int i);
+B200SAM_API size_t b200sam_decoder_workspace_bytes(int n_prompts, int n_points);
+B200SAM_API int b200sam_decoder_create(const void* const* weights, int n_weights, b200sam_decoder** out, void* stream);
+B200SAM_API void b200sam_decoder_destroy(b200sam_decoder* dec);
+/* dense positional encoding, token-major [4096,256] (PromptEncoder.get_dense_pe, prompt_encoder.py:62-71) */
+B200SAM_API const float* b200sam_decoder_dense_pe(const b200sam_decoder* dec);
+/* embedding: [256,64,64]; coords: [n_prompts,n_points,2] (x,y) in the 1024 input frame; labels:
+ * [n_prompts,n_points] with -1 padding point, 0 negative, 1 positive, 2/3 box corners; mask_prev: optional
+ * [n_prompts,256,256] logits; outputs low_res: [n_prompts,(multimask?3:1),256,256], iou: [n_prompts,(3|1)] */
+B200SAM_API int b200sam_decode(const b200sam_decoder* dec, const float* embedding, int n_prompts, int n_points,
+                   const float* coords, const int32_t* labels, const float* mask_prev, int multimask,
+                   float* low_res_out, float* iou_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- mask post-processing
+ * Replaces postprocess_masks + threshold (segment_anything/sam_mask_decoder_head.py:99-135,
+ * modeling/sam.py:133-162) and the nearest-exact resample of utils/seg_refinement.py:111.
+ * low_res: [n,low,low]; any of mask_out [n,out_h,out_w] (0/1 bytes), logits_out [n,out_h,out_w] float32,
+ * small_out [n,small_h,small_w] may be NULL. */
+B200SAM_API int b200sam_upscale_threshold(const float* low_res, int n, int low, int img_size, int in_h, int in_w, int out_h,
+                              int out_w, float threshold, uint8_t* mask_out, float* logits_out, uint8_t* small_out,
+                              int small_h, int small_w, void* stream);
+
+/* ---------------------------------------------------------------- building blocks (exposed for parity tests)
+ * D[M,N] = A[M,K] W[N,K]^T (+bias) (+GELU) (+residual[row % res_row_mod]); bf16 operands, fp32 accumulate (tcgen05). */
+B200SAM_API int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M,
+                      int N, int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_bf16,
+                      int max_ctas, void* stream);
+B200SAM_API int b200sam_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
+                      int out_bf16, void* stream);
+/* qkv: [B*4096, 3*heads*hd] bf16; out: [B*4096, heads*hd] bf16; global_attn: 0 = 14x14 windows, 1 = global */
+B200SAM_API int b200sam_encoder_attention(const void* qkv, const void* qkv_bias_bf16, const void* rel_h_bf16,
+                              const void* rel_w_bf16, void* out, int batch, int heads, int hd, int global_attn,
+                              void* stream);
+B200SAM_API int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, int w, const float* mean3_host,
+                                const float* std3_host, void* out_bf16, void* stream);
+B200SAM_API int b200sam_linear_f32(const float* A, const float* A2, int a2_row_mod, const float* W, const float* bias,
+                       const float* residual, float* out, int M, int N, int K, int act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SAM_H */

@@ -1,0 +1,517 @@
+"""CPU oracle for the SAM pseudo-label refinement hot path.  TEST INFRASTRUCTURE ONLY.
+
+A functional, state-dict-driven restatement (plain torch fp32 on CPU + numpy integer code) of the reference
+algorithm in multimodallearning/SamCarriesTheBurden.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / `--impl reference` leg may import this module — never the product path.
+
+Pinning: the reference ships no golden vectors or tests, so the oracle is pinned against
+OUTPUTS OF THE REFERENCE ITSELF: tests/golden/make_golden.py imports /root/reference in the build container,
+runs its modules on seeded inputs and stores inputs + outputs as fixtures; tests/test_oracle_golden.py checks
+this file against those fixtures (and directly against the live reference when /root/reference exists).
+
+Every function cites the reference file:line it follows (paths relative to the reference root).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+# segment_anything/build_sam.py:14-44
+VIT_CONFIGS = {
+    "vit_h": dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31)),
+    "vit_l": dict(embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23)),
+    "vit_b": dict(embed_dim=768, depth=12, num_heads=12, global_attn_indexes=(2, 5, 8, 11)),
+}
+PIXEL_MEAN = (123.675, 116.28, 103.53)  # build_sam.py:99
+PIXEL_STD = (58.395, 57.12, 57.375)     # build_sam.py:100
+
+
+# ----------------------------------------------------------------------------------------------- encoder
+def preprocess(x: torch.Tensor, img_size: int = 1024) -> torch.Tensor:
+    """modeling/sam.py:164-174 — normalise then zero-pad bottom/right to img_size."""
+    mean = torch.tensor(PIXEL_MEAN).view(-1, 1, 1)
+    std = torch.tensor(PIXEL_STD).view(-1, 1, 1)
+    x = (x - mean) / std
+    h, w = x.shape[-2:]
+    return F.pad(x, (0, img_size - w, 0, img_size - h))
+
+
+def _rel_pos_bias(q: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, S: int) -> torch.Tensor:
+    """modeling/image_encoder.py:292-361 for q_size == k_size == (S, S): table length is 2S-1 so no
+    interpolation; bias[b, (qh,qw), (kh,kw)] = q . rel_h[qh-kh+S-1] + q . rel_w[qw-kw+S-1]."""
+    assert rel_h.shape[0] == 2 * S - 1 and rel_w.shape[0] == 2 * S - 1
+    idx = torch.arange(S)[:, None] - torch.arange(S)[None, :] + (S - 1)
+    Rh, Rw = rel_h[idx], rel_w[idx]  # [S, S, hd]
+    Bn, _, hd = q.shape
+    rq = q.reshape(Bn, S, S, hd)
+    bh = torch.einsum("bhwc,hkc->bhwk", rq, Rh)
+    bw = torch.einsum("bhwc,wkc->bhwk", rq, Rw)
+    return (bh[:, :, :, :, None] + bw[:, :, :, None, :]).reshape(Bn, S * S, S * S)
+
+
+def _encoder_attention(sd: SD, p: str, x: torch.Tensor, heads: int) -> torch.Tensor:
+    """modeling/image_encoder.py:224-240.  x: [B', S, S, D]."""
+    Bn, S, _, D = x.shape
+    hd = D // heads
+    qkv = F.linear(x, sd[p + "qkv.weight"], sd[p + "qkv.bias"])
+    qkv = qkv.reshape(Bn, S * S, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, Bn * heads, S * S, hd)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    attn = attn + _rel_pos_bias(q, sd[p + "rel_pos_h"], sd[p + "rel_pos_w"], S)  # unscaled q (:234)
+    attn = attn.softmax(dim=-1)
+    out = (attn @ v).view(Bn, heads, S, S, hd).permute(0, 2, 3, 1, 4).reshape(Bn, S, S, D)
+    return F.linear(out, sd[p + "proj.weight"], sd[p + "proj.bias"])
+
+
+def _encoder_block(sd: SD, p: str, x: torch.Tensor, heads: int, window: int) -> torch.Tensor:
+    """modeling/image_encoder.py:166-182 with window partition :243-289 (pad AFTER norm1)."""
+    B, H, W, D = x.shape
+    y = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps=1e-6)
+    if window > 0:
+        ph, pw = (-H) % window, (-W) % window
+        y = F.pad(y, (0, 0, 0, pw, 0, ph))
+        Hp, Wp = H + ph, W + pw
+        y = y.view(B, Hp // window, window, Wp // window, window, D).permute(0, 1, 3, 2, 4, 5)
+        y = y.reshape(-1, window, window, D)
+        y = _encoder_attention(sd, p + "attn.", y, heads)
+        y = y.view(B, Hp // window, Wp // window, window, window, D).permute(0, 1, 3, 2, 4, 5)
+        y = y.reshape(B, Hp, Wp, D)[:, :H, :W, :]
+    else:
+        y = _encoder_attention(sd, p + "attn.", y, heads)
+    x = x + y
+    z = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps=1e-6)
+    z = F.linear(F.gelu(F.linear(z, sd[p + "mlp.lin1.weight"], sd[p + "mlp.lin1.bias"])),
+                 sd[p + "mlp.lin2.weight"], sd[p + "mlp.lin2.bias"])  # common.py:25-26 (erf GELU)
+    return x + z
+
+
+def layer_norm_2d(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """modeling/common.py:31-43 — LayerNorm over the channel dim of NCHW (biased variance)."""
+    u = x.mean(1, keepdim=True)
+    s = (x - u).pow(2).mean(1, keepdim=True)
+    return w[:, None, None] * ((x - u) / torch.sqrt(s + eps)) + b[:, None, None]
+
+
+@torch.no_grad()
+def image_encoder(sd: SD, x: torch.Tensor, depth: int, num_heads: int, global_attn_indexes: Sequence[int],
+                  window_size: int = 14, prefix: str = "image_encoder.", **_unused) -> torch.Tensor:
+    """modeling/image_encoder.py:106-116.  x: preprocessed [B,3,1024,1024] -> [B,256,64,64]."""
+    p = prefix
+    t = F.conv2d(x, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"],
+                 stride=sd[p + "patch_embed.proj.weight"].shape[-1]).permute(0, 2, 3, 1)
+    t = t + sd[p + "pos_embed"]
+    for i in range(depth):
+        win = 0 if i in global_attn_indexes else window_size
+        t = _encoder_block(sd, f"{p}blocks.{i}.", t, num_heads, win)
+    t = t.permute(0, 3, 1, 2)
+    t = F.conv2d(t, sd[p + "neck.0.weight"])
+    t = layer_norm_2d(t, sd[p + "neck.1.weight"], sd[p + "neck.1.bias"])
+    t = F.conv2d(t, sd[p + "neck.2.weight"], padding=1)
+    return layer_norm_2d(t, sd[p + "neck.3.weight"], sd[p + "neck.3.bias"])
+
+
+# ----------------------------------------------------------------------------------------------- prompt encoder
+def _pe(sd: SD, coords01: torch.Tensor) -> torch.Tensor:
+    """modeling/prompt_encoder.py:185-192."""
+    c = 2 * coords01 - 1
+    c = c @ sd["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"]
+    c = 2 * np.pi * c
+    return torch.cat([torch.sin(c), torch.cos(c)], dim=-1)
+
+
+def dense_pe(sd: SD, size: int = 64) -> torch.Tensor:
+    """modeling/prompt_encoder.py:62-71,194-206 -> [1, 256, size, size]."""
+    g = torch.ones((size, size), dtype=torch.float32)
+    y = (g.cumsum(0) - 0.5) / size
+    x = (g.cumsum(1) - 0.5) / size
+    return _pe(sd, torch.stack([x, y], dim=-1)).permute(2, 0, 1).unsqueeze(0)
+
+
+def _pe_coords(sd: SD, coords: torch.Tensor, img: int = 1024) -> torch.Tensor:
+    c = coords.clone().to(torch.float)
+    c[:, :, 0] = c[:, :, 0] / img
+    c[:, :, 1] = c[:, :, 1] / img
+    return _pe(sd, c)
+
+
+@torch.no_grad()
+def prompt_encoder(sd: SD, points: Optional[Tuple[torch.Tensor, torch.Tensor]], boxes: Optional[torch.Tensor],
+                   masks: Optional[torch.Tensor], emb_size: int = 64, img_size: int = 1024) -> Tuple[torch.Tensor, torch.Tensor]:
+    """modeling/prompt_encoder.py:128-168 -> (sparse [B,N,256], dense [B,256,64,64])."""
+    pe = "prompt_encoder."
+    if points is not None:
+        bs = points[0].shape[0]
+    elif boxes is not None:
+        bs = boxes.shape[0]
+    elif masks is not None:
+        bs = masks.shape[0]
+    else:
+        bs = 1
+    C = sd[pe + "no_mask_embed.weight"].shape[1]
+    sparse = torch.empty((bs, 0, C))
+    if points is not None:
+        coords, labels = points
+        coords = coords + 0.5
+        if boxes is None:  # pad point, label -1 (:81-85)
+            coords = torch.cat([coords, torch.zeros((coords.shape[0], 1, 2))], dim=1)
+            labels = torch.cat([labels, -torch.ones((labels.shape[0], 1))], dim=1)
+        e = _pe_coords(sd, coords, img_size)
+        e[labels == -1] = 0.0
+        e[labels == -1] += sd[pe + "not_a_point_embed.weight"]
+        e[labels == 0] += sd[pe + "point_embeddings.0.weight"]
+        e[labels == 1] += sd[pe + "point_embeddings.1.weight"]
+        sparse = torch.cat([sparse, e], dim=1)
+    if boxes is not None:
+        c = (boxes + 0.5).reshape(-1, 2, 2)
+        e = _pe_coords(sd, c, img_size)
+        e[:, 0, :] += sd[pe + "point_embeddings.2.weight"]
+        e[:, 1, :] += sd[pe + "point_embeddings.3.weight"]
+        sparse = torch.cat([sparse, e], dim=1)
+    if masks is not None:
+        m = pe + "mask_downscaling."
+        d = F.conv2d(masks, sd[m + "0.weight"], sd[m + "0.bias"], stride=2)
+        d = F.gelu(layer_norm_2d(d, sd[m + "1.weight"], sd[m + "1.bias"]))
+        d = F.conv2d(d, sd[m + "3.weight"], sd[m + "3.bias"], stride=2)
+        d = F.gelu(layer_norm_2d(d, sd[m + "4.weight"], sd[m + "4.bias"]))
+        dense = F.conv2d(d, sd[m + "6.weight"], sd[m + "6.bias"])
+    else:
+        dense = sd[pe + "no_mask_embed.weight"].reshape(1, -1, 1, 1).expand(bs, -1, emb_size, emb_size)
+    return sparse, dense
+
+
+# ----------------------------------------------------------------------------------------------- mask decoder
+def _dec_attention(sd: SD, p: str, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """modeling/transformer.py:218-240 (scale applied after q.k)."""
+    q = F.linear(q, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])
+    k = F.linear(k, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"])
+    v = F.linear(v, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"])
+
+    def split(t):
+        b, n, c = t.shape
+        return t.reshape(b, n, heads, c // heads).transpose(1, 2)
+
+    q, k, v = split(q), split(k), split(v)
+    a = (q @ k.permute(0, 1, 3, 2)) / math.sqrt(q.shape[-1])
+    o = torch.softmax(a, dim=-1) @ v
+    b, h, n, c = o.shape
+    return F.linear(o.transpose(1, 2).reshape(b, n, h * c), sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+
+
+def _ln(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    return F.layer_norm(x, (x.shape[-1],), sd[p + "weight"], sd[p + "bias"], eps=1e-5)
+
+
+def two_way_transformer(sd: SD, src: torch.Tensor, pos: torch.Tensor, tokens: torch.Tensor, heads: int = 8,
+                        depth: int = 2, prefix: str = "mask_decoder.transformer.") -> Tuple[torch.Tensor, torch.Tensor]:
+    """modeling/transformer.py:62-106 and :151-182."""
+    keys = src.flatten(2).permute(0, 2, 1)
+    kpe = pos.flatten(2).permute(0, 2, 1)
+    queries, qpe = tokens, tokens
+    for i in range(depth):
+        L = f"{prefix}layers.{i}."
+        if i == 0:
+            queries = _dec_attention(sd, L + "self_attn.", queries, queries, queries, heads)
+        else:
+            q = queries + qpe
+            queries = queries + _dec_attention(sd, L + "self_attn.", q, q, queries, heads)
+        queries = _ln(sd, L + "norm1.", queries)
+        queries = _ln(sd, L + "norm2.", queries + _dec_attention(
+            sd, L + "cross_attn_token_to_image.", queries + qpe, keys + kpe, keys, heads))
+        mlp = F.linear(F.relu(F.linear(queries, sd[L + "mlp.lin1.weight"], sd[L + "mlp.lin1.bias"])),
+                       sd[L + "mlp.lin2.weight"], sd[L + "mlp.lin2.bias"])
+        queries = _ln(sd, L + "norm3.", queries + mlp)
+        keys = _ln(sd, L + "norm4.", keys + _dec_attention(
+            sd, L + "cross_attn_image_to_token.", keys + kpe, queries + qpe, queries, heads))
+    queries = _ln(sd, prefix + "norm_final_attn.", queries + _dec_attention(
+        sd, prefix + "final_attn_token_to_image.", queries + qpe, keys + kpe, keys, heads))
+    return queries, keys
+
+
+def _mlp(sd: SD, p: str, x: torch.Tensor, n: int = 3) -> torch.Tensor:
+    """modeling/mask_decoder.py:154-176."""
+    for j in range(n):
+        x = F.linear(x, sd[f"{p}layers.{j}.weight"], sd[f"{p}layers.{j}.bias"])
+        if j < n - 1:
+            x = F.relu(x)
+    return x
+
+
+@torch.no_grad()
+def mask_decoder(sd: SD, image_embeddings: torch.Tensor, image_pe: torch.Tensor, sparse: torch.Tensor,
+                 dense: torch.Tensor, multimask_output: bool, heads: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+    """modeling/mask_decoder.py:71-149 -> (masks [B,1|3,4h,4w], iou [B,1|3])."""
+    d = "mask_decoder."
+    n_mask = sd[d + "mask_tokens.weight"].shape[0]
+    out_tokens = torch.cat([sd[d + "iou_token.weight"], sd[d + "mask_tokens.weight"]], dim=0)
+    tokens = torch.cat((out_tokens.unsqueeze(0).expand(sparse.size(0), -1, -1), sparse), dim=1)
+    src = torch.repeat_interleave(image_embeddings, tokens.shape[0], dim=0) + dense
+    pos = torch.repeat_interleave(image_pe, tokens.shape[0], dim=0)
+    b, c, h, w = src.shape
+    hs, src = two_way_transformer(sd, src, pos, tokens, heads)
+    iou_tok, mask_toks = hs[:, 0, :], hs[:, 1:1 + n_mask, :]
+    src = src.transpose(1, 2).view(b, c, h, w)
+    u = d + "output_upscaling."
+    up = F.conv_transpose2d(src, sd[u + "0.weight"], sd[u + "0.bias"], stride=2)
+    up = F.gelu(layer_norm_2d(up, sd[u + "1.weight"], sd[u + "1.bias"]))
+    up = F.gelu(F.conv_transpose2d(up, sd[u + "3.weight"], sd[u + "3.bias"], stride=2))
+    hyper = torch.stack([_mlp(sd, f"{d}output_hypernetworks_mlps.{i}.", mask_toks[:, i, :]) for i in range(n_mask)], 1)
+    b, c, h, w = up.shape
+    masks = (hyper @ up.view(b, c, h * w)).view(b, -1, h, w)
+    iou = _mlp(sd, d + "iou_prediction_head.", iou_tok)
+    sl = slice(1, None) if multimask_output else slice(0, 1)
+    return masks[:, sl], iou[:, sl]
+
+
+# ----------------------------------------------------------------------------------------------- post-processing
+def postprocess_masks(masks: torch.Tensor, input_size: Sequence[int], original_size: Sequence[int],
+                      img_size: int = 1024) -> torch.Tensor:
+    """modeling/sam.py:133-162 == sam_mask_decoder_head.py:106-135."""
+    m = F.interpolate(masks, (img_size, img_size), mode="bilinear", align_corners=False)
+    m = m[..., : input_size[0], : input_size[1]]
+    return F.interpolate(m, tuple(original_size), mode="bilinear", align_corners=False)
+
+
+def get_preprocess_shape(oldh: int, oldw: int, long_side: int = 1024) -> Tuple[int, int]:
+    """utils/transforms.py:93-102."""
+    scale = long_side * 1.0 / max(oldh, oldw)
+    return int(oldh * scale + 0.5), int(oldw * scale + 0.5)
+
+
+# ----------------------------------------------------------------------------------------------- prompt extraction
+@dataclass
+class OraclePrompt:
+    class_idx: int
+    img_size: Tuple[int, int]
+    pos_seeds: np.ndarray  # int32 [1, 2] (x, y)
+    neg_seeds: np.ndarray  # int32 [K-1, 2]
+    box: Optional[np.ndarray]  # int32 [4] xmin, ymin, xmax, ymax
+
+
+def _round_half_even_f32(s: int, n: int) -> int:
+    """fp32(sum) / fp32(n) with IEEE division, then round-half-to-even — what torch's CPU
+    `coords.float().mean(0).round().int()` evaluates to (prompt_utils.py:41-42)."""
+    q = np.float32(s) / np.float32(n)
+    return int(np.rint(q))
+
+
+def extract_seeds_boxes(mask: np.ndarray):
+    """utils/prompt_utils.py:34-67: per-class seed on the non-overlap area, box on the full class mask.
+    mask: bool [C,H,W] -> seeds int32 [C,2] (x,y), has_seed [C], boxes int32 [C,4], has_box [C]."""
+    mask = np.asarray(mask).astype(bool)
+    C = mask.shape[0]
+    seeds = np.zeros((C, 2), np.int32)
+    boxes = np.zeros((C, 4), np.int32)
+    has_seed = np.zeros(C, bool)
+    has_box = np.zeros(C, bool)
+    if C == 0 or mask[0].size == 0:
+        return seeds, has_seed, boxes, has_box
+    non_overlap = mask.sum(0) < 2
+    for c in range(C):
+        rows, cols = np.nonzero(mask[c] & non_overlap)
+        if rows.size:
+            has_seed[c] = True
+            seeds[c] = (_round_half_even_f32(int(cols.sum()), cols.size), _round_half_even_f32(int(rows.sum()), rows.size))
+        rows, cols = np.nonzero(mask[c])
+        if rows.size:
+            has_box[c] = True
+            boxes[c] = (cols.min(), rows.min(), cols.max(), rows.max())
+    return seeds, has_seed, boxes, has_box
+
+
+def prompt_extract(mask: np.ndarray) -> List[OraclePrompt]:
+    """utils/prompt_utils.py:112-143 (seeds=True, boxes=True, mask=False)."""
+    seeds, has_seed, boxes, has_box = extract_seeds_boxes(mask)
+    idx = [c for c in range(mask.shape[0]) if has_seed[c]]
+    out = []
+    for c in idx:
+        others = [seeds[i] for i in idx if i != c]
+        if not others:  # torch.cat of an empty list raises in the reference (:122-123)
+            raise ValueError("torch.cat(): expected a non-empty list of Tensors")
+        out.append(OraclePrompt(c, tuple(mask.shape[-2:]), seeds[c][None].copy(), np.stack(others).astype(np.int32),
+                                boxes[c].copy() if has_box[c] else None))
+    return out
+
+
+def scale_coords(coords: torch.Tensor, original_size: Sequence[int], target_size: Sequence[int]) -> torch.Tensor:
+    """utils/prompt_utils.py:146-166 — fp32 (target/original) flipped to (x, y), then multiply."""
+    o = torch.tensor(original_size, dtype=torch.float)
+    t = torch.tensor(target_size, dtype=torch.float)
+    return coords.float() * (t / o).flip(-1)
+
+
+# ----------------------------------------------------------------------------------------------- refinement loop
+@torch.no_grad()
+def predict_mask(sd: SD, features: torch.Tensor, prompt: OraclePrompt, prompt2use: Sequence[str],
+                 input_size: Sequence[int], original_size: Sequence[int], mask_prev: Optional[torch.Tensor] = None):
+    """sam_mask_decoder_head.py:37-104 for one prompt (B = 1)."""
+    pts, labs = [], []
+    if "pos_points" in prompt2use:
+        p = scale_coords(torch.from_numpy(prompt.pos_seeds), prompt.img_size, input_size)
+        pts.append(p); labs.append(torch.ones(p.shape[0]))
+    if "neg_points" in prompt2use:
+        p = scale_coords(torch.from_numpy(prompt.neg_seeds), prompt.img_size, input_size)
+        pts.append(p); labs.append(torch.zeros(p.shape[0]))
+    box = None
+    if "box" in prompt2use:
+        b = torch.from_numpy(prompt.box).unsqueeze(0).reshape(-1, 2)
+        box = scale_coords(b, prompt.img_size, input_size).reshape(-1, 4).float()
+    points = (torch.cat(pts).float().unsqueeze(0), torch.cat(labs).int().unsqueeze(0)) if pts else None
+    sparse, dense = prompt_encoder(sd, points, box, mask_prev)
+    low, iou = mask_decoder(sd, features, dense_pe(sd), sparse, dense, multimask_output=False)
+    masks = postprocess_masks(low, input_size, original_size) > 0.0
+    return masks, iou, low
+
+
+@torch.no_grad()
+def refine(sd: SD, features: torch.Tensor, seg: np.ndarray, input_size: Sequence[int], original_size: Sequence[int],
+           prompts1=("box",), prompts2=("pos_points", "neg_points")):
+    """utils/seg_refinement.py:99-116 -> (seg bool [C,H,W], est_dice [C], extras for testing)."""
+    seg = np.asarray(seg).astype(bool).copy()
+    est = np.full(seg.shape[0], np.nan, np.float32)
+    prompts = prompt_extract(seg)
+    native, lows = {}, {}
+    for p in prompts:
+        mask, score, low1 = predict_mask(sd, features, p, prompts1, input_size, original_size)
+        low = low1
+        if prompts2 is not None:
+            mask, score, low = predict_mask(sd, features, p, prompts2, input_size, original_size, low1)
+        small = F.interpolate(mask.float(), size=seg.shape[-2:], mode="nearest-exact")
+        seg[p.class_idx] = small.squeeze().numpy() > 0.5
+        s = float(score.reshape(-1)[0])
+        est[p.class_idx] = 2 * s / (1 + s)
+        native[p.class_idx] = mask[0, 0].numpy()
+        lows[p.class_idx] = (low1[0, 0].numpy(), low[0, 0].numpy())
+    return seg, est, native, lows
+
+
+# ----------------------------------------------------------------------------------------------- synthetic inputs
+def random_state_dict(model_type: str = "vit_b", seed: int = 0) -> SD:
+    """Random-init weights with the reference's parameter names/shapes (build_sam.py:55-107), PyTorch
+    default initialisers, plus N(0, 0.02) pos_embed / rel_pos tables (zero at init in the reference,
+    image_encoder.py:68-70,221-222 — randomised so the rel-pos path is exercised)."""
+    cfg = VIT_CONFIGS[model_type]
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+
+    def lin(name, out_f, in_f, bias=True):
+        bound = 1.0 / math.sqrt(in_f)
+        sd[name + ".weight"] = (torch.rand((out_f, in_f), generator=g) * 2 - 1) * bound
+        if bias:
+            sd[name + ".bias"] = (torch.rand((out_f,), generator=g) * 2 - 1) * bound
+
+    def conv(name, out_c, in_c, k, bias=True, transposed=False):
+        fan_in = (out_c if transposed else in_c) * k * k
+        bound = 1.0 / math.sqrt(fan_in)
+        shape = (in_c, out_c, k, k) if transposed else (out_c, in_c, k, k)
+        sd[name + ".weight"] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        if bias:
+            sd[name + ".bias"] = (torch.rand((out_c,), generator=g) * 2 - 1) * bound
+
+    def norm(name, n):
+        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn((n,), generator=g)
+        sd[name + ".bias"] = 0.1 * torch.randn((n,), generator=g)
+
+    D, depth, heads = cfg["embed_dim"], cfg["depth"], cfg["num_heads"]
+    hd = D // heads
+    ie = "image_encoder."
+    conv(ie + "patch_embed.proj", D, 3, 16)
+    sd[ie + "pos_embed"] = 0.02 * torch.randn((1, 64, 64, D), generator=g)
+    for i in range(depth):
+        b = f"{ie}blocks.{i}."
+        S = 64 if i in cfg["global_attn_indexes"] else 14
+        norm(b + "norm1", D)
+        lin(b + "attn.qkv", 3 * D, D)
+        lin(b + "attn.proj", D, D)
+        sd[b + "attn.rel_pos_h"] = 0.02 * torch.randn((2 * S - 1, hd), generator=g)
+        sd[b + "attn.rel_pos_w"] = 0.02 * torch.randn((2 * S - 1, hd), generator=g)
+        norm(b + "norm2", D)
+        lin(b + "mlp.lin1", 4 * D, D)
+        lin(b + "mlp.lin2", D, 4 * D)
+    conv(ie + "neck.0", 256, D, 1, bias=False)
+    norm(ie + "neck.1", 256)
+    conv(ie + "neck.2", 256, 256, 3, bias=False)
+    norm(ie + "neck.3", 256)
+
+    pe = "prompt_encoder."
+    sd[pe + "pe_layer.positional_encoding_gaussian_matrix"] = torch.randn((2, 128), generator=g)
+    for i in range(4):
+        sd[f"{pe}point_embeddings.{i}.weight"] = torch.randn((1, 256), generator=g)
+    sd[pe + "not_a_point_embed.weight"] = torch.randn((1, 256), generator=g)
+    sd[pe + "no_mask_embed.weight"] = torch.randn((1, 256), generator=g)
+    conv(pe + "mask_downscaling.0", 4, 1, 2)
+    norm(pe + "mask_downscaling.1", 4)
+    conv(pe + "mask_downscaling.3", 16, 4, 2)
+    norm(pe + "mask_downscaling.4", 16)
+    conv(pe + "mask_downscaling.6", 256, 16, 1)
+
+    d = "mask_decoder."
+    sd[d + "iou_token.weight"] = torch.randn((1, 256), generator=g)
+    sd[d + "mask_tokens.weight"] = torch.randn((4, 256), generator=g)
+    t = d + "transformer."
+
+    def attn(name, internal):
+        for pr in ("q_proj", "k_proj", "v_proj"):
+            lin(f"{name}.{pr}", internal, 256)
+        lin(f"{name}.out_proj", 256, internal)
+
+    for i in range(2):
+        L = f"{t}layers.{i}."
+        attn(L + "self_attn", 256)
+        norm(L + "norm1", 256)
+        attn(L + "cross_attn_token_to_image", 128)
+        norm(L + "norm2", 256)
+        lin(L + "mlp.lin1", 2048, 256)
+        lin(L + "mlp.lin2", 256, 2048)
+        norm(L + "norm3", 256)
+        norm(L + "norm4", 256)
+        attn(L + "cross_attn_image_to_token", 128)
+    attn(t + "final_attn_token_to_image", 128)
+    norm(t + "norm_final_attn", 256)
+    conv(d + "output_upscaling.0", 64, 256, 2, transposed=True)
+    norm(d + "output_upscaling.1", 64)
+    conv(d + "output_upscaling.3", 32, 64, 2, transposed=True)
+    for i in range(4):
+        m = f"{d}output_hypernetworks_mlps.{i}.layers."
+        lin(m + "0", 256, 256); lin(m + "1", 256, 256); lin(m + "2", 32, 256)
+    m = d + "iou_prediction_head.layers."
+    lin(m + "0", 256, 256); lin(m + "1", 256, 256); lin(m + "2", 4, 256)
+    return sd
+
+
+def synthetic_radiograph(seed: int, h: int = 1024, w: int = 1024) -> np.ndarray:
+    """Smooth blobs + noise, grayscale replicated to RGB like generate_img_embeddings.py:39-40. uint8 HWC."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w), np.float32)
+    for _ in range(6):
+        cy, cx = rng.uniform(0, h), rng.uniform(0, w)
+        sy, sx = rng.uniform(h / 12, h / 3), rng.uniform(w / 12, w / 3)
+        img += rng.uniform(0.3, 1.0) * np.exp(-(((yy - cy) / sy) ** 2 + ((xx - cx) / sx) ** 2))
+    img = img / max(float(img.max()), 1e-6) * 200.0 + rng.uniform(0, 40, size=(h, w)).astype(np.float32)
+    g = np.clip(img, 0, 255).astype(np.uint8)
+    return np.repeat(g[:, :, None], 3, axis=2)
+
+
+def synthetic_unet_masks(seed: int, C: int = 17, H: int = 384, W: int = 224) -> np.ndarray:
+    """Bool [C,H,W]: one ellipse per class (+ optional distractor blob), some overlaps, 1-2 empty classes."""
+    rng = np.random.default_rng(1000 + seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    m = np.zeros((C, H, W), bool)
+    empty = set(rng.choice(C, size=int(rng.integers(1, 3)), replace=False).tolist())
+    for c in range(C):
+        if c in empty:
+            continue
+        cy, cx = rng.uniform(0.1 * H, 0.9 * H), rng.uniform(0.15 * W, 0.85 * W)
+        ry, rx = rng.uniform(8, 45), rng.uniform(6, 30)
+        m[c] = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0
+        if rng.random() < 0.4:
+            by, bx = rng.uniform(0, H), rng.uniform(0, W)
+            m[c] |= ((yy - by) / 4.0) ** 2 + ((xx - bx) / 4.0) ** 2 <= 1.0
+    return m

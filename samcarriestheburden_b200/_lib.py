@@ -1,0 +1,97 @@
+"""ctypes binding of libb200sam.so (the C ABI declared in include/b200sam.h).
+
+There is no CPU fallback: if the library cannot be loaded (or, later, no CUDA device is present) the
+product path raises.  Tensors cross the boundary as raw device pointers (`tensor.data_ptr()`) plus the
+current torch CUDA stream handle — no torch types in any signature.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libb200sam.so"
+
+_lib = None
+
+
+class B200SamError(RuntimeError):
+    pass
+
+
+class EncoderConfig(C.Structure):
+    _fields_ = [("embed_dim", C.c_int), ("depth", C.c_int), ("num_heads", C.c_int),
+                ("global_attn_mask", C.c_int), ("out_chans", C.c_int)]
+
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_PROTOTYPES = {
+    "b200sam_last_error": (C.c_char_p, []),
+    "b200sam_abi_version": (_i, []),
+    "b200sam_encoder_weight_count": (_i, [C.POINTER(EncoderConfig)]),
+    "b200sam_encoder_weight_name": (C.c_char_p, [C.POINTER(EncoderConfig), _i]),
+    "b200sam_encoder_workspace_bytes": (_sz, [C.POINTER(EncoderConfig), _i]),
+    "b200sam_encoder_create": (_i, [C.POINTER(EncoderConfig), C.POINTER(_vp), _i, C.POINTER(_vp)]),
+    "b200sam_encoder_destroy": (None, [_vp]),
+    "b200sam_encoder_forward": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp, _sz, _vp]),
+    "b200sam_prompt_extract_scratch_bytes": (_sz, [_i, _i]),
+    "b200sam_prompt_extract": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200sam_decoder_weight_count": (_i, []),
+    "b200sam_decoder_weight_name": (C.c_char_p, [_i]),
+    "b200sam_decoder_workspace_bytes": (_sz, [_i, _i]),
+    "b200sam_decoder_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp), _vp]),
+    "b200sam_decoder_destroy": (None, [_vp]),
+    "b200sam_decoder_dense_pe": (_vp, [_vp]),
+    "b200sam_decode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200sam_upscale_threshold": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
+    "b200sam_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200sam_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _i, _vp]),
+    "b200sam_encoder_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200sam_preprocess_patchify": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
+    "b200sam_linear_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+
+def load(build_if_missing: bool = True):
+    """dlopen the in-tree library (building it with nvcc if absent) and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if not build_if_missing:
+            raise B200SamError(f"{LIB_PATH} is missing; run `python -m samcarriestheburden_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI drift between header and library
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().b200sam_last_error()
+        raise B200SamError(f"{what or 'b200sam call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(device=None):
+    import torch
+    if not torch.cuda.is_available():
+        raise B200SamError("b200sam has no CPU fallback: a CUDA (sm_100a) device is required")
+    return torch.device(device if device is not None else "cuda")

@@ -1,0 +1,163 @@
+// extern "C" boundary (include/b200sam.h): argument validation + error plumbing, then the launchers.
+#include <stdarg.h>
+#include <stdio.h>
+#include "../../include/b200sam.h"
+#include "decoder.h"
+#include "encoder.h"
+#include "kernels.h"
+
+namespace b200sam {
+namespace {
+thread_local char g_err[1024] = "";
+}
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+}  // namespace b200sam
+
+using namespace b200sam;
+
+struct b200sam_encoder { Encoder* impl; };
+struct b200sam_decoder { Decoder* impl; };
+
+static EncoderConfig to_cfg(const b200sam_encoder_config* c) {
+  EncoderConfig e;
+  e.embed_dim = c->embed_dim; e.depth = c->depth; e.num_heads = c->num_heads;
+  e.global_mask_lo = c->global_attn_mask; e.out_chans = c->out_chans;
+  return e;
+}
+
+extern "C" {
+
+const char* b200sam_last_error(void) { return get_last_error(); }
+int b200sam_abi_version(void) { return 1; }
+
+int b200sam_encoder_weight_count(const b200sam_encoder_config* cfg) {
+  if (!cfg) return -1;
+  return encoder_weight_count(to_cfg(cfg));
+}
+const char* b200sam_encoder_weight_name(const b200sam_encoder_config* cfg, int i) {
+  if (!cfg) return nullptr;
+  return encoder_weight_name(to_cfg(cfg), i);
+}
+size_t b200sam_encoder_workspace_bytes(const b200sam_encoder_config* cfg, int batch) {
+  if (!cfg) return 0;
+  return encoder_workspace_bytes(to_cfg(cfg), batch);
+}
+int b200sam_encoder_create(const b200sam_encoder_config* cfg, const void* const* weights, int n_weights,
+                           b200sam_encoder** out) {
+  if (!cfg || !weights || !out) { set_last_error("encoder_create: null argument"); return 2; }
+  Encoder* e = nullptr;
+  if (int rc = encoder_create(to_cfg(cfg), weights, n_weights, &e)) return rc;
+  *out = new b200sam_encoder{e};
+  return 0;
+}
+void b200sam_encoder_destroy(b200sam_encoder* enc) {
+  if (!enc) return;
+  encoder_destroy(enc->impl);
+  delete enc;
+}
+int b200sam_encoder_forward(const b200sam_encoder* enc, const void* image, int is_u8, int batch, int h, int w,
+                            const float* mean3, const float* std3, float* embedding_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (!enc || !mean3 || !std3) { set_last_error("encoder_forward: null argument"); return 2; }
+  return encoder_forward(enc->impl, image, is_u8, batch, h, w, mean3, std3, embedding_out, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+size_t b200sam_prompt_extract_scratch_bytes(int n_img, int n_classes) {
+  if (n_img < 0 || n_classes < 0) return 0;
+  return prompt_extract_scratch_bytes(n_img, n_classes);
+}
+int b200sam_prompt_extract(const uint8_t* masks, int n_img, int n_classes, int H, int W, int32_t* seeds,
+                           int32_t* boxes, uint8_t* has_seed, uint8_t* has_box, void* scratch, void* stream) {
+  if (n_img > 0 && n_classes > 0 && (!masks || !seeds || !boxes || !has_seed || !has_box || !scratch)) {
+    set_last_error("prompt_extract: null argument");
+    return 2;
+  }
+  return prompt_extract(masks, n_img, n_classes, H, W, seeds, boxes, has_seed, has_box,
+                        static_cast<int32_t*>(scratch), static_cast<cudaStream_t>(stream));
+}
+
+int b200sam_decoder_weight_count(void) { return decoder_weight_count(); }
+const char* b200sam_decoder_weight_name(int i) { return decoder_weight_name(i); }
+size_t b200sam_decoder_workspace_bytes(int n_prompts, int n_points) {
+  return decoder_workspace_bytes(n_prompts, n_points);
+}
+int b200sam_decoder_create(const void* const* weights, int n_weights, b200sam_decoder** out, void* stream) {
+  if (!weights || !out) { set_last_error("decoder_create: null argument"); return 2; }
+  Decoder* d = nullptr;
+  if (int rc = decoder_create(weights, n_weights, &d, static_cast<cudaStream_t>(stream))) return rc;
+  *out = new b200sam_decoder{d};
+  return 0;
+}
+void b200sam_decoder_destroy(b200sam_decoder* dec) {
+  if (!dec) return;
+  decoder_destroy(dec->impl);
+  delete dec;
+}
+const float* b200sam_decoder_dense_pe(const b200sam_decoder* dec) { return dec ? decoder_dense_pe(dec->impl) : nullptr; }
+int b200sam_decode(const b200sam_decoder* dec, const float* embedding, int n_prompts, int n_points,
+                   const float* coords, const int32_t* labels, const float* mask_prev, int multimask,
+                   float* low_res_out, float* iou_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dec) { set_last_error("decode: null decoder"); return 2; }
+  DecodeArgs a;
+  a.emb = embedding; a.NB = n_prompts; a.Np = n_points; a.coords = coords; a.labels = labels; a.mask_prev = mask_prev;
+  a.img_w = 1024.0f; a.img_h = 1024.0f; a.multimask = multimask; a.low_res_out = low_res_out; a.iou_out = iou_out;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return decoder_forward(dec->impl, a, static_cast<cudaStream_t>(stream));
+}
+
+int b200sam_upscale_threshold(const float* low_res, int n, int low, int img_size, int in_h, int in_w, int out_h,
+                              int out_w, float threshold, uint8_t* mask_out, float* logits_out, uint8_t* small_out,
+                              int small_h, int small_w, void* stream) {
+  if (n > 0 && !low_res) { set_last_error("upscale: null input"); return 2; }
+  return upscale_threshold(low_res, n, low, img_size, in_h, in_w, out_h, out_w, threshold, mask_out, logits_out,
+                           small_out, small_h, small_w, static_cast<cudaStream_t>(stream));
+}
+
+int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M, int N,
+                      int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_bf16, int max_ctas,
+                      void* stream) {
+  if (!A || !W || !out) { set_last_error("gemm: null argument"); return 2; }
+  GemmArgs g;
+  g.A = static_cast<const __nv_bfloat16*>(A); g.B = static_cast<const __nv_bfloat16*>(W); g.out = out;
+  g.bias = bias; g.residual = residual; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldo = ldo; g.ldr = ldr;
+  g.res_row_mod = res_row_mod; g.gelu = gelu; g.out_bf16 = out_bf16; g.max_ctas = max_ctas;
+  return gemm_bf16_tn(g, static_cast<cudaStream_t>(stream));
+}
+int b200sam_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
+                      int out_bf16, void* stream) {
+  if (!x || !gamma || !beta || !y) { set_last_error("layernorm: null argument"); return 2; }
+  return layernorm_rows(x, gamma, beta, eps, M, D, y, out_bf16, static_cast<cudaStream_t>(stream));
+}
+int b200sam_encoder_attention(const void* qkv, const void* qkv_bias_bf16, const void* rel_h_bf16,
+                              const void* rel_w_bf16, void* out, int batch, int heads, int hd, int global_attn,
+                              void* stream) {
+  AttnArgs a;
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.qkv_bias = static_cast<const __nv_bfloat16*>(qkv_bias_bf16);
+  a.rel_h = static_cast<const __nv_bfloat16*>(rel_h_bf16); a.rel_w = static_cast<const __nv_bfloat16*>(rel_w_bf16);
+  a.out = static_cast<__nv_bfloat16*>(out); a.B = batch; a.heads = heads; a.hd = hd;
+  return global_attn ? global_attention(a, static_cast<cudaStream_t>(stream))
+                     : window_attention(a, static_cast<cudaStream_t>(stream));
+}
+int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, int w, const float* mean3,
+                                const float* std3, void* out_bf16, void* stream) {
+  if (!image || !mean3 || !std3 || !out_bf16) { set_last_error("preprocess: null argument"); return 2; }
+  return preprocess_patchify(image, is_u8, batch, h, w, mean3, std3, static_cast<__nv_bfloat16*>(out_bf16),
+                             static_cast<cudaStream_t>(stream));
+}
+int b200sam_linear_f32(const float* A, const float* A2, int a2_row_mod, const float* W, const float* bias,
+                       const float* residual, float* out, int M, int N, int K, int act, void* stream) {
+  if (!A || !W || !out) { set_last_error("linear_f32: null argument"); return 2; }
+  LinearArgs p;
+  p.A = A; p.A2 = A2; p.W = W; p.bias = bias; p.residual = residual; p.out = out; p.M = M; p.N = N; p.K = K;
+  p.lda = K; p.lda2 = K; p.ldo = N; p.ldr = N; p.a2_row_mod = a2_row_mod; p.act = act;
+  return linear_f32(p, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

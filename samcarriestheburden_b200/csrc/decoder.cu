@@ -1,0 +1,257 @@
+// Host-side orchestration of the prompt encoder + mask decoder for ALL prompts of one image in one
+// batched pass (reference loop being replaced: utils/seg_refinement.py:105-109 calling
+// sam_mask_decoder_head.py:79-96 once per class with B=1).  Pure launch sequencing: no allocation, no
+// synchronisation; every buffer lives in the caller-provided workspace.
+#include "decoder.h"
+#include <string>
+#include <vector>
+
+namespace b200sam {
+
+namespace {
+
+const char* kAttnParts[8] = {"q_proj.weight", "q_proj.bias", "k_proj.weight", "k_proj.bias",
+                             "v_proj.weight", "v_proj.bias", "out_proj.weight", "out_proj.bias"};
+
+std::vector<std::string> build_names() {
+  std::vector<std::string> n;
+  const std::string pe = "prompt_encoder.";
+  n.push_back(pe + "pe_layer.positional_encoding_gaussian_matrix");
+  n.push_back(pe + "point_embeddings|cat4");  // [4,256] = cat(point_embeddings.{0..3}.weight)
+  n.push_back(pe + "not_a_point_embed.weight");
+  n.push_back(pe + "no_mask_embed.weight");
+  const char* md[5] = {"0", "1", "3", "4", "6"};
+  for (int i = 0; i < 5; ++i) {
+    n.push_back(pe + "mask_downscaling." + md[i] + ".weight");
+    n.push_back(pe + "mask_downscaling." + md[i] + ".bias");
+  }
+  const std::string dec = "mask_decoder.";
+  n.push_back(dec + "iou_token.weight");
+  n.push_back(dec + "mask_tokens.weight");
+  for (int l = 0; l < 2; ++l) {
+    const std::string L = dec + "transformer.layers." + std::to_string(l) + ".";
+    for (int i = 0; i < 8; ++i) n.push_back(L + "self_attn." + kAttnParts[i]);
+    n.push_back(L + "norm1.weight"); n.push_back(L + "norm1.bias");
+    for (int i = 0; i < 8; ++i) n.push_back(L + "cross_attn_token_to_image." + kAttnParts[i]);
+    n.push_back(L + "norm2.weight"); n.push_back(L + "norm2.bias");
+    n.push_back(L + "mlp.lin1.weight"); n.push_back(L + "mlp.lin1.bias");
+    n.push_back(L + "mlp.lin2.weight"); n.push_back(L + "mlp.lin2.bias");
+    n.push_back(L + "norm3.weight"); n.push_back(L + "norm3.bias");
+    n.push_back(L + "norm4.weight"); n.push_back(L + "norm4.bias");
+    for (int i = 0; i < 8; ++i) n.push_back(L + "cross_attn_image_to_token." + kAttnParts[i]);
+  }
+  for (int i = 0; i < 8; ++i) n.push_back(dec + "transformer.final_attn_token_to_image." + kAttnParts[i]);
+  n.push_back(dec + "transformer.norm_final_attn.weight");
+  n.push_back(dec + "transformer.norm_final_attn.bias");
+  n.push_back(dec + "output_upscaling.0.weight|convT");  // [(dy*2+dx)*Cout+co, ci]
+  n.push_back(dec + "output_upscaling.0.bias|repeat4");
+  n.push_back(dec + "output_upscaling.1.weight");
+  n.push_back(dec + "output_upscaling.1.bias");
+  n.push_back(dec + "output_upscaling.3.weight|convT");
+  n.push_back(dec + "output_upscaling.3.bias|repeat4");
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const std::string M = dec + "output_hypernetworks_mlps." + std::to_string(i) + ".layers." + std::to_string(j);
+      n.push_back(M + ".weight");
+      n.push_back(M + ".bias");
+    }
+  for (int j = 0; j < 3; ++j) {
+    const std::string M = dec + "iou_prediction_head.layers." + std::to_string(j);
+    n.push_back(M + ".weight");
+    n.push_back(M + ".bias");
+  }
+  return n;
+}
+
+const std::vector<std::string>& names() {
+  static std::vector<std::string> n = build_names();
+  return n;
+}
+
+// offsets into the table (must mirror build_names)
+enum : int {
+  W_GAUSS = 0, W_POINT4 = 1, W_NOT_A_POINT = 2, W_NO_MASK = 3, W_MASKDOWN = 4 /*10*/, W_IOU_TOKEN = 14,
+  W_MASK_TOKENS = 15, W_LAYER0 = 16, LAYER_STRIDE = 36,
+  L_SELF = 0, L_N1 = 8, L_T2I = 10, L_N2 = 18, L_MLP = 20, L_N3 = 24, L_N4 = 26, L_I2T = 28,
+  W_FINAL = W_LAYER0 + 2 * LAYER_STRIDE, W_NF = W_FINAL + 8, W_UP = W_NF + 2 /*6*/, W_HYPER = W_UP + 6 /*24*/,
+  W_IOUHEAD = W_HYPER + 24 /*6*/, W_COUNT = W_IOUHEAD + 6
+};
+
+__global__ void slice_iou_kernel(const float* __restrict__ iou4, float* __restrict__ out, int NB, int tok0, int ntok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < NB * ntok) out[i] = iou4[(i / ntok) * 4 + tok0 + (i % ntok)];
+}
+
+inline size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+struct Workspace {
+  float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *abuf, *up1, *up2;
+  float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4;
+  size_t total;
+};
+
+Workspace carve(uint8_t* base, int NB, int T) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* p = reinterpret_cast<float*>(base + off);
+    off += align_up(nfloat * sizeof(float));
+    return p;
+  };
+  const size_t Mi = static_cast<size_t>(NB) * 4096, Mt = static_cast<size_t>(NB) * T;
+  w.emb_tok = take(4096 * 256);
+  w.keys = take(Mi * 256);
+  w.kbuf = take(Mi * 128);
+  w.vbuf = take(Mi * 128);
+  w.qibuf = take(Mi * 128);
+  w.abuf = take(Mi * 128);
+  w.up1 = take(Mi * 256);
+  w.up2 = take(Mi * 512);
+  w.tokens = take(Mt * 256);
+  w.queries = take(Mt * 256);
+  w.tq = take(Mt * 256);
+  w.tk = take(Mt * 256);
+  w.tv = take(Mt * 256);
+  w.ta = take(Mt * 256);
+  w.th = take(Mt * 2048);
+  w.hyper = take(static_cast<size_t>(NB) * 128);
+  w.iou4 = take(static_cast<size_t>(NB) * 4);
+  w.total = off;
+  return w;
+}
+
+int lin(const float* A, const float* A2, int a2mod, const float* W, const float* b, const float* res, float* out, int M,
+        int N, int K, int act, cudaStream_t s) {
+  LinearArgs p;
+  p.A = A; p.A2 = A2; p.W = W; p.bias = b; p.residual = res; p.out = out;
+  p.M = M; p.N = N; p.K = K; p.lda = K; p.lda2 = K; p.ldo = N; p.ldr = N; p.a2_row_mod = a2mod; p.act = act;
+  return linear_f32(p, s);
+}
+
+#define TRY(x) do { if (int _rc = (x)) return _rc; } while (0)
+
+}  // namespace
+
+int decoder_weight_count() { return W_COUNT; }
+const char* decoder_weight_name(int i) {
+  if (i < 0 || i >= static_cast<int>(names().size())) return nullptr;
+  return names()[i].c_str();
+}
+
+size_t decoder_workspace_bytes(int NB, int Np) {
+  if (NB <= 0 || Np < 0) return 0;
+  return carve(nullptr, NB, 5 + Np).total + 256;
+}
+
+int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_t stream) {
+  B200SAM_REQUIRE(n == W_COUNT && static_cast<int>(names().size()) == W_COUNT,
+                  "decoder_create: expected %d weight pointers, got %d", W_COUNT, n);
+  for (int i = 0; i < n; ++i) B200SAM_REQUIRE(weights[i] != nullptr, "decoder_create: weight %d (%s) is null", i,
+                                              names()[i].c_str());
+  Decoder* d = new Decoder();
+  d->w.assign(reinterpret_cast<const float* const*>(weights), reinterpret_cast<const float* const*>(weights) + n);
+  d->pe_tok = nullptr;
+  if (cudaMalloc(&d->pe_tok, 4096 * 256 * sizeof(float)) != cudaSuccess) {
+    set_last_error("decoder_create: cudaMalloc of the dense PE table failed");
+    delete d;
+    return 1;
+  }
+  if (int rc = dense_pe_tokens(d->w[W_GAUSS], d->pe_tok, stream)) { cudaFree(d->pe_tok); delete d; return rc; }
+  *out = d;
+  return 0;
+}
+
+void decoder_destroy(Decoder* d) {
+  if (d == nullptr) return;
+  if (d->pe_tok) cudaFree(d->pe_tok);
+  delete d;
+}
+
+const float* decoder_dense_pe(const Decoder* d) { return d->pe_tok; }
+
+int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
+  B200SAM_REQUIRE(a.NB > 0 && a.Np >= 0, "decode: bad prompt batch NB=%d Np=%d", a.NB, a.Np);
+  const int NB = a.NB, T = 5 + a.Np;
+  B200SAM_REQUIRE(T <= 32, "decode: at most 27 sparse prompt tokens per prompt supported, got %d", a.Np);
+  B200SAM_REQUIRE(a.Np == 0 || (a.coords != nullptr && a.labels != nullptr), "decode: coords/labels missing");
+  B200SAM_REQUIRE(a.emb != nullptr && a.low_res_out != nullptr && a.iou_out != nullptr, "decode: null in/out pointer");
+  B200SAM_REQUIRE(a.workspace != nullptr && (reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0,
+                  "decode: workspace must be non-null and 256-byte aligned");
+  Workspace w = carve(reinterpret_cast<uint8_t*>(a.workspace), NB, T);
+  B200SAM_REQUIRE(w.total <= a.workspace_bytes, "decode: workspace too small (%zu < %zu)", a.workspace_bytes, w.total);
+  const float* const* W = d->w.data();
+  const int Mi = NB * 4096, Mt = NB * T;
+  const float* pe = d->pe_tok;
+
+  // ---- prompt encoder (prompt_encoder.py:128-168) + output tokens (mask_decoder.py:120-122)
+  TRY(prompt_tokens(a.coords, a.labels, NB, a.Np, W[W_GAUSS], W[W_POINT4], W[W_NOT_A_POINT], W[W_IOU_TOKEN],
+                    W[W_MASK_TOKENS], a.img_w, a.img_h, w.tokens, s));
+  TRY(nchw_to_tokens(a.emb, w.emb_tok, s));
+  if (a.mask_prev != nullptr) TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, s));
+  else TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, s));
+  B200SAM_CHECK_CUDA(cudaMemcpyAsync(w.queries, w.tokens, static_cast<size_t>(Mt) * 256 * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+
+  // ---- two-way transformer (transformer.py:62-106, :151-182)
+  for (int l = 0; l < 2; ++l) {
+    const float* const* L = W + W_LAYER0 + l * LAYER_STRIDE;
+    const float* const* SA = L + L_SELF;
+    const float* qpe = l == 0 ? nullptr : w.tokens;  // layer 0 skips the PE and REPLACES the queries
+    TRY(lin(w.queries, qpe, 0, SA[0], SA[1], nullptr, w.tq, Mt, 256, 256, 0, s));
+    TRY(lin(w.queries, qpe, 0, SA[2], SA[3], nullptr, w.tk, Mt, 256, 256, 0, s));
+    TRY(lin(w.queries, nullptr, 0, SA[4], SA[5], nullptr, w.tv, Mt, 256, 256, 0, s));
+    TRY(attn_few_queries(w.tq, w.tk, w.tv, w.ta, NB, T, T, 8, 32, s));
+    TRY(lin(w.ta, nullptr, 0, SA[6], SA[7], l == 0 ? nullptr : w.queries, w.queries, Mt, 256, 256, 0, s));
+    TRY(layernorm_rows(w.queries, L[L_N1], L[L_N1 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
+
+    const float* const* TI = L + L_T2I;
+    TRY(lin(w.queries, w.tokens, 0, TI[0], TI[1], nullptr, w.tq, Mt, 128, 256, 0, s));
+    TRY(lin(w.keys, pe, 4096, TI[2], TI[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
+    TRY(lin(w.keys, nullptr, 0, TI[4], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
+    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, s));
+    TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
+    TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
+
+    TRY(lin(w.queries, nullptr, 0, L[L_MLP], L[L_MLP + 1], nullptr, w.th, Mt, 2048, 256, 1, s));
+    TRY(lin(w.th, nullptr, 0, L[L_MLP + 2], L[L_MLP + 3], w.queries, w.queries, Mt, 256, 2048, 0, s));
+    TRY(layernorm_rows(w.queries, L[L_N3], L[L_N3 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
+
+    const float* const* IT = L + L_I2T;  // image tokens are the queries here
+    TRY(lin(w.keys, pe, 4096, IT[0], IT[1], nullptr, w.qibuf, Mi, 128, 256, 0, s));
+    TRY(lin(w.queries, w.tokens, 0, IT[2], IT[3], nullptr, w.tk, Mt, 128, 256, 0, s));
+    TRY(lin(w.queries, nullptr, 0, IT[4], IT[5], nullptr, w.tv, Mt, 128, 256, 0, s));
+    TRY(attn_few_keys(w.qibuf, w.tk, w.tv, w.abuf, NB, 4096, T, s));
+    TRY(lin(w.abuf, nullptr, 0, IT[6], IT[7], w.keys, w.keys, Mi, 256, 128, 0, s));
+    TRY(layernorm_rows(w.keys, L[L_N4], L[L_N4 + 1], 1e-5f, Mi, 256, w.keys, 0, s));
+  }
+  {
+    const float* const* F = W + W_FINAL;
+    TRY(lin(w.queries, w.tokens, 0, F[0], F[1], nullptr, w.tq, Mt, 128, 256, 0, s));
+    TRY(lin(w.keys, pe, 4096, F[2], F[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
+    TRY(lin(w.keys, nullptr, 0, F[4], F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
+    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, s));
+    TRY(lin(w.ta, nullptr, 0, F[6], F[7], w.queries, w.queries, Mt, 256, 128, 0, s));
+    TRY(layernorm_rows(w.queries, W[W_NF], W[W_NF + 1], 1e-5f, Mt, 256, w.queries, 0, s));
+  }
+
+  // ---- upscaling + hypernetwork heads (mask_decoder.py:137-147)
+  const float* const* U = W + W_UP;
+  TRY(lin(w.keys, nullptr, 0, U[0], U[1], nullptr, w.up1, Mi, 256, 256, 0, s));      // ConvT 256->64, k2 s2
+  TRY(ln64_gelu(w.up1, U[2], U[3], static_cast<size_t>(Mi) * 4, s));                  // LayerNorm2d(64) + GELU
+  TRY(lin(w.up1, nullptr, 0, U[4], U[5], nullptr, w.up2, Mi * 4, 128, 64, 2, s));     // ConvT 64->32 + GELU
+  {
+    const float* wt[15];
+    const float* bs[15];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 3; ++j) { wt[i * 3 + j] = W[W_HYPER + (i * 3 + j) * 2]; bs[i * 3 + j] = W[W_HYPER + (i * 3 + j) * 2 + 1]; }
+    for (int j = 0; j < 3; ++j) { wt[12 + j] = W[W_IOUHEAD + 2 * j]; bs[12 + j] = W[W_IOUHEAD + 2 * j + 1]; }
+    TRY(mlp3_tokens(w.queries, NB, T, wt, bs, w.hyper, w.iou4, s));
+  }
+  const int tok0 = a.multimask ? 1 : 0, ntok = a.multimask ? 3 : 1;  // mask_decoder.py:101-107
+  TRY(mask_dot(w.up2, w.hyper, NB, tok0, ntok, a.low_res_out, s));
+  slice_iou_kernel<<<(NB * ntok + 127) / 128, 128, 0, s>>>(w.iou4, a.iou_out, NB, tok0, ntok);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200sam

@@ -1,0 +1,36 @@
+// Decoder context: borrowed fp32 weight pointers (owned by the Python modules) + the cached dense PE.
+#pragma once
+#include <vector>
+#include "decoder_ops.h"
+
+namespace b200sam {
+
+struct Decoder {
+  std::vector<const float*> w;  // in decoder_weight_name() order
+  float* pe_tok;                // [4096, 256] token-major dense positional encoding (owned)
+};
+
+struct DecodeArgs {
+  const float* emb;        // [256, 64, 64] fp32 image embedding (NCHW, one image)
+  int NB;                  // prompts in this batch
+  int Np;                  // sparse points per prompt (incl. pad / box corners), same for all prompts
+  const float* coords;     // [NB, Np, 2] (x, y) in the encoder input frame
+  const int* labels;       // [NB, Np]: -1 pad, 0 neg, 1 pos, 2/3 box corners
+  const float* mask_prev;  // [NB, 256, 256] logits of a previous pass, or null
+  float img_w, img_h;      // prompt_encoder.input_image_size (W, H) = (1024, 1024)
+  int multimask;           // 0: mask token 0 only, 1: tokens 1..3
+  float* low_res_out;      // [NB, 1|3, 256, 256]
+  float* iou_out;          // [NB, 1|3]
+  void* workspace;
+  size_t workspace_bytes;
+};
+
+int decoder_weight_count();
+const char* decoder_weight_name(int i);
+size_t decoder_workspace_bytes(int NB, int Np);
+int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_t stream);
+void decoder_destroy(Decoder* d);
+const float* decoder_dense_pe(const Decoder* d);
+int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t stream);
+
+}  // namespace b200sam

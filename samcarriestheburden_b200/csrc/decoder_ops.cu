@@ -1,0 +1,640 @@
+// fp32 kernels for the prompt encoder + two-way-transformer mask decoder, batched over all prompts of
+// an image (reference: segment_anything/modeling/prompt_encoder.py, mask_decoder.py, transformer.py).
+// The decoder has to run at ~fp32 accuracy (random-init logits hug the 0.0 threshold; bf16 flips
+// pixels - SURVEY section 7), so everything here is FFMA with fp32 data, tiled through shared memory.
+#include "common.cuh"
+#include "decoder_ops.h"
+
+namespace b200sam {
+
+namespace {
+
+constexpr float TWO_PI = 6.283185307179586f;
+
+B200SAM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------ generic fp32 linear
+// out[m, n] = act( sum_k (A[m,k] + A2[m2,k]) * W[n,k] + bias[n] ) + residual[m, n]
+constexpr int LBM = 128, LBN = 64, LBK = 16;
+
+__global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
+  __shared__ __align__(16) float As[2][LBK][LBM + 4];
+  __shared__ __align__(16) float Bs[2][LBK][LBN + 4];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.y * LBM, n0 = blockIdx.x * LBN;
+  const int nk = p.K / LBK;
+
+  float4 ra[2], rb;
+  auto gload = [&](int kt) {
+    const int k0 = kt * LBK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + 256 * i;
+      const int row = f >> 2, kq = f & 3;
+      const int m = m0 + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < p.M) {
+        v = *reinterpret_cast<const float4*>(p.A + static_cast<size_t>(m) * p.lda + k0 + kq * 4);
+        if (p.A2 != nullptr) {
+          const int m2 = p.a2_row_mod > 0 ? (m % p.a2_row_mod) : m;
+          const float4 w = *reinterpret_cast<const float4*>(p.A2 + static_cast<size_t>(m2) * p.lda2 + k0 + kq * 4);
+          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+      }
+      ra[i] = v;
+    }
+    {
+      const int row = tid >> 2, kq = tid & 3;
+      const int n = n0 + row;
+      rb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < p.N) rb = *reinterpret_cast<const float4*>(p.W + static_cast<size_t>(n) * p.K + k0 + kq * 4);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + 256 * i;
+      const int row = f >> 2, kq = f & 3;
+      As[buf][kq * 4 + 0][row] = ra[i].x;
+      As[buf][kq * 4 + 1][row] = ra[i].y;
+      As[buf][kq * 4 + 2][row] = ra[i].z;
+      As[buf][kq * 4 + 3][row] = ra[i].w;
+    }
+    const int row = tid >> 2, kq = tid & 3;
+    Bs[buf][kq * 4 + 0][row] = rb.x;
+    Bs[buf][kq * 4 + 1][row] = rb.y;
+    Bs[buf][kq * 4 + 2][row] = rb.z;
+    Bs[buf][kq * 4 + 3][row] = rb.w;
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+    for (int k = 0; k < LBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const int n = n0 + tx * 4;
+  if (n >= p.N) return;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr) bias = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    float4 v = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
+    if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    else if (p.act == 2) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+    if (p.residual != nullptr) {
+      const float4 r = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * p.ldr + n);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    *reinterpret_cast<float4*>(p.out + static_cast<size_t>(m) * p.ldo + n) = v;
+  }
+}
+
+// ------------------------------------------------------------------ attention, few queries x many keys
+// One CTA per (batch, head). Queries (<= 32 per pass) are split over the 8 warps; keys/values stream
+// through shared memory in tiles; each lane keeps an online-softmax state for its share of the keys and
+// the lanes are merged at the end.  scale = 1/sqrt(DH) applied after q.k (transformer.py:231-232).
+template <int DH>
+__global__ void __launch_bounds__(256) attn_fewq_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                        const float* __restrict__ v, float* __restrict__ out, int Tq,
+                                                        int Tk, int heads) {
+  constexpr int KT = 128;       // keys per tile
+  constexpr int PAD = DH + 4;   // conflict-free float4 rows
+  constexpr int QPW = 4;        // queries per warp per pass
+  __shared__ __align__(16) float ks[KT][PAD];
+  __shared__ __align__(16) float vs[KT][PAD];
+  __shared__ __align__(16) float qs[32][DH];
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int C = heads * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float scale = rsqrtf(static_cast<float>(DH));
+  const float* kb = k + static_cast<size_t>(b) * Tk * C + h * DH;
+  const float* vb = v + static_cast<size_t>(b) * Tk * C + h * DH;
+
+  for (int qbase = 0; qbase < Tq; qbase += 32) {
+    const int nq = min(32, Tq - qbase);
+    __syncthreads();
+    for (int i = tid; i < nq * DH; i += 256) {
+      const int qi = i / DH, d = i - qi * DH;
+      qs[qi][d] = q[(static_cast<size_t>(b) * Tq + qbase + qi) * C + h * DH + d];
+    }
+    float m[QPW], l[QPW], acc[QPW][DH];
+#pragma unroll
+    for (int j = 0; j < QPW; ++j) {
+      m[j] = -INFINITY;
+      l[j] = 0.0f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) acc[j][d] = 0.0f;
+    }
+    for (int k0 = 0; k0 < Tk; k0 += KT) {
+      const int nk = min(KT, Tk - k0);
+      __syncthreads();
+      for (int i = tid; i < KT * (DH / 4); i += 256) {
+        const int r = i / (DH / 4), c4 = i - r * (DH / 4);
+        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+        if (r < nk) {
+          kv = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(k0 + r) * C + c4 * 4);
+          vv = *reinterpret_cast<const float4*>(vb + static_cast<size_t>(k0 + r) * C + c4 * 4);
+        }
+        *reinterpret_cast<float4*>(&ks[r][c4 * 4]) = kv;
+        *reinterpret_cast<float4*>(&vs[r][c4 * 4]) = vv;
+      }
+      __syncthreads();
+      for (int r = lane; r < nk; r += 32) {
+        float kr[DH], vr[DH];
+#pragma unroll
+        for (int c4 = 0; c4 < DH / 4; ++c4) {
+          const float4 a = *reinterpret_cast<const float4*>(&ks[r][c4 * 4]);
+          const float4 c = *reinterpret_cast<const float4*>(&vs[r][c4 * 4]);
+          kr[c4 * 4] = a.x; kr[c4 * 4 + 1] = a.y; kr[c4 * 4 + 2] = a.z; kr[c4 * 4 + 3] = a.w;
+          vr[c4 * 4] = c.x; vr[c4 * 4 + 1] = c.y; vr[c4 * 4 + 2] = c.z; vr[c4 * 4 + 3] = c.w;
+        }
+#pragma unroll
+        for (int j = 0; j < QPW; ++j) {
+          const int qi = warp + 8 * j;
+          if (qi < nq) {
+            float s = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) s = fmaf(qs[qi][d], kr[d], s);
+            s *= scale;
+            if (s > m[j]) {
+              const float c = expf(m[j] - s);
+              l[j] *= c;
+#pragma unroll
+              for (int d = 0; d < DH; ++d) acc[j][d] *= c;
+              m[j] = s;
+            }
+            const float pw = expf(s - m[j]);
+            l[j] += pw;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[j][d] = fmaf(pw, vr[d], acc[j][d]);
+          }
+        }
+      }
+    }
+    // merge the 32 per-lane partial softmax states
+#pragma unroll
+    for (int j = 0; j < QPW; ++j) {
+      const int qi = warp + 8 * j;
+      if (qi >= nq) continue;  // warp-uniform
+      const float mall = warp_max(m[j]);
+      const float c = (m[j] == -INFINITY) ? 0.0f : expf(m[j] - mall);
+      const float lall = warp_sum(l[j] * c);
+      const float inv = 1.0f / lall;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) {
+        const float o = warp_sum(acc[j][d] * c);
+        if (lane == 0) out[(static_cast<size_t>(b) * Tq + qbase + qi) * C + h * DH + d] = o * inv;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ attention, many queries x few keys
+// image -> token cross attention (transformer.py:175-180): every image token attends over <= 32 prompt
+// tokens. One thread per (image token, head); K/V of the tokens sit in shared memory.
+__global__ void __launch_bounds__(256) attn_fewk_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                        const float* __restrict__ v, float* __restrict__ out, int Nq,
+                                                        int Tk) {
+  constexpr int DH = 16, HEADS = 8, C = 128, PAD = 20, MAXK = 32;
+  __shared__ __align__(16) float ks[MAXK][HEADS][PAD];
+  __shared__ __align__(16) float vs[MAXK][HEADS][PAD];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < Tk * C; i += 256) {
+    const int t = i / C, c = i - t * C;
+    ks[t][c / DH][c % DH] = k[(static_cast<size_t>(b) * Tk + t) * C + c];
+    vs[t][c / DH][c % DH] = v[(static_cast<size_t>(b) * Tk + t) * C + c];
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int row = idx >> 3, h = idx & 7;
+  if (row >= Nq) return;
+  const float* qp = q + (static_cast<size_t>(b) * Nq + row) * C + h * DH;
+  float qr[DH];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const float4 a = *reinterpret_cast<const float4*>(qp + c4 * 4);
+    qr[c4 * 4] = a.x; qr[c4 * 4 + 1] = a.y; qr[c4 * 4 + 2] = a.z; qr[c4 * 4 + 3] = a.w;
+  }
+  float s[MAXK];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < MAXK; ++t) {
+    if (t < Tk) {
+      float d = 0.0f;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&ks[t][h][c4 * 4]);
+        d = fmaf(qr[c4 * 4], kk.x, d); d = fmaf(qr[c4 * 4 + 1], kk.y, d);
+        d = fmaf(qr[c4 * 4 + 2], kk.z, d); d = fmaf(qr[c4 * 4 + 3], kk.w, d);
+      }
+      s[t] = d * 0.25f;  // 1/sqrt(16)
+      mx = fmaxf(mx, s[t]);
+    }
+  }
+  float sum = 0.0f;
+  float o[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) o[d] = 0.0f;
+#pragma unroll
+  for (int t = 0; t < MAXK; ++t) {
+    if (t < Tk) {
+      const float pw = expf(s[t] - mx);
+      sum += pw;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&vs[t][h][c4 * 4]);
+        o[c4 * 4] = fmaf(pw, vv.x, o[c4 * 4]); o[c4 * 4 + 1] = fmaf(pw, vv.y, o[c4 * 4 + 1]);
+        o[c4 * 4 + 2] = fmaf(pw, vv.z, o[c4 * 4 + 2]); o[c4 * 4 + 3] = fmaf(pw, vv.w, o[c4 * 4 + 3]);
+      }
+    }
+  }
+  const float inv = 1.0f / sum;
+  float* op = out + (static_cast<size_t>(b) * Nq + row) * C + h * DH;
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4)
+    *reinterpret_cast<float4*>(op + c4 * 4) =
+        make_float4(o[c4 * 4] * inv, o[c4 * 4 + 1] * inv, o[c4 * 4 + 2] * inv, o[c4 * 4 + 3] * inv);
+}
+
+// ------------------------------------------------------------------ positional encodings
+// PositionEmbeddingRandom._pe_encoding (prompt_encoder.py:185-192): c = 2c-1; c @ G; * 2pi; [sin | cos]
+B200SAM_DEVINL void pe_encode(float cx, float cy, const float* __restrict__ G, int j, float& s, float& c) {
+  const float x = 2.0f * cx - 1.0f, y = 2.0f * cy - 1.0f;
+  const float t = TWO_PI * (x * G[j] + y * G[128 + j]);
+  s = sinf(t);
+  c = cosf(t);
+}
+
+// dense PE on the 64x64 grid, token-major [4096, 256] (prompt_encoder.py:194-206 / get_dense_pe)
+__global__ void dense_pe_kernel(const float* __restrict__ G, float* __restrict__ pe) {
+  const int tok = blockIdx.x, j = threadIdx.x;  // 128 threads
+  const float cy = (static_cast<float>(tok >> 6) + 0.5f) / 64.0f;
+  const float cx = (static_cast<float>(tok & 63) + 0.5f) / 64.0f;
+  float s, c;
+  pe_encode(cx, cy, G, j, s, c);
+  pe[tok * 256 + j] = s;
+  pe[tok * 256 + 128 + j] = c;
+}
+
+// tokens[b, 0] = iou_token, tokens[b, 1..4] = mask_tokens, tokens[b, 5 + i] = embedding of point i
+// labels: -1 not-a-point (PE zeroed), 0/1 neg/pos point, 2/3 box corners (prompt_encoder.py:73-100)
+__global__ void prompt_tokens_kernel(const float* __restrict__ coords, const int* __restrict__ labels, int Np,
+                                     const float* __restrict__ G, const float* __restrict__ point_emb /*[4,256]*/,
+                                     const float* __restrict__ not_a_point, const float* __restrict__ iou_token,
+                                     const float* __restrict__ mask_tokens, float img_w, float img_h,
+                                     float* __restrict__ tokens) {
+  const int b = blockIdx.y, t = blockIdx.x, j = threadIdx.x;  // 128 threads, T = 5 + Np
+  const int T = 5 + Np;
+  float* dst = tokens + (static_cast<size_t>(b) * T + t) * 256;
+  if (t == 0) { dst[j] = iou_token[j]; dst[128 + j] = iou_token[128 + j]; return; }
+  if (t < 5) { dst[j] = mask_tokens[(t - 1) * 256 + j]; dst[128 + j] = mask_tokens[(t - 1) * 256 + 128 + j]; return; }
+  const int i = t - 5;
+  const int lab = labels[b * Np + i];
+  if (lab < 0) { dst[j] = not_a_point[j]; dst[128 + j] = not_a_point[128 + j]; return; }
+  const float px = coords[(static_cast<size_t>(b) * Np + i) * 2 + 0] + 0.5f;
+  const float py = coords[(static_cast<size_t>(b) * Np + i) * 2 + 1] + 0.5f;
+  float s, c;
+  pe_encode(px / img_w, py / img_h, G, j, s, c);
+  dst[j] = s + point_emb[lab * 256 + j];
+  dst[128 + j] = c + point_emb[lab * 256 + 128 + j];
+}
+
+// ------------------------------------------------------------------ layout helpers
+// NCHW [C=256, 4096] -> token-major [4096, 256] (32x32 smem transpose)
+__global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) tile[i][tx] = in[static_cast<size_t>(c0 + i) * 4096 + t0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) out[static_cast<size_t>(t0 + i) * 256 + c0 + tx] = tile[tx][i];
+}
+
+// keys[b, tok, c] = emb_tok[tok, c] + no_mask_embed[c]  (prompt_encoder.py:164-166 + mask_decoder.py:126)
+__global__ void keys_init_kernel(const float4* __restrict__ emb_tok, const float4* __restrict__ no_mask,
+                                 float4* __restrict__ keys, int NB) {
+  const size_t n4 = 4096 * 64;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 e = emb_tok[i];
+    const float4 d = no_mask[i & 63];
+    const float4 v = make_float4(e.x + d.x, e.y + d.y, e.z + d.z, e.w + d.w);
+    for (int b = 0; b < NB; ++b) keys[static_cast<size_t>(b) * n4 + i] = v;
+  }
+}
+
+// mask prompt: conv2x2s2(1->4) LN2d GELU conv2x2s2(4->16) LN2d GELU conv1x1(16->256)
+// (prompt_encoder.py:51-59,102-105) fused, + image embedding -> keys[b, tok, c]
+struct MaskDownW {
+  const float *c1w, *c1b, *l1w, *l1b, *c2w, *c2b, *l2w, *l2b, *c3w, *c3b;
+};
+__global__ void __launch_bounds__(256) mask_downscale_keys_kernel(const float* __restrict__ mask /*[NB,256,256]*/,
+                                                                  MaskDownW w, const float* __restrict__ emb_tok,
+                                                                  float* __restrict__ keys) {
+  __shared__ float hid[32][17];
+  const int b = blockIdx.y;
+  const int tok0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    const int tok = tok0 + tid;
+    const int ty = tok >> 6, tx = tok & 63;
+    const float* mp = mask + static_cast<size_t>(b) * 65536 + (ty * 4) * 256 + tx * 4;
+    float px[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(mp + r * 256);
+      px[r][0] = v.x; px[r][1] = v.y; px[r][2] = v.z; px[r][3] = v.w;
+    }
+    float h1[2][2][4];  // [sy][sx][channel] after conv1 + LN + GELU
+#pragma unroll
+    for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+      for (int sx = 0; sx < 2; ++sx) {
+        float o[4];
+        float mean = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float a = w.c1b[c];
+#pragma unroll
+          for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 2; ++kx) a = fmaf(w.c1w[c * 4 + ky * 2 + kx], px[2 * sy + ky][2 * sx + kx], a);
+          o[c] = a;
+          mean += a;
+        }
+        mean *= 0.25f;
+        float var = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const float d = o[c] - mean; var = fmaf(d, d, var); }
+        const float rstd = 1.0f / sqrtf(var * 0.25f + 1e-6f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) h1[sy][sx][c] = gelu_erf(w.l1w[c] * ((o[c] - mean) * rstd) + w.l1b[c]);
+      }
+    float o2[16];
+    float mean = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float a = w.c2b[c];
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 2; ++kx) a = fmaf(w.c2w[((c * 4 + ci) * 2 + ky) * 2 + kx], h1[ky][kx][ci], a);
+      o2[c] = a;
+      mean += a;
+    }
+    mean *= (1.0f / 16.0f);
+    float var = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { const float d = o2[c] - mean; var = fmaf(d, d, var); }
+    const float rstd = 1.0f / sqrtf(var * (1.0f / 16.0f) + 1e-6f);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) hid[tid][c] = gelu_erf(w.l2w[c] * ((o2[c] - mean) * rstd) + w.l2b[c]);
+  }
+  __syncthreads();
+  float wr[16];
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) wr[kk] = w.c3w[tid * 16 + kk];
+  const float bias = w.c3b[tid];
+  for (int t = 0; t < 32; ++t) {
+    float a = bias;
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) a = fmaf(wr[kk], hid[t][kk], a);
+    const size_t o = static_cast<size_t>(tok0 + t) * 256 + tid;
+    keys[static_cast<size_t>(b) * 4096 * 256 + o] = emb_tok[o] + a;
+  }
+}
+
+// in-place LayerNorm2d(64, eps 1e-6) + GELU over contiguous groups of 64 channels (mask_decoder.py:54-56)
+__global__ void __launch_bounds__(256) ln64_gelu_kernel(float* __restrict__ x, const float* __restrict__ g,
+                                                        const float* __restrict__ bta, size_t ngroups) {
+  const size_t grp = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 4;  // 16 lanes per group
+  const int sl = threadIdx.x & 15;
+  if (grp >= ngroups) return;
+  float4 v = reinterpret_cast<float4*>(x + grp * 64)[sl];
+  float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+  const float mean = s * (1.0f / 64.0f);
+  const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+  float q = (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o, 16);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 64.0f) + 1e-6f);
+  const float4 gg = reinterpret_cast<const float4*>(g)[sl];
+  const float4 bb = reinterpret_cast<const float4*>(bta)[sl];
+  v.x = gelu_erf(a * rstd * gg.x + bb.x);
+  v.y = gelu_erf(b * rstd * gg.y + bb.y);
+  v.z = gelu_erf(c * rstd * gg.z + bb.z);
+  v.w = gelu_erf(d * rstd * gg.w + bb.w);
+  reinterpret_cast<float4*>(x + grp * 64)[sl] = v;
+}
+
+// 3-layer MLPs on single tokens (hypernetwork MLPs + IoU head, mask_decoder.py:139-147,154-176).
+// grid (NB, 5): y < 4 -> hypernet MLP y on mask token y (out 32), y == 4 -> IoU head on token 0 (out 4)
+struct Mlp3W {
+  const float* w[5][3];
+  const float* b[5][3];
+};
+__global__ void __launch_bounds__(256) mlp3_tokens_kernel(const float* __restrict__ hs /*[NB,T,256]*/, int T, Mlp3W p,
+                                                          float* __restrict__ hyper /*[NB,4,32]*/,
+                                                          float* __restrict__ iou /*[NB,4]*/) {
+  __shared__ float x0[256], x1[256];
+  const int b = blockIdx.x, which = blockIdx.y;
+  const int tok = which < 4 ? 1 + which : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  x0[threadIdx.x] = hs[(static_cast<size_t>(b) * T + tok) * 256 + threadIdx.x];
+  __syncthreads();
+  for (int layer = 0; layer < 3; ++layer) {
+    const float* in = (layer & 1) ? x1 : x0;
+    float* outv = (layer & 1) ? x0 : x1;
+    const int nout = layer < 2 ? 256 : (which < 4 ? 32 : 4);
+    const float* W = p.w[which][layer];
+    const float* B = p.b[which][layer];
+    for (int o = warp; o < nout; o += 8) {
+      float a = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a = fmaf(W[o * 256 + lane + 32 * i], in[lane + 32 * i], a);
+      a = warp_sum(a) + B[o];
+      if (layer < 2) a = fmaxf(a, 0.0f);
+      if (lane == 0) {
+        if (layer < 2) outv[o] = a;
+        else if (which < 4) hyper[(static_cast<size_t>(b) * 4 + which) * 32 + o] = a;
+        else iou[b * 4 + o] = a;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// masks[b, j, Y, X] = sum_c hyper[b, tok0 + j, c] * up[b, (y, x, dy, dx), (dy2, dx2, c)]
+// with Y = 4y + 2dy + dy2, X = 4x + 2dx + dx2  (mask_decoder.py:143-145; only the requested tokens)
+__global__ void __launch_bounds__(256) mask_dot_kernel(const float* __restrict__ up /*[NB*16384, 128]*/,
+                                                       const float* __restrict__ hyper /*[NB,4,32]*/, int tok0,
+                                                       int ntok, float* __restrict__ masks /*[NB,ntok,256,256]*/) {
+  __shared__ float hy[4][32];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 128) hy[threadIdx.x >> 5][threadIdx.x & 31] = hyper[static_cast<size_t>(b) * 128 + threadIdx.x];
+  __syncthreads();
+  // one thread = one output pixel: 32 contiguous floats of `up`
+  const int idx = blockIdx.x * 256 + threadIdx.x;  // (row r in 0..16383, sub in 0..3)
+  const int r = idx >> 2, sub = idx & 3;
+  const float4* src = reinterpret_cast<const float4*>(up + (static_cast<size_t>(b) * 16384 + r) * 128 + sub * 32);
+  float u[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = src[i];
+    u[4 * i] = t.x; u[4 * i + 1] = t.y; u[4 * i + 2] = t.z; u[4 * i + 3] = t.w;
+  }
+  const int tok = r >> 2, q = r & 3;
+  const int y = tok >> 6, x = tok & 63;
+  const int Y = 4 * y + 2 * (q >> 1) + (sub >> 1);
+  const int X = 4 * x + 2 * (q & 1) + (sub & 1);
+  for (int j = 0; j < ntok; ++j) {
+    float a = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a = fmaf(hy[tok0 + j][c], u[c], a);
+    masks[((static_cast<size_t>(b) * ntok + j) * 256 + Y) * 256 + X] = a;
+  }
+}
+
+__global__ void add_rows_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
+                                size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
+
+}  // namespace
+
+int linear_f32(const LinearArgs& p, cudaStream_t stream) {
+  B200SAM_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "linear_f32: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  B200SAM_REQUIRE(p.K % LBK == 0 && p.N % 4 == 0 && p.lda % 4 == 0 && p.ldo % 4 == 0,
+                  "linear_f32: need K%%16==0, N%%4==0, lda%%4==0, ldo%%4==0 (M=%d N=%d K=%d lda=%d ldo=%d)", p.M, p.N,
+                  p.K, p.lda, p.ldo);
+  dim3 grid((p.N + LBN - 1) / LBN, (p.M + LBM - 1) / LBM);
+  linear_f32_kernel<<<grid, 256, 0, stream>>>(p);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
+                     int dh, cudaStream_t stream) {
+  B200SAM_REQUIRE(NB > 0 && Tq > 0 && Tk > 0, "attn_few_queries: empty problem");
+  dim3 grid(heads, NB);
+  if (dh == 16) attn_fewq_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads);
+  else if (dh == 32) attn_fewq_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads);
+  else { set_last_error("attn_few_queries: unsupported head dim %d", dh); return 2; }
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
+                  cudaStream_t stream) {
+  B200SAM_REQUIRE(Tk > 0 && Tk <= 32, "attn_few_keys: at most 32 prompt tokens supported, got %d", Tk);
+  dim3 grid((Nq * 8 + 255) / 256, NB);
+  attn_fewk_kernel<<<grid, 256, 0, stream>>>(q, k, v, out, Nq, Tk);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dense_pe_tokens(const float* G, float* pe, cudaStream_t stream) {
+  dense_pe_kernel<<<4096, 128, 0, stream>>>(G, pe);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int prompt_tokens(const float* coords, const int* labels, int NB, int Np, const float* G, const float* point_emb,
+                  const float* not_a_point, const float* iou_token, const float* mask_tokens, float img_w, float img_h,
+                  float* tokens, cudaStream_t stream) {
+  dim3 grid(5 + Np, NB);
+  prompt_tokens_kernel<<<grid, 128, 0, stream>>>(coords, labels, Np, G, point_emb, not_a_point, iou_token, mask_tokens,
+                                                 img_w, img_h, tokens);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int nchw_to_tokens(const float* in, float* out, cudaStream_t stream) {
+  nchw_to_tokens_kernel<<<dim3(128, 8), dim3(32, 8), 0, stream>>>(in, out);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, cudaStream_t stream) {
+  keys_init_kernel<<<296, 256, 0, stream>>>(reinterpret_cast<const float4*>(emb_tok),
+                                            reinterpret_cast<const float4*>(no_mask),
+                                            reinterpret_cast<float4*>(keys), NB);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mask_downscale_keys(const float* mask, const float* const* w10, const float* emb_tok, float* keys, int NB,
+                        cudaStream_t stream) {
+  MaskDownW w{w10[0], w10[1], w10[2], w10[3], w10[4], w10[5], w10[6], w10[7], w10[8], w10[9]};
+  mask_downscale_keys_kernel<<<dim3(128, NB), 256, 0, stream>>>(mask, w, emb_tok, keys);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, cudaStream_t stream) {
+  const size_t threads = ngroups * 16;
+  ln64_gelu_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, g, b, ngroups);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const float* const* b15, float* hyper,
+                float* iou, cudaStream_t stream) {
+  Mlp3W p;
+  for (int i = 0; i < 5; ++i)
+    for (int l = 0; l < 3; ++l) { p.w[i][l] = w15[i * 3 + l]; p.b[i][l] = b15[i * 3 + l]; }
+  mlp3_tokens_kernel<<<dim3(NB, 5), 256, 0, stream>>>(hs, T, p, hyper, iou);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mask_dot(const float* up, const float* hyper, int NB, int tok0, int ntok, float* masks, cudaStream_t stream) {
+  mask_dot_kernel<<<dim3(256, NB), 256, 0, stream>>>(up, hyper, tok0, ntok, masks);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int add_rows(const float* a, const float* b, float* out, size_t n, cudaStream_t stream) {
+  B200SAM_REQUIRE(n % 4 == 0, "add_rows: n must be a multiple of 4");
+  add_rows_kernel<<<148 * 4, 256, 0, stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                               reinterpret_cast<float4*>(out), n / 4);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200sam

@@ -1,0 +1,44 @@
+// Launchers of the fp32 decoder kernels (decoder_ops.cu); used by decoder.cu and the op-level C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "kernels.h"
+
+namespace b200sam {
+
+struct LinearArgs {
+  const float* A;    // [M, K], pitch lda
+  const float* A2;   // optional addend to A (e.g. positional encoding), pitch lda2
+  const float* W;    // [N, K] (nn.Linear layout)
+  const float* bias; // [N] or null
+  const float* residual;  // [M, N] pitch ldr or null; added AFTER the activation
+  float* out;        // [M, N], pitch ldo
+  int M, N, K;
+  int lda, lda2, ldo, ldr;
+  int a2_row_mod;    // >0: A2 row = m % a2_row_mod
+  int act;           // 0 none, 1 ReLU, 2 GELU(erf)
+};
+int linear_f32(const LinearArgs& p, cudaStream_t stream);
+
+// q [NB,Tq,heads*dh], k/v [NB,Tk,heads*dh] -> out [NB,Tq,heads*dh]; dh in {16, 32}
+int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
+                     int dh, cudaStream_t stream);
+// q [NB,Nq,128], k/v [NB,Tk<=32,128] (8 heads x 16) -> out [NB,Nq,128]
+int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
+                  cudaStream_t stream);
+int dense_pe_tokens(const float* G, float* pe, cudaStream_t stream);
+int prompt_tokens(const float* coords, const int* labels, int NB, int Np, const float* G, const float* point_emb,
+                  const float* not_a_point, const float* iou_token, const float* mask_tokens, float img_w, float img_h,
+                  float* tokens, cudaStream_t stream);
+int nchw_to_tokens(const float* in, float* out, cudaStream_t stream);
+int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, cudaStream_t stream);
+int mask_downscale_keys(const float* mask, const float* const* w10, const float* emb_tok, float* keys, int NB,
+                        cudaStream_t stream);
+int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, cudaStream_t stream);
+int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const float* const* b15, float* hyper,
+                float* iou, cudaStream_t stream);
+int mask_dot(const float* up, const float* hyper, int NB, int tok0, int ntok, float* masks, cudaStream_t stream);
+int add_rows(const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
+
+}  // namespace b200sam

@@ -1,0 +1,175 @@
+// Host-side orchestration of the ViT image encoder (reference: ImageEncoderViT.forward,
+// segment_anything/modeling/image_encoder.py:106-116; Block.forward :166-182).  Launch sequence per block:
+//   LN1 -> qkv GEMM -> fused (window|global) attention -> proj GEMM(+residual) -> LN2 -> lin1 GEMM(+GELU)
+//   -> lin2 GEMM(+residual).  The residual stream stays fp32 in HBM; GEMM operands are bf16.
+#include "encoder.h"
+#include <string>
+
+namespace b200sam {
+
+namespace {
+
+enum : int { G_PATCH_W = 0, G_PATCH_B, G_POS, G_BLOCK0 };
+enum : int { B_N1W = 0, B_N1B, B_QKVW, B_QKVB, B_QKVB16, B_RELH, B_RELW, B_PROJW, B_PROJB, B_N2W, B_N2B, B_L1W, B_L1B,
+             B_L2W, B_L2B, B_STRIDE };
+enum : int { N_C0W = 0, N_L1W, N_L1B, N_C2W, N_L3W, N_L3B, N_COUNT };
+
+std::string name_of(const EncoderConfig& c, int i) {
+  const std::string ie = "image_encoder.";
+  if (i == G_PATCH_W) return ie + "patch_embed.proj.weight|bf16_flat";
+  if (i == G_PATCH_B) return ie + "patch_embed.proj.bias|f32";
+  if (i == G_POS) return ie + "pos_embed|f32_tokens";
+  const int nb = c.depth * B_STRIDE;
+  if (i < G_BLOCK0 + nb) {
+    const int b = (i - G_BLOCK0) / B_STRIDE, k = (i - G_BLOCK0) % B_STRIDE;
+    const std::string p = ie + "blocks." + std::to_string(b) + ".";
+    switch (k) {
+      case B_N1W: return p + "norm1.weight|f32";
+      case B_N1B: return p + "norm1.bias|f32";
+      case B_QKVW: return p + "attn.qkv.weight|bf16";
+      case B_QKVB: return p + "attn.qkv.bias|f32";
+      case B_QKVB16: return p + "attn.qkv.bias|bf16";
+      case B_RELH: return p + "attn.rel_pos_h|bf16";
+      case B_RELW: return p + "attn.rel_pos_w|bf16";
+      case B_PROJW: return p + "attn.proj.weight|bf16";
+      case B_PROJB: return p + "attn.proj.bias|f32";
+      case B_N2W: return p + "norm2.weight|f32";
+      case B_N2B: return p + "norm2.bias|f32";
+      case B_L1W: return p + "mlp.lin1.weight|bf16";
+      case B_L1B: return p + "mlp.lin1.bias|f32";
+      case B_L2W: return p + "mlp.lin2.weight|bf16";
+      case B_L2B: return p + "mlp.lin2.bias|f32";
+    }
+  }
+  const int k = i - G_BLOCK0 - nb;
+  switch (k) {
+    case N_C0W: return ie + "neck.0.weight|bf16_flat";
+    case N_L1W: return ie + "neck.1.weight|f32";
+    case N_L1B: return ie + "neck.1.bias|f32";
+    case N_C2W: return ie + "neck.2.weight|bf16_tap";
+    case N_L3W: return ie + "neck.3.weight|f32";
+    case N_L3B: return ie + "neck.3.bias|f32";
+  }
+  return "";
+}
+
+inline size_t align_up(size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); }
+
+struct Workspace {
+  float* x;             // [M, D] fp32 residual stream
+  __nv_bfloat16* xn;    // [M, D] LN output / bf16 copy of x      (neck: fp32 [M,256] conv3x3 output)
+  __nv_bfloat16* qkv;   // [M, 3D]                                (neck: fp32 [M,256] conv1x1 output)
+  __nv_bfloat16* att;   // [M, D] attention output                (neck: bf16 [M,256] LN output)
+  __nv_bfloat16* h;     // [M, 4D] MLP hidden; also patch im2col [M,768] and neck im2col [M,2304]
+  size_t total;
+};
+
+Workspace carve(uint8_t* base, const EncoderConfig& c, int B) {
+  Workspace w;
+  const size_t M = static_cast<size_t>(B) * 4096, D = c.embed_dim;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base + off; off += align_up(bytes); return p; };
+  w.x = reinterpret_cast<float*>(take(M * D * 4));
+  w.xn = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
+  w.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D * 2));
+  w.att = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
+  w.h = reinterpret_cast<__nv_bfloat16*>(take(M * 4 * D * 2));
+  w.total = off;
+  return w;
+}
+
+int gemm(const __nv_bfloat16* A, const void* W, void* out, const float* bias, const float* res, int M, int N, int K,
+         int ldr, int res_mod, int gelu, int out_bf16, cudaStream_t s) {
+  GemmArgs g;
+  g.A = A; g.B = reinterpret_cast<const __nv_bfloat16*>(W); g.out = out; g.bias = bias; g.residual = res;
+  g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldo = N; g.ldr = ldr; g.res_row_mod = res_mod;
+  g.gelu = gelu; g.out_bf16 = out_bf16; g.max_ctas = 0;
+  return gemm_bf16_tn(g, s);
+}
+
+#define TRY(x) do { if (int _rc = (x)) return _rc; } while (0)
+
+}  // namespace
+
+int encoder_weight_count(const EncoderConfig& c) { return G_BLOCK0 + c.depth * B_STRIDE + N_COUNT; }
+
+const char* encoder_weight_name(const EncoderConfig& c, int i) {
+  static thread_local std::string buf;
+  if (i < 0 || i >= encoder_weight_count(c)) return nullptr;
+  buf = name_of(c, i);
+  return buf.c_str();
+}
+
+size_t encoder_workspace_bytes(const EncoderConfig& c, int B) {
+  if (B <= 0) return 0;
+  return carve(nullptr, c, B).total + 1024;
+}
+
+int encoder_create(const EncoderConfig& c, const void* const* weights, int n, Encoder** out) {
+  B200SAM_REQUIRE(c.embed_dim > 0 && c.embed_dim % 128 == 0 && c.num_heads > 0 && c.embed_dim % c.num_heads == 0,
+                  "encoder_create: bad embed_dim=%d num_heads=%d", c.embed_dim, c.num_heads);
+  const int hd = c.embed_dim / c.num_heads;
+  B200SAM_REQUIRE(hd == 64 || hd == 80, "encoder_create: head dim %d unsupported (64 or 80)", hd);
+  B200SAM_REQUIRE(c.depth > 0 && c.depth <= 32, "encoder_create: depth %d unsupported (1..32)", c.depth);
+  B200SAM_REQUIRE(c.out_chans == 256, "encoder_create: out_chans must be 256, got %d", c.out_chans);
+  B200SAM_REQUIRE(n == encoder_weight_count(c), "encoder_create: expected %d weight pointers, got %d",
+                  encoder_weight_count(c), n);
+  for (int i = 0; i < n; ++i)
+    B200SAM_REQUIRE(weights[i] != nullptr, "encoder_create: weight %d (%s) is null", i, name_of(c, i).c_str());
+  Encoder* e = new Encoder();
+  e->cfg = c;
+  e->w.assign(weights, weights + n);
+  *out = e;
+  return 0;
+}
+
+void encoder_destroy(Encoder* e) { delete e; }
+
+int encoder_forward(const Encoder* e, const void* img, int is_u8, int B, int h, int w, const float* mean3,
+                    const float* std3, float* out, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  const EncoderConfig& c = e->cfg;
+  B200SAM_REQUIRE(B > 0 && img != nullptr && out != nullptr, "encoder_forward: bad arguments");
+  B200SAM_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+                  "encoder_forward: workspace must be non-null and 1024-byte aligned");
+  Workspace ws = carve(reinterpret_cast<uint8_t*>(workspace), c, B);
+  B200SAM_REQUIRE(ws.total <= workspace_bytes, "encoder_forward: workspace too small (%zu < %zu)", workspace_bytes,
+                  ws.total);
+  const int D = c.embed_dim, M = B * 4096;
+  const void* const* W = e->w.data();
+  auto F = [&](int i) { return reinterpret_cast<const float*>(W[i]); };
+  auto H = [&](int i) { return reinterpret_cast<const __nv_bfloat16*>(W[i]); };
+
+  // patch embedding (+bias +abs pos embed) : image_encoder.py:107-109
+  TRY(preprocess_patchify(img, is_u8, B, h, w, mean3, std3, ws.h, s));
+  TRY(gemm(ws.h, W[G_PATCH_W], ws.x, F(G_PATCH_B), F(G_POS), M, D, 768, D, 4096, 0, 0, s));
+
+  AttnArgs at;
+  at.qkv = ws.qkv; at.out = ws.att; at.B = B; at.heads = c.num_heads; at.hd = D / c.num_heads;
+  for (int b = 0; b < c.depth; ++b) {
+    const int o = G_BLOCK0 + b * B_STRIDE;
+    TRY(layernorm_rows(ws.x, F(o + B_N1W), F(o + B_N1B), 1e-6f, M, D, ws.xn, 1, s));
+    TRY(gemm(ws.xn, W[o + B_QKVW], ws.qkv, F(o + B_QKVB), nullptr, M, 3 * D, D, 0, 0, 0, 1, s));
+    at.qkv_bias = H(o + B_QKVB16); at.rel_h = H(o + B_RELH); at.rel_w = H(o + B_RELW);
+    if ((c.global_mask_lo >> b) & 1) TRY(global_attention(at, s));
+    else TRY(window_attention(at, s));
+    TRY(gemm(ws.att, W[o + B_PROJW], ws.x, F(o + B_PROJB), ws.x, M, D, D, D, 0, 0, 0, s));
+    TRY(layernorm_rows(ws.x, F(o + B_N2W), F(o + B_N2B), 1e-6f, M, D, ws.xn, 1, s));
+    TRY(gemm(ws.xn, W[o + B_L1W], ws.h, F(o + B_L1B), nullptr, M, 4 * D, D, 0, 0, 1, 1, s));
+    TRY(gemm(ws.h, W[o + B_L2W], ws.x, F(o + B_L2B), ws.x, M, D, 4 * D, D, 0, 0, 0, s));
+  }
+
+  // neck: conv1x1 -> LayerNorm2d -> conv3x3(pad 1) -> LayerNorm2d (image_encoder.py:88-104), NCHW fp32 out
+  const int o = G_BLOCK0 + c.depth * B_STRIDE;
+  const int C = c.out_chans;
+  float* n0 = reinterpret_cast<float*>(ws.qkv);
+  float* n2 = reinterpret_cast<float*>(ws.xn);
+  TRY(f32_to_bf16(ws.x, ws.att, static_cast<size_t>(M) * D, s));
+  TRY(gemm(ws.att, W[o + N_C0W], n0, nullptr, nullptr, M, C, D, 0, 0, 0, 0, s));
+  TRY(layernorm_rows(n0, F(o + N_L1W), F(o + N_L1B), 1e-6f, M, C, ws.att, 1, s));
+  TRY(im2col3x3_tokens(ws.att, B, C, ws.h, s));
+  TRY(gemm(ws.h, W[o + N_C2W], n2, nullptr, nullptr, M, C, 9 * C, 0, 0, 0, 0, s));
+  TRY(layernorm_to_nchw(n2, F(o + N_L3W), F(o + N_L3B), 1e-6f, B, C, out, s));
+  return 0;
+}
+
+}  // namespace b200sam

@@ -1,0 +1,346 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (+ epilogue)
+//
+//   * operands: both K-major bf16 (activations [M,K], nn.Linear weight [N,K]) fetched by TMA
+//     (cp.async.bulk.tensor, SWIZZLE_128B) into a 4-stage shared-memory ring,
+//   * math: tcgen05.mma cta_group::1 kind::f16, 128x256x16 per instruction, fp32 accumulators in
+//     TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the mainloop of i+1),
+//   * epilogue: 8 warps read TMEM with tcgen05.ld, apply bias / exact-erf GELU / fp32 residual,
+//     transpose through a padded per-warp shared tile and write 64 B row segments.
+//
+// This one kernel carries every linear layer of the ViT encoder (reference call sites:
+// segment_anything/modeling/image_encoder.py:227 qkv, :238 proj, common.py:25-26 lin1/lin2,
+// image_encoder.py:391 patch-embed conv as GEMM, :88-104 neck convs as GEMMs).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200sam {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 4;
+constexpr int GEMM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;  // 384
+constexpr int A_STAGE_BYTES = BM * BK * 2;                       // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;                       // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int EPI_PITCH = 17;                                    // words, padded transpose tile
+constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH * 4;              // 2176 B per warp
+constexpr int EPI_BIAS_BYTES = 128 * 4;                          // 128 columns per warp
+constexpr int SMEM_TILES = STAGES * STAGE_BYTES;
+constexpr int SMEM_EPI = NUM_EPI_WARPS * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
+constexpr int SMEM_BARRIERS = 256;
+constexpr int GEMM_SMEM_BYTES = SMEM_TILES + SMEM_EPI + SMEM_BARRIERS + 1024;  // +1024 align slack
+constexpr uint32_t TMEM_COLS = 512;
+
+struct EpiParams {
+  const float* bias;      // [N] or null
+  const float* residual;  // fp32 [*, ldr] or null
+  void* out;              // bf16 or fp32 [M, ldo]
+  int ldo;
+  int ldr;
+  int res_row_mod;  // >0: residual row = row % res_row_mod (broadcast table, e.g. pos_embed)
+  int gelu;
+};
+
+B200SAM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    EpiParams ep, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024 B alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_epi = smem + SMEM_TILES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES + SMEM_EPI);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+            umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue warps =====================
+    const int e = warp - EPI_WARP0;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = e >> 2;    // which 128-column half of the 256-wide tile
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smem_epi + e * (EPI_STAGE_BYTES + EPI_BIAS_BYTES));
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stg) + EPI_STAGE_BYTES);
+    const int sub = lane >> 4;  // transposed read: which of two rows
+    const int w = lane & 15;    // transposed read: word within the 16-word row segment
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM;
+      const int n0 = (tile % num_n) * BN + half * 128;
+      // stage this warp's 128 bias values (zero when absent / out of range)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = n0 + lane + 32 * i;
+        sbias[lane + 32 * i] = (ep.bias != nullptr && c < N) ? __ldg(ep.bias + c) : 0.0f;
+      }
+      __syncwarp();
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                              static_cast<uint32_t>(as * BN + half * 128);
+      const int row_base = m0 + quad * 32;
+      if constexpr (OUT_BF16) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v0 = __uint_as_float(r[2 * j]) + sbias[ch * 32 + 2 * j];
+            float v1 = __uint_as_float(r[2 * j + 1]) + sbias[ch * 32 + 2 * j + 1];
+            if (ep.gelu) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+            stg[lane * EPI_PITCH + j] = pack_bf16x2(v0, v1);
+          }
+          __syncwarp();
+          const int col = n0 + ch * 32 + 2 * w;
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int rl = 2 * it + sub;
+            const int row = row_base + rl;
+            const uint32_t v = stg[rl * EPI_PITCH + w];
+            if (row < M && col < N)
+              *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row) * ep.ldo + col) = v;
+          }
+          __syncwarp();
+        }
+      } else {
+        float* out = reinterpret_cast<float*>(ep.out);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns, each written as 2 x 16
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) stg[lane * EPI_PITCH + j] = r[hf * 16 + j];
+            __syncwarp();
+            const int col = n0 + ch * 32 + hf * 16 + w;
+            const float b = sbias[ch * 32 + hf * 16 + w];
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+              const int rl = 2 * it + sub;
+              const int row = row_base + rl;
+              float v = __uint_as_float(stg[rl * EPI_PITCH + w]) + b;
+              if (row < M && col < N) {
+                if (ep.residual != nullptr) {
+                  const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
+                  v += ep.residual[static_cast<size_t>(rr) * ep.ldr + col];
+                }
+                if (ep.gelu) v = gelu_erf(v);
+                out[static_cast<size_t>(row) * ep.ldo + col] = v;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with row pitch ld (elements);
+// box = [box_rows, 64 cols], SWIZZLE_128B.
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr=%p rows=%llu cols=%llu ld=%llu)", (int)r, ptr,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return 1;
+  }
+  return 0;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace
+
+int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
+  B200SAM_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  B200SAM_REQUIRE(g.K % 8 == 0 && g.lda % 8 == 0 && g.ldb % 8 == 0,
+                  "gemm: K/lda/ldb must be multiples of 8 (16 B TMA alignment), got K=%d lda=%d ldb=%d", g.K, g.lda,
+                  g.ldb);
+  B200SAM_REQUIRE(g.N % 2 == 0 && g.ldo % 2 == 0, "gemm: N and ldo must be even (N=%d ldo=%d)", g.N, g.ldo);
+  B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0,
+                  "gemm: A and B must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  if (make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BM)) return 1;
+  if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, BN)) return 1;
+  EpiParams ep;
+  ep.bias = g.bias;
+  ep.residual = g.residual;
+  ep.out = g.out;
+  ep.ldo = g.ldo;
+  ep.ldr = g.ldr;
+  ep.res_row_mod = g.res_row_mod;
+  ep.gelu = g.gelu;
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
+  static bool attr_set[2] = {false, false};
+  if (g.out_bf16) {
+    if (!attr_set[0]) {
+      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              GEMM_SMEM_BYTES));
+      attr_set[0] = true;
+    }
+    gemm_bf16_tn_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K);
+  } else {
+    if (!attr_set[1]) {
+      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              GEMM_SMEM_BYTES));
+      attr_set[1] = true;
+    }
+    gemm_bf16_tn_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K);
+  }
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200sam

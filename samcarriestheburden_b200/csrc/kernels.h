@@ -1,0 +1,84 @@
+// Internal host-side launch interface shared by the .cu translation units and api.cu.
+// Everything here takes raw device pointers + a stream; no allocation, no synchronisation.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace b200sam {
+
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+
+// error plumbing: launchers return 0 on success and leave a message for b200sam_last_error() otherwise
+#define B200SAM_CHECK_CUDA(expr)                                                        \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      b200sam::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,             \
+                              cudaGetErrorString(_e));                                  \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+#define B200SAM_REQUIRE(cond, ...)                                                      \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      b200sam::set_last_error(__VA_ARGS__);                                             \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+
+// ---- gemm_tcgen05.cu -------------------------------------------------------------------------
+struct GemmArgs {
+  const __nv_bfloat16* A;  // [M, K] row-major, pitch lda
+  const __nv_bfloat16* B;  // [N, K] row-major (nn.Linear weight), pitch ldb
+  void* out;               // bf16 or fp32 [M, N], pitch ldo
+  const float* bias;       // [N] or null
+  const float* residual;   // fp32, pitch ldr, or null (only with fp32 out)
+  int M, N, K;
+  int lda, ldb, ldo, ldr;
+  int res_row_mod;  // >0: residual row index = row % res_row_mod
+  int gelu;         // exact erf GELU after bias
+  int out_bf16;     // 1: bf16 output, 0: fp32 output
+  int max_ctas;     // 0 = one CTA per SM
+};
+int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
+
+// ---- encoder_ops.cu --------------------------------------------------------------------------
+// image [B,3,h,w] (uint8 or fp32) -> normalised, zero-padded 1024^2, im2col'd bf16 [B*4096, 768]
+int preprocess_patchify(const void* img, int is_u8, int B, int h, int w, const float* mean3, const float* std3,
+                        __nv_bfloat16* out, cudaStream_t stream);
+// y = LN(x) over the last dim (fp32 statistics, biased variance); x fp32 [M,D]; y bf16 or fp32
+int layernorm_rows(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
+                   int out_bf16, cudaStream_t stream);
+// 3x3/pad1 im2col over a 64x64 token grid: in bf16 [B*4096, C] -> out bf16 [B*4096, 9*C] (tap-major)
+int im2col3x3_tokens(const __nv_bfloat16* in, int B, int C, __nv_bfloat16* out, cudaStream_t stream);
+// LayerNorm2d over channels + token-major -> NCHW transpose: in fp32 [B*4096, C] -> out fp32 [B,C,64,64]
+int layernorm_to_nchw(const float* x, const float* gamma, const float* beta, float eps, int B, int C, float* out,
+                      cudaStream_t stream);
+int f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+
+// ---- attention.cu ----------------------------------------------------------------------------
+struct AttnArgs {
+  const __nv_bfloat16* qkv;       // [B*4096, 3*D] bf16 (q | k | v, each heads x hd)
+  const __nv_bfloat16* qkv_bias;  // [3*D] bf16 (K/V of zero-padded window tokens)
+  const __nv_bfloat16* rel_h;     // [2S-1, hd] bf16
+  const __nv_bfloat16* rel_w;     // [2S-1, hd] bf16
+  __nv_bfloat16* out;             // [B*4096, D] bf16
+  int B, heads, hd;
+};
+int window_attention(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows over the 64x64 grid
+int global_attention(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096
+
+// ---- prompt_extract.cu -----------------------------------------------------------------------
+int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t* seeds, int32_t* boxes,
+                   uint8_t* has_seed, uint8_t* has_box, int32_t* scratch, cudaStream_t stream);
+size_t prompt_extract_scratch_bytes(int n_img, int C);
+
+// ---- upscale.cu ------------------------------------------------------------------------------
+int upscale_threshold(const float* low_res, int n, int low, int img_size, int in_h, int in_w, int out_h, int out_w,
+                      float thresh, uint8_t* mask_out, float* logits_out, uint8_t* small_out, int small_h,
+                      int small_w, cudaStream_t stream);
+
+}  // namespace b200sam

@@ -1,0 +1,164 @@
+// Prompt extraction from U-Net masks (reference: segment_anything/utils/prompt_utils.py:34-67,112-143).
+//
+// For every class c of every image, in ONE pass over the bool masks:
+//   seed  = round_half_even( mean of (row, col) over  mask[c] & (sum_c mask < 2) )  -> stored (x, y)
+//   box   = [min col, min row, max col, max row] over the FULL mask[c]
+// All accumulation is integer (exact); the mean is one IEEE fp32 division of the fp32-converted sums,
+// which is what torch's CPU `coords.float().mean(0)` evaluates to while the sums stay below 2^24.
+#include "common.cuh"
+#include "kernels.h"
+#include <limits.h>
+
+namespace b200sam {
+
+namespace {
+
+constexpr int SLOT = 12;  // int32 words per (image, class) accumulator, 48 B (keeps the u64 sums aligned)
+// [0,1] sum_r (u64)  [2,3] sum_c (u64)  [4] n_seed  [5] n_all  [6] min_r  [7] max_r  [8] min_c  [9] max_c
+constexpr int MAX_C = 64;
+
+__global__ void prompt_init_kernel(int32_t* scratch, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t* s = scratch + static_cast<size_t>(i) * SLOT;
+#pragma unroll
+  for (int k = 0; k < SLOT; ++k) s[k] = 0;
+  s[6] = INT_MAX;
+  s[7] = -1;
+  s[8] = INT_MAX;
+  s[9] = -1;
+}
+
+struct Acc {
+  unsigned long long sum_r, sum_c;
+  int n_seed, n_all, min_r, max_r, min_c, max_c;
+};
+
+__global__ void __launch_bounds__(256) prompt_accum_kernel(const uint8_t* __restrict__ masks, int C, int H, int W,
+                                                           int32_t* __restrict__ scratch) {
+  __shared__ unsigned long long s_sum[MAX_C][2];
+  __shared__ int s_cnt[MAX_C][2];
+  __shared__ int s_mm[MAX_C][4];
+  const int img = blockIdx.y;
+  const int HW = H * W;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_sum[c][0] = s_sum[c][1] = 0ull;
+    s_cnt[c][0] = s_cnt[c][1] = 0;
+    s_mm[c][0] = INT_MAX; s_mm[c][1] = -1; s_mm[c][2] = INT_MAX; s_mm[c][3] = -1;
+  }
+  __syncthreads();
+  const uint8_t* base = masks + static_cast<size_t>(img) * C * HW;
+  const bool vec_ok = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 3) == 0);
+  const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // 4 consecutive pixels per thread
+  if (p0 < HW) {
+    const int npx = min(4, HW - p0);
+    // pass 1: how many classes cover each of the 4 pixels
+    uint32_t words[MAX_C];
+    int cover[4] = {0, 0, 0, 0};
+    for (int c = 0; c < C; ++c) {
+      uint32_t wv = 0;
+      if (vec_ok) {
+        wv = __ldg(reinterpret_cast<const uint32_t*>(base + static_cast<size_t>(c) * HW + p0));
+      } else {
+        for (int k = 0; k < npx; ++k) wv |= static_cast<uint32_t>(base[static_cast<size_t>(c) * HW + p0 + k]) << (8 * k);
+      }
+      words[c] = wv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cover[k] += ((wv >> (8 * k)) & 0xffu) != 0u;
+    }
+    int rr[4], cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { rr[k] = (p0 + k) / W; cc[k] = (p0 + k) - rr[k] * W; }
+    // pass 2: per class contributions
+    for (int c = 0; c < C; ++c) {
+      const uint32_t wv = words[c];
+      if (wv == 0u) continue;
+      unsigned long long sr = 0, sc = 0;
+      int ns = 0, na = 0, mnr = INT_MAX, mxr = -1, mnc = INT_MAX, mxc = -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (((wv >> (8 * k)) & 0xffu) != 0u && k < npx) {
+          ++na;
+          mnr = min(mnr, rr[k]); mxr = max(mxr, rr[k]);
+          mnc = min(mnc, cc[k]); mxc = max(mxc, cc[k]);
+          if (cover[k] < 2) { ++ns; sr += rr[k]; sc += cc[k]; }
+        }
+      }
+      if (na) {
+        atomicAdd(&s_cnt[c][1], na);
+        atomicMin(&s_mm[c][0], mnr); atomicMax(&s_mm[c][1], mxr);
+        atomicMin(&s_mm[c][2], mnc); atomicMax(&s_mm[c][3], mxc);
+        if (ns) {
+          atomicAdd(&s_cnt[c][0], ns);
+          atomicAdd(&s_sum[c][0], sr);
+          atomicAdd(&s_sum[c][1], sc);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (s_cnt[c][1] == 0) continue;
+    int32_t* s = scratch + (static_cast<size_t>(img) * C + c) * SLOT;
+    atomicAdd(&s[5], s_cnt[c][1]);
+    atomicMin(&s[6], s_mm[c][0]); atomicMax(&s[7], s_mm[c][1]);
+    atomicMin(&s[8], s_mm[c][2]); atomicMax(&s[9], s_mm[c][3]);
+    if (s_cnt[c][0]) {
+      atomicAdd(&s[4], s_cnt[c][0]);
+      atomicAdd(reinterpret_cast<unsigned long long*>(s), s_sum[c][0]);
+      atomicAdd(reinterpret_cast<unsigned long long*>(s + 2), s_sum[c][1]);
+    }
+  }
+}
+
+__global__ void prompt_finalize_kernel(const int32_t* __restrict__ scratch, int n, int32_t* __restrict__ seeds,
+                                       int32_t* __restrict__ boxes, uint8_t* __restrict__ has_seed,
+                                       uint8_t* __restrict__ has_box) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t* s = scratch + static_cast<size_t>(i) * SLOT;
+  const unsigned long long sum_r = *reinterpret_cast<const unsigned long long*>(s);
+  const unsigned long long sum_c = *reinterpret_cast<const unsigned long long*>(s + 2);
+  const int n_seed = s[4], n_all = s[5];
+  int sx = 0, sy = 0;
+  if (n_seed > 0) {
+    const float nf = static_cast<float>(n_seed);
+    sy = static_cast<int>(rintf(__fdiv_rn(__ull2float_rn(sum_r), nf)));  // rintf = round half to even
+    sx = static_cast<int>(rintf(__fdiv_rn(__ull2float_rn(sum_c), nf)));
+  }
+  seeds[2 * i + 0] = sx;  // (x, y): the reference flips HW -> WH (prompt_utils.py:43)
+  seeds[2 * i + 1] = sy;
+  has_seed[i] = n_seed > 0;
+  has_box[i] = n_all > 0;
+  boxes[4 * i + 0] = n_all > 0 ? s[8] : 0;
+  boxes[4 * i + 1] = n_all > 0 ? s[6] : 0;
+  boxes[4 * i + 2] = n_all > 0 ? s[9] : 0;
+  boxes[4 * i + 3] = n_all > 0 ? s[7] : 0;
+}
+
+}  // namespace
+
+size_t prompt_extract_scratch_bytes(int n_img, int C) {
+  return static_cast<size_t>(n_img) * C * SLOT * sizeof(int32_t);
+}
+
+int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t* seeds, int32_t* boxes,
+                   uint8_t* has_seed, uint8_t* has_box, int32_t* scratch, cudaStream_t stream) {
+  B200SAM_REQUIRE(n_img >= 0 && C >= 0 && H >= 0 && W >= 0, "prompt_extract: negative dimension");
+  B200SAM_REQUIRE(C <= MAX_C, "prompt_extract: at most %d classes supported, got %d", MAX_C, C);
+  B200SAM_REQUIRE(n_img <= 65535, "prompt_extract: at most 65535 images per launch, got %d", n_img);
+  const int n = n_img * C;
+  if (n == 0) return 0;
+  B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7) == 0, "prompt_extract: scratch must be 8-byte aligned");
+  prompt_init_kernel<<<(n + 127) / 128, 128, 0, stream>>>(scratch, n);
+  const int HW = H * W;
+  if (HW > 0) {
+    dim3 grid((HW + 1023) / 1024, n_img);
+    prompt_accum_kernel<<<grid, 256, 0, stream>>>(masks, C, H, W, scratch);
+  }
+  prompt_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(scratch, n, seeds, boxes, has_seed, has_box);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200sam
