@@ -75,8 +75,9 @@ B200SAM_API const char* b200sam_decoder_weight_name(int i);
 B200SAM_API size_t b200sam_decoder_workspace_bytes(int n_prompts, int n_points);
 B200SAM_API int b200sam_decoder_create(const void* const* weights, int n_weights, b200sam_decoder** out, void* stream);
 B200SAM_API void b200sam_decoder_destroy(b200sam_decoder* dec);
-/* dense positional encoding, token-major [4096,256] (PromptEncoder.get_dense_pe, prompt_encoder.py:62-71) */
-B200SAM_API const float* b200sam_decoder_dense_pe(const b200sam_decoder* dec);
+/* copy the dense positional encoding, token-major [4096,256], into out (PromptEncoder.get_dense_pe,
+ * prompt_encoder.py:62-71; NCHW view = out.view(64,64,256).permute(2,0,1)) */
+B200SAM_API int b200sam_decoder_copy_dense_pe(const b200sam_decoder* dec, float* out, void* stream);
 /* embedding: [256,64,64]; coords: [n_prompts,n_points,2] (x,y) in the 1024 input frame; labels:
  * [n_prompts,n_points] with -1 padding point, 0 negative, 1 positive, 2/3 box corners; mask_prev: optional
  * [n_prompts,256,256] logits; outputs low_res: [n_prompts,(multimask?3:1),256,256], iou: [n_prompts,(3|1)] */

@@ -41,7 +41,7 @@ _PROTOTYPES = {
     "b200sam_decoder_workspace_bytes": (_sz, [_i, _i]),
     "b200sam_decoder_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp), _vp]),
     "b200sam_decoder_destroy": (None, [_vp]),
-    "b200sam_decoder_dense_pe": (_vp, [_vp]),
+    "b200sam_decoder_copy_dense_pe": (_i, [_vp, _vp, _vp]),
     "b200sam_decode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200sam_upscale_threshold": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "b200sam_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -100,7 +100,12 @@ void b200sam_decoder_destroy(b200sam_decoder* dec) {
   decoder_destroy(dec->impl);
   delete dec;
 }
-const float* b200sam_decoder_dense_pe(const b200sam_decoder* dec) { return dec ? decoder_dense_pe(dec->impl) : nullptr; }
+int b200sam_decoder_copy_dense_pe(const b200sam_decoder* dec, float* out, void* stream) {
+  if (!dec || !out) { set_last_error("decoder_copy_dense_pe: null argument"); return 2; }
+  B200SAM_CHECK_CUDA(cudaMemcpyAsync(out, decoder_dense_pe(dec->impl), 4096 * 256 * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
 int b200sam_decode(const b200sam_decoder* dec, const float* embedding, int n_prompts, int n_points,
                    const float* coords, const int32_t* labels, const float* mask_prev, int multimask,
                    float* low_res_out, float* iou_out, void* workspace, size_t workspace_bytes, void* stream) {

@@ -1,0 +1,182 @@
+"""ViT image encoder (reference: segment_anything/modeling/image_encoder.py).
+
+Same constructor, attributes and state_dict as the reference `ImageEncoderViT`; `forward` runs the whole
+encoder through `b200sam_encoder_forward` (tcgen05 GEMMs + fused attention kernels, see csrc/encoder.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple, Type
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from .common import FusedAway, LayerNorm2d, MLPBlock
+
+
+class PatchEmbed(FusedAway):
+    def __init__(self, kernel_size=(16, 16), stride=(16, 16), padding=(0, 0), in_chans=3, embed_dim=768) -> None:
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=kernel_size, stride=stride, padding=padding)
+
+
+class Attention(FusedAway):
+    def __init__(self, dim, num_heads=8, qkv_bias=True, use_rel_pos=False, rel_pos_zero_init=True,
+                 input_size: Optional[Tuple[int, int]] = None) -> None:
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.use_rel_pos = use_rel_pos
+        if use_rel_pos:
+            assert input_size is not None, "Input size must be provided if using relative positional encoding."
+            self.rel_pos_h = nn.Parameter(torch.zeros(2 * input_size[0] - 1, head_dim))
+            self.rel_pos_w = nn.Parameter(torch.zeros(2 * input_size[1] - 1, head_dim))
+
+
+class Block(FusedAway):
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=True, norm_layer=nn.LayerNorm, act_layer=nn.GELU,
+                 use_rel_pos=False, rel_pos_zero_init=True, window_size=0, input_size=None) -> None:
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, use_rel_pos=use_rel_pos,
+                              rel_pos_zero_init=rel_pos_zero_init,
+                              input_size=input_size if window_size == 0 else (window_size, window_size))
+        self.norm2 = norm_layer(dim)
+        self.mlp = MLPBlock(embedding_dim=dim, mlp_dim=int(dim * mlp_ratio), act=act_layer)
+        self.window_size = window_size
+
+
+def _pack(t: torch.Tensor, packing: str) -> torch.Tensor:
+    t = t.detach()
+    if packing == "f32":
+        return t.float().contiguous()
+    if packing == "bf16":
+        return t.to(torch.bfloat16).contiguous()
+    if packing == "bf16_flat":  # conv weight [out, in, kh, kw] -> [out, in*kh*kw]
+        return t.reshape(t.shape[0], -1).to(torch.bfloat16).contiguous()
+    if packing == "bf16_tap":  # 3x3 conv weight -> [out, (ky*3+kx)*Cin + c]
+        return t.permute(0, 2, 3, 1).reshape(t.shape[0], -1).to(torch.bfloat16).contiguous()
+    if packing == "f32_tokens":  # pos_embed [1, 64, 64, D] -> [4096, D]
+        return t.reshape(-1, t.shape[-1]).float().contiguous()
+    raise ValueError(f"unknown packing {packing}")
+
+
+class _EncoderEngine:
+    """Owns the packed weights + the C-side encoder handle for one device."""
+
+    def __init__(self, module: "ImageEncoderViT", device: torch.device) -> None:
+        lib = _lib.load()
+        self.lib = lib
+        self.device = device
+        gmask = 0
+        for i, blk in enumerate(module.blocks):
+            if blk.window_size == 0:
+                gmask |= 1 << i
+        self.cfg = _lib.EncoderConfig(module.embed_dim, len(module.blocks), module.num_heads, gmask, module.out_chans)
+        sd = {"image_encoder." + k: v for k, v in module.state_dict().items()}
+        n = lib.b200sam_encoder_weight_count(C.byref(self.cfg))
+        self.packed = []
+        for i in range(n):
+            key, packing = lib.b200sam_encoder_weight_name(C.byref(self.cfg), i).decode().split("|")
+            if key not in sd:
+                raise _lib.B200SamError(f"encoder weight {key} missing from the module state_dict")
+            self.packed.append(_pack(sd[key].to(device), packing))
+        arr = (C.c_void_p * n)(*[t.data_ptr() for t in self.packed])
+        handle = C.c_void_p()
+        _lib.check(lib.b200sam_encoder_create(C.byref(self.cfg), arr, n, C.byref(handle)), "b200sam_encoder_create")
+        self.handle = handle
+        self._ws = {}
+
+    def workspace(self, batch: int) -> torch.Tensor:
+        ws = self._ws.get(batch)
+        if ws is None:
+            nbytes = self.lib.b200sam_encoder_workspace_bytes(C.byref(self.cfg), batch)
+            self._ws = {batch: torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)}
+            ws = self._ws[batch]
+        return ws
+
+    def forward(self, image: torch.Tensor, mean, std, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert image.dim() == 4 and image.shape[1] == 3, "expected [B,3,h,w]"
+        B, _, h, w = image.shape
+        if image.dtype != torch.uint8:
+            image = image.float()
+        image = image.contiguous()
+        if out is None:
+            out = torch.empty((B, self.cfg.out_chans, 64, 64), dtype=torch.float32, device=self.device)
+        ws = self.workspace(B)
+        base = (ws.data_ptr() + 1023) & ~1023
+        mean3 = (C.c_float * 3)(*mean)
+        std3 = (C.c_float * 3)(*std)
+        _lib.check(self.lib.b200sam_encoder_forward(self.handle, image.data_ptr(), int(image.dtype == torch.uint8), B, h,
+                                                   w, mean3, std3, out.data_ptr(), base,
+                                                   ws.numel() - (base - ws.data_ptr()), _lib.current_stream()),
+                   "b200sam_encoder_forward")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.b200sam_encoder_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class ImageEncoderViT(nn.Module):
+    def __init__(self, img_size: int = 1024, patch_size: int = 16, in_chans: int = 3, embed_dim: int = 768,
+                 depth: int = 12, num_heads: int = 12, mlp_ratio: float = 4.0, out_chans: int = 256,
+                 qkv_bias: bool = True, norm_layer: Type[nn.Module] = nn.LayerNorm,
+                 act_layer: Type[nn.Module] = nn.GELU, use_abs_pos: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, window_size: int = 0,
+                 global_attn_indexes: Tuple[int, ...] = ()) -> None:
+        super().__init__()
+        if img_size != 1024 or patch_size != 16 or in_chans != 3 or not use_abs_pos or not use_rel_pos \
+                or window_size != 14 or mlp_ratio != 4:
+            raise NotImplementedError("b200sam implements the SAM configuration only: 1024 px, 16 px patches, "
+                                      "abs+rel pos, 14x14 windows, mlp_ratio 4 (build_sam.py:62-80)")
+        self.img_size = img_size
+        self.embed_dim, self.num_heads, self.out_chans = embed_dim, num_heads, out_chans
+        self.patch_embed = PatchEmbed((patch_size, patch_size), (patch_size, patch_size), in_chans=in_chans,
+                                      embed_dim=embed_dim)
+        self.pos_embed = nn.Parameter(torch.zeros(1, img_size // patch_size, img_size // patch_size, embed_dim))
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            self.blocks.append(Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                     norm_layer=norm_layer, act_layer=act_layer, use_rel_pos=use_rel_pos,
+                                     rel_pos_zero_init=rel_pos_zero_init,
+                                     window_size=window_size if i not in global_attn_indexes else 0,
+                                     input_size=(img_size // patch_size, img_size // patch_size)))
+        self.neck = nn.Sequential(nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False), LayerNorm2d(out_chans),
+                                  nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False),
+                                  LayerNorm2d(out_chans))
+        self._engine: Optional[_EncoderEngine] = None
+
+    # weights changed / moved -> re-pack lazily
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def engine(self) -> _EncoderEngine:
+        dev = self.pos_embed.device
+        if dev.type != "cuda":
+            raise _lib.B200SamError("b200sam ImageEncoderViT has no CPU path: move the model to a CUDA device")
+        if self._engine is None or self._engine.device != dev:
+            self._engine = _EncoderEngine(self, dev)
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: already normalised + padded [B,3,1024,1024] (reference image_encoder.py:106-116)."""
+        return self.engine().forward(x, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+
+    @torch.no_grad()
+    def forward_raw(self, image: torch.Tensor, pixel_mean, pixel_std) -> torch.Tensor:
+        """Fused Sam.preprocess + forward: un-normalised uint8/float [B,3,h,w] with long side 1024."""
+        return self.engine().forward(image, pixel_mean, pixel_std)

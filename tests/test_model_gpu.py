@@ -1,0 +1,128 @@
+"""End-to-end parity of the CUDA path behind the reference API against the CPU oracle (same seeded inputs)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sam_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def dice(a, b):
+    a, b = np.asarray(a, bool), np.asarray(b, bool)
+    den = a.sum() + b.sum()
+    return 1.0 if den == 0 else 2.0 * (a & b).sum() / den
+
+
+@pytest.fixture(scope="module")
+def vit_b():
+    from samcarriestheburden_b200.segment_anything import sam_model_registry
+    sd = O.random_state_dict("vit_b", seed=0)
+    sam = sam_model_registry["vit_b"]()
+    sam.load_state_dict(sd, strict=True)
+    return sam.to(DEV), sd
+
+
+@pytest.fixture(scope="module")
+def embedding(vit_b):
+    """(image, oracle fp32 embedding, CUDA embedding) for one non-square synthetic radiograph."""
+    from samcarriestheburden_b200.segment_anything import SamPredictor
+    sam, sd = vit_b
+    img = O.synthetic_radiograph(3, 754, 589)
+    pred = SamPredictor(sam)
+    pred.set_image(img)
+    resized = pred.transform.apply_image(img)
+    x = O.preprocess(torch.from_numpy(resized).permute(2, 0, 1).float())[None]
+    ref = O.image_encoder(sd, x, **O.VIT_CONFIGS["vit_b"])
+    return img, ref, pred
+
+
+def test_encoder_embedding_tolerance(embedding):
+    """bf16 operands / fp32 accumulate: rel-L2 <= 2e-2, cosine >= 0.9995."""
+    _, ref, pred = embedding
+    got = pred.get_image_embedding().float().cpu()
+    assert got.shape == (1, 256, 64, 64)
+    rel = float((got - ref).norm() / ref.norm())
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+    print(f"encoder vit_b rel_l2={rel:.3e} cos={cos:.6f}")
+    assert rel <= 2e-2 and cos >= 0.9995, (rel, cos)
+
+
+def test_encoder_batch_matches_single(vit_b):
+    sam, _ = vit_b
+    imgs = torch.stack([torch.from_numpy(O.synthetic_radiograph(s)).permute(2, 0, 1) for s in (11, 12, 13)]).to(DEV)
+    batch = sam.encode_image(imgs)
+    single = torch.cat([sam.encode_image(imgs[i:i + 1]) for i in range(3)])
+    torch.cuda.synchronize()
+    assert torch.equal(batch, single)
+
+
+def test_predict_box_matches_oracle(vit_b, embedding):
+    """Decode stage from IDENTICAL fp32 embeddings: SamPredictor.predict(box)."""
+    sam, sd = vit_b
+    img, ref_emb, pred = embedding
+    saved = pred.features
+    pred.features = ref_emb.to(DEV)
+    box = np.array([100.0, 150.0, 400.0, 600.0])
+    masks, iou, low = pred.predict(box=box, multimask_output=False)
+    m3, iou3, low3 = pred.predict(point_coords=np.array([[200.0, 300.0], [50.0, 60.0]]), point_labels=np.array([1, 0]),
+                                  mask_input=low, multimask_output=True)
+    pred.features = saved
+    bt = torch.from_numpy(pred.transform.apply_boxes(box[None], (754, 589))).float()
+    sp, de = O.prompt_encoder(sd, None, bt, None)
+    low_o, iou_o = O.mask_decoder(sd, ref_emb, O.dense_pe(sd), sp, de, False)
+    assert np.abs(low - low_o[0].numpy()).max() < 5e-4, np.abs(low - low_o[0].numpy()).max()
+    assert np.abs(iou - iou_o[0].numpy()).max() < 5e-4
+    m_o = (O.postprocess_masks(low_o, pred.input_size, (754, 589)) > 0)[0].numpy()
+    d = dice(masks, m_o)
+    print(f"predict(box): dice={d:.6f} mismatched={int((masks != m_o).sum())}")
+    assert d >= 0.999
+    pts = torch.from_numpy(pred.transform.apply_coords(np.array([[200.0, 300.0], [50.0, 60.0]]), (754, 589))).float()[None]
+    sp, de = O.prompt_encoder(sd, (pts, torch.tensor([[1, 0]])), None, low_o)
+    low3_o, iou3_o = O.mask_decoder(sd, ref_emb, O.dense_pe(sd), sp, de, True)
+    assert low3.shape == (3, 256, 256)
+    assert np.abs(low3 - low3_o[0].numpy()).max() < 1e-3
+    assert np.abs(iou3 - iou3_o[0].numpy()).max() < 1e-3
+
+
+def test_dense_pe_matches_oracle(vit_b):
+    sam, sd = vit_b
+    pe = sam.prompt_encoder.get_dense_pe().cpu()
+    assert pe.shape == (1, 256, 64, 64)
+    assert (pe - O.dense_pe(sd)).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("orig", [(754, 589), (1024, 1024)])
+def test_refine_matches_oracle(vit_b, orig):
+    """Full two-pass refinement (box, then pos/neg points + previous logits), all prompts batched, against the
+    oracle's per-class B=1 loop from the same fp32 embedding: Dice >= 0.999 per class, mismatches reported."""
+    from samcarriestheburden_b200.segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
+    from samcarriestheburden_b200.utils.seg_refinement import SAMSegRefiner
+    sam, sd = vit_b
+    g = torch.Generator().manual_seed(orig[0])
+    feats = torch.randn((1, 256, 64, 64), generator=g)
+    inp = O.get_preprocess_shape(*orig)
+    store = EmbeddingStore()
+    store.add("img", feats.to(DEV), orig, inp)
+    head = SAMMaskDecoderHead(None, "vit_b", DEV, store, sam_model=sam)
+    refiner = SAMSegRefiner("SAM", DEV, [["box"], ["pos_points", "neg_points"]], sam_predictor=head)
+    seg = O.synthetic_unet_masks(7)
+    got_seg, got_dice = refiner.refine(torch.from_numpy(seg.copy()), "img")
+    ref_seg, ref_dice, ref_native, _ = O.refine(sd, feats, seg, inp, orig)
+    got_seg = got_seg.cpu().numpy()
+    ds = [dice(got_seg[c], ref_seg[c]) for c in range(seg.shape[0])]
+    mism = int((got_seg != ref_seg).sum())
+    print(f"refine {orig}: min dice={min(ds):.6f} mismatched px={mism} of {got_seg.size}")
+    assert min(ds) >= 0.999, ds
+    assert np.allclose(got_dice.numpy(), ref_dice, atol=1e-3, equal_nan=True)
+    # native-resolution masks of the second pass through the reference-shaped predict_mask API
+    from samcarriestheburden_b200.segment_anything.utils.prompt_utils import PromptExtractor
+    prompts = PromptExtractor(torch.from_numpy(seg).to(DEV)).extract()
+    p = prompts[0]
+    m1, s1, low1 = head.predict_mask("img", p, ["box"])
+    m2, s2, _ = head.predict_mask("img", p, ["pos_points", "neg_points"], low1)
+    assert m2.shape == (1, 1) + tuple(orig) and m2.dtype == torch.bool
+    d = dice(m2[0, 0].cpu().numpy(), ref_native[p.class_idx])
+    print(f"predict_mask native {orig}: dice={d:.6f}")
+    assert d >= 0.999

@@ -1,0 +1,204 @@
+"""Op-level parity of the CUDA kernels (through the C ABI) against plain torch fp32 restatements."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sam_oracle as O
+from samcarriestheburden_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _gemm(A, W, bias=None, residual=None, res_row_mod=0, gelu=False, out_bf16=True, max_ctas=0):
+    lib = _lib.load()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=DEV)
+    ldr = residual.shape[1] if residual is not None else 0
+    _lib.check(lib.b200sam_gemm_bf16(A.data_ptr(), W.data_ptr(), out.data_ptr(), _lib.ptr(bias), _lib.ptr(residual), M,
+                                     N, K, A.stride(0), W.stride(0), N, ldr, res_row_mod, int(gelu), int(out_bf16),
+                                     max_ctas, _lib.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (4096, 3840, 1280), (4096, 1280, 5120),
+                                   (200, 384, 192), (4096, 768, 768), (1000, 264, 72)])
+def test_gemm_bf16_bias(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn((M, K), generator=g).to(DEV).bfloat16()
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(DEV).bfloat16()
+    b = torch.randn((N,), generator=g).to(DEV)
+    ref = A.float() @ W.float().T + b
+    out = _gemm(A, W, b)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, err
+    # fp32 output isolates accumulation error (inputs are exact bf16): tight tolerance
+    out32 = _gemm(A, W, b, out_bf16=False)
+    assert torch.allclose(out32, ref, atol=2e-3, rtol=2e-3), (out32 - ref).abs().max().item()
+
+
+def test_gemm_epilogues():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    M, N, K = 8192, 1280, 1280
+    A = torch.randn((M, K), generator=g).to(DEV).bfloat16()
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(DEV).bfloat16()
+    b = torch.randn((N,), generator=g).to(DEV)
+    lin = A.float() @ W.float().T + b
+    out = _gemm(A, W, b, gelu=True)
+    assert torch.allclose(out.float(), F.gelu(lin), atol=3e-2, rtol=2e-2)
+    res = torch.randn((M, N), generator=g).to(DEV)
+    got = res.clone()  # in-place residual, as used for the residual stream
+    lib = _lib.load()
+    _lib.check(lib.b200sam_gemm_bf16(A.data_ptr(), W.data_ptr(), got.data_ptr(), b.data_ptr(), got.data_ptr(), M, N, K,
+                                     K, K, N, N, 0, 0, 0, 0, _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.allclose(got, lin + res, atol=2e-3, rtol=2e-3)
+    pos = torch.randn((4096, N), generator=g).to(DEV)  # broadcast table (pos_embed) over 2 images
+    out = _gemm(A, W, b, residual=pos, res_row_mod=4096, out_bf16=False)
+    assert torch.allclose(out, lin + pos.repeat(2, 1), atol=2e-3, rtol=2e-3)
+    # a persistent grid smaller than the tile count must give identical results
+    assert torch.equal(_gemm(A, W, b, max_ctas=7), _gemm(A, W, b))
+
+
+@pytest.mark.parametrize("D", [256, 768, 1024, 1280])
+def test_layernorm(D):
+    g = torch.Generator(device="cpu").manual_seed(D)
+    x = (torch.randn((777, D), generator=g) * 3 + 1.5).to(DEV)
+    w, b = torch.randn((D,), generator=g).to(DEV), torch.randn((D,), generator=g).to(DEV)
+    lib = _lib.load()
+    ref = F.layer_norm(x, (D,), w, b, eps=1e-6)
+    y32 = torch.empty_like(x)
+    _lib.check(lib.b200sam_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), 1e-6, 777, D, y32.data_ptr(), 0,
+                                     _lib.current_stream()))
+    y16 = torch.empty((777, D), dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.b200sam_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), 1e-6, 777, D, y16.data_ptr(), 1,
+                                     _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.allclose(y32, ref, atol=1e-5, rtol=1e-5)
+    assert torch.equal(y16, ref.bfloat16()) or (y16.float() - ref).abs().max() < 4e-2
+
+
+def _attention_reference(qkv, bias16, rel_h, rel_w, heads, hd, window):
+    """fp32 restatement of Attention.forward + window partition on bf16-rounded inputs (image_encoder.py:166-240)."""
+    D = heads * hd
+    B = qkv.shape[0] // 4096
+    x = qkv.float().view(B, 64, 64, 3 * D)
+    if window:
+        pad = (-64) % window
+        grid = bias16.float().view(1, 1, 1, 3 * D).expand(B, 64 + pad, 64 + pad, 3 * D).clone()
+        grid[:, :64, :64] = x
+        S = window
+        nw = (64 + pad) // window
+        t = grid.view(B, nw, S, nw, S, 3 * D).permute(0, 1, 3, 2, 4, 5).reshape(-1, S * S, 3, heads, hd)
+    else:
+        S = 64
+        t = x.reshape(B, S * S, 3, heads, hd)
+    t = t.permute(2, 0, 3, 1, 4).reshape(3, -1, S * S, hd)
+    q, k, v = t[0], t[1], t[2]
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1) + O._rel_pos_bias(q, rel_h.float(), rel_w.float(), S)
+    o = attn.softmax(-1) @ v
+    o = o.view(-1, heads, S, S, hd).permute(0, 2, 3, 1, 4).reshape(-1, S, S, D)
+    if window:
+        o = o.view(B, nw, nw, S, S, D).permute(0, 1, 3, 2, 4, 5).reshape(B, nw * S, nw * S, D)[:, :64, :64]
+    return o.reshape(B * 4096, D)
+
+
+@pytest.mark.parametrize("heads,hd,glob", [(16, 80, 0), (12, 64, 0), (4, 80, 1), (3, 64, 1)])
+def test_encoder_attention(heads, hd, glob):
+    g = torch.Generator(device="cpu").manual_seed(heads * 100 + hd + glob)
+    D = heads * hd
+    B = 2 if not glob else 1
+    S = 64 if glob else 14
+    qkv = torch.randn((B * 4096, 3 * D), generator=g).to(DEV).bfloat16()
+    bias = torch.randn((3 * D,), generator=g).to(DEV).bfloat16()
+    rel_h = (0.3 * torch.randn((2 * S - 1, hd), generator=g)).to(DEV).bfloat16()
+    rel_w = (0.3 * torch.randn((2 * S - 1, hd), generator=g)).to(DEV).bfloat16()
+    out = torch.empty((B * 4096, D), dtype=torch.bfloat16, device=DEV)
+    lib = _lib.load()
+    _lib.check(lib.b200sam_encoder_attention(qkv.data_ptr(), bias.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(),
+                                             out.data_ptr(), B, heads, hd, glob, _lib.current_stream()))
+    torch.cuda.synchronize()
+    ref = _attention_reference(qkv, bias, rel_h, rel_w, heads, hd, 0 if glob else 14)
+    err = (out.float() - ref).abs()
+    assert err.max().item() < 3e-2, (err.max().item(), err.mean().item())
+    assert err.mean().item() < 3e-3
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_prompt_extraction_bit_exact(seed):
+    from samcarriestheburden_b200.segment_anything.utils.prompt_utils import extract_seeds_boxes
+    masks = np.stack([O.synthetic_unet_masks(10 * seed + i) for i in range(3)])
+    if seed == 1:
+        masks[0, 3] = masks[0, 5]
+    if seed == 2:
+        rng = np.random.default_rng(5)
+        masks &= rng.random(masks.shape) < 0.5
+    if seed == 3:
+        masks[1] = False  # image without any class
+    seeds, boxes, has_seed, has_box = extract_seeds_boxes(torch.from_numpy(masks).to(DEV))
+    torch.cuda.synchronize()
+    for i in range(masks.shape[0]):
+        s, hs, b, hb = O.extract_seeds_boxes(masks[i])
+        assert np.array_equal(has_seed[i].cpu().numpy().astype(bool), hs)
+        assert np.array_equal(has_box[i].cpu().numpy().astype(bool), hb)
+        assert np.array_equal(seeds[i].cpu().numpy()[hs], s[hs])
+        assert np.array_equal(boxes[i].cpu().numpy()[hb], b[hb])
+
+
+def test_prompt_extraction_ragged_shapes():
+    from samcarriestheburden_b200.segment_anything.utils.prompt_utils import extract_seeds_boxes
+    rng = np.random.default_rng(0)
+    for (C_, H, W) in [(1, 1, 1), (5, 37, 53), (17, 384, 224), (3, 1, 1000), (64, 33, 31)]:
+        masks = rng.random((2, C_, H, W)) < 0.3
+        seeds, boxes, has_seed, has_box = extract_seeds_boxes(torch.from_numpy(masks).to(DEV))
+        for i in range(2):
+            s, hs, b, hb = O.extract_seeds_boxes(masks[i])
+            assert np.array_equal(has_seed[i].cpu().numpy().astype(bool), hs)
+            assert np.array_equal(seeds[i].cpu().numpy()[hs], s[hs])
+            assert np.array_equal(boxes[i].cpu().numpy()[hb], b[hb])
+
+
+@pytest.mark.parametrize("orig", [(1024, 1024), (1182, 754), (578, 881), (2570, 2040), (301, 299)])
+def test_upscale_threshold(orig):
+    from samcarriestheburden_b200.segment_anything.modeling.sam import upscale_masks
+    g = torch.Generator(device="cpu").manual_seed(orig[0])
+    low = torch.randn((3, 1, 256, 256), generator=g)
+    inp = O.get_preprocess_shape(*orig)
+    ref = O.postprocess_masks(low, inp, orig)
+    mask, small = upscale_masks(low.to(DEV), inp, orig, small_size=(384, 224))
+    logits = upscale_masks(low.to(DEV), inp, orig, return_logits=True)
+    torch.cuda.synchronize()
+    assert (logits.cpu() - ref).abs().max().item() < 1e-5
+    ref_mask = ref > 0
+    mism = int((mask.cpu() != ref_mask).sum())
+    inter = float((mask.cpu() & ref_mask).sum())
+    dice = 2 * inter / float(mask.sum().cpu() + ref_mask.sum())
+    assert mism <= 3 and dice >= 0.9999, (mism, dice)
+    ref_small = F.interpolate(ref_mask.float(), size=(384, 224), mode="nearest-exact") > 0.5
+    assert int((small.cpu() != ref_small).sum()) <= 1
+
+
+def test_linear_f32():
+    g = torch.Generator(device="cpu").manual_seed(3)
+    lib = _lib.load()
+    for (M, N, K, act) in [(35, 256, 256, 0), (4096, 128, 256, 0), (391, 2048, 256, 1), (391, 256, 2048, 0),
+                           (16384, 128, 64, 2)]:
+        A = torch.randn((M, K), generator=g).to(DEV)
+        A2 = torch.randn((64, K), generator=g).to(DEV)
+        W = (torch.randn((N, K), generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn((N,), generator=g).to(DEV)
+        res = torch.randn((M, N), generator=g).to(DEV)
+        out = torch.empty((M, N), device=DEV)
+        _lib.check(lib.b200sam_linear_f32(A.data_ptr(), A2.data_ptr(), 64, W.data_ptr(), b.data_ptr(), res.data_ptr(),
+                                          out.data_ptr(), M, N, K, act, _lib.current_stream()))
+        torch.cuda.synchronize()
+        idx = torch.arange(M, device=DEV) % 64
+        ref = (A.double() + A2.double()[idx]) @ W.double().T + b.double()
+        ref = F.relu(ref) if act == 1 else (F.gelu(ref) if act == 2 else ref)
+        ref = (ref + res.double()).float()
+        assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5), (M, N, K, (out - ref).abs().max().item())
