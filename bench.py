@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Headline benchmark: SAM ViT-H image-embedding generation @1024^2 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--model vit_h] [--impl reference]
+
+A "step" = one pass of the hot path over one batch of B synthetic 1024x1024 radiographs (uint8, random-init
+ViT-H weights): normalise+pad+patchify -> ViT encoder -> neck -> [B,256,64,64] fp32 embeddings.
+  value : images/s over all ranks, inputs already resident in HBM, CUDA-event timed, max over ranks.
+  e2e   : same metric through the public API (Sam.encode_image, what SamPredictor.set_torch_image calls) with
+          pinned-host uint8 inputs copied H2D and the embeddings copied D2H inside the timed region.
+  roofline: the dominant kernel (tcgen05 GEMM) timed live with CUDA events on the encoder's four linear shapes.
+  cpu_baseline / --impl reference: the CPU oracle (a port of the reference's PyTorch path, oracle/sam_oracle.py)
+          on the box's host cores; the reference itself is Python under /root/reference and cannot travel.
+Multi-GPU: one process per GPU (torchrun); images shard by rank, no collective on the critical path, one final
+NCCL all_gather of the last embeddings (weak scaling: per-GPU batch is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ENC_GFLOP = {"vit_h": 5641.8, "vit_l": 2837.0, "vit_b": 937.6}  # algorithmic, per image
+METRIC = "ViT-H embeds/sec @1024^2"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured")
+    return dict(tf_burst=1590.0, tf_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows)]
+        out.update(sm_mhz=statistics.median(busy), sm_max_mhz=float(rows[0][2]), reasons=reasons,
+                   power_w_max=max(float(r[3]) for r in rows), samples=len(rows))
+        return out
+
+
+def build_model(model: str, device):
+    import torch
+    from oracle import sam_oracle as O  # synthetic weights only (seeded init shared with the parity tests)
+    from samcarriestheburden_b200.segment_anything import sam_model_registry
+    sam = sam_model_registry[model]()
+    sam.load_state_dict(O.random_state_dict(model, seed=0), strict=True)
+    return sam.to(device)
+
+
+def synthetic_batch(batch: int, seed: int):
+    import numpy as np
+    import torch
+    from oracle import sam_oracle as O
+    base = torch.from_numpy(O.synthetic_radiograph(seed)).permute(2, 0, 1).contiguous()
+    rng = np.random.default_rng(seed)
+    imgs = [torch.roll(base, shifts=(int(rng.integers(0, 1024)), int(rng.integers(0, 1024))), dims=(1, 2))
+            for _ in range(batch)]
+    return torch.stack(imgs)
+
+
+def gemm_roofline(model: str, batch: int, reps: int = 10):
+    """Time the tcgen05 GEMM kernel alone (CUDA events, same stream) on the four linear shapes of one block."""
+    import torch
+    from samcarriestheburden_b200 import _lib
+    lib = _lib.load()
+    D = {"vit_h": 1280, "vit_l": 1024, "vit_b": 768}[model]
+    M = batch * 4096
+    shapes = [("qkv", 3 * D, D, 1, 0), ("proj", D, D, 0, 0), ("lin1", 4 * D, D, 1, 1), ("lin2", D, 4 * D, 0, 0)]
+    dev = "cuda"
+    stream = _lib.current_stream()
+    tot_flop, tot_ms, per = 0.0, 0.0, {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for name, N, K, out_bf16, gelu in shapes:
+        A = torch.randn((M, K), device=dev).bfloat16()
+        W = (torch.randn((N, K), device=dev) / K ** 0.5).bfloat16()
+        b = torch.randn((N,), device=dev)
+        out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        res = out if not out_bf16 else None
+        ms = []
+        for i in range(reps + 3):
+            flush.zero_()  # evict L2 between launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.b200sam_gemm_bf16(A.data_ptr(), W.data_ptr(), out.data_ptr(), b.data_ptr(), _lib.ptr(res), M,
+                                             N, K, K, K, N, N, 0, gelu, out_bf16, 0, stream))
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                ms.append(e0.elapsed_time(e1))
+        t = statistics.mean(ms)
+        flop = 2.0 * M * N * K
+        per[name] = {"ms": round(t, 4), "tflops": round(flop / t / 1e9, 1)}
+        tot_flop += flop
+        tot_ms += t
+    return tot_flop / tot_ms / 1e9, tot_ms / 4, per  # TFLOP/s over the 4 launches, mean launch ms
+
+
+def cpu_encoder_images_per_s(model: str, n_images: int, warm: int = 0):
+    import torch
+    from oracle import sam_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.random_state_dict(model, seed=0)
+    cfg = O.VIT_CONFIGS[model]
+    times = []
+    for i in range(warm + n_images):
+        img = torch.from_numpy(O.synthetic_radiograph(i)).permute(2, 0, 1).float()
+        t0 = time.perf_counter()
+        O.image_encoder(sd, O.preprocess(img)[None], **cfg)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return len(times) / sum(times), torch.get_num_threads(), times
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import sam_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.random_state_dict(args.model, seed=0)
+    cfg = O.VIT_CONFIGS[args.model]
+
+    def step(i):
+        img = torch.from_numpy(O.synthetic_radiograph(i)).permute(2, 0, 1).float()
+        t0 = time.perf_counter()
+        O.image_encoder(sd, O.preprocess(img)[None], **cfg)
+        return time.perf_counter() - t0
+
+    budget = 280.0  # seconds: keep the whole run within a few minutes
+    first = step(0)
+    warm_left = max(0, min(args.warmup, int(budget * 0.2 / first)) - 1)
+    for i in range(warm_left):
+        step(1 + i)
+    k = max(1, min(args.steps, int((budget - first * (1 + warm_left)) / first)))
+    times = [step(100 + i) for i in range(k)]
+    T = sum(times)
+    v = k / T
+    cores = torch.get_num_threads()
+    sample = f"1 image per step through the full {args.model} encoder (fp32, {cores} threads); {k} timed steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": k,
+        "warmup": 1 + warm_left, "ms_per_step": 1e3 * T / k, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SAM {args.model} image-embedding generation, synthetic 1024x1024 radiographs "
+                               "(BASELINE.json configs[1]); CPU oracle port of the reference PyTorch path"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--model", default="vit_h")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-refine", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the b200sam product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K, B = args.steps, args.batch
+
+    sam = build_model(args.model, dev)
+    pool = [synthetic_batch(B, 1000 * rank + s) for s in range(2)]
+    dev_pool = [p.to(dev) for p in pool]
+    host_pool = [p.pin_memory() for p in pool]
+    host_out = torch.empty((B, 256, 64, 64), dtype=torch.float32).pin_memory()
+    enc = sam.image_encoder
+    launches_per_step = 2 + 7 * len(enc.blocks) + 6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for s in range(steps):
+            last = fn(s)
+        if world > 1:  # the only collective: final gather of embeddings over NVLink, off the critical path
+            gathered = torch.empty((world,) + tuple(last.shape), dtype=last.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, last.contiguous())
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident(s):
+        return sam.encode_image(dev_pool[s % len(dev_pool)])
+
+    def step_e2e(s):
+        x = host_pool[s % len(host_pool)].to(dev, non_blocking=True)
+        emb = sam.encode_image(x)
+        host_out.copy_(emb, non_blocking=True)
+        return emb
+
+    for s in range(W):
+        step_resident(s)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(step_resident, K)
+    clocks = sampler.stop() if sampler else {}
+    for s in range(2):
+        step_e2e(s)
+    ms_e2e = timed(step_e2e, K)
+
+    value = world * B * K / (ms / 1e3)
+    e2e = world * B * K / (ms_e2e / 1e3)
+    peaks = _peaks()
+    out = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"SAM {args.model} image-embedding generation (generate_img_embeddings), synthetic "
+                               f"1024x1024 uint8 radiographs, random-init weights (BASELINE.json configs[1])",
+                   "batch_per_gpu": B, "parallelism": f"dp{world} (images sharded by rank, final NCCL all_gather)",
+                   "l2": "activations per step (>100 MB per image) exceed the 126 MB L2; no explicit flush",
+                   "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate"},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 1024 * 1024,
+                "d2h_bytes_per_step": B * 256 * 64 * 64 * 4},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clocks,
+        "encoder_frac_of_bf16_peak": {
+            "algorithmic_gflop_per_image": ENC_GFLOP[args.model],
+            "achieved_tflops_per_gpu": value / world * ENC_GFLOP[args.model] / 1e3,
+            "frac_of_burst": value / world * ENC_GFLOP[args.model] / 1e3 / peaks["tf_burst"],
+            "frac_of_sustained": value / world * ENC_GFLOP[args.model] / 1e3 / peaks["tf_sustained"],
+            "peak_source": peaks["src"]},
+    }
+    if rank == 0:
+        tf, launch_ms, per = gemm_roofline(args.model, B)
+        out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                           "frac": tf / peaks["tf_burst"], "traffic": None,
+                           "kernel": "gemm_bf16_tn_kernel (tcgen05, 128x256x64 tiles)",
+                           "launch_ms_mean": launch_ms, "per_shape": per, "peak_source": peaks["src"] + " burst"}
+        if not args.no_refine:
+            out["refine"] = refine_throughput(sam, dev)
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, times = cpu_encoder_images_per_s(args.model, 1)
+            out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                   "sample": f"1 image through the full {args.model} fp32 encoder of the CPU oracle "
+                                             f"({times[0]:.1f} s)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def refine_throughput(sam, dev, n_images: int = 6):
+    """Secondary metric (BASELINE.json configs[2]): refined masks/s of the decoder stage from precomputed
+    embeddings: prompt extraction + box pass + point/mask pass (all prompts batched) + upscale + threshold."""
+    import torch
+    from oracle import sam_oracle as O
+    from samcarriestheburden_b200.segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
+    from samcarriestheburden_b200.utils.seg_refinement import SAMSegRefiner
+    store = EmbeddingStore()
+    g = torch.Generator().manual_seed(0)
+    segs = []
+    for i in range(n_images):
+        store.add(f"img{i}", torch.randn((1, 256, 64, 64), generator=g).to(dev), (1024, 1024), (1024, 1024))
+        segs.append(torch.from_numpy(O.synthetic_unet_masks(i)).to(dev))
+    head = SAMMaskDecoderHead(None, "vit_h", str(dev), store, sam_model=sam)
+    refiner = SAMSegRefiner("SAM", str(dev), [["box"], ["pos_points", "neg_points"]], sam_predictor=head)
+    refiner.refine(segs[0].clone(), "img0")
+    torch.cuda.synchronize()
+    n_masks = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_images):
+        _, est = refiner.refine(segs[i].clone(), f"img{i}")
+        n_masks += int((~torch.isnan(est)).sum())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"metric": "refined masks/s (decode stage, 1024^2 native, 2 passes, prompts batched per image)",
+            "value": n_masks / (ms / 1e3), "unit": "masks/s", "images": n_images, "masks": n_masks,
+            "ms_per_image": ms / n_images}
+
+
+if __name__ == "__main__":
+    main()

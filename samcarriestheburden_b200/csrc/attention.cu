@@ -22,10 +22,16 @@ namespace {
 
 constexpr float LOG2E = 1.4426950408889634f;
 
+B200SAM_DEVINL float ex2_approx(float x) {  // MUFU.EX2, flush-to-zero: exp2(-inf) = 0 as the online softmax needs
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // One key tile: S = Q K^T (NT n-tiles of 8 keys), online softmax in the exp2 domain, O += P V.
-template <int NT, int HD, typename BiasFn>
+template <int NT, int VALID, int HD, typename BiasFn>
 B200SAM_DEVINL void attn_tile(const uint32_t (&qf)[HD / 16][4], uint32_t k_base, uint32_t v_base, float scale_l2,
-                              BiasFn bias, int valid, float (&o)[HD / 8][4], float (&m)[2], float (&l)[2]) {
+                              BiasFn bias, float (&o)[HD / 8][4], float (&m)[2], float (&l)[2]) {
   constexpr int P = HD + 8;
   const int lane = lane_id();
   float s[NT][4];
@@ -52,7 +58,9 @@ B200SAM_DEVINL void attn_tile(const uint32_t (&qf)[HD / 16][4], uint32_t k_base,
       const int i = e >> 1;
       const int col = nt * 8 + c0 + (e & 1);
       float v = fmaf(s[nt][e], scale_l2, bias(i, nt, e & 1, col));
-      if (col >= valid) v = -INFINITY;
+      if constexpr (VALID < NT * 8) {
+        if (col >= VALID) v = -INFINITY;
+      }
       s[nt][e] = v;
       mx[i] = fmaxf(mx[i], v);
     }
@@ -63,7 +71,7 @@ B200SAM_DEVINL void attn_tile(const uint32_t (&qf)[HD / 16][4], uint32_t k_base,
     mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
     mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
     mnew[i] = fmaxf(m[i], mx[i]);
-    corr[i] = exp2f(m[i] - mnew[i]);
+    corr[i] = ex2_approx(m[i] - mnew[i]);
     m[i] = mnew[i];
     l[i] *= corr[i];
   }
@@ -78,7 +86,7 @@ B200SAM_DEVINL void attn_tile(const uint32_t (&qf)[HD / 16][4], uint32_t k_base,
   for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float p = exp2f(s[nt][e] - mnew[e >> 1]);
+      const float p = ex2_approx(s[nt][e] - mnew[e >> 1]);
       s[nt][e] = p;
       l[e >> 1] += p;
     }
@@ -257,19 +265,19 @@ __global__ void __launch_bounds__(WIN_THREADS, 2) window_attn_kernel(AttnArgs a)
     float m[2] = {-INFINITY, -INFINITY};
     float l[2] = {0.0f, 0.0f};
     {
-      auto bias0 = [&](int i, int, int, int col) {
-        const int kh = col / WIN, kw = col - kh * WIN;
-        const float* brow = bs + (g + 8 * i) * 28;
-        return brow[kh] + brow[14 + kw];
+      // 208 padded keys in three tiles of 80 / 64 / 64 (the last one has 52 valid keys): keeps the score
+      // fragment at <= 40 registers so two CTAs fit per SM without spilling.
+      auto make_bias = [&](int k0) {
+        return [&, k0](int i, int, int, int col) {
+          const int k = k0 + col;
+          const int kh = k / WIN, kw = k - kh * WIN;  // k >= 196 is masked via VALID; index stays inside [0, 28)
+          const float* brow = bs + (g + 8 * i) * 28;
+          return brow[kh < WIN ? kh : 0] + brow[14 + kw];
+        };
       };
-      attn_tile<14, HD>(qf, smem_u32(Ks), smem_u32(Vs), scale_l2, bias0, 112, o, m, l);
-      auto bias1 = [&](int i, int, int, int col) {
-        const int k = 112 + col;
-        const int kh = k / WIN, kw = k - kh * WIN;  // k >= 196 is masked by `valid`; index stays < 28
-        const float* brow = bs + (g + 8 * i) * 28;
-        return brow[kh < WIN ? kh : 0] + brow[14 + kw];
-      };
-      attn_tile<12, HD>(qf, smem_u32(Ks + 112 * P), smem_u32(Vs + 112 * P), scale_l2, bias1, WTOK - 112, o, m, l);
+      attn_tile<10, 80, HD>(qf, smem_u32(Ks), smem_u32(Vs), scale_l2, make_bias(0), o, m, l);
+      attn_tile<8, 64, HD>(qf, smem_u32(Ks + 80 * P), smem_u32(Vs + 80 * P), scale_l2, make_bias(80), o, m, l);
+      attn_tile<8, WTOK - 144, HD>(qf, smem_u32(Ks + 144 * P), smem_u32(Vs + 144 * P), scale_l2, make_bias(144), o, m, l);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -411,8 +419,8 @@ __global__ void __launch_bounds__(GLB_THREADS, 1) global_attn_kernel(AttnArgs a)
     bh[1] = Th[(warp * 16 + g + 8) * 64 + t];
     const int buf = t & 1;
     auto bias = [&](int i, int nt, int ee, int) { return bw[i][nt][ee] + bh[i]; };
-    attn_tile<8, HD>(qf, smem_u32(KV + (buf * 2 + 0) * GK * P), smem_u32(KV + (buf * 2 + 1) * GK * P), scale_l2, bias,
-                     GK, o, m, l);
+    attn_tile<8, GK, HD>(qf, smem_u32(KV + (buf * 2 + 0) * GK * P), smem_u32(KV + (buf * 2 + 1) * GK * P), scale_l2,
+                         bias, o, m, l);
     __syncthreads();
   }
 #pragma unroll
