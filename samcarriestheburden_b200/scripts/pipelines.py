@@ -1,0 +1,81 @@
+"""Drivers mirroring the reference's two hot-path scripts, restructured for a B200 box:
+
+  generate_img_embeddings (reference scripts/generate_img_embeddings.py:36-72)
+      per image, B=1, H2D + encoder + D2H + gzip-9 h5 write, one fixed device
+   -> batched encoder launches per GPU, images sharded by rank, embeddings kept resident in an EmbeddingStore
+      (or gathered once at the end); disk I/O is left to the caller.
+
+  refine_segmentations (reference scripts/save_refined_segmentations.py:60-80 after the U-Net)
+      per image: prompt extraction + 2 B=1 decoder calls per class
+   -> per image: one prompt-extraction launch, two batched decoder passes over all classes, one fused
+      upscale/threshold/nearest-exact launch.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import sharding
+from ..segment_anything.predictor import SamPredictor
+from ..segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
+from ..utils.seg_refinement import SAMSegRefiner
+
+
+@torch.no_grad()
+def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[str], batch: int = 8,
+                            store: EmbeddingStore | None = None, gather: bool = False):
+    """images: HWC uint8 RGB arrays (gray replicated to 3 channels like the reference :39-40).  Each rank encodes
+    its shard in batches (same-shape images are batched together) and registers the results in `store`.
+    Returns (store, gathered [N,256,64,64] tensor or None)."""
+    assert len(images) == len(names)
+    dev = sam.device
+    store = store if store is not None else EmbeddingStore(img_encoder_img_size=sam.image_encoder.img_size)
+    pred = SamPredictor(sam)
+    mine = sharding.shard_indices(len(images))
+    local = torch.empty((len(mine), 256, 64, 64), dtype=torch.float32, device=dev)
+    pending: Dict[Tuple[int, int], List[Tuple[int, torch.Tensor, tuple]]] = {}
+
+    def flush(key):
+        items = pending.pop(key)
+        x = torch.stack([t for _, t, _ in items]).to(dev, non_blocking=True)
+        emb = sam.encode_image(x)
+        for j, (slot, _, orig) in enumerate(items):
+            local[slot] = emb[j]
+            store.add(names[mine[slot]], local[slot:slot + 1], orig, key)
+
+    for slot, i in enumerate(mine):
+        img = images[i]
+        resized = pred.transform.apply_image(img)
+        t = torch.from_numpy(np.ascontiguousarray(resized)).permute(2, 0, 1).contiguous()
+        key = tuple(t.shape[-2:])
+        pending.setdefault(key, []).append((slot, t, tuple(img.shape[:2])))
+        if len(pending[key]) == batch:
+            flush(key)
+    for key in list(pending):
+        flush(key)
+    gathered = sharding.gather_sharded(local, len(images)) if gather else None
+    return store, gathered
+
+
+@torch.no_grad()
+def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor], names: Sequence[str],
+                         prompts2use=(("box",), ("pos_points", "neg_points")), gather: bool = False):
+    """segs[i]: [C,H,W] bool (or probabilities) U-Net masks of image names[i]; every rank refines the images of its
+    shard whose embeddings it holds.  Returns (list of (index, seg bool [C,H,W], est_dice [C]) for the local
+    shard, gathered [N,C,H,W] uint8 tensor or None)."""
+    dev = sam.device
+    head = SAMMaskDecoderHead(None, "", str(dev), store, sam_model=sam)
+    refiner = SAMSegRefiner("SAM", str(dev), [list(p) for p in prompts2use], sam_predictor=head)
+    mine = sharding.shard_indices(len(segs))
+    results = []
+    for i in mine:
+        seg, est = refiner.refine(segs[i].to(dev), names[i])
+        results.append((i, seg, est))
+    gathered = None
+    if gather and len(segs):
+        local = torch.stack([r[1] for r in results]).to(torch.uint8) if results else \
+            torch.zeros((0,) + tuple(segs[0].shape), dtype=torch.uint8, device=dev)
+        gathered = sharding.gather_sharded(local, len(segs))
+    return results, gathered

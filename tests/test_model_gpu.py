@@ -126,3 +126,32 @@ def test_refine_matches_oracle(vit_b, orig):
     d = dice(m2[0, 0].cpu().numpy(), ref_native[p.class_idx])
     print(f"predict_mask native {orig}: dice={d:.6f}")
     assert d >= 0.999
+
+
+def test_pipeline_drivers_match_single_image_api(vit_b):
+    """generate_img_embeddings / refine_segmentations drivers (batched, mixed native sizes) == per-image API."""
+    from samcarriestheburden_b200.scripts.pipelines import generate_img_embeddings, refine_segmentations
+    from samcarriestheburden_b200.segment_anything import SamPredictor
+    sam, sd = vit_b
+    imgs = [O.synthetic_radiograph(21), O.synthetic_radiograph(22, 754, 589), O.synthetic_radiograph(23),
+            O.synthetic_radiograph(24, 754, 589), O.synthetic_radiograph(25, 600, 1000)]
+    names = [f"im{i}" for i in range(len(imgs))]
+    store, gathered = generate_img_embeddings(sam, imgs, names, batch=2, gather=True)
+    assert gathered.shape == (5, 256, 64, 64)
+    pred = SamPredictor(sam)
+    for i, img in enumerate(imgs):
+        pred.set_image(img)
+        assert torch.equal(pred.features[0], gathered[i]), i
+        assert list(store[names[i]].attrs["original_size"]) == list(img.shape[:2])
+        assert tuple(store[names[i]].attrs["input_size"]) == tuple(pred.input_size)
+    segs = [torch.from_numpy(O.synthetic_unet_masks(30 + i)) for i in range(len(imgs))]
+    results, allseg = refine_segmentations(sam, store, segs, names, gather=True)
+    assert allseg.shape == (5, 17, 384, 224)
+    # decode stage vs oracle from the SAME (CUDA-produced) embedding for one non-square image
+    i = 1
+    ref_seg, ref_dice, _, _ = O.refine(sd, gathered[i:i + 1].cpu(), segs[i].numpy(), store[names[i]].attrs["input_size"],
+                                       store[names[i]].attrs["original_size"])
+    got = allseg[i].bool().cpu().numpy()
+    ds = [dice(got[c], ref_seg[c]) for c in range(17)]
+    print(f"pipeline refine: min dice={min(ds):.6f} mismatched={int((got != ref_seg).sum())}")
+    assert min(ds) >= 0.999
