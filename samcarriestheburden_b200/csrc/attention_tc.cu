@@ -1,0 +1,379 @@
+// Global (64x64-token) attention of the SAM ViT encoder on the 5th-generation tensor cores.
+// Reference semantics: segment_anything/modeling/image_encoder.py:224-240 (+ :325-361 decomposed rel-pos).
+//
+// One CTA = 128 queries (two rows of the token grid) x one head x one image; two CTAs per SM.
+//   warp 0 (1 thread)  TMA producer: Q, the rel-pos tables, then K/V tiles of 64 keys (= one key row of the grid)
+//                      as [rows x 16 dims] slabs, SWIZZLE_32B (16 bf16 = one UMMA K-step = one 32 B swizzle row)
+//   warp 1 (1 thread)  tcgen05.mma issuer:  S[128x64]  = Q K^T           (5 x 128x64x16,  K-major x K-major)
+//                                           O[128xhd] += P V             (4 x 128xhdx16,  V consumed MN-major)
+//   warp 2             TMEM allocator (256 columns: S | O | Tw)
+//   warps 4-7          softmax, one thread per query row: S and the w-bias come from TMEM (tcgen05.ld), the
+//                      h-bias is one scalar per (row, tile) from shared memory; P is written as bf16 into a
+//                      SWIZZLE_128B K-major tile that feeds the PV MMA; O is rescaled in TMEM only when the
+//                      running maximum moved by more than 2^8 (lazy rescale), so most tiles skip it.
+// Decomposed rel-pos: bias[q, (kh,kw)] = q.Rh[qh-kh+63] + q.Rw[qw-kw+63].  Both terms are produced by two
+// prologue MMAs (Q x Rw^T, Q x Rh[qh0 .. qh0+64]^T); each thread gathers its row's 64 w-terms into a TMEM
+// region (tile-invariant) and its 64 h-terms into shared memory (one per key row).
+#include "common.cuh"
+#include "kernels.h"
+#include "tma.h"
+
+namespace b200sam {
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int TQ = 128;  // queries per CTA
+constexpr int TK = 64;   // keys per tile
+constexpr int TC_THREADS = 256;
+constexpr uint32_t TC_TMEM_COLS = 256;
+constexpr uint32_t COL_S = 0;
+constexpr uint32_t COL_O = 64;
+constexpr uint32_t COL_TW = 160;
+constexpr float LAZY_RESCALE = 8.0f;
+
+template <int HD>
+struct TcLayout {
+  static constexpr int NS = HD / 16;               // 16-dim slabs
+  static constexpr int Q_SLAB = TQ * 32;           // 4096 B
+  static constexpr int KV_SLAB = TK * 32;          // 2048 B
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_KV = NS * Q_SLAB;       // 2 buffers x (K slabs | V slabs); prologue: Rw | Rh tables
+  static constexpr int KV_BUF = 2 * NS * KV_SLAB;  // bytes per buffer
+  static constexpr int OFF_P = OFF_KV + 2 * KV_BUF;
+  static constexpr int OFF_TH = OFF_P + TQ * 128;          // [64 key rows][128 queries] fp32; prologue scratch
+  static constexpr int OFF_BAR = OFF_TH + TK * TQ * 4;
+  static constexpr int BYTES = OFF_BAR + 128;
+  static_assert(OFF_P % 1024 == 0, "P tile must be 1024 B aligned for SWIZZLE_128B");
+  static_assert(2 * KV_BUF == 2 * NS * Q_SLAB, "rel-pos tables alias the K/V ring exactly");
+};
+
+B200SAM_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct TcParams {
+  __nv_bfloat16* out;
+  int heads;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                      const __grid_constant__ CUtensorMap map_rh, const __grid_constant__ CUtensorMap map_rw,
+                      TcParams prm) {
+  using L = TcLayout<HD>;
+  constexpr int NS = L::NS;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* tab_full = bars + 1;
+  uint64_t* pre_full = bars + 2;
+  uint64_t* pre_done = bars + 3;
+  uint64_t* tab_free = bars + 4;
+  uint64_t* kv_full = bars + 5;   // [2]
+  uint64_t* kv_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* th_t = reinterpret_cast<float*>(smem + L::OFF_TH);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int D = prm.heads * HD;
+  const int q0 = qt * TQ;
+  const int qh0 = q0 >> 6;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+    tma_prefetch_desc(&map_rh);
+    tma_prefetch_desc(&map_rw);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(tab_full, 1);
+    mbar_init(pre_full, 1);
+    mbar_init(pre_done, TQ);
+    mbar_init(tab_free, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, TQ);
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr int NT = 4096 / TK;  // 64 key tiles
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- Q (this CTA's 128 rows of the head) and the two rel-pos tables
+      mbar_arrive_expect_tx(q_full, NS * L::Q_SLAB);
+      for (int kk = 0; kk < NS; ++kk)
+        tma_load_2d(smem + L::OFF_Q + kk * L::Q_SLAB, &map_q, q_full, head * HD + kk * 16, b * 4096 + q0);
+      mbar_arrive_expect_tx(tab_full, 2 * NS * L::Q_SLAB);
+      for (int kk = 0; kk < NS; ++kk) {
+        tma_load_2d(smem + L::OFF_KV + kk * L::Q_SLAB, &map_rw, tab_full, kk * 16, 0);
+        tma_load_2d(smem + L::OFF_KV + (NS + kk) * L::Q_SLAB, &map_rh, tab_full, kk * 16, qh0);
+      }
+      mbar_wait(tab_free, 0);  // both prologue MMAs have consumed the tables
+      for (int t = 0; t < NT; ++t) {
+        const int buf = t & 1;
+        if (t >= 2) mbar_wait(&kv_empty[buf], ((t >> 1) - 1) & 1);
+        uint8_t* kb = smem + L::OFF_KV + buf * L::KV_BUF;
+        mbar_arrive_expect_tx(&kv_full[buf], L::KV_BUF);
+        for (int kk = 0; kk < NS; ++kk) {
+          tma_load_2d(kb + kk * L::KV_SLAB, &map_kv, &kv_full[buf], D + head * HD + kk * 16, b * 4096 + t * TK);
+          tma_load_2d(kb + (NS + kk) * L::KV_SLAB, &map_kv, &kv_full[buf], 2 * D + head * HD + kk * 16,
+                      b * 4096 + t * TK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sq = smem_u32(smem + L::OFF_Q);
+      const uint32_t skv = smem_u32(smem + L::OFF_KV);
+      const uint32_t sp = smem_u32(smem + L::OFF_P);
+      constexpr uint32_t SW32 = 6, SW128 = 2;
+      mbar_wait(q_full, 0);
+      mbar_wait(tab_full, 0);
+      tcgen05_fence_after();
+      // ---- prologue 1: Tw_full[128 x 128] = Q . Rw^T  (columns 0..126 valid)
+      for (int kk = 0; kk < NS; ++kk)
+        umma_bf16_ss(tmem + 0, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
+                     make_smem_desc(skv + kk * L::Q_SLAB, 16, 256, SW32), make_idesc_bf16_f32_ex(128, 128, 0), kk > 0);
+      umma_commit(pre_full);
+      mbar_wait(pre_done, 0);
+      tcgen05_fence_after();
+      // ---- prologue 2: Th_full[128 x 80] = Q . Rh[qh0 .. qh0+79]^T  (columns 0..64 used)
+      for (int kk = 0; kk < NS; ++kk)
+        umma_bf16_ss(tmem + 0, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
+                     make_smem_desc(skv + (NS + kk) * L::Q_SLAB, 16, 256, SW32), make_idesc_bf16_f32_ex(128, 80, 0),
+                     kk > 0);
+      umma_commit(pre_full);
+      umma_commit(tab_free);
+      mbar_wait(pre_done, 1);
+      tcgen05_fence_after();
+      for (int t = 0; t < NT; ++t) {
+        const int buf = t & 1;
+        const uint32_t kb = skv + buf * L::KV_BUF;
+        mbar_wait(&kv_full[buf], (t >> 1) & 1);
+        tcgen05_fence_after();
+        for (int kk = 0; kk < NS; ++kk)
+          umma_bf16_ss(tmem + COL_S, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
+                       make_smem_desc(kb + kk * L::KV_SLAB, 16, 256, SW32), make_idesc_bf16_f32_ex(128, TK, 0), kk > 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, t & 1);
+        tcgen05_fence_after();
+        // O += P V: A = P (K-major, SWIZZLE_128B, 32 B per K-step), B = V slabs consumed MN-major
+        // (N = head dim: 16-dim slabs KV_SLAB apart = LBO; K = keys: 8-key groups 256 B apart = SBO)
+        for (int ks = 0; ks < TK / 16; ++ks)
+          umma_bf16_ss(tmem + COL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
+                       make_smem_desc(kb + NS * L::KV_SLAB + ks * 512, L::KV_SLAB, 256, SW32),
+                       make_idesc_bf16_f32_ex(128, HD, 1), (t > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[buf]);
+      }
+      umma_commit(o_done);
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // query row inside the tile
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    const int qw = r & 63;
+    // ---- prologue 1: gather the row's 64 w-bias terms Tw[kw] = Tw_full[qw - kw + 63] into TMEM (x log2 e)
+    {
+      float* scratch = th_t;  // [64][128], column r is private to this thread
+      uint32_t v[64];
+      mbar_wait(pre_full, 0);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t a[32];
+          tmem_ld_32x32b_x32(tl + hf * 64 + c2 * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) scratch[(c2 * 32 + j) * TQ + r] = __uint_as_float(a[j]) * LOG2E;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 64; ++kw) {
+          const int idx = qw + 63 - kw;
+          if ((idx >> 6) == hf) v[kw] = __float_as_uint(scratch[(idx & 63) * TQ + r]);
+        }
+      }
+      uint32_t w0[32], w1[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { w0[j] = v[j]; w1[j] = v[32 + j]; }
+      tmem_st_32x32b_x32(tl + COL_TW, w0);
+      tmem_st_32x32b_x32(tl + COL_TW + 32, w1);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(pre_done);
+    }
+    // ---- prologue 2: h-bias Th[kh] = Th_full[63 - kh + hi], hi = 1 for the second grid row of the tile
+    {
+      mbar_wait(pre_full, 1);
+      tcgen05_fence_after();
+      const int hi = r >> 6;  // warp-uniform
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(tl + c2 * 32, a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int kh = 63 + hi - (c2 * 32 + j);
+          if (kh >= 0 && kh < 64) th_t[kh * TQ + r] = __uint_as_float(a[j]) * LOG2E;
+        }
+      }
+      {
+        uint32_t a[16];
+        tmem_ld_32x32b_x16(tl + 64, a);
+        tmem_ld_wait();
+        if (hi) th_t[0 * TQ + r] = __uint_as_float(a[0]) * LOG2E;  // column 64 <-> kh = 0 when hi = 1
+      }
+      tcgen05_fence_before();
+      mbar_arrive(pre_done);
+    }
+
+    const float scale_l2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
+    float m_run = -INFINITY, l_run = 0.0f;
+    uint8_t* prow = smem + L::OFF_P + r * 128;
+    for (int t = 0; t < NT; ++t) {
+      mbar_wait(s_full, t & 1);
+      tcgen05_fence_after();
+      const float th = th_t[t * TQ + r];
+      float sv[64];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t a[32], w[32];
+        tmem_ld_32x32b_x32(tl + COL_S + hf * 32, a);
+        tmem_ld_32x32b_x32(tl + COL_TW + hf * 32, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sv[hf * 32 + j] = fmaf(__uint_as_float(a[j]), scale_l2, __uint_as_float(w[j]));
+      }
+      float mx = sv[0];
+#pragma unroll
+      for (int j = 1; j < 64; ++j) mx = fmaxf(mx, sv[j]);
+      const float mt = mx + th;
+      // lazy rescale: keep the old reference maximum unless the new one exceeds it by more than 2^8
+      const float m_new = (mt > m_run + LAZY_RESCALE) ? mt : m_run;
+      const float corr = ex2_approx(m_run - m_new);  // 1 when unchanged, 0 on the first tile
+      if (t > 0 && __any_sync(0xffffffffu, m_new != m_run)) {
+#pragma unroll
+        for (int c = 0; c < HD / 16; ++c) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(tl + COL_O + c * 16, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
+          tmem_st_32x32b_x16(tl + COL_O + c * 16, o);
+        }
+        tmem_st_wait();
+      }
+      l_run *= corr;
+      m_run = m_new;
+      const float off = m_new - th;
+      float sum = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B of bf16
+        float p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          p[j] = ex2_approx(sv[c * 8 + j] - off);
+          sum += p[j];
+        }
+        uint4 pk;
+        pk.x = pack_bf16x2(p[0], p[1]);
+        pk.y = pack_bf16x2(p[2], p[3]);
+        pk.z = pack_bf16x2(p[4], p[5]);
+        pk.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
+      }
+      l_run += sum;
+      fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the MMA's async-proxy reads
+      tcgen05_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 -> out[b, q0 + r, head*HD ...]
+    mbar_wait(o_done, 0);
+    tcgen05_fence_after();
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* dst = prm.out + (static_cast<size_t>(b) * 4096 + q0 + r) * D + head * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld_32x32b_x16(tl + COL_O + c * 16, o);
+      tmem_ld_wait();
+      uint4 lo, hi4;
+      lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+      lo.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+      lo.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+      lo.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+      hi4.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+      hi4.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+      hi4.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+      hi4.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+      *reinterpret_cast<uint4*>(dst + c * 16) = lo;
+      *reinterpret_cast<uint4*>(dst + c * 16 + 8) = hi4;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, TC_TMEM_COLS);
+  }
+}
+
+template <int HD>
+int launch_tc(const AttnArgs& a, cudaStream_t stream) {
+  using L = TcLayout<HD>;
+  const int D = a.heads * HD;
+  CUtensorMap mq, mkv, mrh, mrw;
+  const uint64_t rows = static_cast<uint64_t>(a.B) * 4096;
+  if (make_tmap_bf16(&mq, a.qkv, rows, 3 * D, 3 * D, TQ, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+  if (make_tmap_bf16(&mkv, a.qkv, rows, 3 * D, 3 * D, TK, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+  if (make_tmap_bf16(&mrh, a.rel_h, 127, HD, HD, TQ, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+  if (make_tmap_bf16(&mrw, a.rel_w, 127, HD, HD, TQ, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+  static bool once = false;
+  if (!once) {
+    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(global_attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            L::BYTES));
+    once = true;
+  }
+  TcParams p;
+  p.out = a.out;
+  p.heads = a.heads;
+  dim3 grid(4096 / TQ, a.heads, a.B);
+  global_attn_tc_kernel<HD><<<grid, TC_THREADS, L::BYTES, stream>>>(mq, mkv, mrh, mrw, p);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int global_attention_tc(const AttnArgs& a, cudaStream_t stream) {
+  B200SAM_REQUIRE(a.B > 0 && a.heads > 0 && (a.hd == 64 || a.hd == 80),
+                  "global_attention_tc: unsupported shape B=%d heads=%d hd=%d", a.B, a.heads, a.hd);
+  B200SAM_REQUIRE(a.qkv && a.rel_h && a.rel_w && a.out, "global_attention_tc: null pointer argument");
+  return a.hd == 80 ? launch_tc<80>(a, stream) : launch_tc<64>(a, stream);
+}
+
+}  // namespace b200sam

@@ -12,6 +12,7 @@
 // image_encoder.py:391 patch-embed conv as GEMM, :88-104 neck convs as GEMMs).
 #include "common.cuh"
 #include "kernels.h"
+#include "tma.h"
 
 namespace b200sam {
 
@@ -319,58 +320,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
-  }
-  return fn;
-}
-
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with row pitch ld (elements);
-// box = [box_rows, 64 cols], SWIZZLE_128B.
-int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (enc == nullptr) {
-    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    return 1;
-  }
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr=%p rows=%llu cols=%llu ld=%llu)", (int)r, ptr,
-                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
-    return 1;
-  }
-  return 0;
-}
-
-int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
 }  // namespace
 
 int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
@@ -385,8 +334,8 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0,
                   "gemm: A and B must be 16-byte aligned");
   CUtensorMap ta, tb;
-  if (make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BM)) return 1;
-  if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, BN)) return 1;
+  if (make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   EpiParams ep;
   ep.bias = g.bias;
   ep.residual = g.residual;

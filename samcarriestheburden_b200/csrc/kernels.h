@@ -69,7 +69,8 @@ struct AttnArgs {
   int B, heads, hd;
 };
 int window_attention(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows over the 64x64 grid
-int global_attention(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096
+int global_attention(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096, mma.sync path (A/B reference)
+int global_attention_tc(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096 on tcgen05 / TMEM (attention_tc.cu)
 
 // ---- prompt_extract.cu -----------------------------------------------------------------------
 int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t* seeds, int32_t* boxes,

@@ -108,11 +108,11 @@ def _attention_reference(qkv, bias16, rel_h, rel_w, heads, hd, window):
     return o.reshape(B * 4096, D)
 
 
-@pytest.mark.parametrize("heads,hd,glob", [(16, 80, 0), (12, 64, 0), (4, 80, 1), (3, 64, 1)])
+@pytest.mark.parametrize("heads,hd,glob", [(16, 80, 0), (12, 64, 0), (4, 80, 1), (3, 64, 1), (2, 80, 2), (2, 64, 2)])
 def test_encoder_attention(heads, hd, glob):
     g = torch.Generator(device="cpu").manual_seed(heads * 100 + hd + glob)
     D = heads * hd
-    B = 2 if not glob else 1
+    B = 2 if glob != 2 else 1
     S = 64 if glob else 14
     qkv = torch.randn((B * 4096, 3 * D), generator=g).to(DEV).bfloat16()
     bias = torch.randn((3 * D,), generator=g).to(DEV).bfloat16()

@@ -16,7 +16,7 @@ qkv = torch.randn((B * 4096, 3 * D), device=dev).bfloat16()
 bias = torch.randn((3 * D,), device=dev).bfloat16()
 out = torch.empty((B * 4096, D), dtype=torch.bfloat16, device=dev)
 for it in range(3):
-    for glob, S in ((0, 14), (1, 64)):
+    for glob, S in ((0, 14), (1, 64), (2, 64)):
         rel_h = (0.02 * torch.randn((2 * S - 1, hd), device=dev)).bfloat16()
         rel_w = (0.02 * torch.randn((2 * S - 1, hd), device=dev)).bfloat16()
         _lib.check(lib.b200sam_encoder_attention(qkv.data_ptr(), bias.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(),
