@@ -38,14 +38,16 @@ struct TcLayout {
   static constexpr int Q_SLAB = TQ * 32;           // 4096 B
   static constexpr int KV_SLAB = TK * 32;          // 2048 B
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_KV = NS * Q_SLAB;       // 2 buffers x (K slabs | V slabs); prologue: Rw | Rh tables
-  static constexpr int KV_BUF = 2 * NS * KV_SLAB;  // bytes per buffer
-  static constexpr int OFF_P = OFF_KV + 2 * KV_BUF;
+  static constexpr int OFF_KV = NS * Q_SLAB;       // K ring (2 tiles) | V ring (2 tiles); prologue: Rw | Rh tables
+  static constexpr int KV_TILE = NS * KV_SLAB;     // bytes of one K (or V) tile
+  static constexpr int OFF_K = OFF_KV;
+  static constexpr int OFF_V = OFF_KV + 2 * KV_TILE;
+  static constexpr int OFF_P = OFF_KV + 4 * KV_TILE;
   static constexpr int OFF_TH = OFF_P + TQ * 128;          // [64 key rows][128 queries] fp32; prologue scratch
   static constexpr int OFF_BAR = OFF_TH + TK * TQ * 4;
-  static constexpr int BYTES = OFF_BAR + 128;
+  static constexpr int BYTES = OFF_BAR + 256;
   static_assert(OFF_P % 1024 == 0, "P tile must be 1024 B aligned for SWIZZLE_128B");
-  static_assert(2 * KV_BUF == 2 * NS * Q_SLAB, "rel-pos tables alias the K/V ring exactly");
+  static_assert(2 * KV_TILE == NS * Q_SLAB, "each rel-pos table aliases one of the K / V rings exactly");
 };
 
 B200SAM_DEVINL float ex2_approx(float x) {
@@ -73,12 +75,16 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint64_t* pre_full = bars + 2;
   uint64_t* pre_done = bars + 3;
   uint64_t* tab_free = bars + 4;
-  uint64_t* kv_full = bars + 5;   // [2]
-  uint64_t* kv_empty = bars + 7;  // [2]
+  uint64_t* k_full = bars + 5;    // [2]
+  uint64_t* k_empty = bars + 7;   // [2]  QK(t) retired -> K slot free (two tiles of look-ahead for K)
   uint64_t* s_full = bars + 9;
   uint64_t* p_full = bars + 10;
   uint64_t* o_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_read = bars + 12;   // softmax has copied S(t) to registers -> QK(t+1) may overwrite S
+  uint64_t* o_ready = bars + 13;  // PV(t) retired -> O / P may be touched by softmax(t+1)
+  uint64_t* v_full = bars + 14;   // [2]
+  uint64_t* v_empty = bars + 16;  // [2]  PV(t) retired -> V slot free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   float* th_t = reinterpret_cast<float*>(smem + L::OFF_TH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,13 +105,17 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     mbar_init(pre_full, 1);
     mbar_init(pre_done, TQ);
     mbar_init(tab_free, 1);
-    mbar_init(&kv_full[0], 1);
-    mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1);
-    mbar_init(&kv_empty[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(p_full, TQ);
     mbar_init(o_done, 1);
+    mbar_init(s_read, TQ);
+    mbar_init(o_ready, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -130,16 +140,27 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tma_load_2d(smem + L::OFF_KV + (NS + kk) * L::Q_SLAB, &map_rh, tab_full, kk * 16, qh0);
       }
       mbar_wait(tab_free, 0);  // both prologue MMAs have consumed the tables
-      for (int t = 0; t < NT; ++t) {
+      auto load_k = [&](int t) {
         const int buf = t & 1;
-        if (t >= 2) mbar_wait(&kv_empty[buf], ((t >> 1) - 1) & 1);
-        uint8_t* kb = smem + L::OFF_KV + buf * L::KV_BUF;
-        mbar_arrive_expect_tx(&kv_full[buf], L::KV_BUF);
-        for (int kk = 0; kk < NS; ++kk) {
-          tma_load_2d(kb + kk * L::KV_SLAB, &map_kv, &kv_full[buf], D + head * HD + kk * 16, b * 4096 + t * TK);
-          tma_load_2d(kb + (NS + kk) * L::KV_SLAB, &map_kv, &kv_full[buf], 2 * D + head * HD + kk * 16,
-                      b * 4096 + t * TK);
-        }
+        if (t >= 2) mbar_wait(&k_empty[buf], ((t >> 1) - 1) & 1);
+        uint8_t* kb = smem + L::OFF_K + buf * L::KV_TILE;
+        mbar_arrive_expect_tx(&k_full[buf], L::KV_TILE);
+        for (int kk = 0; kk < NS; ++kk)
+          tma_load_2d(kb + kk * L::KV_SLAB, &map_kv, &k_full[buf], D + head * HD + kk * 16, b * 4096 + t * TK);
+      };
+      auto load_v = [&](int t) {
+        const int buf = t & 1;
+        if (t >= 2) mbar_wait(&v_empty[buf], ((t >> 1) - 1) & 1);
+        uint8_t* vb = smem + L::OFF_V + buf * L::KV_TILE;
+        mbar_arrive_expect_tx(&v_full[buf], L::KV_TILE);
+        for (int kk = 0; kk < NS; ++kk)
+          tma_load_2d(vb + kk * L::KV_SLAB, &map_kv, &v_full[buf], 2 * D + head * HD + kk * 16, b * 4096 + t * TK);
+      };
+      // K runs one tile ahead of V: the K slot is recycled as soon as QK(t) retires, V only after PV(t)
+      load_k(0);
+      for (int t = 0; t < NT; ++t) {
+        if (t + 1 < NT) load_k(t + 1);
+        load_v(t);
       }
     }
   } else if (warp == 1) {
@@ -167,24 +188,37 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       umma_commit(tab_free);
       mbar_wait(pre_done, 1);
       tcgen05_fence_after();
-      for (int t = 0; t < NT; ++t) {
+      // Software pipeline: QK(t+1) is issued as soon as the softmax warps have copied S(t) into registers, i.e.
+      // while they are still exponentiating tile t; PV(t) follows when P(t) is in shared memory.
+      auto issue_qk = [&](int t) {
         const int buf = t & 1;
-        const uint32_t kb = skv + buf * L::KV_BUF;
-        mbar_wait(&kv_full[buf], (t >> 1) & 1);
+        const uint32_t kb = skv + buf * L::KV_TILE;
+        mbar_wait(&k_full[buf], (t >> 1) & 1);
         tcgen05_fence_after();
         for (int kk = 0; kk < NS; ++kk)
           umma_bf16_ss(tmem + COL_S, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
                        make_smem_desc(kb + kk * L::KV_SLAB, 16, 256, SW32), make_idesc_bf16_f32_ex(128, TK, 0), kk > 0);
         umma_commit(s_full);
+        umma_commit(&k_empty[buf]);
+      };
+      issue_qk(0);
+      for (int t = 0; t < NT; ++t) {
+        const int buf = t & 1;
+        const uint32_t vb = skv + 2 * L::KV_TILE + buf * L::KV_TILE;
+        mbar_wait(s_read, t & 1);
+        tcgen05_fence_after();
+        if (t + 1 < NT) issue_qk(t + 1);
+        mbar_wait(&v_full[buf], (t >> 1) & 1);
         mbar_wait(p_full, t & 1);
         tcgen05_fence_after();
         // O += P V: A = P (K-major, SWIZZLE_128B, 32 B per K-step), B = V slabs consumed MN-major
         // (N = head dim: 16-dim slabs KV_SLAB apart = LBO; K = keys: 8-key groups 256 B apart = SBO)
         for (int ks = 0; ks < TK / 16; ++ks)
           umma_bf16_ss(tmem + COL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
-                       make_smem_desc(kb + NS * L::KV_SLAB + ks * 512, L::KV_SLAB, 256, SW32),
+                       make_smem_desc(vb + ks * 512, L::KV_SLAB, 256, SW32),
                        make_idesc_bf16_f32_ex(128, HD, 1), (t > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&kv_empty[buf]);
+        umma_commit(&v_empty[buf]);
+        umma_commit(o_ready);
       }
       umma_commit(o_done);
     }
@@ -267,45 +301,53 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) sv[hf * 32 + j] = fmaf(__uint_as_float(a[j]), scale_l2, __uint_as_float(w[j]));
       }
-      float mx = sv[0];
+      tcgen05_fence_before();
+      mbar_arrive(s_read);  // S(t) is in registers: the MMA warp may start QK(t+1)
+      // 8 independent partial maxima (a serial 63-deep FMNMX chain would cost ~250 cycles of pure latency)
+      float pm[8];
 #pragma unroll
-      for (int j = 1; j < 64; ++j) mx = fmaxf(mx, sv[j]);
+      for (int j = 0; j < 8; ++j) pm[j] = sv[j];
+#pragma unroll
+      for (int j = 8; j < 64; ++j) pm[j & 7] = fmaxf(pm[j & 7], sv[j]);
+      const float mx = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
       const float mt = mx + th;
       // lazy rescale: keep the old reference maximum unless the new one exceeds it by more than 2^8
       const float m_new = (mt > m_run + LAZY_RESCALE) ? mt : m_run;
       const float corr = ex2_approx(m_run - m_new);  // 1 when unchanged, 0 on the first tile
-      if (t > 0 && __any_sync(0xffffffffu, m_new != m_run)) {
+      const float off = m_new - th;
 #pragma unroll
-        for (int c = 0; c < HD / 16; ++c) {
-          uint32_t o[16];
-          tmem_ld_32x32b_x16(tl + COL_O + c * 16, o);
-          tmem_ld_wait();
+      for (int j = 0; j < 64; ++j) sv[j] = ex2_approx(sv[j] - off);
+      if (t > 0) {
+        mbar_wait(o_ready, (t - 1) & 1);  // PV(t-1) retired: P and O are free again
+        tcgen05_fence_after();
+        if (__any_sync(0xffffffffu, m_new != m_run)) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
-          tmem_st_32x32b_x16(tl + COL_O + c * 16, o);
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tl + COL_O + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
+            tmem_st_32x32b_x16(tl + COL_O + c * 16, o);
+          }
+          tmem_st_wait();
         }
-        tmem_st_wait();
       }
       l_run *= corr;
       m_run = m_new;
-      const float off = m_new - th;
-      float sum = 0.0f;
+      float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B of bf16
-        float p[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          p[j] = ex2_approx(sv[c * 8 + j] - off);
-          sum += p[j];
-        }
         uint4 pk;
-        pk.x = pack_bf16x2(p[0], p[1]);
-        pk.y = pack_bf16x2(p[2], p[3]);
-        pk.z = pack_bf16x2(p[4], p[5]);
-        pk.w = pack_bf16x2(p[6], p[7]);
+        pk.x = pack_bf16x2(sv[c * 8 + 0], sv[c * 8 + 1]);
+        pk.y = pack_bf16x2(sv[c * 8 + 2], sv[c * 8 + 3]);
+        pk.z = pack_bf16x2(sv[c * 8 + 4], sv[c * 8 + 5]);
+        pk.w = pack_bf16x2(sv[c * 8 + 6], sv[c * 8 + 7]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ps[j] += sv[c * 8 + j];
         *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
       }
-      l_run += sum;
+      l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
       fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the MMA's async-proxy reads
       tcgen05_fence_before();
       mbar_arrive(p_full);
