@@ -147,10 +147,11 @@ int b200sam_encoder_attention(const void* qkv, const void* qkv_bias_bf16, const 
   a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.qkv_bias = static_cast<const __nv_bfloat16*>(qkv_bias_bf16);
   a.rel_h = static_cast<const __nv_bfloat16*>(rel_h_bf16); a.rel_w = static_cast<const __nv_bfloat16*>(rel_w_bf16);
   a.out = static_cast<__nv_bfloat16*>(out); a.B = batch; a.heads = heads; a.hd = hd;
-  // global_attn: 0 = 14x14 windows, 1 = global on tcgen05 (product path), 2 = global on mma.sync (A/B reference)
+  // 0 = windows on tcgen05, 1 = global on tcgen05 (product paths); 2 / 3 = global / windows on mma.sync (A/B reference)
   if (global_attn == 1) return global_attention_tc(a, static_cast<cudaStream_t>(stream));
   if (global_attn == 2) return global_attention(a, static_cast<cudaStream_t>(stream));
-  return window_attention(a, static_cast<cudaStream_t>(stream));
+  if (global_attn == 3) return window_attention(a, static_cast<cudaStream_t>(stream));
+  return window_attention_tc(a, static_cast<cudaStream_t>(stream));
 }
 int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, int w, const float* mean3,
                                 const float* std3, void* out_bf16, void* stream) {

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tma.h"
+#include <type_traits>
 
 namespace b200sam {
 
@@ -384,6 +385,418 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   }
 }
 
+// ================================================================================================
+// 14x14 windowed attention on tcgen05 (image_encoder.py:166-182 window path, :243-289 partition/unpartition)
+//
+// One CTA = one (window, head, image); two CTAs per SM.  The window's 196 key/value tokens (zero-padded tokens
+// included, their K/V = the qkv bias because padding happens after norm1) are resident in shared memory, fetched
+// by ONE 4-D TMA box per 16-dim slab straight out of the raster-order qkv tensor (no window-partition copy; the
+// out-of-grid part of edge windows is zero-filled by TMA and patched with the bias).  Queries are the window's
+// real tokens (196 / 112 / 64 -> two or one M=128 tiles).  Keys are consumed in tiles of 64, 64, 64, 16 with an
+// online softmax; the decomposed rel-pos bias is 14 + 14 fp32 values per query row, produced by a prologue MMA
+// (q . [rel_h ; rel_w]^T), gathered per thread and held in registers (thread = query row, so kh / kw of every
+// score column are compile-time constants).
+constexpr int WIN = 14;
+constexpr int WTOK = WIN * WIN;
+constexpr uint32_t WCOL_S = 0;
+constexpr uint32_t WCOL_O = 64;
+constexpr uint32_t WCOL_B = 160;  // + 32 per M tile: 14 h-terms, 14 w-terms
+
+template <int HD>
+struct WinLayout {
+  static constexpr int NS = HD / 16;
+  static constexpr int Q_SLAB = 200 * 32;   // 196 query rows (+4 so slabs stay 256 B aligned)
+  static constexpr int KV_SLAB = 208 * 32;  // 196 keys padded to 13 K-steps of 16
+  static constexpr int OFF_P = 0;           // P tile [128 x 64 keys], SWIZZLE_128B; prologue: [rel_h ; rel_w] table, then
+                                            // the fp32 gather scratch [32][128]
+  static constexpr int OFF_Q = 16384;
+  static constexpr int OFF_K = OFF_Q + NS * Q_SLAB;
+  static constexpr int OFF_V = OFF_K + NS * KV_SLAB;
+  static constexpr int V_END = OFF_V + NS * KV_SLAB;
+  static constexpr int OFF_BAR = V_END;
+  static constexpr int BYTES = OFF_BAR + 256;
+  static constexpr int BOX_BYTES = WTOK * 32;  // one 14x14 slab
+  static_assert(OFF_K % 256 == 0 && OFF_V % 256 == 0, "slabs must be 256 B aligned for SWIZZLE_32B");
+  static_assert(NS * 2048 <= 16384, "rel-pos table must fit in the P tile");
+};
+
+struct WinParams {
+  __nv_bfloat16* out;
+  const __nv_bfloat16* qkv_bias;
+  int heads;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __grid_constant__ CUtensorMap map_q0814,
+                      const __grid_constant__ CUtensorMap map_q1408, const __grid_constant__ CUtensorMap map_q0808,
+                      const __grid_constant__ CUtensorMap map_rh, const __grid_constant__ CUtensorMap map_rw,
+                      WinParams prm) {
+  using L = WinLayout<HD>;
+  constexpr int NS = L::NS;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* tab_full = bars + 1;
+  uint64_t* k_full = bars + 2;
+  uint64_t* v_full = bars + 3;
+  uint64_t* qz_done = bars + 4;   // query-slab tails zeroed
+  uint64_t* pre_full = bars + 5;  // prologue MMAs retired
+  uint64_t* pre_done = bars + 6;  // bias gathered into TMEM (P region free again)
+  uint64_t* fix_done = bars + 7;  // pad tokens patched
+  uint64_t* s_full = bars + 8;
+  uint64_t* s_read = bars + 9;
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_ready = bars + 11;
+  uint64_t* o_free = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int win = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int wy = win / 5, wx = win % 5;
+  const int D = prm.heads * HD;
+  const int wrows = min(WIN, 64 - wy * WIN);
+  const int wcols = min(WIN, 64 - wx * WIN);
+  const int nq = wrows * wcols;
+  const int nmt = (nq + TQ - 1) / TQ;
+  const CUtensorMap* map_q = wcols == WIN ? (wrows == WIN ? &map_q1414 : &map_q1408)
+                                          : (wrows == WIN ? &map_q0814 : &map_q0808);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(map_q);
+    tma_prefetch_desc(&map_q1414);
+    tma_prefetch_desc(&map_rh);
+    tma_prefetch_desc(&map_rw);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(tab_full, 1);
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(qz_done, TQ);
+    mbar_init(pre_full, 1);
+    mbar_init(pre_done, TQ);
+    mbar_init(fix_done, TQ);
+    mbar_init(s_full, 1);
+    mbar_init(s_read, TQ);
+    mbar_init(p_full, TQ);
+    mbar_init(o_ready, 1);
+    mbar_init(o_free, TQ);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, NS * nq * 32);
+      for (int kk = 0; kk < NS; ++kk)
+        tma_load_4d(smem + L::OFF_Q + kk * L::Q_SLAB, map_q, q_full, head * HD + kk * 16, wx * WIN, wy * WIN, b);
+      mbar_arrive_expect_tx(tab_full, NS * 2048);
+      for (int kk = 0; kk < NS; ++kk) {
+        tma_load_2d(smem + L::OFF_P + kk * 2048, &map_rh, tab_full, kk * 16, 0);         // table rows 0..31
+        tma_load_2d(smem + L::OFF_P + kk * 2048 + 1024, &map_rw, tab_full, kk * 16, 0);  // table rows 32..63
+      }
+      mbar_arrive_expect_tx(k_full, NS * L::BOX_BYTES);
+      for (int kk = 0; kk < NS; ++kk)
+        tma_load_4d(smem + L::OFF_K + kk * L::KV_SLAB, &map_q1414, k_full, D + head * HD + kk * 16, wx * WIN, wy * WIN, b);
+      mbar_arrive_expect_tx(v_full, NS * L::BOX_BYTES);
+      for (int kk = 0; kk < NS; ++kk)
+        tma_load_4d(smem + L::OFF_V + kk * L::KV_SLAB, &map_q1414, v_full, 2 * D + head * HD + kk * 16, wx * WIN,
+                    wy * WIN, b);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sq = smem_u32(smem + L::OFF_Q);
+      const uint32_t sk = smem_u32(smem + L::OFF_K);
+      const uint32_t sv = smem_u32(smem + L::OFF_V);
+      const uint32_t sp = smem_u32(smem + L::OFF_P);
+      constexpr uint32_t SW32 = 6, SW128 = 2;
+      mbar_wait(q_full, 0);
+      mbar_wait(tab_full, 0);
+      mbar_wait(qz_done, 0);
+      tcgen05_fence_after();
+      // ---- prologue: T_mt[128 x 64] = Q_mt . [rel_h(27) ; pad ; rel_w(27) ; pad]^T
+      for (int mt = 0; mt < nmt; ++mt)
+        for (int kk = 0; kk < NS; ++kk)
+          umma_bf16_ss(tmem + mt * 64, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
+                       make_smem_desc(sp + kk * 2048, 16, 256, SW32), make_idesc_bf16_f32_ex(128, 64, 0), kk > 0);
+      umma_commit(pre_full);
+      mbar_wait(pre_done, 0);
+      mbar_wait(k_full, 0);
+      mbar_wait(fix_done, 0);
+      tcgen05_fence_after();
+      auto issue_qk = [&](int g) {
+        const int mt = g >> 2, kt = g & 3;
+        const uint32_t idesc = kt < 3 ? make_idesc_bf16_f32_ex(128, 64, 0) : make_idesc_bf16_f32_ex(128, 16, 0);
+        for (int kk = 0; kk < NS; ++kk)
+          umma_bf16_ss(tmem + WCOL_S, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
+                       make_smem_desc(sk + kk * L::KV_SLAB + kt * 2048, 16, 256, SW32), idesc, kk > 0);
+        umma_commit(s_full);
+      };
+      const int nsteps = nmt * 4;
+      issue_qk(0);
+      for (int g = 0; g < nsteps; ++g) {
+        const int mt = g >> 2, kt = g & 3;
+        mbar_wait(s_read, g & 1);
+        tcgen05_fence_after();
+        if (g + 1 < nsteps) issue_qk(g + 1);
+        mbar_wait(p_full, g & 1);
+        if (kt == 0 && mt > 0) mbar_wait(o_free, (mt - 1) & 1);  // previous tile's O has been stored
+        tcgen05_fence_after();
+        const int nks = kt < 3 ? 4 : 1;
+        for (int ks = 0; ks < nks; ++ks)
+          umma_bf16_ss(tmem + WCOL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
+                       make_smem_desc(sv + kt * 2048 + ks * 512, L::KV_SLAB, 256, SW32),
+                       make_idesc_bf16_f32_ex(128, HD, 1), (kt > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(o_ready);
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int st = threadIdx.x - 128;  // 0..127
+    const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    // ---- zero the tails of the query slabs (rows nq..199) so the M=128 tiles only ever see finite values
+    for (int i = st; i < NS * (200 - nq) * 2; i += TQ) {
+      const int kk = i / ((200 - nq) * 2), rem = i - kk * (200 - nq) * 2;
+      *reinterpret_cast<uint4*>(smem + L::OFF_Q + kk * L::Q_SLAB + (nq + (rem >> 1)) * 32 + (rem & 1) * 16) =
+          make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(qz_done);
+    // ---- prologue: gather the row's 14 + 14 rel-pos terms of every M tile into TMEM (x log2 e)
+    {
+      // scratch = the P tile region: [32][128] fp32, column `row` is private to this thread.  The rel-pos table that
+      // lived there is dead once pre_full fired; T columns 0..31 carry the h-terms, 32..63 the w-terms.
+      float* scratch = reinterpret_cast<float*>(smem + L::OFF_P);
+      mbar_wait(pre_full, 0);
+      tcgen05_fence_after();
+      for (int mt = 0; mt < nmt; ++mt) {
+        const int qi = mt * TQ + row;
+        const int qr = min(qi / wcols, WIN - 1), qc = qi - (qi / wcols) * wcols;
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t a[32];
+          tmem_ld_32x32b_x32(tl + mt * 64 + c2 * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) scratch[j * TQ + row] = __uint_as_float(a[j]) * LOG2E;
+          if (c2 == 0) {
+#pragma unroll
+            for (int kh = 0; kh < WIN; ++kh) v[kh] = __float_as_uint(scratch[(qr + 13 - kh) * TQ + row]);
+          } else {
+#pragma unroll
+            for (int kw = 0; kw < WIN; ++kw) v[14 + kw] = __float_as_uint(scratch[(qc + 13 - kw) * TQ + row]);
+          }
+        }
+        tmem_st_32x32b_x32(tl + WCOL_B + mt * 32, v);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(pre_done);
+    }
+    // ---- patch the zero-filled pad tokens with the qkv bias, zero the key padding rows 196..207
+    {
+      const __nv_bfloat16* bk = prm.qkv_bias + D + head * HD;
+      const __nv_bfloat16* bv = prm.qkv_bias + 2 * D + head * HD;
+      mbar_wait(k_full, 0);
+      mbar_wait(v_full, 0);
+      for (int rr = st; rr < 208; rr += TQ) {
+        const int r = rr / WIN, c = rr - r * WIN;
+        const bool tail = rr >= WTOK;
+        const bool pad = !tail && (wy * WIN + r >= 64 || wx * WIN + c >= 64);
+        if (!tail && !pad) continue;
+        const int sw = (rr >> 2) & 1;
+        for (int kk = 0; kk < NS; ++kk)
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            uint4 kvv = make_uint4(0, 0, 0, 0), vvv = kvv;
+            if (pad) {
+              kvv = *reinterpret_cast<const uint4*>(bk + kk * 16 + ch * 8);
+              vvv = *reinterpret_cast<const uint4*>(bv + kk * 16 + ch * 8);
+            }
+            const int off = kk * L::KV_SLAB + rr * 32 + ((ch ^ sw) << 4);
+            *reinterpret_cast<uint4*>(smem + L::OFF_K + off) = kvv;
+            *reinterpret_cast<uint4*>(smem + L::OFF_V + off) = vvv;
+          }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(fix_done);
+    }
+
+    const float scale_l2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
+    uint8_t* prow = smem + L::OFF_P + row * 128;
+    int g = 0;
+    for (int mt = 0; mt < nmt; ++mt) {
+      float bh[WIN], bw[WIN];
+      {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tl + WCOL_B + mt * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) { bh[i] = __uint_as_float(v[i]); bw[i] = __uint_as_float(v[14 + i]); }
+      }
+      float m_run = -INFINITY, l_run = 0.0f;
+      auto step = [&](auto kt_c) {
+        constexpr int KT = decltype(kt_c)::value;
+        constexpr int NK = KT < 3 ? 64 : 16;
+        mbar_wait(s_full, g & 1);
+        tcgen05_fence_after();
+        float sv[NK];
+        if constexpr (KT < 3) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t a[32];
+            tmem_ld_32x32b_x32(tl + WCOL_S + hf * 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              const int k = KT * 64 + hf * 32 + j;
+              sv[hf * 32 + j] = fmaf(__uint_as_float(a[j]), scale_l2, bh[k / WIN] + bw[k % WIN]);
+            }
+          }
+        } else {
+          uint32_t a[16];
+          tmem_ld_32x32b_x16(tl + WCOL_S, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = 192 + j;
+            sv[j] = k < WTOK ? fmaf(__uint_as_float(a[j]), scale_l2, bh[13] + bw[k % WIN]) : -INFINITY;
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(s_read);
+        float pm[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pm[j] = sv[j];
+#pragma unroll
+        for (int j = 8; j < NK; ++j) pm[j & 7] = fmaxf(pm[j & 7], sv[j]);
+        const float mt_ = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])),
+                                fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
+        const float m_new = (mt_ > m_run + LAZY_RESCALE) ? mt_ : m_run;
+        const float corr = ex2_approx(m_run - m_new);
+#pragma unroll
+        for (int j = 0; j < NK; ++j) sv[j] = ex2_approx(sv[j] - m_new);
+        if (g > 0) {
+          mbar_wait(o_ready, (g - 1) & 1);  // previous PV retired: P (and O) are free again
+          tcgen05_fence_after();
+        }
+        if (KT > 0 && __any_sync(0xffffffffu, m_new != m_run)) {
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tl + WCOL_O + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
+            tmem_st_32x32b_x16(tl + WCOL_O + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+        l_run *= corr;
+        m_run = m_new;
+        float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < NK / 8; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16x2(sv[c * 8 + 0], sv[c * 8 + 1]);
+          pk.y = pack_bf16x2(sv[c * 8 + 2], sv[c * 8 + 3]);
+          pk.z = pack_bf16x2(sv[c * 8 + 4], sv[c * 8 + 5]);
+          pk.w = pack_bf16x2(sv[c * 8 + 6], sv[c * 8 + 7]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ps[j] += sv[c * 8 + j];
+          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = pk;
+        }
+        l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        mbar_arrive(p_full);
+        ++g;
+      };
+      step(std::integral_constant<int, 0>{});
+      step(std::integral_constant<int, 1>{});
+      step(std::integral_constant<int, 2>{});
+      step(std::integral_constant<int, 3>{});
+      // ---- epilogue of the M tile
+      mbar_wait(o_ready, (g - 1) & 1);
+      tcgen05_fence_after();
+      const int qi = mt * TQ + row;
+      const float inv = 1.0f / l_run;
+      const int qr = qi / wcols, qc = qi - qr * wcols;
+      const int tok = (wy * WIN + qr) * 64 + wx * WIN + qc;
+      __nv_bfloat16* dst = prm.out + (static_cast<size_t>(b) * 4096 + tok) * D + head * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(tl + WCOL_O + c * 16, o);
+        tmem_ld_wait();
+        if (qi < nq) {
+          uint4 lo, hi4;
+          lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+          lo.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+          lo.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+          lo.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+          hi4.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+          hi4.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+          hi4.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+          hi4.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 16) = lo;
+          *reinterpret_cast<uint4*>(dst + c * 16 + 8) = hi4;
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(o_free);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, TC_TMEM_COLS);
+  }
+}
+
+template <int HD>
+int launch_win_tc(const AttnArgs& a, cudaStream_t stream) {
+  using L = WinLayout<HD>;
+  const int D = a.heads * HD;
+  CUtensorMap m1414, m0814, m1408, m0808, mrh, mrw;
+  if (make_tmap_bf16_grid4d(&m1414, a.qkv, a.B, 3 * D, 14, 14)) return 1;
+  if (make_tmap_bf16_grid4d(&m0814, a.qkv, a.B, 3 * D, 8, 14)) return 1;
+  if (make_tmap_bf16_grid4d(&m1408, a.qkv, a.B, 3 * D, 14, 8)) return 1;
+  if (make_tmap_bf16_grid4d(&m0808, a.qkv, a.B, 3 * D, 8, 8)) return 1;
+  if (make_tmap_bf16(&mrh, a.rel_h, 27, HD, HD, 32, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+  if (make_tmap_bf16(&mrw, a.rel_w, 27, HD, HD, 32, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+  static bool once = false;
+  if (!once) {
+    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            L::BYTES));
+    once = true;
+  }
+  WinParams p;
+  p.out = a.out;
+  p.qkv_bias = a.qkv_bias;
+  p.heads = a.heads;
+  dim3 grid(25, a.heads, a.B);
+  window_attn_tc_kernel<HD><<<grid, TC_THREADS, L::BYTES, stream>>>(m1414, m0814, m1408, m0808, mrh, mrw, p);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int HD>
 int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   using L = TcLayout<HD>;
@@ -410,6 +823,13 @@ int launch_tc(const AttnArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+int window_attention_tc(const AttnArgs& a, cudaStream_t stream) {
+  B200SAM_REQUIRE(a.B > 0 && a.heads > 0 && (a.hd == 64 || a.hd == 80),
+                  "window_attention_tc: unsupported shape B=%d heads=%d hd=%d", a.B, a.heads, a.hd);
+  B200SAM_REQUIRE(a.qkv && a.qkv_bias && a.rel_h && a.rel_w && a.out, "window_attention_tc: null pointer argument");
+  return a.hd == 80 ? launch_win_tc<80>(a, stream) : launch_win_tc<64>(a, stream);
+}
 
 int global_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   B200SAM_REQUIRE(a.B > 0 && a.heads > 0 && (a.hd == 64 || a.hd == 80),

@@ -151,7 +151,7 @@ int encoder_forward(const Encoder* e, const void* img, int is_u8, int B, int h, 
     TRY(gemm(ws.xn, W[o + B_QKVW], ws.qkv, F(o + B_QKVB), nullptr, M, 3 * D, D, 0, 0, 0, 1, s));
     at.qkv_bias = H(o + B_QKVB16); at.rel_h = H(o + B_RELH); at.rel_w = H(o + B_RELW);
     if ((c.global_mask_lo >> b) & 1) TRY(global_attention_tc(at, s));
-    else TRY(window_attention(at, s));
+    else TRY(window_attention_tc(at, s));
     TRY(gemm(ws.att, W[o + B_PROJW], ws.x, F(o + B_PROJB), ws.x, M, D, D, D, 0, 0, 0, s));
     TRY(layernorm_rows(ws.x, F(o + B_N2W), F(o + B_N2B), 1e-6f, M, D, ws.xn, 1, s));
     TRY(gemm(ws.xn, W[o + B_L1W], ws.h, F(o + B_L1B), nullptr, M, 4 * D, D, 0, 0, 1, 1, s));

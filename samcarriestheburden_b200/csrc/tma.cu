@@ -48,6 +48,28 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
   return 0;
 }
 
+int make_tmap_bf16_grid4d(CUtensorMap* map, const void* ptr, uint64_t batch, uint64_t cols, uint32_t box_x,
+                          uint32_t box_y) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t dims[4] = {cols, 64, 64, batch};
+  cuuint64_t strides[3] = {cols * 2, 64 * cols * 2, 4096 * cols * 2};
+  cuuint32_t box[4] = {16, box_x, box_y, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(4d) failed with CUresult %d (ptr=%p batch=%llu cols=%llu box=%ux%u)", (int)r,
+                   ptr, (unsigned long long)batch, (unsigned long long)cols, box_x, box_y);
+    return 1;
+  }
+  return 0;
+}
+
 int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;

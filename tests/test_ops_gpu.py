@@ -108,12 +108,12 @@ def _attention_reference(qkv, bias16, rel_h, rel_w, heads, hd, window):
     return o.reshape(B * 4096, D)
 
 
-@pytest.mark.parametrize("heads,hd,glob", [(16, 80, 0), (12, 64, 0), (4, 80, 1), (3, 64, 1), (2, 80, 2), (2, 64, 2)])
+@pytest.mark.parametrize("heads,hd,glob", [(16, 80, 0), (12, 64, 0), (4, 80, 1), (3, 64, 1), (2, 80, 2), (2, 64, 2), (3, 80, 3), (2, 64, 3)])
 def test_encoder_attention(heads, hd, glob):
     g = torch.Generator(device="cpu").manual_seed(heads * 100 + hd + glob)
     D = heads * hd
     B = 2 if glob != 2 else 1
-    S = 64 if glob else 14
+    S = 64 if glob in (1, 2) else 14
     qkv = torch.randn((B * 4096, 3 * D), generator=g).to(DEV).bfloat16()
     bias = torch.randn((3 * D,), generator=g).to(DEV).bfloat16()
     rel_h = (0.3 * torch.randn((2 * S - 1, hd), generator=g)).to(DEV).bfloat16()
@@ -123,7 +123,7 @@ def test_encoder_attention(heads, hd, glob):
     _lib.check(lib.b200sam_encoder_attention(qkv.data_ptr(), bias.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(),
                                              out.data_ptr(), B, heads, hd, glob, _lib.current_stream()))
     torch.cuda.synchronize()
-    ref = _attention_reference(qkv, bias, rel_h, rel_w, heads, hd, 0 if glob else 14)
+    ref = _attention_reference(qkv, bias, rel_h, rel_w, heads, hd, 0 if glob in (1, 2) else 14)
     err = (out.float() - ref).abs()
     assert err.max().item() < 3e-2, (err.max().item(), err.mean().item())
     assert err.mean().item() < 3e-3
