@@ -87,6 +87,7 @@ inline size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 struct Workspace {
   float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *abuf, *up1, *up2;
   float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4;
+  __nv_bfloat16 *sa, *sb;  // hi/lo split operands [Mi, 768] bf16 each
   size_t total;
 };
 
@@ -116,6 +117,8 @@ Workspace carve(uint8_t* base, int NB, int T) {
   w.th = take(Mt * 2048);
   w.hyper = take(static_cast<size_t>(NB) * 128);
   w.iou4 = take(static_cast<size_t>(NB) * 4);
+  w.sa = reinterpret_cast<__nv_bfloat16*>(take(Mi * 768 / 2));
+  w.sb = reinterpret_cast<__nv_bfloat16*>(take(Mi * 768 / 2));
   w.total = off;
   return w;
 }
@@ -126,6 +129,16 @@ int lin(const float* A, const float* A2, int a2mod, const float* W, const float*
   p.A = A; p.A2 = A2; p.W = W; p.bias = b; p.residual = res; p.out = out;
   p.M = M; p.N = N; p.K = K; p.lda = K; p.lda2 = K; p.ldo = N; p.ldr = N; p.a2_row_mod = a2mod; p.act = act;
   return linear_f32(p, s);
+}
+
+// out[M,N] fp32 = A'[M,3K] . W'[N,3K]^T + bias (+GELU) (+residual): tcgen05 GEMM on the split operands
+int tc_lin(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* b, const float* res, float* out, int M, int N,
+           int K, int gelu, cudaStream_t s) {
+  GemmArgs g;
+  g.A = As; g.B = Ws; g.out = out; g.bias = b; g.residual = res;
+  g.M = M; g.N = N; g.K = 3 * K; g.lda = 3 * K; g.ldb = 3 * K; g.ldo = N; g.ldr = N; g.res_row_mod = 0;
+  g.gelu = gelu; g.out_bf16 = 0; g.max_ctas = 0;
+  return gemm_bf16_tn(g, s);
 }
 
 #define TRY(x) do { if (int _rc = (x)) return _rc; } while (0)
@@ -157,6 +170,37 @@ int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_
     return 1;
   }
   if (int rc = dense_pe_tokens(d->w[W_GAUSS], d->pe_tok, stream)) { cudaFree(d->pe_tok); delete d; return rc; }
+  // hi/hi/lo splits of the image-side weights ([N, 3K] bf16)
+  struct Item { int idx, N, K; const __nv_bfloat16** dst; };
+  std::vector<Item> items;
+  for (int l = 0; l < 2; ++l) {
+    const int L = W_LAYER0 + l * LAYER_STRIDE;
+    items.push_back({L + L_T2I + 2, 128, 256, &d->ws_t2i_k[l]});
+    items.push_back({L + L_T2I + 4, 128, 256, &d->ws_t2i_v[l]});
+    items.push_back({L + L_I2T + 0, 128, 256, &d->ws_i2t_q[l]});
+    items.push_back({L + L_I2T + 6, 256, 128, &d->ws_i2t_o[l]});
+  }
+  items.push_back({W_FINAL + 2, 128, 256, &d->ws_fin_k});
+  items.push_back({W_FINAL + 4, 128, 256, &d->ws_fin_v});
+  items.push_back({W_UP + 0, 256, 256, &d->ws_up1});
+  items.push_back({W_UP + 4, 128, 64, &d->ws_up2});
+  size_t total = 0;
+  for (const Item& it : items) total += static_cast<size_t>(it.N) * 3 * it.K;
+  d->wsplit = nullptr;
+  if (cudaMalloc(&d->wsplit, total * sizeof(__nv_bfloat16)) != cudaSuccess) {
+    set_last_error("decoder_create: cudaMalloc of the split weights failed");
+    cudaFree(d->pe_tok);
+    delete d;
+    return 1;
+  }
+  size_t off = 0;
+  for (const Item& it : items) {
+    *it.dst = d->wsplit + off;
+    if (int rc = split3_bf16(d->w[it.idx], nullptr, 0, d->wsplit + off, it.N, it.K, 1, stream)) {
+      cudaFree(d->wsplit); cudaFree(d->pe_tok); delete d; return rc;
+    }
+    off += static_cast<size_t>(it.N) * 3 * it.K;
+  }
   *out = d;
   return 0;
 }
@@ -164,6 +208,7 @@ int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_
 void decoder_destroy(Decoder* d) {
   if (d == nullptr) return;
   if (d->pe_tok) cudaFree(d->pe_tok);
+  if (d->wsplit) cudaFree(d->wsplit);
   delete d;
 }
 
@@ -206,8 +251,13 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
 
     const float* const* TI = L + L_T2I;
     TRY(lin(w.queries, w.tokens, 0, TI[0], TI[1], nullptr, w.tq, Mt, 128, 256, 0, s));
-    TRY(lin(w.keys, pe, 4096, TI[2], TI[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
-    TRY(lin(w.keys, nullptr, 0, TI[4], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
+    // image-side projections on the tensor cores (3-way bf16 split operands, fp32 accumulate); keys are constant
+    // until the end of the layer, so the two split operands also serve the image->token query projection
+    TRY(split3_bf16(w.keys, pe, 4096, w.sa, Mi, 256, 0, s));
+    TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
+    TRY(tc_lin(w.sa, d->ws_t2i_k[l], TI[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
+    TRY(tc_lin(w.sb, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
+    TRY(tc_lin(w.sa, d->ws_i2t_q[l], L[L_I2T + 1], nullptr, w.qibuf, Mi, 128, 256, 0, s));
     TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, s));
     TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
@@ -217,18 +267,20 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(layernorm_rows(w.queries, L[L_N3], L[L_N3 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
     const float* const* IT = L + L_I2T;  // image tokens are the queries here
-    TRY(lin(w.keys, pe, 4096, IT[0], IT[1], nullptr, w.qibuf, Mi, 128, 256, 0, s));
     TRY(lin(w.queries, w.tokens, 0, IT[2], IT[3], nullptr, w.tk, Mt, 128, 256, 0, s));
     TRY(lin(w.queries, nullptr, 0, IT[4], IT[5], nullptr, w.tv, Mt, 128, 256, 0, s));
     TRY(attn_few_keys(w.qibuf, w.tk, w.tv, w.abuf, NB, 4096, T, s));
-    TRY(lin(w.abuf, nullptr, 0, IT[6], IT[7], w.keys, w.keys, Mi, 256, 128, 0, s));
+    TRY(split3_bf16(w.abuf, nullptr, 0, w.sa, Mi, 128, 0, s));
+    TRY(tc_lin(w.sa, d->ws_i2t_o[l], IT[7], w.keys, w.keys, Mi, 256, 128, 0, s));
     TRY(layernorm_rows(w.keys, L[L_N4], L[L_N4 + 1], 1e-5f, Mi, 256, w.keys, 0, s));
   }
   {
     const float* const* F = W + W_FINAL;
     TRY(lin(w.queries, w.tokens, 0, F[0], F[1], nullptr, w.tq, Mt, 128, 256, 0, s));
-    TRY(lin(w.keys, pe, 4096, F[2], F[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
-    TRY(lin(w.keys, nullptr, 0, F[4], F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
+    TRY(split3_bf16(w.keys, pe, 4096, w.sa, Mi, 256, 0, s));
+    TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
+    TRY(tc_lin(w.sa, d->ws_fin_k, F[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
+    TRY(tc_lin(w.sb, d->ws_fin_v, F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
     TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, s));
     TRY(lin(w.ta, nullptr, 0, F[6], F[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, W[W_NF], W[W_NF + 1], 1e-5f, Mt, 256, w.queries, 0, s));
@@ -236,9 +288,11 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
 
   // ---- upscaling + hypernetwork heads (mask_decoder.py:137-147)
   const float* const* U = W + W_UP;
-  TRY(lin(w.keys, nullptr, 0, U[0], U[1], nullptr, w.up1, Mi, 256, 256, 0, s));      // ConvT 256->64, k2 s2
+  // w.sb still holds the split of the final keys (they do not change after the last image->token block)
+  TRY(tc_lin(w.sb, d->ws_up1, U[1], nullptr, w.up1, Mi, 256, 256, 0, s));             // ConvT 256->64, k2 s2
   TRY(ln64_gelu(w.up1, U[2], U[3], static_cast<size_t>(Mi) * 4, s));                  // LayerNorm2d(64) + GELU
-  TRY(lin(w.up1, nullptr, 0, U[4], U[5], nullptr, w.up2, Mi * 4, 128, 64, 2, s));     // ConvT 64->32 + GELU
+  TRY(split3_bf16(w.up1, nullptr, 0, w.sa, static_cast<size_t>(Mi) * 4, 64, 0, s));
+  TRY(tc_lin(w.sa, d->ws_up2, U[5], nullptr, w.up2, Mi * 4, 128, 64, 1, s));          // ConvT 64->32 + GELU
   {
     const float* wt[15];
     const float* bs[15];

@@ -526,6 +526,49 @@ __global__ void __launch_bounds__(256) mask_dot_kernel(const float* __restrict__
   }
 }
 
+// fp32 -> 3-way bf16 split operand for the tensor-core path of the big decoder linears:
+//   x = hi + lo (+ 2^-17 relative remainder), hi = bf16(x), lo = bf16(x - hi)
+//   mode 0 (activations): out[m] = [hi | lo | hi];  mode 1 (weights): out[n] = [hi | hi | lo]
+// so that <A'[m], W'[n]> = hi.hi + lo.hi + hi.lo  ~= fp32 product (the lo.lo term, 2^-18 relative, is dropped).
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                     int x2_row_mod, __nv_bfloat16* __restrict__ out, size_t M, int K,
+                                                     int mode) {
+  const int vec_per_row = K / 8;
+  const size_t total = M * vec_per_row;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t m = idx / vec_per_row;
+    const int v = static_cast<int>(idx - m * vec_per_row);
+    const float4* src = reinterpret_cast<const float4*>(x + m * K + v * 8);
+    float4 a = src[0], b = src[1];
+    if (x2 != nullptr) {
+      const size_t m2 = x2_row_mod > 0 ? (m % x2_row_mod) : m;
+      const float4* s2 = reinterpret_cast<const float4*>(x2 + m2 * K + v * 8);
+      const float4 c = s2[0], d = s2[1];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
+      const float r0 = f[2 * i] - __bfloat162float(h0), r1 = f[2 * i + 1] - __bfloat162float(h1);
+      __nv_bfloat162 hp, lp;
+      hp.x = h0; hp.y = h1;
+      lp = __floats2bfloat162_rn(r0, r1);
+      hi[i] = *reinterpret_cast<uint32_t*>(&hp);
+      lo[i] = *reinterpret_cast<uint32_t*>(&lp);
+    }
+    const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    const uint4 Lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    __nv_bfloat16* o = out + m * (3 * static_cast<size_t>(K)) + v * 8;
+    *reinterpret_cast<uint4*>(o) = H;
+    *reinterpret_cast<uint4*>(o + K) = mode == 0 ? Lo : H;
+    *reinterpret_cast<uint4*>(o + 2 * K) = mode == 0 ? H : Lo;
+  }
+}
+
 __global__ void add_rows_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
                                 size_t n4) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -625,6 +668,18 @@ int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const f
 
 int mask_dot(const float* up, const float* hyper, int NB, int tok0, int ntok, float* masks, cudaStream_t stream) {
   mask_dot_kernel<<<dim3(256, NB), 256, 0, stream>>>(up, hyper, tok0, ntok, masks);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int split3_bf16(const float* x, const float* x2, int x2_row_mod, __nv_bfloat16* out, size_t M, int K, int mode,
+                cudaStream_t stream) {
+  B200SAM_REQUIRE(K % 8 == 0, "split3: K=%d must be a multiple of 8", K);
+  if (M == 0) return 0;
+  const size_t total = M * (K / 8);
+  size_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  split3_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(x, x2, x2_row_mod, out, M, K, mode);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

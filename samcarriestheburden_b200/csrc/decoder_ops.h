@@ -39,6 +39,9 @@ int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, cudaStre
 int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const float* const* b15, float* hyper,
                 float* iou, cudaStream_t stream);
 int mask_dot(const float* up, const float* hyper, int NB, int tok0, int ntok, float* masks, cudaStream_t stream);
+// fp32 [M,K] (+ optional addend) -> bf16 [M,3K] hi/lo split operand (mode 0: activations, 1: weights)
+int split3_bf16(const float* x, const float* x2, int x2_row_mod, __nv_bfloat16* out, size_t M, int K, int mode,
+                cudaStream_t stream);
 int add_rows(const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
 
 }  // namespace b200sam

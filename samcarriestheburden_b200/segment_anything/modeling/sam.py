@@ -160,21 +160,25 @@ class Sam(nn.Module):
         """PromptEncoder.forward + MaskDecoder.forward for a batch of prompts of ONE image
         (prompt_encoder.py:128-168, mask_decoder.py:71-110).  Returns (low_res [B,1|3,256,256], iou [B,1|3])."""
         dev = self.device
+        # assemble [points | pad point | box corners] + labels on the inputs' own device (CPU tensors stay on the
+        # host and cross in ONE copy each), then hand raw pointers to the C ABI
         coords, labels = [], []
         if point_coords is not None:
-            pc = point_coords.to(dev).float()
-            pl = point_labels.to(dev).to(torch.int32)
+            pc = point_coords.float()
+            pl = point_labels.to(device=pc.device, dtype=torch.int32)
             coords.append(pc)
             labels.append(pl)
             if boxes is None:  # pad point, label -1 (prompt_encoder.py:81-85)
-                coords.append(torch.zeros((pc.shape[0], 1, 2), device=dev))
-                labels.append(-torch.ones((pc.shape[0], 1), dtype=torch.int32, device=dev))
+                coords.append(torch.zeros((pc.shape[0], 1, 2), device=pc.device))
+                labels.append(-torch.ones((pc.shape[0], 1), dtype=torch.int32, device=pc.device))
         if boxes is not None:
-            b = boxes.to(dev).float().reshape(-1, 2, 2)
+            b = boxes.float().reshape(-1, 2, 2)
+            if coords:
+                b = b.to(coords[0].device)
             coords.append(b)
-            labels.append(torch.tensor([[2, 3]], dtype=torch.int32, device=dev).expand(b.shape[0], 2))
-        c = torch.cat(coords, dim=1) if coords else None
-        l = torch.cat(labels, dim=1) if labels else None
+            labels.append(torch.tensor([[2, 3]], dtype=torch.int32, device=b.device).expand(b.shape[0], 2))
+        c = torch.cat(coords, dim=1).to(dev, non_blocking=True) if coords else None
+        l = torch.cat(labels, dim=1).to(dev, non_blocking=True) if labels else None
         m = mask_input.to(dev) if mask_input is not None else None
         return self.decoder_engine().decode(features, c, l, m, multimask_output)
 

@@ -10,6 +10,7 @@ from typing import List, Union
 
 import torch
 
+from ..segment_anything.modeling.sam import upscale_masks
 from ..segment_anything.sam_mask_decoder_head import SAMMaskDecoderHead
 from ..segment_anything.utils.prompt_utils import PromptExtractor
 
@@ -49,21 +50,48 @@ class SAMSegRefiner(SegRefiner):
         """seg: [C,H,W] (bool or probabilities>0 -> bool like the reference's `.bool()`), returns
         (seg bool [C,H,W], est_dice float [C] with NaN for classes without prompts)."""
         seg = seg.bool().to(self.sam_predictor.device)
-        prompts = PromptExtractor(seg).extract()
+        ex = PromptExtractor(seg)
+        packed = ex._extracted  # CPU int32 [C, 8]: sx, sy, xmin, ymin, xmax, ymax, has_seed, has_box (one D2H copy)
+        idx = torch.nonzero(packed[:, 6]).flatten()
         est_dice = torch.full((seg.shape[0],), float("nan"))
-        if not prompts:
+        K = int(idx.numel())
+        if K == 0:
             return seg, est_dice
+        if K == 1:
+            ex.extract()  # raises like the reference: torch.cat of an empty neg-seed list (prompt_utils.py:122-123)
+        head = self.sam_predictor
+        feats, input_size, original_size = head._entry(file_name)
+        # vectorised restatement of scale_coords / scale_box (prompt_utils.py:146-184) for all K prompts at once:
+        # fp32 (target / original) flipped to (x, y), one multiply per coordinate - same arithmetic, on the host
+        scale = (torch.tensor(input_size, dtype=torch.float) / torch.tensor(tuple(seg.shape[-2:]), dtype=torch.float)).flip(-1)
+        pos = packed[idx, 0:2]                                   # [K, 2] (x, y)
+        boxes = (packed[idx, 2:6].reshape(K, 2, 2).float() * scale).reshape(K, 4)
+        sel = (~torch.eye(K, dtype=torch.bool)).nonzero()[:, 1].reshape(K, K - 1)  # other classes, in class order
+        pts = torch.cat([pos[:, None, :], pos[sel]], dim=1).float() * scale       # [K, K, 2]: pos seed, then negatives
+        labs = torch.zeros((K, K), dtype=torch.int32)
+        labs[:, 0] = 1
+
+        def run(kinds, mask_prev, upscale, small_size):
+            use_pts = [k for k in kinds if k in ("pos_points", "neg_points")]
+            p = l = None
+            if use_pts:
+                cols = ([0] if "pos_points" in kinds else []) + (list(range(1, K)) if "neg_points" in kinds else [])
+                p, l = pts[:, cols], labs[:, cols]
+            bx = boxes if "box" in kinds else None
+            low, iou = head.sam.decode_prompts(feats, p, l, bx, mask_prev, multimask_output=False)
+            small = None
+            if upscale:
+                _, small = upscale_masks(low, input_size, original_size, head.img_enc_img_size, head.mask_threshold,
+                                         small_size=small_size)
+            return low, iou, small
+
         small_size = tuple(seg.shape[-2:])
         if self.prompts2use2nd is None:
-            _, score, _, small = self.sam_predictor.predict_masks_batched(file_name, prompts, self.prompts2use1st,
-                                                                        small_size=small_size)
+            _, score, small = run(self.prompts2use1st, None, True, small_size)
         else:
-            _, _, low1, _ = self.sam_predictor.predict_masks_batched(file_name, prompts, self.prompts2use1st,
-                                                                     upscale=False)
-            _, score, _, small = self.sam_predictor.predict_masks_batched(file_name, prompts, self.prompts2use2nd,
-                                                                        mask_prev_iter=low1, small_size=small_size)
-        idx = torch.tensor([p.class_idx for p in prompts], device=seg.device)
-        seg[idx] = small[:, 0]
+            low1, _, _ = run(self.prompts2use1st, None, False, None)  # pass-1 native mask is dead work (SURVEY 3.B)
+            _, score, small = run(self.prompts2use2nd, low1, True, small_size)
+        seg[idx.to(seg.device)] = small[:, 0]
         s = score[:, 0].float().cpu()
-        est_dice[idx.cpu()] = 2 * s / (1 + s)
+        est_dice[idx] = 2 * s / (1 + s)
         return seg, est_dice
