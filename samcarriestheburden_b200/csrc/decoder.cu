@@ -86,7 +86,7 @@ inline size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 
 struct Workspace {
   float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *abuf, *up1, *up2;
-  float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4;
+  float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4, *part;
   __nv_bfloat16 *sa, *sb;  // hi/lo split operands [Mi, 768] bf16 each
   size_t total;
 };
@@ -117,6 +117,7 @@ Workspace carve(uint8_t* base, int NB, int T) {
   w.th = take(Mt * 2048);
   w.hyper = take(static_cast<size_t>(NB) * 128);
   w.iou4 = take(static_cast<size_t>(NB) * 4);
+  w.part = take(static_cast<size_t>(NB) * 8 * ATTN_FEWQ_SPLITS * T * 18);
   w.sa = reinterpret_cast<__nv_bfloat16*>(take(Mi * 768 / 2));
   w.sb = reinterpret_cast<__nv_bfloat16*>(take(Mi * 768 / 2));
   w.total = off;
@@ -245,7 +246,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(lin(w.queries, qpe, 0, SA[0], SA[1], nullptr, w.tq, Mt, 256, 256, 0, s));
     TRY(lin(w.queries, qpe, 0, SA[2], SA[3], nullptr, w.tk, Mt, 256, 256, 0, s));
     TRY(lin(w.queries, nullptr, 0, SA[4], SA[5], nullptr, w.tv, Mt, 256, 256, 0, s));
-    TRY(attn_few_queries(w.tq, w.tk, w.tv, w.ta, NB, T, T, 8, 32, s));
+    TRY(attn_few_queries(w.tq, w.tk, w.tv, w.ta, NB, T, T, 8, 32, nullptr, s));
     TRY(lin(w.ta, nullptr, 0, SA[6], SA[7], l == 0 ? nullptr : w.queries, w.queries, Mt, 256, 256, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N1], L[L_N1 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
@@ -258,7 +259,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(tc_lin(w.sa, d->ws_t2i_k[l], TI[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sb, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sa, d->ws_i2t_q[l], L[L_I2T + 1], nullptr, w.qibuf, Mi, 128, 256, 0, s));
-    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, s));
+    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, s));
     TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
@@ -281,7 +282,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
     TRY(tc_lin(w.sa, d->ws_fin_k, F[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sb, d->ws_fin_v, F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
-    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, s));
+    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, s));
     TRY(lin(w.ta, nullptr, 0, F[6], F[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, W[W_NF], W[W_NF + 1], 1e-5f, Mt, 256, w.queries, 0, s));
   }

@@ -15,26 +15,32 @@ B200SAM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70
 
 // ------------------------------------------------------------------ generic fp32 linear
 // out[m, n] = act( sum_k (A[m,k] + A2[m2,k]) * W[n,k] + bias[n] ) + residual[m, n]
-constexpr int LBM = 128, LBN = 64, LBK = 16;
+// BM = 128 for the tall image-side operands, BM = 32 for the token-side ones (M = prompts x tokens <= ~400 rows:
+// small row tiles keep enough CTAs in flight; those launches are latency-, not FLOP-bound).
+constexpr int LBN = 64, LBK = 16;
 
+template <int BM>
 __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
-  __shared__ __align__(16) float As[2][LBK][LBM + 4];
+  constexpr int RM = BM / 16;          // rows per thread
+  constexpr int A_VEC = BM * 4;        // float4 per A tile
+  constexpr int A_PER_THREAD = (A_VEC + 255) / 256;
+  __shared__ __align__(16) float As[2][LBK][BM + 4];
   __shared__ __align__(16) float Bs[2][LBK][LBN + 4];
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
-  const int m0 = blockIdx.y * LBM, n0 = blockIdx.x * LBN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * LBN;
   const int nk = p.K / LBK;
 
-  float4 ra[2], rb;
+  float4 ra[A_PER_THREAD], rb;
   auto gload = [&](int kt) {
     const int k0 = kt * LBK;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < A_PER_THREAD; ++i) {
       const int f = tid + 256 * i;
       const int row = f >> 2, kq = f & 3;
       const int m = m0 + row;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M) {
+      if (f < A_VEC && m < p.M) {
         v = *reinterpret_cast<const float4*>(p.A + static_cast<size_t>(m) * p.lda + k0 + kq * 4);
         if (p.A2 != nullptr) {
           const int m2 = p.a2_row_mod > 0 ? (m % p.a2_row_mod) : m;
@@ -53,13 +59,15 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
   };
   auto sstore = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < A_PER_THREAD; ++i) {
       const int f = tid + 256 * i;
-      const int row = f >> 2, kq = f & 3;
-      As[buf][kq * 4 + 0][row] = ra[i].x;
-      As[buf][kq * 4 + 1][row] = ra[i].y;
-      As[buf][kq * 4 + 2][row] = ra[i].z;
-      As[buf][kq * 4 + 3][row] = ra[i].w;
+      if (f < A_VEC) {
+        const int row = f >> 2, kq = f & 3;
+        As[buf][kq * 4 + 0][row] = ra[i].x;
+        As[buf][kq * 4 + 1][row] = ra[i].y;
+        As[buf][kq * 4 + 2][row] = ra[i].z;
+        As[buf][kq * 4 + 3][row] = ra[i].w;
+      }
     }
     const int row = tid >> 2, kq = tid & 3;
     Bs[buf][kq * 4 + 0][row] = rb.x;
@@ -68,9 +76,9 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
     Bs[buf][kq * 4 + 3][row] = rb.w;
   };
 
-  float acc[8][4];
+  float acc[RM][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
@@ -82,13 +90,13 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
     if (kt + 1 < nk) gload(kt + 1);
 #pragma unroll
     for (int k = 0; k < LBK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      float av[RM];
+#pragma unroll
+      for (int i = 0; i < RM; ++i) av[i] = As[buf][k][ty * RM + i];
       const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -102,8 +110,8 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.bias != nullptr) bias = *reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + ty * 8 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= p.M) continue;
     float4 v = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
     if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
 template <int DH>
 __global__ void __launch_bounds__(256) attn_fewq_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                         const float* __restrict__ v, float* __restrict__ out, int Tq,
-                                                        int Tk, int heads) {
+                                                        int Tk, int heads, int nsplit, float* __restrict__ part) {
   constexpr int KT = 128;       // keys per tile
   constexpr int PAD = DH + 4;   // conflict-free float4 rows
   constexpr int QPW = 4;        // queries per warp per pass
@@ -152,8 +160,12 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(const float* __restrict_
 #pragma unroll
       for (int d = 0; d < DH; ++d) acc[j][d] = 0.0f;
     }
-    for (int k0 = 0; k0 < Tk; k0 += KT) {
-      const int nk = min(KT, Tk - k0);
+    // flash-decoding style key split: CTA z of nsplit owns keys [kbeg, kend); partial (m, l, acc) states are merged
+    // by attn_fewq_combine_kernel (keeps > 148 CTAs in flight although there are only batch x heads problems)
+    const int per = (Tk + nsplit - 1) / nsplit;
+    const int kbeg = blockIdx.z * per, kend = min(Tk, kbeg + per);
+    for (int k0 = kbeg; k0 < kend; k0 += KT) {
+      const int nk = min(KT, kend - k0);
       __syncthreads();
       for (int i = tid; i < KT * (DH / 4); i += 256) {
         const int r = i / (DH / 4), c4 = i - r * (DH / 4);
@@ -206,13 +218,44 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(const float* __restrict_
       const float mall = warp_max(m[j]);
       const float c = (m[j] == -INFINITY) ? 0.0f : expf(m[j] - mall);
       const float lall = warp_sum(l[j] * c);
-      const float inv = 1.0f / lall;
+      if (nsplit == 1) {
+        const float inv = 1.0f / lall;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) {
-        const float o = warp_sum(acc[j][d] * c);
-        if (lane == 0) out[(static_cast<size_t>(b) * Tq + qbase + qi) * C + h * DH + d] = o * inv;
+        for (int d = 0; d < DH; ++d) {
+          const float o = warp_sum(acc[j][d] * c);
+          if (lane == 0) out[(static_cast<size_t>(b) * Tq + qbase + qi) * C + h * DH + d] = o * inv;
+        }
+      } else {
+        float* pp = part + (((static_cast<size_t>(b) * heads + h) * nsplit + blockIdx.z) * Tq + qbase + qi) * (DH + 2);
+#pragma unroll
+        for (int d = 0; d < DH; ++d) {
+          const float o = warp_sum(acc[j][d] * c);
+          if (lane == 0) pp[2 + d] = o;
+        }
+        if (lane == 0) { pp[0] = mall; pp[1] = lall; }
       }
     }
+  }
+}
+
+template <int DH>
+__global__ void attn_fewq_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int Tq, int heads,
+                                         int nsplit) {
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int C = heads * DH;
+  for (int i = threadIdx.x; i < Tq * DH; i += blockDim.x) {
+    const int qi = i / DH, d = i - qi * DH;
+    const float* base = part + ((static_cast<size_t>(b) * heads + h) * nsplit * Tq + qi) * (DH + 2);
+    float mall = -INFINITY;
+    for (int z = 0; z < nsplit; ++z) mall = fmaxf(mall, base[static_cast<size_t>(z) * Tq * (DH + 2)]);
+    float l = 0.0f, o = 0.0f;
+    for (int z = 0; z < nsplit; ++z) {
+      const float* pz = base + static_cast<size_t>(z) * Tq * (DH + 2);
+      const float c = pz[0] == -INFINITY ? 0.0f : expf(pz[0] - mall);
+      l = fmaf(pz[1], c, l);
+      o = fmaf(pz[2 + d], c, o);
+    }
+    out[(static_cast<size_t>(b) * Tq + qi) * C + h * DH + d] = o / l;
   }
 }
 
@@ -585,19 +628,30 @@ int linear_f32(const LinearArgs& p, cudaStream_t stream) {
   B200SAM_REQUIRE(p.K % LBK == 0 && p.N % 4 == 0 && p.lda % 4 == 0 && p.ldo % 4 == 0,
                   "linear_f32: need K%%16==0, N%%4==0, lda%%4==0, ldo%%4==0 (M=%d N=%d K=%d lda=%d ldo=%d)", p.M, p.N,
                   p.K, p.lda, p.ldo);
-  dim3 grid((p.N + LBN - 1) / LBN, (p.M + LBM - 1) / LBM);
-  linear_f32_kernel<<<grid, 256, 0, stream>>>(p);
+  if (p.M > 1024) {
+    dim3 grid((p.N + LBN - 1) / LBN, (p.M + 127) / 128);
+    linear_f32_kernel<128><<<grid, 256, 0, stream>>>(p);
+  } else {
+    dim3 grid((p.N + LBN - 1) / LBN, (p.M + 31) / 32);
+    linear_f32_kernel<32><<<grid, 256, 0, stream>>>(p);
+  }
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
-                     int dh, cudaStream_t stream) {
+                     int dh, float* part, cudaStream_t stream) {
   B200SAM_REQUIRE(NB > 0 && Tq > 0 && Tk > 0, "attn_few_queries: empty problem");
-  dim3 grid(heads, NB);
-  if (dh == 16) attn_fewq_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads);
-  else if (dh == 32) attn_fewq_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads);
+  const int nsplit = (part != nullptr && Tk >= 1024) ? ATTN_FEWQ_SPLITS : 1;
+  dim3 grid(heads, NB, nsplit);
+  if (dh == 16) attn_fewq_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part);
+  else if (dh == 32) attn_fewq_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part);
   else { set_last_error("attn_few_queries: unsupported head dim %d", dh); return 2; }
+  if (nsplit > 1) {
+    dim3 g2(heads, NB);
+    if (dh == 16) attn_fewq_combine_kernel<16><<<g2, 128, 0, stream>>>(part, out, Tq, heads, nsplit);
+    else attn_fewq_combine_kernel<32><<<g2, 128, 0, stream>>>(part, out, Tq, heads, nsplit);
+  }
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

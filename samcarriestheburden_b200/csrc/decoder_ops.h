@@ -22,8 +22,10 @@ struct LinearArgs {
 int linear_f32(const LinearArgs& p, cudaStream_t stream);
 
 // q [NB,Tq,heads*dh], k/v [NB,Tk,heads*dh] -> out [NB,Tq,heads*dh]; dh in {16, 32}
+// part: optional scratch of NB*heads*ATTN_FEWQ_SPLITS*Tq*(dh+2) floats enabling the key-split path for long Tk
+constexpr int ATTN_FEWQ_SPLITS = 8;
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
-                     int dh, cudaStream_t stream);
+                     int dh, float* part, cudaStream_t stream);
 // q [NB,Nq,128], k/v [NB,Tk<=32,128] (8 heads x 16) -> out [NB,Nq,128]
 int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
                   cudaStream_t stream);
