@@ -1,0 +1,173 @@
+// Epilogue shared by the 1-CTA and 2-CTA tcgen05 GEMM kernels: one warp drains a [32 rows x 128 columns] block of
+// the fp32 accumulator from TMEM (thread = row), applies bias / exact-erf GELU / fp32 residual, transposes through
+// a per-warp [32][16]-word XOR-swizzled shared tile and issues 16-byte global accesses (4 lanes = 64 contiguous
+// bytes of a row, 8 rows per instruction).
+#pragma once
+#include "common.cuh"
+
+namespace b200sam {
+
+struct EpiParams {
+  const float* bias;      // [N] or null
+  const float* residual;  // fp32 [*, ldr] or null
+  void* out;              // bf16 or fp32 [M, ldo]
+  int ldo;
+  int ldr;
+  int res_row_mod;  // >0: residual row = row % res_row_mod (broadcast table, e.g. pos_embed)
+  int gelu;
+};
+
+// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erfc(|z|) from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below the bf16 output rounding); evaluated as erfc so negative x has no 1 + erf cancellation.
+// ~16 instructions (MUFU.RCP + MUFU.EX2, ftz) instead of erff's ~40: the lin1 epilogue must stay below the
+// MMA time of a K=1280 tile (10240 cycles).
+B200SAM_DEVINL float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+B200SAM_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+B200SAM_DEVINL float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = (p * t) * ex2_approx((x * x) * -0.72134752044448170f);  // erfc(|z|) = poly * exp(-x^2/2)
+  const float w = (0.5f * x) * e;
+  return x >= 0.0f ? x - w : w;
+}
+
+
+constexpr int EPI_STAGE_BYTES = 32 * 16 * 4;  // [32 rows][16 words] per warp, XOR-swizzled
+constexpr int EPI_BIAS_BYTES = 128 * 4;       // 128 columns per warp
+
+// before the accumulator is ready: stage the bias slice and pull the residual block towards L2
+template <bool OUT_BF16>
+B200SAM_DEVINL void epilogue_prefetch(const EpiParams& ep, int M, int N, int row_base, int n0, float* sbias, int lane) {
+      // stage this warp's 128 bias values (zero when absent / out of range)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = n0 + lane + 32 * i;
+    sbias[lane + 32 * i] = (ep.bias != nullptr && c < N) ? __ldg(ep.bias + c) : 0.0f;
+  }
+  __syncwarp();
+  if constexpr (!OUT_BF16) {
+    // pull this warp's 32 x 128 residual block towards L2 while the MMAs of the tile are still running
+    const int prow = row_base + lane;
+    if (ep.residual != nullptr && prow < M) {
+      const int rr = ep.res_row_mod > 0 ? (prow % ep.res_row_mod) : prow;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = n0 + 32 * i;
+        if (c < N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + static_cast<size_t>(rr) * ep.ldr + c));
+      }
+    }
+  }
+}
+
+// after tmem_full: drain + store.  taddr0 = TMEM address of (this warp's lane quadrant, first of its 128 columns)
+template <bool OUT_BF16>
+B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_base, int n0, uint32_t taddr0,
+                                   uint32_t* stg, const float* sbias, int lane) {
+  const int wsw = (lane >> 1) & 3;  // write swizzle of this thread's row
+  const int rsub = lane >> 2;       // transposed read: row within a group of 8
+  const int rq = lane & 3;          // transposed read: 16 B quad within the 64 B row segment
+      if constexpr (OUT_BF16) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns = 16 packed words per row
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // 16 B quad j = columns 8j .. 8j+7
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j);
+        const float4 b1 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j + 4);
+        float v[8] = {__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y,
+                      __uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w,
+                      __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
+                      __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+        if (ep.gelu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = gelu_erf(v[k]);
+        }
+        uint4 pk;
+        pk.x = pack_bf16x2(v[0], v[1]);
+        pk.y = pack_bf16x2(v[2], v[3]);
+        pk.z = pack_bf16x2(v[4], v[5]);
+        pk.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ wsw) << 2)) = pk;
+      }
+      __syncwarp();
+      const int col = n0 + ch * 32 + 8 * rq;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rl = it * 8 + rsub;
+        const int row = row_base + rl;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + rl * 16 + ((rq ^ ((rl >> 1) & 3)) << 2));
+        if (row < M && col < N) *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ep.ldo + col) = v;
+      }
+      __syncwarp();
+    }
+  } else {
+    float* out = reinterpret_cast<float*>(ep.out);
+    const bool has_res = ep.residual != nullptr;
+    // residual block of one 16-column half (4 x float4 per thread), issued one half ahead of its use.  `out`
+    // may alias `residual` (in-place residual stream), so the compiler cannot hoist these loads itself.
+    auto load_half = [&](int h, float4 (&buf)[4]) {
+      const int col = n0 + h * 16 + 4 * rq;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = row_base + it * 8 + rsub;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res && row < M && col < N) {
+          const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
+          v = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rr) * ep.ldr + col);
+        }
+        buf[it] = v;
+      }
+    };
+    float4 rbuf[2][4];
+    load_half(0, rbuf[0]);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns, each written as 2 halves of 16
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
+      load_half(2 * ch + 1, rbuf[1]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if (hf == 1 && ch < 3) load_half(2 * ch + 2, rbuf[0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ wsw) << 2)) =
+              make_uint4(r[hf * 16 + 4 * j], r[hf * 16 + 4 * j + 1], r[hf * 16 + 4 * j + 2], r[hf * 16 + 4 * j + 3]);
+        __syncwarp();
+        const int col = n0 + ch * 32 + hf * 16 + 4 * rq;
+        const float4 b = *reinterpret_cast<const float4*>(sbias + ch * 32 + hf * 16 + 4 * rq);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 8 + rsub;
+          const int row = row_base + rl;
+          const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 16 + ((rq ^ ((rl >> 1) & 3)) << 2));
+          float4 v = make_float4(__uint_as_float(u.x) + b.x, __uint_as_float(u.y) + b.y,
+                                 __uint_as_float(u.z) + b.z, __uint_as_float(u.w) + b.w);
+          if (ep.gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+          const float4 rs = rbuf[hf][it];
+          v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
+          if (row < M && col < N) *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ep.ldo + col) = v;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+}  // namespace b200sam

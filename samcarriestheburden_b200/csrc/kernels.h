@@ -41,7 +41,7 @@ struct GemmArgs {
   int res_row_mod;  // >0: residual row index = row % res_row_mod
   int gelu;         // exact erf GELU after bias
   int out_bf16;     // 1: bf16 output, 0: fp32 output
-  int max_ctas;     // 0 = one CTA per SM
+  int max_ctas;     // <= 0: one CTA per SM; > 0 caps the persistent grid
 };
 int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
 

@@ -27,14 +27,14 @@ out16 = torch.zeros((M, N), dtype=torch.bfloat16, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def run(name, out, bias, res, gelu, out_bf16, reps=10):
+def run(name, out, bias, res, gelu, out_bf16, reps=10, max_ctas=0):
     ms = []
     for i in range(reps + 3):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(lib.b200sam_gemm_bf16(A.data_ptr(), W.data_ptr(), out.data_ptr(), _lib.ptr(bias), _lib.ptr(res), M, N,
-                                         K, K, K, N, N, 0, gelu, out_bf16, 0, _lib.current_stream()))
+                                         K, K, K, N, N, 0, gelu, out_bf16, max_ctas, _lib.current_stream()))
         e1.record()
         e1.synchronize()
         if i >= 3:
@@ -44,8 +44,10 @@ def run(name, out, bias, res, gelu, out_bf16, reps=10):
 
 
 run("bf16 out, bias", out16, b, None, 0, 1)
+run("bf16 out, bias [1-CTA]", out16, b, None, 0, 1, max_ctas=-1)
 run("bf16 out, bias, gelu", out16, b, None, 1, 1)
 run("bf16 out, no bias", out16, None, None, 0, 1)
 run("f32 out, bias", out32, b, None, 0, 0)
 run("f32 out, bias, residual(other)", out32, b, res32, 0, 0)
 run("f32 out, bias, residual(inplace)", out32, b, out32, 0, 0)
+run("f32 out, bias, residual(inplace) [1-CTA]", out32, b, out32, 0, 0, max_ctas=-1)
