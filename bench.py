@@ -294,8 +294,11 @@ def main():
     }
     if rank == 0:
         tf, launch_ms, per = gemm_roofline(args.model, B)
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the four shapes at batch 8) from
+        # the one `ncu --set full` capture summarised in profiles/r01_gemm_ncu_summary.md (algorithmic: 471.2 MB)
+        traffic = 446.9e6 if (args.model == "vit_h" and B == 8) else None
         out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                           "frac": tf / peaks["tf_burst"], "traffic": None,
+                           "frac": tf / peaks["tf_burst"], "traffic": traffic,
                            "kernel": "gemm_bf16_tn_kernel (tcgen05, 128x256x64 tiles)",
                            "launch_ms_mean": launch_ms, "per_shape": per, "peak_source": peaks["src"] + " burst"}
         if not args.no_refine:
