@@ -155,3 +155,48 @@ def test_pipeline_drivers_match_single_image_api(vit_b):
     ds = [dice(got[c], ref_seg[c]) for c in range(17)]
     print(f"pipeline refine: min dice={min(ds):.6f} mismatched={int((got != ref_seg).sum())}")
     assert min(ds) >= 0.999
+
+
+def test_vit_l_encoder_batch16_matches_oracle():
+    """BASELINE.json configs[3]: ViT-L (hd = 64, depth 24, global blocks 5/11/17/23), batch 16 per GPU."""
+    from samcarriestheburden_b200.segment_anything import sam_model_registry
+    sd = O.random_state_dict("vit_l", seed=1)
+    sam = sam_model_registry["vit_l"]()
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.to(DEV)
+    imgs = torch.stack([torch.from_numpy(O.synthetic_radiograph(40 + i)).permute(2, 0, 1) for i in range(16)]).to(DEV)
+    emb = sam.encode_image(imgs)
+    torch.cuda.synchronize()
+    assert emb.shape == (16, 256, 64, 64)
+    ref = O.image_encoder(sd, O.preprocess(imgs[5].cpu().float())[None], **O.VIT_CONFIGS["vit_l"])
+    got = emb[5:6].float().cpu()
+    rel = float((got - ref).norm() / ref.norm())
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+    print(f"encoder vit_l rel_l2={rel:.3e} cos={cos:.6f}")
+    assert rel <= 2e-2 and cos >= 0.9995, (rel, cos)
+    del sam
+    torch.cuda.empty_cache()
+
+
+def test_sam_forward_and_return_logits(vit_b, embedding):
+    """Upstream batched API `Sam.forward` (sam.py:53-131) and `predict(return_logits=True)`."""
+    sam, sd = vit_b
+    img, ref_emb, pred = embedding
+    resized = torch.from_numpy(pred.transform.apply_image(img)).permute(2, 0, 1).contiguous().to(DEV)
+    box = torch.tensor([[100.0, 150.0, 400.0, 600.0]], device=DEV)
+    boxes_in = pred.transform.apply_boxes_torch(box, (754, 589))
+    out = sam([{"image": resized, "original_size": (754, 589), "boxes": boxes_in}], multimask_output=False)
+    assert out[0]["masks"].shape == (1, 1, 754, 589) and out[0]["masks"].dtype == torch.bool
+    m1, iou1, low1 = pred.predict(box=box[0].cpu().numpy(), multimask_output=False)
+    assert np.array_equal(out[0]["masks"][0].cpu().numpy(), m1)
+    logits, _, _ = pred.predict(box=box[0].cpu().numpy(), multimask_output=False, return_logits=True)
+    assert logits.dtype == np.float32 and np.array_equal(logits > 0, m1)
+    # error behaviour of the reference API
+    from samcarriestheburden_b200.segment_anything import SamPredictor
+    fresh = SamPredictor(sam)
+    with pytest.raises(RuntimeError):
+        fresh.predict(box=box[0].cpu().numpy())
+    with pytest.raises(RuntimeError):
+        fresh.get_image_embedding()
+    with pytest.raises(AssertionError):
+        fresh.set_image(img, image_format="XYZ")
