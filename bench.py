@@ -304,6 +304,12 @@ def main():
                            "launch_ms_mean": launch_ms, "per_shape": per, "peak_source": peaks["src"] + " burst"}
         if not args.no_refine:
             out["refine"] = refine_throughput(sam, dev)
+            # HBM-bound stages on batched launches: algorithmic bytes / CUDA-event time
+            sys.path.insert(0, str(ROOT / "tools"))
+            import stage_bench
+            out["hbm_stages"] = {k: {"gbs": round(v["gbs"], 1), "frac_of_measured_hbm": round(v["gbs"] / peaks["hbm"], 3),
+                                     "ms": round(v["ms"], 4), "bytes": v["bytes"]}
+                                 for k, v in stage_bench.run(peaks["hbm"]).items()}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, times = cpu_encoder_images_per_s(args.model, 1)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
