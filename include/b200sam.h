@@ -84,6 +84,16 @@ B200SAM_API int b200sam_decoder_copy_dense_pe(const b200sam_decoder* dec, float*
 B200SAM_API int b200sam_decode(const b200sam_decoder* dec, const float* embedding, int n_prompts, int n_points,
                    const float* coords, const int32_t* labels, const float* mask_prev, int multimask,
                    float* low_res_out, float* iou_out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same for the prompts of SEVERAL images in one pass, i.e. additionally the per-image loop of
+ * scripts/save_refined_segmentations.py:60-80.  embeddings: [n_images,256,64,64]; image_of: [n_prompts] image
+ * index of every prompt (may be NULL when n_images == 1).  Prompts may carry different numbers of points:
+ * n_points is the slot count, unused TRAILING slots have label -2 and are masked out of every attention, so each
+ * prompt's result equals what it gets in a call of its own. */
+B200SAM_API size_t b200sam_decoder_workspace_bytes_batch(int n_images, int n_prompts, int n_points);
+B200SAM_API int b200sam_decode_batch(const b200sam_decoder* dec, const float* embeddings, int n_images,
+                         const int32_t* image_of, int n_prompts, int n_points, const float* coords,
+                         const int32_t* labels, const float* mask_prev, int multimask, float* low_res_out,
+                         float* iou_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- mask post-processing
  * Replaces postprocess_masks + threshold (segment_anything/sam_mask_decoder_head.py:99-135,

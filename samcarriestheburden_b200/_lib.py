@@ -43,6 +43,8 @@ _PROTOTYPES = {
     "b200sam_decoder_destroy": (None, [_vp]),
     "b200sam_decoder_copy_dense_pe": (_i, [_vp, _vp, _vp]),
     "b200sam_decode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200sam_decoder_workspace_bytes_batch": (_sz, [_i, _i, _i]),
+    "b200sam_decode_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200sam_upscale_threshold": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "b200sam_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sam_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _i, _vp]),

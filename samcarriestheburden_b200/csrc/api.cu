@@ -86,7 +86,10 @@ int b200sam_prompt_extract(const uint8_t* masks, int n_img, int n_classes, int H
 int b200sam_decoder_weight_count(void) { return decoder_weight_count(); }
 const char* b200sam_decoder_weight_name(int i) { return decoder_weight_name(i); }
 size_t b200sam_decoder_workspace_bytes(int n_prompts, int n_points) {
-  return decoder_workspace_bytes(n_prompts, n_points);
+  return decoder_workspace_bytes(1, n_prompts, n_points);
+}
+size_t b200sam_decoder_workspace_bytes_batch(int n_images, int n_prompts, int n_points) {
+  return decoder_workspace_bytes(n_images, n_prompts, n_points);
 }
 int b200sam_decoder_create(const void* const* weights, int n_weights, b200sam_decoder** out, void* stream) {
   if (!weights || !out) { set_last_error("decoder_create: null argument"); return 2; }
@@ -110,8 +113,17 @@ int b200sam_decode(const b200sam_decoder* dec, const float* embedding, int n_pro
                    const float* coords, const int32_t* labels, const float* mask_prev, int multimask,
                    float* low_res_out, float* iou_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!dec) { set_last_error("decode: null decoder"); return 2; }
+  return b200sam_decode_batch(dec, embedding, 1, nullptr, n_prompts, n_points, coords, labels, mask_prev, multimask,
+                              low_res_out, iou_out, workspace, workspace_bytes, stream);
+}
+int b200sam_decode_batch(const b200sam_decoder* dec, const float* embeddings, int n_images, const int32_t* image_of,
+                         int n_prompts, int n_points, const float* coords, const int32_t* labels,
+                         const float* mask_prev, int multimask, float* low_res_out, float* iou_out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!dec) { set_last_error("decode: null decoder"); return 2; }
   DecodeArgs a;
-  a.emb = embedding; a.NB = n_prompts; a.Np = n_points; a.coords = coords; a.labels = labels; a.mask_prev = mask_prev;
+  a.emb = embeddings; a.n_images = n_images; a.image_of = image_of; a.NB = n_prompts; a.Np = n_points;
+  a.coords = coords; a.labels = labels; a.mask_prev = mask_prev;
   a.img_w = 1024.0f; a.img_h = 1024.0f; a.multimask = multimask; a.low_res_out = low_res_out; a.iou_out = iou_out;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes;
   return decoder_forward(dec->impl, a, static_cast<cudaStream_t>(stream));

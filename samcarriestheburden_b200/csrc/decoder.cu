@@ -1,6 +1,9 @@
-// Host-side orchestration of the prompt encoder + mask decoder for ALL prompts of one image in one
-// batched pass (reference loop being replaced: utils/seg_refinement.py:105-109 calling
-// sam_mask_decoder_head.py:79-96 once per class with B=1).  Pure launch sequencing: no allocation, no
+// Host-side orchestration of the prompt encoder + mask decoder for ALL prompts of one or several images in
+// one batched pass (reference loop being replaced: utils/seg_refinement.py:105-109 calling
+// sam_mask_decoder_head.py:79-96 once per class with B=1, inside the per-image loop of
+// scripts/save_refined_segmentations.py:60-80).  Prompts of different images may carry different numbers of
+// sparse points (label -2 = absent slot): absent token slots are masked out as attention keys, so every prompt
+// computes exactly what it would compute alone.  Pure launch sequencing: no allocation, no
 // synchronisation; every buffer lives in the caller-provided workspace.
 #include "decoder.h"
 #include <string>
@@ -87,11 +90,12 @@ inline size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 struct Workspace {
   float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *abuf, *up1, *up2;
   float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4, *part;
+  int* ntok;               // [NB] valid tokens per prompt (5 + present sparse points)
   __nv_bfloat16 *sa, *sb;  // hi/lo split operands [Mi, 768] bf16 each
   size_t total;
 };
 
-Workspace carve(uint8_t* base, int NB, int T) {
+Workspace carve(uint8_t* base, int n_images, int NB, int T) {
   Workspace w;
   size_t off = 0;
   auto take = [&](size_t nfloat) {
@@ -100,7 +104,8 @@ Workspace carve(uint8_t* base, int NB, int T) {
     return p;
   };
   const size_t Mi = static_cast<size_t>(NB) * 4096, Mt = static_cast<size_t>(NB) * T;
-  w.emb_tok = take(4096 * 256);
+  w.emb_tok = take(static_cast<size_t>(n_images) * 4096 * 256);
+  w.ntok = reinterpret_cast<int*>(take(static_cast<size_t>(NB)));
   w.keys = take(Mi * 256);
   w.kbuf = take(Mi * 128);
   w.vbuf = take(Mi * 128);
@@ -152,9 +157,9 @@ const char* decoder_weight_name(int i) {
   return names()[i].c_str();
 }
 
-size_t decoder_workspace_bytes(int NB, int Np) {
-  if (NB <= 0 || Np < 0) return 0;
-  return carve(nullptr, NB, 5 + Np).total + 256;
+size_t decoder_workspace_bytes(int n_images, int NB, int Np) {
+  if (n_images <= 0 || NB <= 0 || Np < 0) return 0;
+  return carve(nullptr, n_images, NB, 5 + Np).total + 256;
 }
 
 int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_t stream) {
@@ -216,14 +221,17 @@ void decoder_destroy(Decoder* d) {
 const float* decoder_dense_pe(const Decoder* d) { return d->pe_tok; }
 
 int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
-  B200SAM_REQUIRE(a.NB > 0 && a.Np >= 0, "decode: bad prompt batch NB=%d Np=%d", a.NB, a.Np);
+  B200SAM_REQUIRE(a.NB > 0 && a.Np >= 0 && a.n_images > 0, "decode: bad prompt batch NB=%d Np=%d images=%d", a.NB, a.Np,
+                  a.n_images);
+  B200SAM_REQUIRE(a.n_images == 1 || a.image_of != nullptr, "decode: image_of is required for more than one image");
+  B200SAM_REQUIRE(a.NB <= 65535 && a.NB <= (1 << 30) / 16384, "decode: at most 65535 prompts per call, got %d", a.NB);
   const int NB = a.NB, T = 5 + a.Np;
   B200SAM_REQUIRE(T <= 32, "decode: at most 27 sparse prompt tokens per prompt supported, got %d", a.Np);
   B200SAM_REQUIRE(a.Np == 0 || (a.coords != nullptr && a.labels != nullptr), "decode: coords/labels missing");
   B200SAM_REQUIRE(a.emb != nullptr && a.low_res_out != nullptr && a.iou_out != nullptr, "decode: null in/out pointer");
   B200SAM_REQUIRE(a.workspace != nullptr && (reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0,
                   "decode: workspace must be non-null and 256-byte aligned");
-  Workspace w = carve(reinterpret_cast<uint8_t*>(a.workspace), NB, T);
+  Workspace w = carve(reinterpret_cast<uint8_t*>(a.workspace), a.n_images, NB, T);
   B200SAM_REQUIRE(w.total <= a.workspace_bytes, "decode: workspace too small (%zu < %zu)", a.workspace_bytes, w.total);
   const float* const* W = d->w.data();
   const int Mi = NB * 4096, Mt = NB * T;
@@ -231,10 +239,12 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
 
   // ---- prompt encoder (prompt_encoder.py:128-168) + output tokens (mask_decoder.py:120-122)
   TRY(prompt_tokens(a.coords, a.labels, NB, a.Np, W[W_GAUSS], W[W_POINT4], W[W_NOT_A_POINT], W[W_IOU_TOKEN],
-                    W[W_MASK_TOKENS], a.img_w, a.img_h, w.tokens, s));
-  TRY(nchw_to_tokens(a.emb, w.emb_tok, s));
-  if (a.mask_prev != nullptr) TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, s));
-  else TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, s));
+                    W[W_MASK_TOKENS], a.img_w, a.img_h, w.tokens, w.ntok, s));
+  TRY(nchw_to_tokens(a.emb, w.emb_tok, a.n_images, s));
+  if (a.mask_prev != nullptr)
+    TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, a.image_of, s));
+  else
+    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, s));
   B200SAM_CHECK_CUDA(cudaMemcpyAsync(w.queries, w.tokens, static_cast<size_t>(Mt) * 256 * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
 
@@ -246,7 +256,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(lin(w.queries, qpe, 0, SA[0], SA[1], nullptr, w.tq, Mt, 256, 256, 0, s));
     TRY(lin(w.queries, qpe, 0, SA[2], SA[3], nullptr, w.tk, Mt, 256, 256, 0, s));
     TRY(lin(w.queries, nullptr, 0, SA[4], SA[5], nullptr, w.tv, Mt, 256, 256, 0, s));
-    TRY(attn_few_queries(w.tq, w.tk, w.tv, w.ta, NB, T, T, 8, 32, nullptr, s));
+    TRY(attn_few_queries(w.tq, w.tk, w.tv, w.ta, NB, T, T, 8, 32, nullptr, w.ntok, s));
     TRY(lin(w.ta, nullptr, 0, SA[6], SA[7], l == 0 ? nullptr : w.queries, w.queries, Mt, 256, 256, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N1], L[L_N1 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
@@ -259,7 +269,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(tc_lin(w.sa, d->ws_t2i_k[l], TI[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sb, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sa, d->ws_i2t_q[l], L[L_I2T + 1], nullptr, w.qibuf, Mi, 128, 256, 0, s));
-    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, s));
+    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s));
     TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
@@ -270,7 +280,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     const float* const* IT = L + L_I2T;  // image tokens are the queries here
     TRY(lin(w.queries, w.tokens, 0, IT[2], IT[3], nullptr, w.tk, Mt, 128, 256, 0, s));
     TRY(lin(w.queries, nullptr, 0, IT[4], IT[5], nullptr, w.tv, Mt, 128, 256, 0, s));
-    TRY(attn_few_keys(w.qibuf, w.tk, w.tv, w.abuf, NB, 4096, T, s));
+    TRY(attn_few_keys(w.qibuf, w.tk, w.tv, w.abuf, NB, 4096, T, w.ntok, s));
     TRY(split3_bf16(w.abuf, nullptr, 0, w.sa, Mi, 128, 0, s));
     TRY(tc_lin(w.sa, d->ws_i2t_o[l], IT[7], w.keys, w.keys, Mi, 256, 128, 0, s));
     TRY(layernorm_rows(w.keys, L[L_N4], L[L_N4 + 1], 1e-5f, Mi, 256, w.keys, 0, s));
@@ -282,7 +292,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
     TRY(tc_lin(w.sa, d->ws_fin_k, F[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sb, d->ws_fin_v, F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
-    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, s));
+    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s));
     TRY(lin(w.ta, nullptr, 0, F[6], F[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, W[W_NF], W[W_NF + 1], 1e-5f, Mt, 256, w.queries, 0, s));
   }

@@ -22,11 +22,13 @@ struct Decoder {
 };
 
 struct DecodeArgs {
-  const float* emb;        // [256, 64, 64] fp32 image embedding (NCHW, one image)
-  int NB;                  // prompts in this batch
-  int Np;                  // sparse points per prompt (incl. pad / box corners), same for all prompts
+  const float* emb;        // [n_images, 256, 64, 64] fp32 image embeddings (NCHW)
+  int n_images;            // >= 1
+  const int* image_of;     // [NB] device: image index of every prompt; null = all prompts belong to image 0
+  int NB;                  // prompts in this batch (of all images)
+  int Np;                  // sparse point slots per prompt (incl. pad / box corners)
   const float* coords;     // [NB, Np, 2] (x, y) in the encoder input frame
-  const int* labels;       // [NB, Np]: -1 pad, 0 neg, 1 pos, 2/3 box corners
+  const int* labels;       // [NB, Np]: -1 pad, 0 neg, 1 pos, 2/3 box corners, -2 absent slot (trailing; ragged batches)
   const float* mask_prev;  // [NB, 256, 256] logits of a previous pass, or null
   float img_w, img_h;      // prompt_encoder.input_image_size (W, H) = (1024, 1024)
   int multimask;           // 0: mask token 0 only, 1: tokens 1..3
@@ -38,7 +40,7 @@ struct DecodeArgs {
 
 int decoder_weight_count();
 const char* decoder_weight_name(int i);
-size_t decoder_workspace_bytes(int NB, int Np);
+size_t decoder_workspace_bytes(int n_images, int NB, int Np);
 int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_t stream);
 void decoder_destroy(Decoder* d);
 const float* decoder_dense_pe(const Decoder* d);

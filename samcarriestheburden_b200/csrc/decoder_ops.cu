@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
 template <int DH>
 __global__ void __launch_bounds__(256) attn_fewq_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                         const float* __restrict__ v, float* __restrict__ out, int Tq,
-                                                        int Tk, int heads, int nsplit, float* __restrict__ part) {
+                                                        int Tk, int heads, int nsplit, float* __restrict__ part,
+                                                        const int* __restrict__ tk_valid) {
   constexpr int KT = 128;       // keys per tile
   constexpr int PAD = DH + 4;   // conflict-free float4 rows
   constexpr int QPW = 4;        // queries per warp per pass
@@ -162,8 +163,10 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(const float* __restrict_
     }
     // flash-decoding style key split: CTA z of nsplit owns keys [kbeg, kend); partial (m, l, acc) states are merged
     // by attn_fewq_combine_kernel (keeps > 148 CTAs in flight although there are only batch x heads problems)
+    // ragged prompt batches: keys >= tk_valid[b] are absent token slots (row pitch stays Tk)
+    const int tk_eff = tk_valid != nullptr ? min(Tk, tk_valid[b]) : Tk;
     const int per = (Tk + nsplit - 1) / nsplit;
-    const int kbeg = blockIdx.z * per, kend = min(Tk, kbeg + per);
+    const int kbeg = blockIdx.z * per, kend = min(tk_eff, kbeg + per);
     for (int k0 = kbeg; k0 < kend; k0 += KT) {
       const int nk = min(KT, kend - k0);
       __syncthreads();
@@ -264,15 +267,16 @@ __global__ void attn_fewq_combine_kernel(const float* __restrict__ part, float* 
 // tokens. One thread per (image token, head); K/V of the tokens sit in shared memory.
 __global__ void __launch_bounds__(256) attn_fewk_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                         const float* __restrict__ v, float* __restrict__ out, int Nq,
-                                                        int Tk) {
+                                                        int Tk_pitch, const int* __restrict__ tk_valid) {
   constexpr int DH = 16, HEADS = 8, C = 128, PAD = 20, MAXK = 32;
   __shared__ __align__(16) float ks[MAXK][HEADS][PAD];
   __shared__ __align__(16) float vs[MAXK][HEADS][PAD];
   const int b = blockIdx.y;
+  const int Tk = tk_valid != nullptr ? min(Tk_pitch, tk_valid[b]) : Tk_pitch;  // absent token slots are not keys
   for (int i = threadIdx.x; i < Tk * C; i += 256) {
     const int t = i / C, c = i - t * C;
-    ks[t][c / DH][c % DH] = k[(static_cast<size_t>(b) * Tk + t) * C + c];
-    vs[t][c / DH][c % DH] = v[(static_cast<size_t>(b) * Tk + t) * C + c];
+    ks[t][c / DH][c % DH] = k[(static_cast<size_t>(b) * Tk_pitch + t) * C + c];
+    vs[t][c / DH][c % DH] = v[(static_cast<size_t>(b) * Tk_pitch + t) * C + c];
   }
   __syncthreads();
   const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -347,19 +351,30 @@ __global__ void dense_pe_kernel(const float* __restrict__ G, float* __restrict__
 }
 
 // tokens[b, 0] = iou_token, tokens[b, 1..4] = mask_tokens, tokens[b, 5 + i] = embedding of point i
-// labels: -1 not-a-point (PE zeroed), 0/1 neg/pos point, 2/3 box corners (prompt_encoder.py:73-100)
+// labels: -1 not-a-point (PE zeroed), 0/1 neg/pos point, 2/3 box corners (prompt_encoder.py:73-100);
+// -2 = absent slot of a ragged batch (trailing; the token row is zeroed and never used as a key): ntok[b] = 5 + #present
 __global__ void prompt_tokens_kernel(const float* __restrict__ coords, const int* __restrict__ labels, int Np,
                                      const float* __restrict__ G, const float* __restrict__ point_emb /*[4,256]*/,
                                      const float* __restrict__ not_a_point, const float* __restrict__ iou_token,
                                      const float* __restrict__ mask_tokens, float img_w, float img_h,
-                                     float* __restrict__ tokens) {
+                                     float* __restrict__ tokens, int* __restrict__ ntok) {
   const int b = blockIdx.y, t = blockIdx.x, j = threadIdx.x;  // 128 threads, T = 5 + Np
   const int T = 5 + Np;
   float* dst = tokens + (static_cast<size_t>(b) * T + t) * 256;
-  if (t == 0) { dst[j] = iou_token[j]; dst[128 + j] = iou_token[128 + j]; return; }
+  if (t == 0) {
+    dst[j] = iou_token[j];
+    dst[128 + j] = iou_token[128 + j];
+    if (j == 0) {
+      int n = 5;
+      for (int i = 0; i < Np; ++i) n += labels[b * Np + i] != -2;
+      ntok[b] = n;
+    }
+    return;
+  }
   if (t < 5) { dst[j] = mask_tokens[(t - 1) * 256 + j]; dst[128 + j] = mask_tokens[(t - 1) * 256 + 128 + j]; return; }
   const int i = t - 5;
   const int lab = labels[b * Np + i];
+  if (lab == -2) { dst[j] = 0.0f; dst[128 + j] = 0.0f; return; }
   if (lab < 0) { dst[j] = not_a_point[j]; dst[128 + j] = not_a_point[128 + j]; return; }
   const float px = coords[(static_cast<size_t>(b) * Np + i) * 2 + 0] + 0.5f;
   const float py = coords[(static_cast<size_t>(b) * Np + i) * 2 + 1] + 0.5f;
@@ -373,6 +388,8 @@ __global__ void prompt_tokens_kernel(const float* __restrict__ coords, const int
 // NCHW [C=256, 4096] -> token-major [4096, 256] (32x32 smem transpose)
 __global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __restrict__ out) {
   __shared__ float tile[32][33];
+  in += static_cast<size_t>(blockIdx.z) * 256 * 4096;  // one image per grid z
+  out += static_cast<size_t>(blockIdx.z) * 256 * 4096;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
   for (int i = ty; i < 32; i += 8) tile[i][tx] = in[static_cast<size_t>(c0 + i) * 4096 + t0 + tx];
@@ -381,15 +398,18 @@ __global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __res
 }
 
 // keys[b, tok, c] = emb_tok[tok, c] + no_mask_embed[c]  (prompt_encoder.py:164-166 + mask_decoder.py:126)
+// grid (x, NB): prompt b reads the token-major embedding of its image (image_of[b], or image 0)
 __global__ void keys_init_kernel(const float4* __restrict__ emb_tok, const float4* __restrict__ no_mask,
-                                 float4* __restrict__ keys, int NB) {
+                                 float4* __restrict__ keys, const int* __restrict__ image_of) {
   const size_t n4 = 4096 * 64;
+  const int b = blockIdx.y;
+  const float4* e4 = emb_tok + (image_of != nullptr ? image_of[b] : 0) * n4;
+  float4* k4 = keys + static_cast<size_t>(b) * n4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float4 e = emb_tok[i];
+    const float4 e = e4[i];
     const float4 d = no_mask[i & 63];
-    const float4 v = make_float4(e.x + d.x, e.y + d.y, e.z + d.z, e.w + d.w);
-    for (int b = 0; b < NB; ++b) keys[static_cast<size_t>(b) * n4 + i] = v;
+    k4[i] = make_float4(e.x + d.x, e.y + d.y, e.z + d.z, e.w + d.w);
   }
 }
 
@@ -400,9 +420,11 @@ struct MaskDownW {
 };
 __global__ void __launch_bounds__(256) mask_downscale_keys_kernel(const float* __restrict__ mask /*[NB,256,256]*/,
                                                                   MaskDownW w, const float* __restrict__ emb_tok,
-                                                                  float* __restrict__ keys) {
+                                                                  float* __restrict__ keys,
+                                                                  const int* __restrict__ image_of) {
   __shared__ float hid[32][17];
   const int b = blockIdx.y;
+  emb_tok += static_cast<size_t>(image_of != nullptr ? image_of[b] : 0) * 4096 * 256;
   const int tok0 = blockIdx.x * 32;
   const int tid = threadIdx.x;
   if (tid < 32) {
@@ -640,12 +662,12 @@ int linear_f32(const LinearArgs& p, cudaStream_t stream) {
 }
 
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
-                     int dh, float* part, cudaStream_t stream) {
+                     int dh, float* part, const int* tk_valid, cudaStream_t stream) {
   B200SAM_REQUIRE(NB > 0 && Tq > 0 && Tk > 0, "attn_few_queries: empty problem");
   const int nsplit = (part != nullptr && Tk >= 1024) ? ATTN_FEWQ_SPLITS : 1;
   dim3 grid(heads, NB, nsplit);
-  if (dh == 16) attn_fewq_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part);
-  else if (dh == 32) attn_fewq_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part);
+  if (dh == 16) attn_fewq_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part, tk_valid);
+  else if (dh == 32) attn_fewq_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part, tk_valid);
   else { set_last_error("attn_few_queries: unsupported head dim %d", dh); return 2; }
   if (nsplit > 1) {
     dim3 g2(heads, NB);
@@ -657,10 +679,10 @@ int attn_few_queries(const float* q, const float* k, const float* v, float* out,
 }
 
 int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
-                  cudaStream_t stream) {
+                  const int* tk_valid, cudaStream_t stream) {
   B200SAM_REQUIRE(Tk > 0 && Tk <= 32, "attn_few_keys: at most 32 prompt tokens supported, got %d", Tk);
   dim3 grid((Nq * 8 + 255) / 256, NB);
-  attn_fewk_kernel<<<grid, 256, 0, stream>>>(q, k, v, out, Nq, Tk);
+  attn_fewk_kernel<<<grid, 256, 0, stream>>>(q, k, v, out, Nq, Tk, tk_valid);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -673,32 +695,33 @@ int dense_pe_tokens(const float* G, float* pe, cudaStream_t stream) {
 
 int prompt_tokens(const float* coords, const int* labels, int NB, int Np, const float* G, const float* point_emb,
                   const float* not_a_point, const float* iou_token, const float* mask_tokens, float img_w, float img_h,
-                  float* tokens, cudaStream_t stream) {
+                  float* tokens, int* ntok, cudaStream_t stream) {
   dim3 grid(5 + Np, NB);
   prompt_tokens_kernel<<<grid, 128, 0, stream>>>(coords, labels, Np, G, point_emb, not_a_point, iou_token, mask_tokens,
-                                                 img_w, img_h, tokens);
+                                                 img_w, img_h, tokens, ntok);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int nchw_to_tokens(const float* in, float* out, cudaStream_t stream) {
-  nchw_to_tokens_kernel<<<dim3(128, 8), dim3(32, 8), 0, stream>>>(in, out);
+int nchw_to_tokens(const float* in, float* out, int n_images, cudaStream_t stream) {
+  nchw_to_tokens_kernel<<<dim3(128, 8, n_images), dim3(32, 8), 0, stream>>>(in, out);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, cudaStream_t stream) {
-  keys_init_kernel<<<296, 256, 0, stream>>>(reinterpret_cast<const float4*>(emb_tok),
-                                            reinterpret_cast<const float4*>(no_mask),
-                                            reinterpret_cast<float4*>(keys), NB);
+int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of,
+              cudaStream_t stream) {
+  keys_init_kernel<<<dim3(64, NB), 256, 0, stream>>>(reinterpret_cast<const float4*>(emb_tok),
+                                                     reinterpret_cast<const float4*>(no_mask),
+                                                     reinterpret_cast<float4*>(keys), image_of);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int mask_downscale_keys(const float* mask, const float* const* w10, const float* emb_tok, float* keys, int NB,
-                        cudaStream_t stream) {
+                        const int* image_of, cudaStream_t stream) {
   MaskDownW w{w10[0], w10[1], w10[2], w10[3], w10[4], w10[5], w10[6], w10[7], w10[8], w10[9]};
-  mask_downscale_keys_kernel<<<dim3(128, NB), 256, 0, stream>>>(mask, w, emb_tok, keys);
+  mask_downscale_keys_kernel<<<dim3(128, NB), 256, 0, stream>>>(mask, w, emb_tok, keys, image_of);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

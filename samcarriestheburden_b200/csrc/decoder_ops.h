@@ -24,19 +24,23 @@ int linear_f32(const LinearArgs& p, cudaStream_t stream);
 // q [NB,Tq,heads*dh], k/v [NB,Tk,heads*dh] -> out [NB,Tq,heads*dh]; dh in {16, 32}
 // part: optional scratch of NB*heads*ATTN_FEWQ_SPLITS*Tq*(dh+2) floats enabling the key-split path for long Tk
 constexpr int ATTN_FEWQ_SPLITS = 8;
+// tk_valid: optional per-batch count of valid keys (<= Tk; Tk stays the row pitch) for ragged prompt batches
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
-                     int dh, float* part, cudaStream_t stream);
+                     int dh, float* part, const int* tk_valid, cudaStream_t stream);
 // q [NB,Nq,128], k/v [NB,Tk<=32,128] (8 heads x 16) -> out [NB,Nq,128]
 int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
-                  cudaStream_t stream);
+                  const int* tk_valid, cudaStream_t stream);
 int dense_pe_tokens(const float* G, float* pe, cudaStream_t stream);
 int prompt_tokens(const float* coords, const int* labels, int NB, int Np, const float* G, const float* point_emb,
                   const float* not_a_point, const float* iou_token, const float* mask_tokens, float img_w, float img_h,
-                  float* tokens, cudaStream_t stream);
-int nchw_to_tokens(const float* in, float* out, cudaStream_t stream);
-int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, cudaStream_t stream);
+                  float* tokens, int* ntok, cudaStream_t stream);
+// in [n_images, 256, 4096] NCHW -> out [n_images, 4096, 256] token-major
+int nchw_to_tokens(const float* in, float* out, int n_images, cudaStream_t stream);
+// image_of: optional [NB] index of the image (row block of emb_tok) each prompt belongs to; null = image 0
+int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of,
+              cudaStream_t stream);
 int mask_downscale_keys(const float* mask, const float* const* w10, const float* emb_tok, float* keys, int NB,
-                        cudaStream_t stream);
+                        const int* image_of, cudaStream_t stream);
 int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, cudaStream_t stream);
 int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const float* const* b15, float* hyper,
                 float* iou, cudaStream_t stream);

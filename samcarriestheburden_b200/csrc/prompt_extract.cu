@@ -112,10 +112,8 @@ __global__ void __launch_bounds__(256) prompt_accum_kernel(const uint8_t* __rest
 }
 
 // Fast path (W % 16 == 0, 16-byte aligned planes): one thread = 16 consecutive pixels of one image row.
-// Pass 1 streams the C class planes with 16-byte loads (C independent requests in flight per thread) and keeps
-// per-pixel cover counts as packed byte counters; pass 2 revisits only the classes that have a set pixel in this
-// 16-pixel group (a few percent of the groups; the lines are L1/L2 hits) and turns the bytes into 16-bit masks so
-// count / min / max / sum come from popc / ffs / clz instead of per-pixel branches.
+// Pass 1 streams the C class planes with 16-byte loads and keeps per-pixel cover counts as packed byte counters;
+// pass 2 revisits only the classes that have a set pixel in this 16-pixel group (a few percent of the groups).
 B200SAM_DEVINL uint32_t bytes_to_mask4(uint32_t w) {  // 4 bytes (0 or !=0) -> 4-bit mask
   w = (w | (w >> 4)) & 0x0f0f0f0fu;   // fold high nibble
   w = (w | (w >> 2)) & 0x03030303u;
@@ -131,73 +129,101 @@ B200SAM_DEVINL uint32_t norm01(uint32_t w) {  // every non-zero byte -> 1
   return (w | (w >> 1)) & 0x01010101u;
 }
 
-__global__ void __launch_bounds__(256) prompt_accum16_kernel(const uint8_t* __restrict__ masks, int C, int H, int W,
-                                                             int32_t* __restrict__ scratch) {
+// Work item = (image, chunk of 256 groups = 4096 pixels x C classes); a fixed grid of CTAs walks the items of the
+// whole batch with a grid stride (balanced: every CTA gets the same number of items), accumulating one item in shared
+// memory and flushing it to the image's global slots with a handful of atomics.
+__global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* __restrict__ masks, int C, int H, int W,
+                                                             int32_t* __restrict__ scratch, int n_items,
+                                                             int chunks_per_img) {
   __shared__ unsigned long long s_sum[MAX_C][2];
   __shared__ int s_cnt[MAX_C][2];
   __shared__ int s_mm[MAX_C][4];
-  const int img = blockIdx.y;
   const int HW = H * W;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    s_sum[c][0] = s_sum[c][1] = 0ull;
-    s_cnt[c][0] = s_cnt[c][1] = 0;
-    s_mm[c][0] = INT_MAX; s_mm[c][1] = -1; s_mm[c][2] = INT_MAX; s_mm[c][3] = -1;
-  }
-  __syncthreads();
-  const uint8_t* base = masks + static_cast<size_t>(img) * C * HW;
   const int groups = HW / 16;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
-    const int p0 = g * 16;
-    const int r = p0 / W, c0 = p0 - r * W;
-    uint4 cov = make_uint4(0, 0, 0, 0);
-    unsigned long long any = 0ull;
-    for (int c = 0; c < C; ++c) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW + p0));
-      cov.x += norm01(v.x); cov.y += norm01(v.y); cov.z += norm01(v.z); cov.w += norm01(v.w);
-      if ((v.x | v.y | v.z | v.w) != 0u) any |= 1ull << c;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int img = item / chunks_per_img, chunk = item - img * chunks_per_img;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      s_sum[c][0] = s_sum[c][1] = 0ull;
+      s_cnt[c][0] = s_cnt[c][1] = 0;
+      s_mm[c][0] = INT_MAX; s_mm[c][1] = -1; s_mm[c][2] = INT_MAX; s_mm[c][3] = -1;
     }
-    if (any == 0ull) continue;
-    // pixels covered by fewer than two classes: byte counter < 2  <=>  (counter & 0xfe) == 0
-    uint4 single;
-    // per-byte test without cross-byte carries: byte < 2  <=>  (byte >> 1) == 0
-    auto lt2 = [](uint32_t w) {
-      const uint32_t hi = (w >> 1) & 0x7f7f7f7fu;                 // byte >> 1
-      const uint32_t nz = ((hi + 0x7f7f7f7fu) | hi) & 0x80808080u;  // 0x80 where byte>>1 != 0
-      return (~nz & 0x80808080u) >> 7;                            // 1 where byte < 2
-    };
-    single.x = lt2(cov.x); single.y = lt2(cov.y); single.z = lt2(cov.z); single.w = lt2(cov.w);
-    const uint32_t smask = bytes_to_mask16(single);
-    while (any) {
-      const int c = __ffsll(static_cast<long long>(any)) - 1;
-      any &= any - 1;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW + p0));
-      const uint32_t m = bytes_to_mask16(v);
-      const uint32_t sd = m & smask;
-      atomicAdd(&s_cnt[c][1], __popc(m));
-      atomicMin(&s_mm[c][0], r); atomicMax(&s_mm[c][1], r);
-      atomicMin(&s_mm[c][2], c0 + __ffs(m) - 1); atomicMax(&s_mm[c][3], c0 + 31 - __clz(m));
-      if (sd) {
-        const int ns = __popc(sd);
-        int pos = 0;
-        for (uint32_t t = sd; t; t &= t - 1) pos += __ffs(t) - 1;
-        atomicAdd(&s_cnt[c][0], ns);
-        atomicAdd(&s_sum[c][0], static_cast<unsigned long long>(ns) * r);
-        atomicAdd(&s_sum[c][1], static_cast<unsigned long long>(ns) * c0 + pos);
+    __syncthreads();
+    const int g = chunk * 256 + threadIdx.x;
+    if (g < groups) {
+      const int p0 = g * 16;
+      const int r = p0 / W, c0 = p0 - r * W;
+      const uint8_t* base = masks + static_cast<size_t>(img) * C * HW + p0;
+      // pass 1: 8 independent 16-byte loads in flight per thread; bool bytes are 0/1, so the per-pixel cover count is
+      // a plain packed byte add (anything else is detected through `odd` and recounted below)
+      uint4 cov = make_uint4(0, 0, 0, 0), odd = make_uint4(0, 0, 0, 0);
+      unsigned long long any = 0ull;
+      for (int cb = 0; cb < C; cb += 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = cb + j < C ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(cb + j) * HW))
+                            : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          cov.x += v[j].x; cov.y += v[j].y; cov.z += v[j].z; cov.w += v[j].w;
+          odd.x |= v[j].x; odd.y |= v[j].y; odd.z |= v[j].z; odd.w |= v[j].w;
+          if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) any |= 1ull << (cb + j);
+        }
+      }
+      if (any != 0ull) {
+        if (((odd.x | odd.y | odd.z | odd.w) & 0xfefefefeu) != 0u) {  // bytes other than 0/1: recount normalised
+          cov = make_uint4(0, 0, 0, 0);
+          for (unsigned long long t = any; t; t &= t - 1) {
+            const int c = __ffsll(static_cast<long long>(t)) - 1;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW));
+            cov.x += norm01(v.x); cov.y += norm01(v.y); cov.z += norm01(v.z); cov.w += norm01(v.w);
+          }
+        }
+        // pixels covered by fewer than two classes; per-byte test without cross-byte carries: byte < 2 <=> byte >> 1 == 0
+        auto lt2 = [](uint32_t w) {
+          const uint32_t hi = (w >> 1) & 0x7f7f7f7fu;                   // byte >> 1
+          const uint32_t nz = ((hi + 0x7f7f7f7fu) | hi) & 0x80808080u;  // 0x80 where byte >> 1 != 0
+          return (~nz & 0x80808080u) >> 7;                              // 1 where byte < 2
+        };
+        uint4 single;
+        single.x = lt2(cov.x); single.y = lt2(cov.y); single.z = lt2(cov.z); single.w = lt2(cov.w);
+        const uint32_t smask = bytes_to_mask16(single);
+        // pass 2 revisits only the classes with a set pixel in this group (L1 hits): bytes -> 16-bit masks so count /
+        // min / max / sum come from popc / ffs / clz instead of per-pixel branches
+        while (any) {
+          const int c = __ffsll(static_cast<long long>(any)) - 1;
+          any &= any - 1;
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW));
+          const uint32_t m = bytes_to_mask16(v);
+          const uint32_t sd = m & smask;
+          atomicAdd(&s_cnt[c][1], __popc(m));
+          atomicMin(&s_mm[c][0], r); atomicMax(&s_mm[c][1], r);
+          atomicMin(&s_mm[c][2], c0 + __ffs(m) - 1); atomicMax(&s_mm[c][3], c0 + 31 - __clz(m));
+          if (sd) {
+            const int ns = __popc(sd);
+            int pos = 0;
+            for (uint32_t t = sd; t; t &= t - 1) pos += __ffs(t) - 1;
+            atomicAdd(&s_cnt[c][0], ns);
+            atomicAdd(&s_sum[c][0], static_cast<unsigned long long>(ns) * r);
+            atomicAdd(&s_sum[c][1], static_cast<unsigned long long>(ns) * c0 + pos);
+          }
+        }
       }
     }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (s_cnt[c][1] == 0) continue;
-    int32_t* s = scratch + (static_cast<size_t>(img) * C + c) * SLOT;
-    atomicAdd(&s[5], s_cnt[c][1]);
-    atomicMin(&s[6], s_mm[c][0]); atomicMax(&s[7], s_mm[c][1]);
-    atomicMin(&s[8], s_mm[c][2]); atomicMax(&s[9], s_mm[c][3]);
-    if (s_cnt[c][0]) {
-      atomicAdd(&s[4], s_cnt[c][0]);
-      atomicAdd(reinterpret_cast<unsigned long long*>(s), s_sum[c][0]);
-      atomicAdd(reinterpret_cast<unsigned long long*>(s + 2), s_sum[c][1]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (s_cnt[c][1] == 0) continue;
+      int32_t* s = scratch + (static_cast<size_t>(img) * C + c) * SLOT;
+      atomicAdd(&s[5], s_cnt[c][1]);
+      atomicMin(&s[6], s_mm[c][0]); atomicMax(&s[7], s_mm[c][1]);
+      atomicMin(&s[8], s_mm[c][2]); atomicMax(&s[9], s_mm[c][3]);
+      if (s_cnt[c][0]) {
+        atomicAdd(&s[4], s_cnt[c][0]);
+        atomicAdd(reinterpret_cast<unsigned long long*>(s), s_sum[c][0]);
+        atomicAdd(reinterpret_cast<unsigned long long*>(s + 2), s_sum[c][1]);
+      }
     }
+    __syncthreads();  // the accumulators are re-initialised at the top of the next item
   }
 }
 
@@ -245,12 +271,13 @@ int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t
   if (HW > 0) {
     const bool fast = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && (HW % 16 == 0);
     if (fast) {
-      // ~2 waves of CTAs over the whole batch; every CTA walks groups of its image with a grid stride
-      int bx = (HW / 16 + 255) / 256;
-      const int want = (8 * 148 + n_img - 1) / n_img;
-      if (bx > want) bx = want > 0 ? want : 1;
-      dim3 grid(bx, n_img);
-      prompt_accum16_kernel<<<grid, 256, 0, stream>>>(masks, C, H, W, scratch);
+      const int chunks = (HW / 16 + 255) / 256;
+      const long long items = static_cast<long long>(n_img) * chunks;
+      B200SAM_REQUIRE(items < (1ll << 31), "prompt_extract: batch too large");
+      const int max_ctas = 148 * 4;  // all CTAs resident (4 x 256 threads per SM): a persistent, balanced grid
+      const int iters = static_cast<int>((items + max_ctas - 1) / max_ctas);
+      const int ctas = static_cast<int>((items + iters - 1) / iters);  // every CTA walks `iters` (or iters - 1) items
+      prompt_accum16_kernel<<<ctas, 256, 0, stream>>>(masks, C, H, W, scratch, static_cast<int>(items), chunks);
     } else {
       dim3 grid((HW + 1023) / 1024, n_img);
       prompt_accum_kernel<<<grid, 256, 0, stream>>>(masks, C, H, W, scratch);

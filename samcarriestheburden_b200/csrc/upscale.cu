@@ -96,6 +96,257 @@ __global__ void __launch_bounds__(256) nearest_exact_kernel(UpParams p, uint8_t*
   small_out[(static_cast<size_t>(n) * sh + y) * sw + x] = final_value(p, plane, sy, sx) > p.thr;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast mask path (the HBM-bound one: 1 byte out per native pixel).  Both bilinear stages are linear and
+// separable, and with L <= S (stage 1 upsamples) the two stage-1 columns a stage-2 pixel touches are adjacent,
+// so per axis every output coordinate reads at most THREE consecutive low-res samples:
+//     out(oy, ox) = sum_{j<3} c_j(oy) * ( sum_{k<3} d_k(ox) * low[m(oy) + j][l(ox) + k] )
+// with m, l, c, d depending on one coordinate only.  A thread owns 8 adjacent output columns (l, d in
+// registers) and walks down a chunk of rows keeping a 3-row window G_j = sum_k d_k low[m + j][l + k] in
+// registers; a new low-res row (staged in shared memory once per block) is consumed only when m advances (every
+// ~4 output rows at 1024^2), so a pixel costs 2-3 FMAs, a compare and 1/8 of a 64-bit store instead of 16 gathers
+// and 4 source-index computations.  The 'nearest-exact' tap (seg_refinement.py:111) is written by the same
+// threads from the mask bytes they hold in registers.  The products c_j d_k round differently from the nested
+// form by ~1 ulp of the result (the reference's own F.interpolate differs from either by up to 2e-6).
+constexpr int UP_PX = 8;         // output pixels per thread
+constexpr int UP_THREADS = 128;
+constexpr int UP_MAXROWS = 128;  // output rows per block (upper bound; the launch picks rows_per_block)
+constexpr int UP_LOWROWS = 40;   // low-res rows staged per block
+constexpr int UP_MAXS = 3;       // nearest-exact taps per thread and row
+
+// three-tap form of one axis: base index (<= L-3) and the coefficients of low[base .. base+2]
+B200SAM_DEVINL void taps3(float scale2, int in2, float s1, int L, int o, int& base, float& c0, float& c1, float& c2) {
+  int i0, i1, a0, a1, b0, b1;
+  float w0, w1, u0, u1, v0, v1;
+  src_index(scale2, o, in2, i0, i1, w0, w1);
+  src_index(s1, i0, L, a0, a1, u0, u1);
+  src_index(s1, i1, L, b0, b1, v0, v1);
+  base = min(a0, L - 3);
+  c0 = c1 = c2 = 0.0f;
+  auto put = [&](int idx, float w) {
+    const int sl = idx - base;
+    c0 += sl == 0 ? w : 0.0f;
+    c1 += sl == 1 ? w : 0.0f;
+    c2 += sl == 2 ? w : 0.0f;
+  };
+  put(a0, w0 * u0);
+  put(a1, w0 * u1);
+  put(b0, w1 * v0);
+  put(b1, w1 * v1);
+}
+
+B200SAM_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// 4 results -> 4 mask bytes (0/1).  ZERO_THR: v > 0 <=> the int32 pattern of v is in [1, 0x7fffffff]; v is produced
+// by an FMA chain that starts from +0.0, which can never yield -0.0, so `bits - 1` has its sign bit set exactly for
+// v <= 0 and PRMT's sign-replicate mode turns the four sign bits into four bytes.
+template <bool ZERO_THR>
+B200SAM_DEVINL uint32_t pack4(float a, float b, float c, float d, float thr) {
+  if (ZERO_THR) {
+    const uint32_t ia = __float_as_uint(a) - 1u, ib = __float_as_uint(b) - 1u;
+    const uint32_t ic = __float_as_uint(c) - 1u, id = __float_as_uint(d) - 1u;
+    const uint32_t t01 = prmt(ia, ib, 0x00fbu);  // byte0 = sign(a) x 8, byte1 = sign(b) x 8
+    const uint32_t t23 = prmt(ic, id, 0x00fbu);
+    return ~prmt(t01, t23, 0x5410u) & 0x01010101u;
+  }
+  const uint32_t ma = a > thr ? 1u : 0u, mb = b > thr ? 1u : 0u, mc = c > thr ? 1u : 0u, md = d > thr ? 1u : 0u;
+  return ma | (mb << 8) | (mc << 16) | (md << 24);
+}
+
+struct SmallOut {
+  uint8_t* out;  // [n, sh, sw] or null
+  int sh, sw;
+  float ny, nx;  // out_h / sh, out_w / sw
+};
+
+B200SAM_DEVINL int nearest_src(int dst, float scale, int in_size) {
+  return min(static_cast<int>(floorf((static_cast<float>(dst) + 0.5f) * scale)), in_size - 1);
+}
+
+// 8 mask bytes to an address that is only known to be congruent to `al` mod 8 (warp-uniform): the fewest naturally
+// aligned stores that cover them (1 for al = 0, 2 for al = 4, 3 for al = 2 / 6, 8 single bytes for odd al)
+B200SAM_DEVINL void store8(uint8_t* ptr, uint2 w, int al) {
+  if (al == 0) {
+    *reinterpret_cast<uint2*>(ptr) = w;
+  } else if (al == 4) {
+    reinterpret_cast<uint32_t*>(ptr)[0] = w.x;
+    reinterpret_cast<uint32_t*>(ptr)[1] = w.y;
+  } else if ((al & 1) == 0) {  // 2 or 6: u16 | u32 | u16
+    *reinterpret_cast<uint16_t*>(ptr) = static_cast<uint16_t>(w.x);
+    *reinterpret_cast<uint32_t*>(ptr + 2) = __funnelshift_r(w.x, w.y, 16);
+    *reinterpret_cast<uint16_t*>(ptr + 6) = static_cast<uint16_t>(w.y >> 16);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ptr[k] = static_cast<uint8_t>(prmt(w.x, w.y, k));
+  }
+}
+
+// ALIGNED: out_w % 8 == 0 and an 8-byte aligned output -> one 64-bit store per thread and row.  Otherwise the row's
+// (warp-uniform) misalignment picks the store pattern; only the last, partial thread of a row writes single bytes.
+template <bool ALIGNED, bool ZERO_THR>
+__global__ void __launch_bounds__(UP_THREADS) upscale_mask_fast_kernel(UpParams p, uint8_t* __restrict__ mask_out,
+                                                                       int rows_per_block, SmallOut sm) {
+  __shared__ float4 rowtab[UP_MAXROWS];  // c0, c1, c2, bits(m | (small_row + 1) << 12)
+  extern __shared__ __align__(16) uint8_t dyn[];
+  float* lowst = reinterpret_cast<float*>(dyn);  // [UP_LOWROWS][L] staged low-res rows
+  const int n = blockIdx.z;
+  const float* plane = p.low + static_cast<size_t>(n) * p.L * p.L;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int nrows = min(rows_per_block, p.out_h - r0);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nrows; i += UP_THREADS) {
+    int m;
+    float c0, c1, c2;
+    const int oy = r0 + i;
+    taps3(p.sy2, p.in_h, p.s1, p.L, oy, m, c0, c1, c2);
+    int srow = -1;
+    if (sm.out != nullptr) {  // the (at most one, ny >= 1) nearest-exact row that samples native row oy
+      const int y0 = max(0, static_cast<int>(static_cast<float>(oy) / sm.ny) - 1);
+      for (int y = y0; y < min(sm.sh, y0 + 4); ++y)
+        if (nearest_src(y, sm.ny, p.out_h) == oy) srow = y;
+    }
+    rowtab[i] = make_float4(c0, c1, c2, __int_as_float(m | ((srow + 1) << 12)));
+  }
+  const int ox0 = (blockIdx.x * UP_THREADS + tid) * UP_PX;
+  const bool mine = ox0 < p.out_w;  // this thread owns at least one output column
+  int lb[UP_PX];
+  float d0[UP_PX], d1[UP_PX], d2[UP_PX];
+#pragma unroll
+  for (int k = 0; k < UP_PX; ++k) taps3(p.sx2, p.in_w, p.s1, p.L, min(ox0 + k, p.out_w - 1), lb[k], d0[k], d1[k], d2[k]);
+  // nearest-exact columns that sample one of this thread's 8 native columns: x = sx0 + j, byte off[j] of the row word
+  int sx0 = 0;
+  uint32_t soff[UP_MAXS];
+#pragma unroll
+  for (int j = 0; j < UP_MAXS; ++j) soff[j] = 0xffu;
+  if (sm.out != nullptr && mine) {
+    sx0 = max(0, static_cast<int>(static_cast<float>(ox0) / sm.nx) - 1);
+    while (sx0 < sm.sw && nearest_src(sx0, sm.nx, p.out_w) < ox0) ++sx0;
+#pragma unroll
+    for (int j = 0; j < UP_MAXS; ++j) {
+      if (sx0 + j < sm.sw) {
+        const int o = nearest_src(sx0 + j, sm.nx, p.out_w) - ox0;
+        if (o < UP_PX) soff[j] = static_cast<uint32_t>(o);
+      }
+    }
+  }
+  uint8_t* const srp = sm.out != nullptr ? sm.out + static_cast<size_t>(n) * sm.sh * sm.sw + sx0 : nullptr;
+  __syncthreads();
+  // stage the low-res rows this block touches: m(first row) .. m(last row) + 2
+  const int mlo = __float_as_int(rowtab[0].w) & 0xfff;
+  const int mhi = min((__float_as_int(rowtab[nrows - 1].w) & 0xfff) + 2, mlo + UP_LOWROWS - 1);
+  {
+    const float* src = plane + static_cast<size_t>(mlo) * p.L;
+    const int cnt = (mhi - mlo + 1) * p.L;
+    if ((p.L & 3) == 0) {
+      for (int i = tid; i < cnt / 4; i += UP_THREADS)
+        reinterpret_cast<float4*>(lowst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    } else {
+      for (int i = tid; i < cnt; i += UP_THREADS) lowst[i] = __ldg(src + i);
+    }
+  }
+  __syncthreads();
+  if (!mine) return;
+  float g0[UP_PX], g1[UP_PX], g2[UP_PX];
+  auto load_row = [&](int r, float (&g)[UP_PX]) {
+    if (r <= mhi) {  // block-uniform
+      const float* rp = lowst + (r - mlo) * p.L;
+#pragma unroll
+      for (int k = 0; k < UP_PX; ++k) {
+        const float* q = rp + lb[k];
+        g[k] = __fmaf_rn(d2[k], q[2], __fmaf_rn(d1[k], q[1], d0[k] * q[0]));
+      }
+    } else {  // beyond the staged window (only for extreme down-scaling): straight from global / L1
+      const float* rp = plane + static_cast<size_t>(r) * p.L;
+#pragma unroll
+      for (int k = 0; k < UP_PX; ++k) {
+        const float* q = rp + lb[k];
+        g[k] = __fmaf_rn(d2[k], __ldg(q + 2), __fmaf_rn(d1[k], __ldg(q + 1), d0[k] * __ldg(q)));
+      }
+    }
+  };
+  uint8_t* optr = mask_out + (static_cast<size_t>(n) * p.out_h + r0) * p.out_w + ox0;  // this thread's bytes of row i
+  const int valid = min(UP_PX, p.out_w - ox0);
+  // one output row from the window (A, B, C) = G rows (m, m+1, m+2)
+  auto emit = [&](const float4& rt, int packed, const float (&A)[UP_PX], const float (&B)[UP_PX],
+                  const float (&C)[UP_PX]) {
+    float v[UP_PX];
+    if (rt.z == 0.0f) {  // block-uniform: only two low-res rows contribute (always so for an identity stage 2)
+#pragma unroll
+      for (int k = 0; k < UP_PX; ++k) v[k] = __fmaf_rn(rt.y, B[k], __fmaf_rn(rt.x, A[k], 0.0f));
+    } else {
+#pragma unroll
+      for (int k = 0; k < UP_PX; ++k) v[k] = __fmaf_rn(rt.z, C[k], __fmaf_rn(rt.y, B[k], __fmaf_rn(rt.x, A[k], 0.0f)));
+    }
+    uint2 w;
+    w.x = pack4<ZERO_THR>(v[0], v[1], v[2], v[3], p.thr);
+    w.y = pack4<ZERO_THR>(v[4], v[5], v[6], v[7], p.thr);
+    if (ALIGNED) {
+      *reinterpret_cast<uint2*>(optr) = w;
+    } else if (valid == UP_PX) {
+      store8(optr, w, static_cast<int>(reinterpret_cast<uintptr_t>(optr) & 7));
+    } else {
+      for (int k = 0; k < valid; ++k) optr[k] = static_cast<uint8_t>(prmt(w.x, w.y, k));
+    }
+    optr += p.out_w;
+    const int srow = (packed >> 12) - 1;
+    if (srow >= 0) {  // block-uniform: this native row is sampled by the nearest-exact grid
+      uint8_t* q = srp + srow * sm.sw;
+#pragma unroll
+      for (int j = 0; j < UP_MAXS; ++j)
+        if (soff[j] != 0xffu) q[j] = static_cast<uint8_t>(prmt(w.x, w.y, soff[j]));
+    }
+  };
+  // Row loop as a three-state machine: the roles of (g0, g1, g2) rotate when m advances by one, so the window
+  // shifts without moving registers.  All branches are block-uniform.
+  int i = 0, state = 3, mcur = 0;
+  float4 rt = rowtab[0];
+  int packed = __float_as_int(rt.w);
+  while (i < nrows) {
+    const int m = packed & 0xfff;
+    if (state == 3 || (m != mcur && m != mcur + 1)) {
+      load_row(m, g0);
+      load_row(m + 1, g1);
+      load_row(m + 2, g2);
+      state = 0;
+    } else if (m == mcur + 1) {
+      if (state == 0) load_row(m + 2, g0);
+      else if (state == 1) load_row(m + 2, g1);
+      else load_row(m + 2, g2);
+      state = state == 2 ? 0 : state + 1;
+    }
+    mcur = m;
+#define B200SAM_UP_RUN(A, B, C)                                            \
+    do {                                                                   \
+      emit(rt, packed, A, B, C);                                           \
+      if (++i >= nrows) break;                                             \
+      rt = rowtab[i];                                                      \
+      packed = __float_as_int(rt.w);                                       \
+    } while ((packed & 0xfff) == mcur)
+    if (state == 0) B200SAM_UP_RUN(g0, g1, g2);
+    else if (state == 1) B200SAM_UP_RUN(g1, g2, g0);
+    else B200SAM_UP_RUN(g2, g0, g1);
+#undef B200SAM_UP_RUN
+  }
+}
+
+// 'nearest-exact' tap of an already thresholded native-resolution mask (utils/seg_refinement.py:111)
+__global__ void __launch_bounds__(256) nearest_from_mask_kernel(const uint8_t* __restrict__ mask, int out_h, int out_w,
+                                                                uint8_t* __restrict__ small_out, int sh, int sw,
+                                                                float ny, float nx) {
+  const int n = blockIdx.z;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= sh || x >= sw) return;
+  const int sy = min(static_cast<int>(floorf((static_cast<float>(y) + 0.5f) * ny)), out_h - 1);
+  const int sx = min(static_cast<int>(floorf((static_cast<float>(x) + 0.5f) * nx)), out_w - 1);
+  small_out[(static_cast<size_t>(n) * sh + y) * sw + x] = mask[(static_cast<size_t>(n) * out_h + sy) * out_w + sx];
+}
+
 }  // namespace
 
 int upscale_threshold(const float* low_res, int n, int low, int img_size, int in_h, int in_w, int out_h, int out_w,
@@ -115,18 +366,58 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
   p.sy2 = static_cast<float>(in_h) / static_cast<float>(out_h);
   p.sx2 = static_cast<float>(in_w) / static_cast<float>(out_w);
   p.thr = thresh;
+  const float ny = static_cast<float>(out_h) / static_cast<float>(small_h > 0 ? small_h : 1);
+  const float nx = static_cast<float>(out_w) / static_cast<float>(small_w > 0 ? small_w : 1);
+  if (small_out != nullptr)
+    B200SAM_REQUIRE(small_h > 0 && small_w > 0, "upscale: bad nearest-exact size (%d,%d)", small_h, small_w);
+  // masks only, stage 1 upsampling (L <= S): the separable three-tap kernel; logits keep the literal nested form
+  const bool fast = mask_out != nullptr && logits_out == nullptr && low >= 3 && low <= img_size;
+  if (fast) {
+    // rows per block: as many as the staged low-res window (UP_LOWROWS rows) covers, at most UP_MAXROWS
+    const float lowrows_per_row = p.s1 * p.sy2;
+    int rpb = static_cast<int>(static_cast<float>(UP_LOWROWS - 4) / (lowrows_per_row > 1e-6f ? lowrows_per_row : 1e-6f));
+    rpb = rpb > UP_MAXROWS ? UP_MAXROWS : (rpb < 8 ? 8 : (rpb & ~7));
+    // small batches: keep at least ~4 CTAs per SM in flight
+    while (rpb > 32 && static_cast<long long>((out_h + rpb - 1) / rpb) * n * ((out_w + UP_THREADS * UP_PX - 1) / (UP_THREADS * UP_PX)) < 592)
+      rpb >>= 1;
+    const bool aligned = (out_w % 8 == 0) && (reinterpret_cast<uintptr_t>(mask_out) % 8 == 0);
+    dim3 grid((out_w + UP_THREADS * UP_PX - 1) / (UP_THREADS * UP_PX), (out_h + rpb - 1) / rpb, n);
+    // the fused nearest-exact tap needs <= 1 sampled row per native row and <= UP_MAXS sampled columns per 8 pixels
+    const bool fuse_small = small_out != nullptr && ny >= 1.0f && nx >= 8.0f / UP_MAXS + 0.01f;
+    SmallOut so;
+    so.out = fuse_small ? small_out : nullptr;
+    so.sh = small_h; so.sw = small_w; so.ny = ny; so.nx = nx;
+    const size_t low_bytes = static_cast<size_t>(UP_LOWROWS) * low * sizeof(float);
+    const size_t smem = low_bytes;
+    B200SAM_REQUIRE(low < 4096 && smem <= 200 * 1024, "upscale: low-res size %d not supported by the fast path", low);
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    auto kernel = thresh == 0.0f ? (aligned ? upscale_mask_fast_kernel<true, true> : upscale_mask_fast_kernel<false, true>)
+                                 : (aligned ? upscale_mask_fast_kernel<true, false> : upscale_mask_fast_kernel<false, false>);
+    kernel<<<grid, UP_THREADS, smem, stream>>>(p, mask_out, rpb, so);
+    if (small_out != nullptr && !fuse_small) {
+      dim3 block(32, 8);
+      dim3 g2((small_w + 31) / 32, (small_h + 7) / 8, n);
+      nearest_from_mask_kernel<<<g2, block, 0, stream>>>(mask_out, out_h, out_w, small_out, small_h, small_w, ny, nx);
+    }
+    B200SAM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (mask_out != nullptr || logits_out != nullptr) {
     dim3 block(64, 4);
     dim3 grid((out_w + 255) / 256, (out_h + 3) / 4, n);
     upscale_threshold_kernel<<<grid, block, 0, stream>>>(p, mask_out, logits_out);
   }
   if (small_out != nullptr) {
-    B200SAM_REQUIRE(small_h > 0 && small_w > 0, "upscale: bad nearest-exact size (%d,%d)", small_h, small_w);
     dim3 block(32, 8);
     dim3 grid((small_w + 31) / 32, (small_h + 7) / 8, n);
-    nearest_exact_kernel<<<grid, block, 0, stream>>>(p, small_out, small_h, small_w,
-                                                     static_cast<float>(out_h) / static_cast<float>(small_h),
-                                                     static_cast<float>(out_w) / static_cast<float>(small_w));
+    nearest_exact_kernel<<<grid, block, 0, stream>>>(p, small_out, small_h, small_w, ny, nx);
   }
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;

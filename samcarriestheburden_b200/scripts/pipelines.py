@@ -7,8 +7,8 @@
 
   refine_segmentations (reference scripts/save_refined_segmentations.py:60-80 after the U-Net)
       per image: prompt extraction + 2 B=1 decoder calls per class
-   -> per image: one prompt-extraction launch, two batched decoder passes over all classes, one fused
-      upscale/threshold/nearest-exact launch.
+   -> per BATCH of images: one prompt-extraction launch, two batched decoder passes over all classes of all
+      images of the batch, one fused upscale/threshold/nearest-exact launch per distinct native size.
 """
 from __future__ import annotations
 
@@ -61,7 +61,8 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
 
 @torch.no_grad()
 def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor], names: Sequence[str],
-                         prompts2use=(("box",), ("pos_points", "neg_points")), gather: bool = False):
+                         prompts2use=(("box",), ("pos_points", "neg_points")), gather: bool = False,
+                         batch: int = 8):
     """segs[i]: [C,H,W] bool (or probabilities) U-Net masks of image names[i]; every rank refines the images of its
     shard whose embeddings it holds.  Returns (list of (index, seg bool [C,H,W], est_dice [C]) for the local
     shard, gathered [N,C,H,W] uint8 tensor or None)."""
@@ -70,9 +71,10 @@ def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor
     refiner = SAMSegRefiner("SAM", str(dev), [list(p) for p in prompts2use], sam_predictor=head)
     mine = sharding.shard_indices(len(segs))
     results = []
-    for i in mine:
-        seg, est = refiner.refine(segs[i].to(dev), names[i])
-        results.append((i, seg, est))
+    for j in range(0, len(mine), batch):
+        chunk = mine[j:j + batch]
+        seg_b, est_b = refiner.refine_batch(torch.stack([segs[i].to(dev) for i in chunk]), [names[i] for i in chunk])
+        results.extend((i, seg_b[k], est_b[k]) for k, i in enumerate(chunk))
     gathered = None
     if gather and len(segs):
         local = torch.stack([r[1] for r in results]).to(torch.uint8) if results else \

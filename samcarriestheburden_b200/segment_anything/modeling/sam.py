@@ -54,16 +54,21 @@ class _DecoderEngine:
         return self._pe
 
     def decode(self, embedding: torch.Tensor, coords: Optional[torch.Tensor], labels: Optional[torch.Tensor],
-               mask_prev: Optional[torch.Tensor], multimask: bool) -> Tuple[torch.Tensor, torch.Tensor]:
-        """embedding [1|(256),...]; coords [NB,Np,2] fp32; labels [NB,Np] int32; mask_prev [NB,1,256,256]."""
-        emb = embedding.reshape(256, 64, 64).float().contiguous()
+               mask_prev: Optional[torch.Tensor], multimask: bool,
+               image_of: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """embedding [n_img,256,64,64] (or one image in any [.., 256,64,64] view); coords [NB,Np,2] fp32; labels
+        [NB,Np] int32 (-2 = absent trailing slot); mask_prev [NB,1,256,256]; image_of [NB] int32 image index of
+        every prompt (required when n_img > 1)."""
+        emb = embedding.reshape(-1, 256, 64, 64).float().contiguous()
+        n_img = emb.shape[0]
         NB = coords.shape[0] if coords is not None else (mask_prev.shape[0] if mask_prev is not None else 1)
         Np = coords.shape[1] if coords is not None else 0
         nm = 3 if multimask else 1
         low = torch.empty((NB, nm, 256, 256), dtype=torch.float32, device=self.device)
         iou = torch.empty((NB, nm), dtype=torch.float32, device=self.device)
-        need = self.lib.b200sam_decoder_workspace_bytes(NB, Np)
+        need = self.lib.b200sam_decoder_workspace_bytes_batch(n_img, NB, Np)
         if self._ws is None or self._ws.numel() < need + 256:
+            self._ws = None  # release before growing
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
         base = (self._ws.data_ptr() + 255) & ~255
         if coords is not None:
@@ -71,10 +76,16 @@ class _DecoderEngine:
             labels = labels.to(torch.int32).contiguous()
         if mask_prev is not None:
             mask_prev = mask_prev.reshape(NB, 256, 256).float().contiguous()
-        _lib.check(self.lib.b200sam_decode(self.handle, emb.data_ptr(), NB, Np, _lib.ptr(coords), _lib.ptr(labels),
-                                           _lib.ptr(mask_prev), int(multimask), low.data_ptr(), iou.data_ptr(), base,
-                                           self._ws.numel() - (base - self._ws.data_ptr()), _lib.current_stream()),
-                   "b200sam_decode")
+        if image_of is not None:
+            image_of = image_of.to(device=self.device, dtype=torch.int32).contiguous()
+            assert image_of.numel() == NB, "image_of must name one image per prompt"
+        elif n_img != 1:
+            raise ValueError("image_of is required when decoding prompts of more than one image")
+        _lib.check(self.lib.b200sam_decode_batch(self.handle, emb.data_ptr(), n_img, _lib.ptr(image_of), NB, Np,
+                                                 _lib.ptr(coords), _lib.ptr(labels), _lib.ptr(mask_prev),
+                                                 int(multimask), low.data_ptr(), iou.data_ptr(), base,
+                                                 self._ws.numel() - (base - self._ws.data_ptr()),
+                                                 _lib.current_stream()), "b200sam_decode_batch")
         return low, iou
 
     def __del__(self):

@@ -157,6 +157,42 @@ def test_pipeline_drivers_match_single_image_api(vit_b):
     assert min(ds) >= 0.999
 
 
+def test_refine_batch_equals_per_image(vit_b):
+    """Multi-image ragged decode (images with different numbers of classes / native sizes in ONE launch sequence)
+    is bit-identical to the per-image calls: absent token slots never act as attention keys."""
+    from samcarriestheburden_b200.segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
+    from samcarriestheburden_b200.utils.seg_refinement import SAMSegRefiner
+    sam, _ = vit_b
+    store = EmbeddingStore()
+    g = torch.Generator().manual_seed(5)
+    sizes = [(1024, 1024), (754, 589), (1024, 1024), (600, 1000)]
+    segs = []
+    for i, orig in enumerate(sizes):
+        store.add(f"b{i}", torch.randn((1, 256, 64, 64), generator=g).to(DEV), orig, O.get_preprocess_shape(*orig))
+        seg = torch.from_numpy(O.synthetic_unet_masks(50 + i))
+        if i == 1:
+            seg[[0, 4, 9, 11]] = False   # fewer classes -> fewer negative points than the other images
+        if i == 2:
+            seg[:] = False               # an image without any prompt
+        segs.append(seg)
+    head = SAMMaskDecoderHead(None, "vit_b", DEV, store, sam_model=sam)
+    refiner = SAMSegRefiner("SAM", DEV, [["box"], ["pos_points", "neg_points"]], sam_predictor=head)
+    names = [f"b{i}" for i in range(len(sizes))]
+    got_seg, got_dice = refiner.refine_batch(torch.stack(segs), names)
+    ks = set()
+    for i in range(len(sizes)):
+        one_seg, one_dice = refiner.refine(segs[i].clone(), names[i])
+        ks.add(int((~torch.isnan(one_dice)).sum()))
+        assert torch.equal(got_seg[i], one_seg), i
+        assert torch.equal(torch.nan_to_num(got_dice[i], nan=-1.0), torch.nan_to_num(one_dice, nan=-1.0)), i
+    assert len(ks) >= 3, ks  # the batch really was ragged
+    # single-pass configuration (box + points in one pass, no self-refinement)
+    r1 = SAMSegRefiner("SAM", DEV, ["pos_points", "neg_points", "box"], sam_predictor=head)
+    b_seg, _ = r1.refine_batch(torch.stack(segs), names)
+    for i in (0, 1):
+        assert torch.equal(b_seg[i], r1.refine(segs[i].clone(), names[i])[0])
+
+
 def test_vit_l_encoder_batch16_matches_oracle():
     """BASELINE.json configs[3]: ViT-L (hd = 64, depth 24, global blocks 5/11/17/23), batch 16 per GPU."""
     from samcarriestheburden_b200.segment_anything import sam_model_registry

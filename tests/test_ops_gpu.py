@@ -163,6 +163,35 @@ def test_prompt_extraction_ragged_shapes():
             assert np.array_equal(boxes[i].cpu().numpy()[hb], b[hb])
 
 
+def test_prompt_extraction_nonbool_bytes_and_big_batch():
+    """C ABI contract: any non-zero byte is a set pixel (the fast path adds 0/1 bytes and recounts otherwise);
+    and a batch large enough that every CTA of the persistent grid walks several (image, chunk) items."""
+    from samcarriestheburden_b200.segment_anything.utils.prompt_utils import extract_seeds_boxes
+    lib = _lib.load()
+    masks = np.stack([O.synthetic_unet_masks(60 + i) for i in range(40)])
+    t = torch.from_numpy(masks).to(DEV)
+    seeds, boxes, has_seed, has_box = extract_seeds_boxes(t)
+    for i in (0, 17, 39):
+        s, hs, b, hb = O.extract_seeds_boxes(masks[i])
+        assert np.array_equal(has_seed[i].cpu().numpy().astype(bool), hs)
+        assert np.array_equal(seeds[i].cpu().numpy()[hs], s[hs])
+        assert np.array_equal(boxes[i].cpu().numpy()[hb], b[hb])
+    rng = np.random.default_rng(1)
+    raw = (masks[:3].astype(np.uint8) * rng.integers(1, 256, size=masks[:3].shape).astype(np.uint8))
+    u8 = torch.from_numpy(raw).to(DEV)
+    N, Cn, H, W = u8.shape
+    s2 = torch.empty((N, Cn, 2), dtype=torch.int32, device=DEV)
+    b2 = torch.empty((N, Cn, 4), dtype=torch.int32, device=DEV)
+    hs2 = torch.empty((N, Cn), dtype=torch.uint8, device=DEV)
+    hb2 = torch.empty((N, Cn), dtype=torch.uint8, device=DEV)
+    scratch = torch.empty(lib.b200sam_prompt_extract_scratch_bytes(N, Cn) // 8 + 1, dtype=torch.int64, device=DEV)
+    _lib.check(lib.b200sam_prompt_extract(u8.data_ptr(), N, Cn, H, W, s2.data_ptr(), b2.data_ptr(), hs2.data_ptr(),
+                                          hb2.data_ptr(), scratch.data_ptr(), _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(s2, seeds[:3]) and torch.equal(b2, boxes[:3])
+    assert torch.equal(hs2, has_seed[:3]) and torch.equal(hb2, has_box[:3])
+
+
 @pytest.mark.parametrize("orig", [(1024, 1024), (1182, 754), (578, 881), (2570, 2040), (301, 299)])
 def test_upscale_threshold(orig):
     from samcarriestheburden_b200.segment_anything.modeling.sam import upscale_masks
@@ -178,9 +207,54 @@ def test_upscale_threshold(orig):
     mism = int((mask.cpu() != ref_mask).sum())
     inter = float((mask.cpu() & ref_mask).sum())
     dice = 2 * inter / float(mask.sum().cpu() + ref_mask.sum())
-    assert mism <= 3 and dice >= 0.9999, (mism, dice)
+    # the mask path evaluates the same bilinear composition in its separable three-tap form (rounding differs by
+    # ~1 ulp of the value): only pixels whose logit is within the restatement's own 2e-6 band of 0 may flip
+    flipped = mask.cpu() != ref_mask
+    band = float(ref.abs()[flipped].max()) if mism else 0.0
+    print(f"upscale {orig}: {mism} flipped px of {ref_mask.numel()}, max |logit| at a flip {band:.2e}")
+    assert mism <= 6 and band < 2e-6 and dice >= 0.9999, (mism, band, dice)
     ref_small = F.interpolate(ref_mask.float(), size=(384, 224), mode="nearest-exact") > 0.5
-    assert int((small.cpu() != ref_small).sum()) <= 1
+    assert int((small.cpu() != ref_small).sum()) <= 2
+    # the nearest-exact tap is taken from the native mask the same launch produced
+    own_small = F.interpolate(mask.float().cpu(), size=(384, 224), mode="nearest-exact") > 0.5
+    assert torch.equal(small.cpu(), own_small)
+
+
+def test_upscale_nonzero_threshold_and_exact_zero_logits():
+    from samcarriestheburden_b200.segment_anything.modeling.sam import upscale_masks
+    g = torch.Generator(device="cpu").manual_seed(4)
+    low = torch.randn((2, 1, 256, 256), generator=g)
+    low[1, 0, 100:140] = 0.0      # exact zeros: 0 > 0 is False
+    low[1, 0, 140:160] = -0.0
+    for orig in [(1024, 1024), (200, 120)]:
+        inp = O.get_preprocess_shape(*orig)
+        ref = O.postprocess_masks(low, inp, orig)
+        for thr in (0.0, 0.25):
+            m, small = upscale_masks(low.to(DEV), inp, orig, threshold=thr, small_size=(96, 56))
+            torch.cuda.synchronize()
+            refm = ref > thr
+            flipped = m.cpu() != refm
+            band = float((ref - thr).abs()[flipped].max()) if bool(flipped.any()) else 0.0
+            assert int(flipped.sum()) <= 6 and band < 2e-6, (orig, thr, int(flipped.sum()), band)
+            own = F.interpolate(m.float().cpu(), size=(96, 56), mode="nearest-exact") > 0.5
+            assert torch.equal(small.cpu(), own), (orig, thr)
+    zero_rows = upscale_masks(low[1:].to(DEV), (1024, 1024), (1024, 1024))[0, 0, 410:550]
+    assert not bool(zero_rows.any())
+
+
+def test_upscale_mask_only_small_and_odd_pitch():
+    """mask-only / small-only calls and output pitches that are not multiples of 8 (staged write-out path)."""
+    from samcarriestheburden_b200.segment_anything.modeling.sam import upscale_masks
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for orig in [(57, 1027), (1025, 8 * 131 + 5), (33, 9)]:
+        low = torch.randn((2, 1, 256, 256), generator=g)
+        inp = O.get_preprocess_shape(*orig)
+        ref_mask = O.postprocess_masks(low, inp, orig) > 0
+        canary = torch.full((2 * orig[0] * orig[1] + 64,), 7, dtype=torch.uint8, device=DEV)
+        mask = upscale_masks(low.to(DEV), inp, orig)
+        torch.cuda.synchronize()
+        assert int((mask.cpu() != ref_mask).sum()) <= 2, orig
+        assert bool((canary == 7).all())
 
 
 def test_linear_f32():
