@@ -91,7 +91,7 @@ struct Workspace {
   float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *abuf, *up1, *up2;
   float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4, *part;
   int* ntok;               // [NB] valid tokens per prompt (5 + present sparse points)
-  __nv_bfloat16 *sa, *sb;  // hi/lo split operands [Mi, 768] bf16 each
+  __nv_bfloat16 *sa, *sb;  // hi/lo split operands [Mi, 512] bf16 each
   size_t total;
 };
 
@@ -123,8 +123,8 @@ Workspace carve(uint8_t* base, int n_images, int NB, int T) {
   w.hyper = take(static_cast<size_t>(NB) * 128);
   w.iou4 = take(static_cast<size_t>(NB) * 4);
   w.part = take(static_cast<size_t>(NB) * 8 * ATTN_FEWQ_SPLITS * T * 18);
-  w.sa = reinterpret_cast<__nv_bfloat16*>(take(Mi * 768 / 2));
-  w.sb = reinterpret_cast<__nv_bfloat16*>(take(Mi * 768 / 2));
+  w.sa = reinterpret_cast<__nv_bfloat16*>(take(Mi * 512 / 2));
+  w.sb = reinterpret_cast<__nv_bfloat16*>(take(Mi * 512 / 2));
   w.total = off;
   return w;
 }
@@ -137,13 +137,14 @@ int lin(const float* A, const float* A2, int a2mod, const float* W, const float*
   return linear_f32(p, s);
 }
 
-// out[M,N] fp32 = A'[M,3K] . W'[N,3K]^T + bias (+GELU) (+residual): tcgen05 GEMM on the split operands
+// out[M,N] fp32 = [hi|lo|hi][M,3K] . W'[N,3K]^T + bias (+GELU) (+residual): tcgen05 GEMM on the split operands
+// (A is stored as [hi|lo] with pitch 2K; the kernel's A loader wraps the third K segment back to hi)
 int tc_lin(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* b, const float* res, float* out, int M, int N,
            int K, int gelu, cudaStream_t s) {
   GemmArgs g;
   g.A = As; g.B = Ws; g.out = out; g.bias = b; g.residual = res;
-  g.M = M; g.N = N; g.K = 3 * K; g.lda = 3 * K; g.ldb = 3 * K; g.ldo = N; g.ldr = N; g.res_row_mod = 0;
-  g.gelu = gelu; g.out_bf16 = 0; g.max_ctas = 0;
+  g.M = M; g.N = N; g.K = 3 * K; g.lda = 2 * K; g.ldb = 3 * K; g.ldo = N; g.ldr = N; g.res_row_mod = 0;
+  g.gelu = gelu; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * K;
   return gemm_bf16_tn(g, s);
 }
 

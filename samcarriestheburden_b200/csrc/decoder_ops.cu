@@ -241,6 +241,144 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ token -> image attention (few queries, 4096 keys)
+// transformer.py:164-168 / :99-104 (internal dim 128 = 8 heads x 16).  grid (heads, NB, nsplit): one CTA owns a
+// slice of the keys of one (prompt, head); its K / V rows (64 B each) are staged once in shared memory.  A lane is a
+// (query, key-subset) pair: QL = 8 / 16 / 32 lanes carry the queries (T <= QL) and the 32 / QL lane groups x 8 warps
+// split the keys, so every shared-memory read is a broadcast (or a conflict-free 4-address access) and the per-key
+// cost is 32 FMAs per lane with the query in registers.  Scores are produced 8 keys at a time, so the running
+// maximum / rescale happens once per 8 keys.  q is pre-scaled by log2(e)/sqrt(16) and the softmax uses ex2 (MUFU):
+// relative error ~2^-22 per weight.  Partial (m, l, acc) states go to `part`; attn_fewq_combine_kernel merges them.
+constexpr int FQL_KEYS = 256;  // keys per CTA
+constexpr int FQL_PAD = 20;    // floats per staged row (16 + 4: conflict-free 16-byte reads of 4 different rows)
+
+B200SAM_DEVINL float ex2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int QL>
+__global__ void __launch_bounds__(256) attn_fewq_long_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                             const float* __restrict__ v, int Tq, int Tk, int heads,
+                                                             int nsplit, float* __restrict__ part) {
+  constexpr int DH = 16, KS = 32 / QL, NSUB = 8 * KS;  // key subsets per warp / per CTA
+  __shared__ __align__(16) float ks[FQL_KEYS][FQL_PAD];
+  __shared__ __align__(16) float vs[FQL_KEYS][FQL_PAD];
+  float (*red)[QL][DH + 2] = reinterpret_cast<float (*)[QL][DH + 2]>(&ks[0][0]);  // [8][QL][18], aliases ks after the loop
+  static_assert(8 * QL * (DH + 2) <= FQL_KEYS * FQL_PAD, "reduction scratch must fit in the K tile");
+  const int h = blockIdx.x, b = blockIdx.y, z = blockIdx.z;
+  const int C = heads * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kbeg = z * FQL_KEYS, nk = min(FQL_KEYS, Tk - kbeg);
+  const float* kb = k + (static_cast<size_t>(b) * Tk + kbeg) * C + h * DH;
+  const float* vb = v + (static_cast<size_t>(b) * Tk + kbeg) * C + h * DH;
+  for (int i = tid; i < FQL_KEYS * 4; i += 256) {
+    const int r = i >> 2, c4 = i & 3;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (r < nk) {
+      kv = __ldg(reinterpret_cast<const float4*>(kb + static_cast<size_t>(r) * C) + c4);
+      vv = __ldg(reinterpret_cast<const float4*>(vb + static_cast<size_t>(r) * C) + c4);
+    }
+    *reinterpret_cast<float4*>(&ks[r][c4 * 4]) = kv;
+    *reinterpret_cast<float4*>(&vs[r][c4 * 4]) = vv;
+  }
+  const int qi = lane % QL, sub = warp * KS + lane / QL;
+  float qr[DH];
+  {
+    const float sc = 0.25f * 1.4426950408889634f;  // 1/sqrt(16) * log2(e)
+    const float* qp = q + (static_cast<size_t>(b) * Tq + min(qi, Tq - 1)) * C + h * DH;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(qp) + c4);
+      qr[c4 * 4] = a.x * sc; qr[c4 * 4 + 1] = a.y * sc; qr[c4 * 4 + 2] = a.z * sc; qr[c4 * 4 + 3] = a.w * sc;
+    }
+  }
+  __syncthreads();
+  float m = -INFINITY, l = 0.0f, acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.0f;
+  // keys of this lane group: sub, sub + NSUB, ...; 8 at a time
+  for (int k0 = sub; k0 < nk; k0 += 8 * NSUB) {
+    float sv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = k0 + j * NSUB;
+      float sdot = -INFINITY;
+      if (kk < nk) {
+        sdot = 0.0f;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 a = *reinterpret_cast<const float4*>(&ks[kk][c4 * 4]);
+          sdot = fmaf(qr[c4 * 4], a.x, sdot); sdot = fmaf(qr[c4 * 4 + 1], a.y, sdot);
+          sdot = fmaf(qr[c4 * 4 + 2], a.z, sdot); sdot = fmaf(qr[c4 * 4 + 3], a.w, sdot);
+        }
+      }
+      sv[j] = sdot;
+    }
+    float mx = m;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, sv[j]);
+    const float c = ex2f_approx(m - mx);  // 0 on the first chunk (m = -inf), 1 when the maximum did not move
+    m = mx;
+    l *= c;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] *= c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = k0 + j * NSUB;
+      if (kk < nk) {
+        const float pw = ex2f_approx(sv[j] - mx);
+        l += pw;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 a = *reinterpret_cast<const float4*>(&vs[kk][c4 * 4]);
+          acc[c4 * 4] = fmaf(pw, a.x, acc[c4 * 4]); acc[c4 * 4 + 1] = fmaf(pw, a.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(pw, a.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(pw, a.w, acc[c4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  // merge the KS lane groups of the warp (same query, different key subsets), then the 8 warps through smem
+#pragma unroll
+  for (int o = QL; o < 32; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float mn = fmaxf(m, m2);
+    const float c1 = m == -INFINITY ? 0.0f : ex2f_approx(m - mn);
+    const float c2 = m2 == -INFINITY ? 0.0f : ex2f_approx(m2 - mn);
+    l = l * c1 + __shfl_xor_sync(0xffffffffu, l, o) * c2;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = acc[d] * c1 + __shfl_xor_sync(0xffffffffu, acc[d], o) * c2;
+    m = mn;
+  }
+  __syncthreads();  // every warp is done with ks / vs
+  if (lane < QL) {
+    red[warp][lane][0] = m;
+    red[warp][lane][1] = l;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) red[warp][lane][2 + d] = acc[d];
+  }
+  __syncthreads();
+  // thread (query t, dim d): fold the 8 warps; scores are in the log2 domain -> the partial maximum is stored in the
+  // natural-log domain the combine kernel expects
+  for (int i = tid; i < Tq * DH; i += 256) {
+    const int t = i / DH, d = i - t * DH;
+    float mall = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mall = fmaxf(mall, red[w][t][0]);
+    float lsum = 0.0f, o = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float cw = red[w][t][0] == -INFINITY ? 0.0f : ex2f_approx(red[w][t][0] - mall);
+      lsum = fmaf(red[w][t][1], cw, lsum);
+      o = fmaf(red[w][t][2 + d], cw, o);
+    }
+    float* pp = part + (((static_cast<size_t>(b) * heads + h) * nsplit + z) * Tq + t) * (DH + 2);
+    pp[2 + d] = o;
+    if (d == 0) { pp[0] = mall * 0.6931471805599453f; pp[1] = lsum; }
+  }
+}
+
 template <int DH>
 __global__ void attn_fewq_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int Tq, int heads,
                                          int nsplit) {
@@ -593,7 +731,8 @@ __global__ void __launch_bounds__(256) mask_dot_kernel(const float* __restrict__
 
 // fp32 -> 3-way bf16 split operand for the tensor-core path of the big decoder linears:
 //   x = hi + lo (+ 2^-17 relative remainder), hi = bf16(x), lo = bf16(x - hi)
-//   mode 0 (activations): out[m] = [hi | lo | hi];  mode 1 (weights): out[n] = [hi | hi | lo]
+//   mode 0 (activations): out[m] = [hi | lo] (pitch 2K; the GEMM's A loader wraps k >= 2K back to the hi half, i.e.
+//   it multiplies the virtual operand [hi | lo | hi]);  mode 1 (weights): out[n] = [hi | hi | lo] (pitch 3K)
 // so that <A'[m], W'[n]> = hi.hi + lo.hi + hi.lo  ~= fp32 product (the lo.lo term, 2^-18 relative, is dropped).
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                      int x2_row_mod, __nv_bfloat16* __restrict__ out, size_t M, int K,
@@ -627,10 +766,16 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
     }
     const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     const uint4 Lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    __nv_bfloat16* o = out + m * (3 * static_cast<size_t>(K)) + v * 8;
-    *reinterpret_cast<uint4*>(o) = H;
-    *reinterpret_cast<uint4*>(o + K) = mode == 0 ? Lo : H;
-    *reinterpret_cast<uint4*>(o + 2 * K) = mode == 0 ? H : Lo;
+    if (mode == 0) {
+      __nv_bfloat16* o = out + m * (2 * static_cast<size_t>(K)) + v * 8;
+      *reinterpret_cast<uint4*>(o) = H;
+      *reinterpret_cast<uint4*>(o + K) = Lo;
+    } else {
+      __nv_bfloat16* o = out + m * (3 * static_cast<size_t>(K)) + v * 8;
+      *reinterpret_cast<uint4*>(o) = H;
+      *reinterpret_cast<uint4*>(o + K) = H;
+      *reinterpret_cast<uint4*>(o + 2 * K) = Lo;
+    }
   }
 }
 
@@ -664,7 +809,20 @@ int linear_f32(const LinearArgs& p, cudaStream_t stream) {
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
                      int dh, float* part, const int* tk_valid, cudaStream_t stream) {
   B200SAM_REQUIRE(NB > 0 && Tq > 0 && Tk > 0, "attn_few_queries: empty problem");
-  const int nsplit = (part != nullptr && Tk >= 1024) ? ATTN_FEWQ_SPLITS : 1;
+  if (part != nullptr && Tk >= 1024 && dh == 16 && Tq <= 32 && tk_valid == nullptr) {
+    // token -> image attention: keys split over ceil(Tk / 256) CTAs per (prompt, head)
+    const int nsplit = (Tk + FQL_KEYS - 1) / FQL_KEYS;
+    B200SAM_REQUIRE(nsplit <= ATTN_FEWQ_SPLITS, "attn_few_queries: at most %d keys supported, got %d",
+                    ATTN_FEWQ_SPLITS * FQL_KEYS, Tk);
+    dim3 grid(heads, NB, nsplit);
+    if (Tq <= 8) attn_fewq_long_kernel<8><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part);
+    else if (Tq <= 16) attn_fewq_long_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part);
+    else attn_fewq_long_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part);
+    attn_fewq_combine_kernel<16><<<dim3(heads, NB), 128, 0, stream>>>(part, out, Tq, heads, nsplit);
+    B200SAM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const int nsplit = (part != nullptr && Tk >= 1024) ? 8 : 1;
   dim3 grid(heads, NB, nsplit);
   if (dh == 16) attn_fewq_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part, tk_valid);
   else if (dh == 32) attn_fewq_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part, tk_valid);

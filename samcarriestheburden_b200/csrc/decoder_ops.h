@@ -23,7 +23,7 @@ int linear_f32(const LinearArgs& p, cudaStream_t stream);
 
 // q [NB,Tq,heads*dh], k/v [NB,Tk,heads*dh] -> out [NB,Tq,heads*dh]; dh in {16, 32}
 // part: optional scratch of NB*heads*ATTN_FEWQ_SPLITS*Tq*(dh+2) floats enabling the key-split path for long Tk
-constexpr int ATTN_FEWQ_SPLITS = 8;
+constexpr int ATTN_FEWQ_SPLITS = 16;
 // tk_valid: optional per-batch count of valid keys (<= Tk; Tk stays the row pitch) for ragged prompt batches
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
                      int dh, float* part, const int* tk_valid, cudaStream_t stream);
@@ -45,7 +45,8 @@ int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, cudaStre
 int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const float* const* b15, float* hyper,
                 float* iou, cudaStream_t stream);
 int mask_dot(const float* up, const float* hyper, int NB, int tok0, int ntok, float* masks, cudaStream_t stream);
-// fp32 [M,K] (+ optional addend) -> bf16 [M,3K] hi/lo split operand (mode 0: activations, 1: weights)
+// fp32 [M,K] (+ optional addend) -> bf16 hi/lo split operand: mode 0 activations [M,2K] = [hi|lo], mode 1 weights
+// [M,3K] = [hi|hi|lo]
 int split3_bf16(const float* x, const float* x2, int x2_row_mod, __nv_bfloat16* out, size_t M, int K, int mode,
                 cudaStream_t stream);
 int add_rows(const float* a, const float* b, float* out, size_t n, cudaStream_t stream);

@@ -37,10 +37,15 @@ constexpr int GEMM_SMEM_BYTES = SMEM_TILES + SMEM_EPI + SMEM_BARRIERS;
 constexpr uint32_t TMEM_COLS = 512;
 
 
-template <bool OUT_BF16>
+// BN_EFF = 256 (full tiles) or 128: problems with N <= 128 (the decoder's 128-wide image-side projections) fetch and
+// multiply only 128 weight rows per k-block - half the shared-memory / L2 traffic and MMA time of a zero-padded
+// 256-wide tile; the TMEM layout and the epilogue are those of the 256-wide kernel.
+// a_wrap > 0: the A operand is stored with only a_wrap columns and k-blocks past it wrap around to column
+// kb*BK - a_wrap (the [hi | lo | hi] split operand of the decoder is stored as [hi | lo]).
+template <bool OUT_BF16, int BN_EFF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    EpiParams ep, int M, int N, int K) {
+                    EpiParams ep, int M, int N, int K, int a_wrap) {
   // SWIZZLE_128B tiles need 1024 B alignment.  The alignment is requested on the symbol (not by rounding the
   // pointer through an integer): pointer arithmetic through uintptr_t makes the compiler lose the shared
   // state space and emit generic LD/ST (L1TEX path, long-scoreboard latency) for every staging access.
@@ -96,8 +101,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + BN_EFF * BK * 2);
+          const int ka = kb * BK;
+          tma_load_2d(sa, &tma_a, &full_bar[stage], (a_wrap > 0 && ka >= a_wrap) ? ka - a_wrap : ka, m0);
           tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -106,7 +112,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN_EFF);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -187,9 +193,12 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "gemm: out must be 16-byte aligned");
   B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0,
                   "gemm: A and B must be 16-byte aligned");
+  B200SAM_REQUIRE(g.a_wrap == 0 || (g.a_wrap % BK == 0 && g.a_wrap > 0 && g.K <= 2 * g.a_wrap),
+                  "gemm: a_wrap=%d must be a positive multiple of %d with K <= 2 a_wrap", g.a_wrap, BK);
+  const bool narrow = g.N <= 128;
   CUtensorMap ta, tb;
-  if (make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-  if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_tmap_bf16(&ta, g.A, g.M, g.a_wrap > 0 ? g.a_wrap : g.K, g.lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, narrow ? 128 : BN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   EpiParams ep;
   ep.bias = g.bias;
   ep.residual = g.residual;
@@ -201,22 +210,17 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
-  static bool attr_set[2] = {false, false};
-  if (g.out_bf16) {
-    if (!attr_set[0]) {
-      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              GEMM_SMEM_BYTES));
-      attr_set[0] = true;
-    }
-    gemm_bf16_tn_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K);
-  } else {
-    if (!attr_set[1]) {
-      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              GEMM_SMEM_BYTES));
-      attr_set[1] = true;
-    }
-    gemm_bf16_tn_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    attr_set = true;
   }
+  auto kernel = g.out_bf16 ? (narrow ? gemm_bf16_tn_kernel<true, 128> : gemm_bf16_tn_kernel<true, 256>)
+                           : (narrow ? gemm_bf16_tn_kernel<false, 128> : gemm_bf16_tn_kernel<false, 256>);
+  kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K, g.a_wrap);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

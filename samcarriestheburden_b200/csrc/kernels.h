@@ -42,6 +42,7 @@ struct GemmArgs {
   int gelu;         // exact erf GELU after bias
   int out_bf16;     // 1: bf16 output, 0: fp32 output
   int max_ctas;     // <= 0: one CTA per SM; > 0 caps the persistent grid
+  int a_wrap = 0;   // > 0: A has only a_wrap columns; k >= a_wrap reads column k - a_wrap ([hi|lo|hi] stored as [hi|lo])
 };
 int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
 
