@@ -88,7 +88,7 @@ __global__ void slice_iou_kernel(const float* __restrict__ iou4, float* __restri
 inline size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct Workspace {
-  float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *abuf, *up1, *up2;
+  float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *up1, *up2;
   float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4, *part;
   int* ntok;               // [NB] valid tokens per prompt (5 + present sparse points)
   __nv_bfloat16 *sa, *sb;  // hi/lo split operands [Mi, 512] bf16 each
@@ -110,7 +110,6 @@ Workspace carve(uint8_t* base, int n_images, int NB, int T) {
   w.kbuf = take(Mi * 128);
   w.vbuf = take(Mi * 128);
   w.qibuf = take(Mi * 128);
-  w.abuf = take(Mi * 128);
   w.up1 = take(Mi * 256);
   w.up2 = take(Mi * 512);
   w.tokens = take(Mt * 256);
@@ -242,10 +241,15 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   TRY(prompt_tokens(a.coords, a.labels, NB, a.Np, W[W_GAUSS], W[W_POINT4], W[W_NOT_A_POINT], W[W_IOU_TOKEN],
                     W[W_MASK_TOKENS], a.img_w, a.img_h, w.tokens, w.ntok, s));
   TRY(nchw_to_tokens(a.emb, w.emb_tok, a.n_images, s));
-  if (a.mask_prev != nullptr)
+  // the producers of the image-side keys also emit the bf16 split operands of the projections that consume them:
+  // sa = split(keys + pe) feeds the k / image-query projections, sb = split(keys) the v projection and the upscaler
+  if (a.mask_prev != nullptr) {
     TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, a.image_of, s));
-  else
-    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, s));
+    TRY(split3_bf16(w.keys, pe, 4096, w.sa, Mi, 256, 0, s));
+    TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
+  } else {
+    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, pe, w.sa, w.sb, s));
+  }
   B200SAM_CHECK_CUDA(cudaMemcpyAsync(w.queries, w.tokens, static_cast<size_t>(Mt) * 256 * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
 
@@ -265,8 +269,6 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(lin(w.queries, w.tokens, 0, TI[0], TI[1], nullptr, w.tq, Mt, 128, 256, 0, s));
     // image-side projections on the tensor cores (3-way bf16 split operands, fp32 accumulate); keys are constant
     // until the end of the layer, so the two split operands also serve the image->token query projection
-    TRY(split3_bf16(w.keys, pe, 4096, w.sa, Mi, 256, 0, s));
-    TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
     TRY(tc_lin(w.sa, d->ws_t2i_k[l], TI[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sb, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sa, d->ws_i2t_q[l], L[L_I2T + 1], nullptr, w.qibuf, Mi, 128, 256, 0, s));
@@ -281,16 +283,13 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     const float* const* IT = L + L_I2T;  // image tokens are the queries here
     TRY(lin(w.queries, w.tokens, 0, IT[2], IT[3], nullptr, w.tk, Mt, 128, 256, 0, s));
     TRY(lin(w.queries, nullptr, 0, IT[4], IT[5], nullptr, w.tv, Mt, 128, 256, 0, s));
-    TRY(attn_few_keys(w.qibuf, w.tk, w.tv, w.abuf, NB, 4096, T, w.ntok, s));
-    TRY(split3_bf16(w.abuf, nullptr, 0, w.sa, Mi, 128, 0, s));
+    TRY(attn_few_keys(w.qibuf, w.tk, w.tv, nullptr, NB, 4096, T, w.ntok, w.sa, s));  // -> split(attention out)
     TRY(tc_lin(w.sa, d->ws_i2t_o[l], IT[7], w.keys, w.keys, Mi, 256, 128, 0, s));
-    TRY(layernorm_rows(w.keys, L[L_N4], L[L_N4 + 1], 1e-5f, Mi, 256, w.keys, 0, s));
+    TRY(ln256_keys_split(w.keys, L[L_N4], L[L_N4 + 1], pe, Mi, w.sa, w.sb, s));  // norm4 + next splits
   }
   {
     const float* const* F = W + W_FINAL;
     TRY(lin(w.queries, w.tokens, 0, F[0], F[1], nullptr, w.tq, Mt, 128, 256, 0, s));
-    TRY(split3_bf16(w.keys, pe, 4096, w.sa, Mi, 256, 0, s));
-    TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
     TRY(tc_lin(w.sa, d->ws_fin_k, F[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
     TRY(tc_lin(w.sb, d->ws_fin_v, F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
     TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s));
@@ -302,8 +301,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   const float* const* U = W + W_UP;
   // w.sb still holds the split of the final keys (they do not change after the last image->token block)
   TRY(tc_lin(w.sb, d->ws_up1, U[1], nullptr, w.up1, Mi, 256, 256, 0, s));             // ConvT 256->64, k2 s2
-  TRY(ln64_gelu(w.up1, U[2], U[3], static_cast<size_t>(Mi) * 4, s));                  // LayerNorm2d(64) + GELU
-  TRY(split3_bf16(w.up1, nullptr, 0, w.sa, static_cast<size_t>(Mi) * 4, 64, 0, s));
+  TRY(ln64_gelu(w.up1, U[2], U[3], static_cast<size_t>(Mi) * 4, w.sa, s));            // LayerNorm2d(64) + GELU -> split
   TRY(tc_lin(w.sa, d->ws_up2, U[5], nullptr, w.up2, Mi * 4, 128, 64, 1, s));          // ConvT 64->32 + GELU
   {
     const float* wt[15];

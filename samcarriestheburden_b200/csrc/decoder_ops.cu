@@ -13,6 +13,69 @@ constexpr float TWO_PI = 6.283185307179586f;
 
 B200SAM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+// x (8 floats) -> hi = bf16(x), lo = bf16(x - hi) as two 16-byte vectors (the [hi | lo] split operand, see split3_kernel)
+B200SAM_DEVINL void split_hi_lo8(const float (&f)[8], uint4& H, uint4& Lo) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
+    const float r0 = f[2 * i] - __bfloat162float(h0), r1 = f[2 * i + 1] - __bfloat162float(h1);
+    __nv_bfloat162 hp, lp;
+    hp.x = h0; hp.y = h1;
+    lp = __floats2bfloat162_rn(r0, r1);
+    hi[i] = *reinterpret_cast<uint32_t*>(&hp);
+    lo[i] = *reinterpret_cast<uint32_t*>(&lp);
+  }
+  H = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  Lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// row m of a [*, 2K] split operand: columns [c, c+8) of the hi half and of the lo half
+B200SAM_DEVINL void store_split8(__nv_bfloat16* out, size_t m, int K, int c, const float (&f)[8]) {
+  uint4 H, Lo;
+  split_hi_lo8(f, H, Lo);
+  __nv_bfloat16* o = out + m * (2 * static_cast<size_t>(K)) + c;
+  *reinterpret_cast<uint4*>(o) = H;
+  *reinterpret_cast<uint4*>(o + K) = Lo;
+}
+
+// LayerNorm over 256 channels of the image-side keys (transformer.py:180, eps 1e-5), in place, fused with the split
+// operands the next projections consume: sa = split(keys + pe[token]), sb = split(keys).  One warp per row.
+__global__ void __launch_bounds__(256) ln256_keys_split_kernel(float* __restrict__ keys, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               const float* __restrict__ pe, size_t M,
+                                                               __nv_bfloat16* __restrict__ sa,
+                                                               __nv_bfloat16* __restrict__ sb) {
+  const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float4* xr = reinterpret_cast<float4*>(keys + row * 256) + lane * 2;  // 8 consecutive channels per lane
+  const float4 a = xr[0], b = xr[1];
+  float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += f[i];
+  s = warp_sum(s);
+  const float mean = s * (1.0f / 256.0f);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = f[i] - mean; q = fmaf(d, d, q); }
+  q = warp_sum(q);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 256.0f) + 1e-5f);
+  const float4 g0 = reinterpret_cast<const float4*>(gamma)[lane * 2], g1 = reinterpret_cast<const float4*>(gamma)[lane * 2 + 1];
+  const float4 b0 = reinterpret_cast<const float4*>(beta)[lane * 2], b1 = reinterpret_cast<const float4*>(beta)[lane * 2 + 1];
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * gg[i] + bb[i];
+  xr[0] = make_float4(f[0], f[1], f[2], f[3]);
+  xr[1] = make_float4(f[4], f[5], f[6], f[7]);
+  store_split8(sb, row, 256, lane * 8, f);
+  const float4* pr = reinterpret_cast<const float4*>(pe + (row & 4095) * 256) + lane * 2;
+  const float4 p0 = pr[0], p1 = pr[1];
+  f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+  store_split8(sa, row, 256, lane * 8, f);
+}
+
 // ------------------------------------------------------------------ generic fp32 linear
 // out[m, n] = act( sum_k (A[m,k] + A2[m2,k]) * W[n,k] + bias[n] ) + residual[m, n]
 // BM = 128 for the tall image-side operands, BM = 32 for the token-side ones (M = prompts x tokens <= ~400 rows:
@@ -405,7 +468,8 @@ __global__ void attn_fewq_combine_kernel(const float* __restrict__ part, float* 
 // tokens. One thread per (image token, head); K/V of the tokens sit in shared memory.
 __global__ void __launch_bounds__(256) attn_fewk_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                         const float* __restrict__ v, float* __restrict__ out, int Nq,
-                                                        int Tk_pitch, const int* __restrict__ tk_valid) {
+                                                        int Tk_pitch, const int* __restrict__ tk_valid,
+                                                        __nv_bfloat16* __restrict__ split_out) {
   constexpr int DH = 16, HEADS = 8, C = 128, PAD = 20, MAXK = 32;
   __shared__ __align__(16) float ks[MAXK][HEADS][PAD];
   __shared__ __align__(16) float vs[MAXK][HEADS][PAD];
@@ -461,6 +525,16 @@ __global__ void __launch_bounds__(256) attn_fewk_kernel(const float* __restrict_
     }
   }
   const float inv = 1.0f / sum;
+  if (split_out != nullptr) {  // the [hi | lo] split operand of the out-projection GEMM, [NB*Nq, 256] bf16
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = o[hf * 8 + i] * inv;
+      store_split8(split_out, static_cast<size_t>(b) * Nq + row, C, h * DH + hf * 8, f);
+    }
+    return;
+  }
   float* op = out + (static_cast<size_t>(b) * Nq + row) * C + h * DH;
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4)
@@ -537,17 +611,28 @@ __global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __res
 
 // keys[b, tok, c] = emb_tok[tok, c] + no_mask_embed[c]  (prompt_encoder.py:164-166 + mask_decoder.py:126)
 // grid (x, NB): prompt b reads the token-major embedding of its image (image_of[b], or image 0)
+// and emits the split operands of the first layer: sa = split(keys + pe), sb = split(keys)
 __global__ void keys_init_kernel(const float4* __restrict__ emb_tok, const float4* __restrict__ no_mask,
-                                 float4* __restrict__ keys, const int* __restrict__ image_of) {
-  const size_t n4 = 4096 * 64;
+                                 float4* __restrict__ keys, const int* __restrict__ image_of,
+                                 const float4* __restrict__ pe, __nv_bfloat16* __restrict__ sa,
+                                 __nv_bfloat16* __restrict__ sb) {
+  const size_t n8 = 4096 * 32;  // groups of 8 channels
   const int b = blockIdx.y;
-  const float4* e4 = emb_tok + (image_of != nullptr ? image_of[b] : 0) * n4;
-  float4* k4 = keys + static_cast<size_t>(b) * n4;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+  const float4* e4 = emb_tok + (image_of != nullptr ? image_of[b] : 0) * (n8 * 2);
+  float4* k4 = keys + static_cast<size_t>(b) * (n8 * 2);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float4 e = e4[i];
-    const float4 d = no_mask[i & 63];
-    k4[i] = make_float4(e.x + d.x, e.y + d.y, e.z + d.z, e.w + d.w);
+    const float4 e0 = e4[2 * i], e1 = e4[2 * i + 1];
+    const float4 d0 = no_mask[(2 * i) & 63], d1 = no_mask[(2 * i + 1) & 63];
+    float f[8] = {e0.x + d0.x, e0.y + d0.y, e0.z + d0.z, e0.w + d0.w, e1.x + d1.x, e1.y + d1.y, e1.z + d1.z, e1.w + d1.w};
+    k4[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+    k4[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    const size_t row = static_cast<size_t>(b) * 4096 + (i >> 5);
+    const int c = static_cast<int>(i & 31) * 8;
+    store_split8(sb, row, 256, c, f);
+    const float4 p0 = pe[2 * i], p1 = pe[2 * i + 1];
+    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+    store_split8(sa, row, 256, c, f);
   }
 }
 
@@ -637,8 +722,10 @@ __global__ void __launch_bounds__(256) mask_downscale_keys_kernel(const float* _
 }
 
 // in-place LayerNorm2d(64, eps 1e-6) + GELU over contiguous groups of 64 channels (mask_decoder.py:54-56)
+// split_out != null: emit the [hi | lo] bf16 split operand of the next ConvT GEMM ([ngroups, 128]) instead
 __global__ void __launch_bounds__(256) ln64_gelu_kernel(float* __restrict__ x, const float* __restrict__ g,
-                                                        const float* __restrict__ bta, size_t ngroups) {
+                                                        const float* __restrict__ bta, size_t ngroups,
+                                                        __nv_bfloat16* __restrict__ split_out) {
   const size_t grp = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 4;  // 16 lanes per group
   const int sl = threadIdx.x & 15;
   if (grp >= ngroups) return;
@@ -658,7 +745,19 @@ __global__ void __launch_bounds__(256) ln64_gelu_kernel(float* __restrict__ x, c
   v.y = gelu_erf(b * rstd * gg.y + bb.y);
   v.z = gelu_erf(c * rstd * gg.z + bb.z);
   v.w = gelu_erf(d * rstd * gg.w + bb.w);
-  reinterpret_cast<float4*>(x + grp * 64)[sl] = v;
+  if (split_out == nullptr) {
+    reinterpret_cast<float4*>(x + grp * 64)[sl] = v;
+  } else {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    __nv_bfloat162 p0, p1;
+    p0.x = h0; p0.y = h1; p1.x = h2; p1.y = h3;
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+    const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+    __nv_bfloat16* o = split_out + grp * 128 + sl * 4;
+    *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+    *reinterpret_cast<uint2*>(o + 64) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
 }
 
 // 3-layer MLPs on single tokens (hypernetwork MLPs + IoU head, mask_decoder.py:139-147,154-176).
@@ -837,10 +936,10 @@ int attn_few_queries(const float* q, const float* k, const float* v, float* out,
 }
 
 int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
-                  const int* tk_valid, cudaStream_t stream) {
+                  const int* tk_valid, __nv_bfloat16* split_out, cudaStream_t stream) {
   B200SAM_REQUIRE(Tk > 0 && Tk <= 32, "attn_few_keys: at most 32 prompt tokens supported, got %d", Tk);
   dim3 grid((Nq * 8 + 255) / 256, NB);
-  attn_fewk_kernel<<<grid, 256, 0, stream>>>(q, k, v, out, Nq, Tk, tk_valid);
+  attn_fewk_kernel<<<grid, 256, 0, stream>>>(q, k, v, out, Nq, Tk, tk_valid, split_out);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -867,11 +966,12 @@ int nchw_to_tokens(const float* in, float* out, int n_images, cudaStream_t strea
   return 0;
 }
 
-int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of,
-              cudaStream_t stream) {
+int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of, const float* pe,
+              __nv_bfloat16* sa, __nv_bfloat16* sb, cudaStream_t stream) {
   keys_init_kernel<<<dim3(64, NB), 256, 0, stream>>>(reinterpret_cast<const float4*>(emb_tok),
                                                      reinterpret_cast<const float4*>(no_mask),
-                                                     reinterpret_cast<float4*>(keys), image_of);
+                                                     reinterpret_cast<float4*>(keys), image_of,
+                                                     reinterpret_cast<const float4*>(pe), sa, sb);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -884,9 +984,16 @@ int mask_downscale_keys(const float* mask, const float* const* w10, const float*
   return 0;
 }
 
-int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, cudaStream_t stream) {
+int ln256_keys_split(float* keys, const float* gamma, const float* beta, const float* pe, size_t M, __nv_bfloat16* sa,
+                     __nv_bfloat16* sb, cudaStream_t stream) {
+  ln256_keys_split_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, stream>>>(keys, gamma, beta, pe, M, sa, sb);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, __nv_bfloat16* split_out, cudaStream_t stream) {
   const size_t threads = ngroups * 16;
-  ln64_gelu_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, g, b, ngroups);
+  ln64_gelu_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, g, b, ngroups, split_out);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -28,8 +28,9 @@ constexpr int ATTN_FEWQ_SPLITS = 16;
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
                      int dh, float* part, const int* tk_valid, cudaStream_t stream);
 // q [NB,Nq,128], k/v [NB,Tk<=32,128] (8 heads x 16) -> out [NB,Nq,128]
+// split_out != null: write the bf16 [hi | lo] split operand [NB*Nq, 256] instead of the fp32 `out`
 int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
-                  const int* tk_valid, cudaStream_t stream);
+                  const int* tk_valid, __nv_bfloat16* split_out, cudaStream_t stream);
 int dense_pe_tokens(const float* G, float* pe, cudaStream_t stream);
 int prompt_tokens(const float* coords, const int* labels, int NB, int Np, const float* G, const float* point_emb,
                   const float* not_a_point, const float* iou_token, const float* mask_tokens, float img_w, float img_h,
@@ -37,11 +38,16 @@ int prompt_tokens(const float* coords, const int* labels, int NB, int Np, const 
 // in [n_images, 256, 4096] NCHW -> out [n_images, 4096, 256] token-major
 int nchw_to_tokens(const float* in, float* out, int n_images, cudaStream_t stream);
 // image_of: optional [NB] index of the image (row block of emb_tok) each prompt belongs to; null = image 0
-int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of,
-              cudaStream_t stream);
+// also emits the first layer's split operands sa = split(keys + pe), sb = split(keys) ([NB*4096, 512] bf16 each)
+int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of, const float* pe,
+              __nv_bfloat16* sa, __nv_bfloat16* sb, cudaStream_t stream);
+// in-place LayerNorm (eps 1e-5) of the [M, 256] image-side keys fused with sa = split(keys + pe[row % 4096]), sb = split(keys)
+int ln256_keys_split(float* keys, const float* gamma, const float* beta, const float* pe, size_t M, __nv_bfloat16* sa,
+                     __nv_bfloat16* sb, cudaStream_t stream);
 int mask_downscale_keys(const float* mask, const float* const* w10, const float* emb_tok, float* keys, int NB,
                         const int* image_of, cudaStream_t stream);
-int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, cudaStream_t stream);
+// split_out != null: write the bf16 [hi | lo] split operand [ngroups, 128] instead of updating x in place
+int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, __nv_bfloat16* split_out, cudaStream_t stream);
 int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const float* const* b15, float* hyper,
                 float* iou, cudaStream_t stream);
 int mask_dot(const float* up, const float* hyper, int NB, int tok0, int ntok, float* masks, cudaStream_t stream);
