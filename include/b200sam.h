@@ -104,6 +104,19 @@ B200SAM_API int b200sam_upscale_threshold(const float* low_res, int n, int low, 
                               int out_w, float threshold, uint8_t* mask_out, float* logits_out, uint8_t* small_out,
                               int small_h, int small_w, void* stream);
 
+/* ---------------------------------------------------------------- connected-component pre-processing
+ * Replaces remove_all_but_one_connected_component (utils/segmentation_preprocessing.py:7-52, called from
+ * SegEnhance.enhance, utils/seg_refinement.py:64-72) for n_planes = images x classes probability planes at once:
+ * out = prob * (winning 8-connected component of prob > threshold); by_area = 1: 'largest', 0: 'highest_probability'.
+ * Labels follow kornia.contrib.connected_components after convergence (component label = its largest pixel index). */
+B200SAM_API size_t b200sam_ccl_scratch_bytes(int n_planes, int H, int W);
+B200SAM_API int b200sam_ccl_select(const float* prob, int n_planes, int H, int W, float threshold, int by_area,
+                       float* out, void* scratch, void* stream);
+/* Flat grey-scale dilation (dilate = 1) / erosion (0) with a 0/1 structuring element se [kh,kw] (device) anchored at
+ * (origin_y, origin_x); replaces kornia.morphology.dilation / erosion as used by SegEnhance (seg_refinement.py:44-62). */
+B200SAM_API int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw,
+                       int origin_y, int origin_x, int dilate, float* out, void* stream);
+
 /* ---------------------------------------------------------------- building blocks (exposed for parity tests)
  * D[M,N] = A[M,K] W[N,K]^T (+bias) (+GELU) (+residual[row % res_row_mod]); bf16 operands, fp32 accumulate (tcgen05). */
 B200SAM_API int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M,

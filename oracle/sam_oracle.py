@@ -515,3 +515,72 @@ def synthetic_unet_masks(seed: int, C: int = 17, H: int = 384, W: int = 224) -> 
             by, bx = rng.uniform(0, H), rng.uniform(0, W)
             m[c] |= ((yy - by) / 4.0) ** 2 + ((xx - bx) / 4.0) ** 2 <= 1.0
     return m
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Connected-component pre-processing (reference utils/segmentation_preprocessing.py:7-52).
+# The labelling itself lives in kornia 0.7.0 (`kornia.contrib.connected_components`, absent from this image): its
+# published algorithm is `num_iterations` rounds of 3x3 max-pooling of the batch-global pixel indices inside the
+# mask, so after convergence a component's label is the largest global index it contains.  This restatement labels
+# with scipy (8-connectivity) and assigns exactly those converged labels.  Pinned against the reference's own
+# selection code driven by a torch restatement of the kornia loop (tests/golden/make_golden_ccl.py).
+def synthetic_unet_probs(seed: int, C: int = 17, H: int = 384, W: int = 224) -> np.ndarray:
+    """float32 [C,H,W] probabilities: per class a main ellipse (p in [0.6, 0.95]) + 0-2 distractor blobs of higher or
+    lower confidence, smooth background < 0.5, 1-2 empty classes."""
+    rng = np.random.default_rng(5000 + seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    out = np.zeros((C, H, W), np.float32)
+    empty = set(rng.choice(C, size=int(rng.integers(1, 3)), replace=False).tolist())
+    for c in range(C):
+        p = (0.05 + 0.3 * rng.random((H, W))).astype(np.float32)
+        if c not in empty:
+            cy, cx = rng.uniform(0.1 * H, 0.9 * H), rng.uniform(0.15 * W, 0.85 * W)
+            ry, rx = rng.uniform(8, 45), rng.uniform(6, 30)
+            core = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0
+            p[core] = (rng.uniform(0.6, 0.95) + 0.04 * rng.standard_normal(int(core.sum()))).astype(np.float32)
+            for _ in range(int(rng.integers(0, 3))):
+                by, bx, br = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(1.5, 9.0)
+                blob = ((yy - by) / br) ** 2 + ((xx - bx) / br) ** 2 <= 1.0
+                p[blob] = (rng.uniform(0.55, 0.99) + 0.02 * rng.standard_normal(int(blob.sum()))).astype(np.float32)
+        out[c] = np.clip(p, 0.0, 1.0)
+    return out
+
+
+def ccl_labels(bin_mask: np.ndarray) -> np.ndarray:
+    """bool [C,H,W] -> int64 labels like converged kornia.contrib.connected_components on a (C,1,H,W) batch: the
+    largest batch-global pixel index of the 8-connected component (0 = background and, as in the reference, a lone
+    pixel at global index 0)."""
+    from scipy import ndimage
+    C, H, W = bin_mask.shape
+    out = np.zeros((C, H, W), np.int64)
+    gidx = np.arange(C * H * W, dtype=np.int64).reshape(C, H, W)
+    for c in range(C):
+        lab, n = ndimage.label(bin_mask[c], structure=np.ones((3, 3), bool))
+        if n == 0:
+            continue
+        mx = ndimage.maximum(gidx[c], labels=lab, index=np.arange(1, n + 1)).astype(np.int64)
+        out[c] = np.where(lab > 0, mx[np.maximum(lab, 1) - 1], 0)
+    return out
+
+
+def remove_all_but_one_connected_component(prob: np.ndarray, selection: str) -> np.ndarray:
+    """utils/segmentation_preprocessing.py:7-52 on float32 [C,H,W]."""
+    lbl = ccl_labels(prob > np.float32(0.5))
+    refined = np.zeros_like(prob)
+    for c in range(prob.shape[0]):
+        comps = np.unique(lbl[c])
+        comps = comps[comps != 0]
+        if comps.size == 0:
+            continue
+        areas = np.array([(lbl[c] == k).sum() for k in comps])
+        if selection == "largest":
+            win = comps[np.argmax(areas)]
+        elif selection == "highest_probability":
+            # reference: fp32 sum / int64 area -> fp32; the fp64 sum rounded to fp32 is the closest statement of it
+            means = np.array([np.float32(np.float32(prob[c][lbl[c] == k].astype(np.float64).sum()) / np.float32(a))
+                              for k, a in zip(comps, areas)], np.float32)
+            win = comps[np.argmax(means)]
+        else:
+            raise NotImplementedError(selection)
+        refined[c] = lbl[c] == win
+    return refined * prob

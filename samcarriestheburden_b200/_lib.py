@@ -46,6 +46,9 @@ _PROTOTYPES = {
     "b200sam_decoder_workspace_bytes_batch": (_sz, [_i, _i, _i]),
     "b200sam_decode_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200sam_upscale_threshold": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
+    "b200sam_ccl_scratch_bytes": (_sz, [_i, _i, _i]),
+    "b200sam_ccl_select": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "b200sam_morph_flat": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200sam_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sam_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _i, _vp]),
     "b200sam_encoder_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -137,6 +137,19 @@ int b200sam_upscale_threshold(const float* low_res, int n, int low, int img_size
                            small_out, small_h, small_w, static_cast<cudaStream_t>(stream));
 }
 
+size_t b200sam_ccl_scratch_bytes(int n_planes, int H, int W) {
+  if (n_planes < 0 || H <= 0 || W <= 0) return 0;
+  return ccl_scratch_bytes(n_planes, H, W);
+}
+int b200sam_ccl_select(const float* prob, int n_planes, int H, int W, float threshold, int by_area, float* out,
+                       void* scratch, void* stream) {
+  return ccl_select(prob, n_planes, H, W, threshold, by_area, out, scratch, static_cast<cudaStream_t>(stream));
+}
+int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw, int origin_y,
+                       int origin_x, int dilate, float* out, void* stream) {
+  return morph_flat(in, n_planes, H, W, se, kh, kw, origin_y, origin_x, dilate, out, static_cast<cudaStream_t>(stream));
+}
+
 int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M, int N,
                       int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_bf16, int max_ctas,
                       void* stream) {

@@ -84,4 +84,13 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
                       float thresh, uint8_t* mask_out, float* logits_out, uint8_t* small_out, int small_h,
                       int small_w, cudaStream_t stream);
 
+// ---- ccl.cu ----------------------------------------------------------------------------------
+// prob [n_planes, H, W] fp32 -> out = prob * (winning 8-connected component of prob > threshold), per plane
+size_t ccl_scratch_bytes(int n_planes, int H, int W);
+int ccl_select(const float* prob, int n_planes, int H, int W, float threshold, int by_area, float* out, void* scratch,
+               cudaStream_t stream);
+// flat (0/1 structuring element) grey-scale dilation / erosion, out-of-image taps ignored
+int morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw, int origin_y,
+               int origin_x, int dilate, float* out, cudaStream_t stream);
+
 }  // namespace b200sam

@@ -20,7 +20,7 @@ import torch
 from .. import sharding
 from ..segment_anything.predictor import SamPredictor
 from ..segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
-from ..utils.seg_refinement import SAMSegRefiner
+from ..utils.seg_refinement import SAMSegRefiner, SegEnhance
 
 
 @torch.no_grad()
@@ -62,18 +62,22 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
 @torch.no_grad()
 def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor], names: Sequence[str],
                          prompts2use=(("box",), ("pos_points", "neg_points")), gather: bool = False,
-                         batch: int = 8):
+                         batch: int = 8, ccl_selection: str | None = None):
     """segs[i]: [C,H,W] bool (or probabilities) U-Net masks of image names[i]; every rank refines the images of its
-    shard whose embeddings it holds.  Returns (list of (index, seg bool [C,H,W], est_dice [C]) for the local
-    shard, gathered [N,C,H,W] uint8 tensor or None)."""
+    shard whose embeddings it holds.  `ccl_selection` ('highest_probability' | 'largest') runs the SegEnhance
+    connected-component pre-processing (save_refined_segmentations.py:25-33,76) on the probability maps first.
+    Returns (list of (index, seg bool [C,H,W], est_dice [C]) for the local shard, gathered [N,C,H,W] uint8 tensor
+    or None)."""
     dev = sam.device
     head = SAMMaskDecoderHead(None, "", str(dev), store, sam_model=sam)
     refiner = SAMSegRefiner("SAM", str(dev), [list(p) for p in prompts2use], sam_predictor=head)
+    stage = SegEnhance(refiner, ccl_selection, "dilation", "square", 0, str(dev)) if ccl_selection else None
     mine = sharding.shard_indices(len(segs))
     results = []
     for j in range(0, len(mine), batch):
         chunk = mine[j:j + batch]
-        seg_b, est_b = refiner.refine_batch(torch.stack([segs[i].to(dev) for i in chunk]), [names[i] for i in chunk])
+        x, nm = torch.stack([segs[i].to(dev) for i in chunk]), [names[i] for i in chunk]
+        seg_b, est_b = stage.enhance_batch(x, nm) if stage is not None else refiner.refine_batch(x, nm)
         results.extend((i, seg_b[k], est_b[k]) for k, i in enumerate(chunk))
     gathered = None
     if gather and len(segs):

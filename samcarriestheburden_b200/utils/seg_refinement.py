@@ -14,12 +14,54 @@ import torch
 from ..segment_anything.modeling.sam import upscale_masks
 from ..segment_anything.sam_mask_decoder_head import SAMMaskDecoderHead
 from ..segment_anything.utils.prompt_utils import PromptExtractor, extract_seeds_boxes
+from . import segmentation_preprocessing
 
 
 class SegRefiner(ABC):
     @abstractmethod
     def refine(self, seg: torch.Tensor, file_name: str = None) -> torch.Tensor:
         pass
+
+
+class SegEnhance:
+    """Connected-component selection (+ optional flat morphology) in front of a refiner
+    (reference: utils/seg_refinement.py:20-72, same constructor arguments)."""
+
+    def __init__(self, refiner: SegRefiner, ccl_selection, morph_op: str, struct_element: str, radius: int, device: str):
+        self.last_preprocessed_seg = None
+        self.refiner = refiner
+        self.ccl_selection = ccl_selection
+        if morph_op not in ("erosion", "dilation"):
+            raise KeyError(morph_op)
+        if struct_element not in ("square", "disk", "diamond", "star"):
+            raise KeyError(struct_element)
+        self._dilate = morph_op == "dilation"
+        if struct_element == "square" and radius == 0:
+            radius = 1  # identity for the square element, like the reference
+        self._identity = radius == 0 or (struct_element == "square" and radius == 1)
+        self._kernel = None if self._identity else segmentation_preprocessing.structuring_element(struct_element, radius)
+
+    def _pre(self, seg: torch.Tensor) -> torch.Tensor:
+        if self.ccl_selection is None:
+            return seg
+        return segmentation_preprocessing._ccl(seg, self.ccl_selection)
+
+    @torch.inference_mode()
+    def enhance(self, seg: torch.Tensor, file_name: str = None):
+        assert seg.ndim == 3, "seg should be 3D tensor of shape (C, H, W)"
+        seg = self._pre(seg.to(self.refiner.sam_predictor.device) if hasattr(self.refiner, "sam_predictor") else seg)
+        self.last_preprocessed_seg = seg.float() if self._identity else \
+            segmentation_preprocessing.morph_flat(seg, self._kernel, self._dilate)
+        return self.refiner.refine(seg, file_name)
+
+    @torch.inference_mode()
+    def enhance_batch(self, segs: torch.Tensor, file_names: Sequence[str]):
+        """(N, C, H, W) probability maps of N images: one CCL launch sequence + one batched refinement."""
+        assert segs.ndim == 4, "segs should be 4D tensor of shape (N, C, H, W)"
+        segs = self._pre(segs.to(self.refiner.sam_predictor.device))
+        self.last_preprocessed_seg = segs.float() if self._identity else \
+            segmentation_preprocessing.morph_flat(segs, self._kernel, self._dilate)
+        return self.refiner.refine_batch(segs, file_names)
 
 
 class SAMSegRefiner(SegRefiner):
