@@ -117,7 +117,9 @@ def gemm_roofline(model: str, batch: int, reps: int = 10):
         b = torch.randn((N,), device=dev)
         out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
         res = out if not out_bf16 else None
-        ms = []
+        # all launches are queued back to back (flush kernel, event, GEMM, event) and read after ONE synchronise, so
+        # the GPU never idles between samples (an idle gap lets the SM clock drop and under-reports the kernel)
+        evs = []
         for i in range(reps + 3):
             flush.zero_()  # evict L2 between launches
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -125,9 +127,9 @@ def gemm_roofline(model: str, batch: int, reps: int = 10):
             _lib.check(lib.b200sam_gemm_bf16(A.data_ptr(), W.data_ptr(), out.data_ptr(), b.data_ptr(), _lib.ptr(res), M,
                                              N, K, K, K, N, N, 0, gelu, out_bf16, 0, stream))
             e1.record()
-            e1.synchronize()
-            if i >= 3:
-                ms.append(e0.elapsed_time(e1))
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(b_) for a, b_ in evs[3:]]
         t = statistics.mean(ms)
         flop = 2.0 * M * N * K
         per[name] = {"ms": round(t, 4), "tflops": round(flop / t / 1e9, 1)}

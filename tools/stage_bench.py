@@ -16,16 +16,16 @@ from samcarriestheburden_b200.segment_anything.utils.prompt_utils import extract
 
 def timed(fn, reps=8, warm=3):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    ms = []
-    for i in range(reps + warm):
+    evs = []
+    for i in range(reps + warm):  # queued back to back, read after one synchronise (no idle gaps between samples)
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        e1.synchronize()
-        if i >= warm:
-            ms.append(e0.elapsed_time(e1))
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in evs[warm:]]
     return statistics.mean(ms)
 
 
