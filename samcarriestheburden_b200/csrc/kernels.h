@@ -71,7 +71,9 @@ struct AttnArgs {
 };
 int window_attention(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows over the 64x64 grid
 int global_attention(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096, mma.sync path (A/B reference)
-int window_attention_tc(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows on tcgen05 / TMEM (attention_tc.cu)
+int window_attention_tc(const AttnArgs& a, cudaStream_t stream);
+// second generation: both query tiles of a window concurrently, P as a TMEM A-operand (attention_win2.cu)
+int window_attention_tc2(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows on tcgen05 / TMEM (attention_tc.cu)
 int global_attention_tc(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096 on tcgen05 / TMEM (attention_tc.cu)
 
 // ---- prompt_extract.cu -----------------------------------------------------------------------
