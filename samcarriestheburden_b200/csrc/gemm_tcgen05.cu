@@ -37,9 +37,11 @@ constexpr int GEMM_SMEM_BYTES = SMEM_TILES + SMEM_EPI + SMEM_BARRIERS;
 constexpr uint32_t TMEM_COLS = 512;
 
 
-// BN_EFF = 256 (full tiles) or 128: problems with N <= 128 (the decoder's 128-wide image-side projections) fetch and
-// multiply only 128 weight rows per k-block - half the shared-memory / L2 traffic and MMA time of a zero-padded
-// 256-wide tile; the TMEM layout and the epilogue are those of the 256-wide kernel.
+// BN_EFF = 256: 128 x 256 output tiles.  BN_EFF = 128 ("tall" tiles for problems with N <= 128, the decoder's 128-wide
+// image-side projections): 256 x 128 output tiles = two 128-row accumulators that share every weight k-block (A stage
+// 32 KiB, B stage 16 KiB), so the weights are re-streamed from L2 once per 256 rows and no zero-padded columns are
+// fetched or multiplied.  TMEM layout per accumulator stage: [rows 0-127 | rows 128-255] x 128 columns, drained by the
+// same 8 epilogue warps (the `half` index selects the row block instead of the column block).
 // a_wrap > 0: the A operand is stored with only a_wrap columns and k-blocks past it wrap around to column
 // kb*BK - a_wrap (the [hi | lo | hi] split operand of the decoder is stored as [hi | lo]).
 template <bool OUT_BF16, int BN_EFF>
@@ -60,7 +62,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM;
+  constexpr bool TALL = BN_EFF == 128;
+  constexpr int BM_T = TALL ? 2 * BM : BM;                 // rows per tile
+  constexpr int A_BYTES = TALL ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
+  static_assert(A_BYTES + BN_EFF * BK * 2 == STAGE_BYTES, "both tile shapes fill a 48 KiB stage");
+  const int num_m = (M + BM_T - 1) / BM_T;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
@@ -95,13 +101,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM;
+        const int m0 = (tile / num_n) * BM_T;
         const int n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + BN_EFF * BK * 2);
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int ka = kb * BK;
           tma_load_2d(sa, &tma_a, &full_bar[stage], (a_wrap > 0 && ka >= a_wrap) ? ka - a_wrap : ka, m0);
           tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
@@ -126,12 +132,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+          const uint64_t db = make_smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
             umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                          (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TALL)  // rows 128-255 of the tile: second accumulator, same weight tile
+              umma_bf16_ss(tmem_d + 128, make_smem_desc_sw128(sa + A_STAGE_BYTES) + static_cast<uint64_t>(2 * k),
+                           db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -154,8 +163,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * BM;
-      const int n0 = (tile % num_n) * BN + half * 128;
+      const int m0 = (tile / num_n) * BM_T + (TALL ? half * 128 : 0);
+      const int n0 = (tile % num_n) * BN + (TALL ? 0 : half * 128);
       const int row_base = m0 + quad * 32;
       epilogue_prefetch<OUT_BF16>(ep, M, N, row_base, n0, sbias, lane);
       mbar_wait(&tmem_full[as], aphase);
@@ -197,7 +206,8 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
                   "gemm: a_wrap=%d must be a positive multiple of %d with K <= 2 a_wrap", g.a_wrap, BK);
   const bool narrow = g.N <= 128;
   CUtensorMap ta, tb;
-  if (make_tmap_bf16(&ta, g.A, g.M, g.a_wrap > 0 ? g.a_wrap : g.K, g.lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_tmap_bf16(&ta, g.A, g.M, g.a_wrap > 0 ? g.a_wrap : g.K, g.lda, narrow ? 2 * BM : BM, BK,
+                     CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, narrow ? 128 : BN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   EpiParams ep;
   ep.bias = g.bias;
@@ -207,7 +217,8 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   ep.ldr = g.ldr;
   ep.res_row_mod = g.res_row_mod;
   ep.gelu = g.gelu;
-  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int bm_t = narrow ? 2 * BM : BM;
+  const int tiles = ((g.M + bm_t - 1) / bm_t) * ((g.N + BN - 1) / BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
   static bool attr_set = false;

@@ -27,7 +27,9 @@ def _gemm(A, W, bias=None, residual=None, res_row_mod=0, gelu=False, out_bf16=Tr
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (4096, 3840, 1280), (4096, 1280, 5120),
-                                   (200, 384, 192), (4096, 768, 768), (1000, 264, 72)])
+                                   (200, 384, 192), (4096, 768, 768), (1000, 264, 72),
+                                   # N <= 128: tall 256 x 128 tiles (two accumulators per weight k-block), ragged M
+                                   (300, 128, 192), (513, 64, 64), (70000, 128, 768), (131, 8, 64)])
 def test_gemm_bf16_bias(M, N, K):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     A = torch.randn((M, K), generator=g).to(DEV).bfloat16()
