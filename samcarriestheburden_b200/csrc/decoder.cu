@@ -88,7 +88,7 @@ __global__ void slice_iou_kernel(const float* __restrict__ iou4, float* __restri
 inline size_t align_up(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct Workspace {
-  float *emb_tok, *keys, *kbuf, *vbuf, *qibuf, *up1, *up2;
+  float *emb_tok, *keys, *kbuf, *vbuf, *qibuf;
   float *tokens, *queries, *tq, *tk, *tv, *ta, *th, *hyper, *iou4, *part;
   int* ntok;               // [NB] valid tokens per prompt (5 + present sparse points)
   __nv_bfloat16 *sa, *sb;  // hi/lo split operands [Mi, 512] bf16 each
@@ -110,8 +110,6 @@ Workspace carve(uint8_t* base, int n_images, int NB, int T) {
   w.kbuf = take(Mi * 128);
   w.vbuf = take(Mi * 128);
   w.qibuf = take(Mi * 128);
-  w.up1 = take(Mi * 256);
-  w.up2 = take(Mi * 512);
   w.tokens = take(Mt * 256);
   w.queries = take(Mt * 256);
   w.tq = take(Mt * 256);
@@ -297,12 +295,9 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(layernorm_rows(w.queries, W[W_NF], W[W_NF + 1], 1e-5f, Mt, 256, w.queries, 0, s));
   }
 
-  // ---- upscaling + hypernetwork heads (mask_decoder.py:137-147)
+  // ---- hypernetwork heads, then the upscaler with its element-wise stages fused into the two ConvT GEMM epilogues
+  //      (mask_decoder.py:137-147): ConvT1 + LayerNorm2d(64) + GELU -> split operand; ConvT2 + GELU + hyper dot -> masks
   const float* const* U = W + W_UP;
-  // w.sb still holds the split of the final keys (they do not change after the last image->token block)
-  TRY(tc_lin(w.sb, d->ws_up1, U[1], nullptr, w.up1, Mi, 256, 256, 0, s));             // ConvT 256->64, k2 s2
-  TRY(ln64_gelu(w.up1, U[2], U[3], static_cast<size_t>(Mi) * 4, w.sa, s));            // LayerNorm2d(64) + GELU -> split
-  TRY(tc_lin(w.sa, d->ws_up2, U[5], nullptr, w.up2, Mi * 4, 128, 64, 1, s));          // ConvT 64->32 + GELU
   {
     const float* wt[15];
     const float* bs[15];
@@ -312,7 +307,23 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(mlp3_tokens(w.queries, NB, T, wt, bs, w.hyper, w.iou4, s));
   }
   const int tok0 = a.multimask ? 1 : 0, ntok = a.multimask ? 3 : 1;  // mask_decoder.py:101-107
-  TRY(mask_dot(w.up2, w.hyper, NB, tok0, ntok, a.low_res_out, s));
+  {
+    // w.sb still holds the split of the final keys (they do not change after the last image->token block)
+    GemmArgs g;
+    g.A = w.sb; g.B = d->ws_up1; g.out = w.sa; g.bias = U[1]; g.residual = nullptr;
+    g.M = Mi; g.N = 256; g.K = 3 * 256; g.lda = 2 * 256; g.ldb = 3 * 256; g.ldo = 0; g.ldr = 0; g.res_row_mod = 0;
+    g.gelu = 0; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * 256;
+    g.epi_mode = 1; g.aux0 = U[2]; g.aux1 = U[3];
+    TRY(gemm_bf16_tn(g, s));                                                           // ConvT 256->64 + LN2d + GELU
+  }
+  {
+    GemmArgs g;
+    g.A = w.sa; g.B = d->ws_up2; g.out = a.low_res_out; g.bias = U[5]; g.residual = nullptr;
+    g.M = Mi * 4; g.N = 128; g.K = 3 * 64; g.lda = 2 * 64; g.ldb = 3 * 64; g.ldo = 0; g.ldr = 0; g.res_row_mod = 0;
+    g.gelu = 1; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * 64;
+    g.epi_mode = 2; g.aux0 = w.hyper; g.tok0 = tok0; g.ntok = ntok;
+    TRY(gemm_bf16_tn(g, s));                                                           // ConvT 64->32 + GELU + mask dot
+  }
   slice_iou_kernel<<<(NB * ntok + 127) / 128, 128, 0, s>>>(w.iou4, a.iou_out, NB, tok0, ntok);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;

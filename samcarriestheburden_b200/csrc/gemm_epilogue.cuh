@@ -15,6 +15,15 @@ struct EpiParams {
   int ldr;
   int res_row_mod;  // >0: residual row = row % res_row_mod (broadcast table, e.g. pos_embed)
   int gelu;
+  // fused epilogues of the mask decoder's upscaler (mask_decoder.py:53-59,139-145):
+  //   mode 1: N = 256 = 4 sub-pixels x 64 channels (ConvT 256->64): + bias, LayerNorm2d(64, eps 1e-6), erf GELU, then
+  //           the [hi | lo] bf16 split operand of the next ConvT: out = bf16 [M*4, 128]
+  //   mode 2: N = 128 = 4 sub-pixels x 32 channels (ConvT 64->32): + bias, GELU, dot with the prompt's hypernetwork
+  //           vector(s): out = fp32 masks [M/16384, ntok, 256, 256]  (row = (prompt*4096 + token)*4 + sub-pixel of ConvT 1)
+  int mode;
+  const float* aux0;  // mode 1: LN gamma [64];  mode 2: hyper [prompts, 4, 32]
+  const float* aux1;  // mode 1: LN beta [64]
+  int tok0, ntok;     // mode 2: mask tokens tok0 .. tok0 + ntok - 1
 };
 
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erfc(|z|) from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
@@ -166,6 +175,101 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
         }
         __syncwarp();
       }
+    }
+  }
+}
+
+// ---- mode 1: LayerNorm2d(64) + exact-erf GELU + [hi | lo] split; one warp = 32 rows x 128 columns = 2 channel groups
+B200SAM_DEVINL void epilogue_ln64_split(const EpiParams& ep, int M, int row_base, int n0, uint32_t taddr0,
+                                        const float* sbias, int lane) {
+  const int row = row_base + lane;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+#pragma unroll 1
+  for (int grp = 0; grp < 2; ++grp) {
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32b_x32(taddr0 + grp * 64, r0);
+    tmem_ld_32x32b_x32(taddr0 + grp * 64 + 32, r1);
+    tmem_ld_wait();
+    float v[64];
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = __uint_as_float(r0[j]) + sbias[grp * 64 + j];
+      v[32 + j] = __uint_as_float(r1[j]) + sbias[grp * 64 + 32 + j];
+      ps[j & 3] += v[j] + v[32 + j];
+    }
+    const float mean = ((ps[0] + ps[1]) + (ps[2] + ps[3])) * (1.0f / 64.0f);
+    float qs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; qs[j & 3] = fmaf(d, d, qs[j & 3]); }
+    const float rstd = 1.0f / sqrtf(((qs[0] + qs[1]) + (qs[2] + qs[3])) * (1.0f / 64.0f) + 1e-6f);
+    if (row < M) {
+      const int q = (n0 >> 6) + grp;  // sub-pixel (dy*2+dx) of this 64-channel group
+      __nv_bfloat16* o = out + (static_cast<size_t>(row) * 4 + q) * 128;
+#pragma unroll
+      for (int j8 = 0; j8 < 8; ++j8) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.aux0) + 2 * j8);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.aux0) + 2 * j8 + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.aux1) + 2 * j8);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.aux1) + 2 * j8 + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float f[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float x = (v[j8 * 8 + 2 * i + e] - mean) * rstd * gg[2 * i + e] + bb[2 * i + e];
+            f[e] = gelu_erf(x);  // |error| <= 1.5e-7 (erfc form), ~16 instructions instead of erff's ~45
+          }
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
+          __nv_bfloat162 hp, lp;
+          hp.x = h0; hp.y = h1;
+          lp = __floats2bfloat162_rn(f[0] - __bfloat162float(h0), f[1] - __bfloat162float(h1));
+          hi[i] = *reinterpret_cast<uint32_t*>(&hp);
+          lo[i] = *reinterpret_cast<uint32_t*>(&lp);
+        }
+        *reinterpret_cast<uint4*>(o + j8 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(o + 64 + j8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+}
+
+// ---- mode 2: GELU + hypernetwork dot; one warp = 32 rows x 128 columns = 4 sub-pixels x 32 channels
+B200SAM_DEVINL void epilogue_gelu_dot(const EpiParams& ep, int M, int row_base, uint32_t taddr0, const float* sbias,
+                                      int lane) {
+  const int row = row_base + lane;
+  float* masks = reinterpret_cast<float*>(ep.out);
+  const int b = row >> 14;                 // prompt (16384 rows each; uniform over a 128-row tile)
+  const int t4 = row & 16383;
+  const int tok = t4 >> 2, q = t4 & 3;
+  const int Y0 = 4 * (tok >> 6) + 2 * (q >> 1), X0 = 4 * (tok & 63) + 2 * (q & 1);
+#pragma unroll 1
+  for (int j = 0; j < ep.ntok; ++j) {
+    const float* hy = ep.aux0 + (static_cast<size_t>(b < (M >> 14) ? b : 0) * 4 + ep.tok0 + j) * 32;
+    float h[32];
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(hy) + c4);
+      h[4 * c4] = t.x; h[4 * c4 + 1] = t.y; h[4 * c4 + 2] = t.z; h[4 * c4 + 3] = t.w;
+    }
+    float acc[4];
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr0 + sub * 32, r);
+      tmem_ld_wait();
+      float a = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a = fmaf(h[c], gelu_erf(__uint_as_float(r[c]) + sbias[sub * 32 + c]), a);
+      acc[sub] = a;
+    }
+    if (row < M) {
+      float* o = masks + ((static_cast<size_t>(b) * ep.ntok + j) * 256 + Y0) * 256 + X0;
+      *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);        // sub = dy2*2 + dx2
+      *reinterpret_cast<float2*>(o + 256) = make_float2(acc[2], acc[3]);
     }
   }
 }

@@ -171,7 +171,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                               static_cast<uint32_t>(as * BN + half * 128);
-      epilogue_store<OUT_BF16>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane);
+      if (ep.mode == 1) epilogue_ln64_split(ep, M, row_base, n0, taddr0, sbias, lane);
+      else if (ep.mode == 2) epilogue_gelu_dot(ep, M, row_base, taddr0, sbias, lane);
+      else epilogue_store<OUT_BF16>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -196,7 +198,7 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   B200SAM_REQUIRE(g.K % 8 == 0 && g.lda % 8 == 0 && g.ldb % 8 == 0,
                   "gemm: K/lda/ldb must be multiples of 8 (16 B TMA alignment), got K=%d lda=%d ldb=%d", g.K, g.lda,
                   g.ldb);
-  B200SAM_REQUIRE(g.N % 8 == 0 && g.ldo % 8 == 0, "gemm: N and ldo must be multiples of 8 (N=%d ldo=%d)", g.N, g.ldo);
+  B200SAM_REQUIRE(g.N % 8 == 0 && (g.ldo % 8 == 0 || g.epi_mode != 0), "gemm: N and ldo must be multiples of 8 (N=%d ldo=%d)", g.N, g.ldo);
   B200SAM_REQUIRE(g.residual == nullptr || (g.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0),
                   "gemm: residual must be 16-byte aligned with ldr %% 4 == 0");
   B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "gemm: out must be 16-byte aligned");
@@ -217,6 +219,14 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   ep.ldr = g.ldr;
   ep.res_row_mod = g.res_row_mod;
   ep.gelu = g.gelu;
+  ep.mode = g.epi_mode;
+  ep.aux0 = g.aux0;
+  ep.aux1 = g.aux1;
+  ep.tok0 = g.tok0;
+  ep.ntok = g.ntok;
+  B200SAM_REQUIRE(g.epi_mode == 0 || (g.epi_mode == 1 && g.N == 256 && g.aux0 && g.aux1) ||
+                      (g.epi_mode == 2 && g.N == 128 && g.M % 16384 == 0 && g.aux0 && g.ntok >= 1 && g.ntok <= 3),
+                  "gemm: bad fused-epilogue configuration (mode %d, M=%d, N=%d)", g.epi_mode, g.M, g.N);
   const int bm_t = narrow ? 2 * BM : BM;
   const int tiles = ((g.M + bm_t - 1) / bm_t) * ((g.N + BN - 1) / BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
