@@ -57,6 +57,22 @@ B200SAM_DEVINL float ex2_approx(float x) {
   return y;
 }
 
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot per two elements in the softmax inner loops
+B200SAM_DEVINL void fma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
+B200SAM_DEVINL void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 struct TcParams {
   __nv_bfloat16* out;
   int heads;
@@ -300,7 +316,9 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tmem_ld_32x32b_x32(tl + COL_TW + hf * 32, w);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sv[hf * 32 + j] = fmaf(__uint_as_float(a[j]), scale_l2, __uint_as_float(w[j]));
+        for (int j = 0; j < 32; j += 2)
+          fma2(sv[hf * 32 + j], sv[hf * 32 + j + 1], __uint_as_float(a[j]), __uint_as_float(a[j + 1]), scale_l2,
+               __uint_as_float(w[j]), __uint_as_float(w[j + 1]));
       }
       tcgen05_fence_before();
       mbar_arrive(s_read);  // S(t) is in registers: the MMA warp may start QK(t+1)
@@ -315,9 +333,14 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // lazy rescale: keep the old reference maximum unless the new one exceeds it by more than 2^8
       const float m_new = (mt > m_run + LAZY_RESCALE) ? mt : m_run;
       const float corr = ex2_approx(m_run - m_new);  // 1 when unchanged, 0 on the first tile
-      const float off = m_new - th;
+      const float noff = th - m_new;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) sv[j] = ex2_approx(sv[j] - off);
+      for (int j = 0; j < 64; j += 2) {
+        float x0, x1;
+        add2(x0, x1, sv[j], sv[j + 1], noff, noff);
+        sv[j] = ex2_approx(x0);
+        sv[j + 1] = ex2_approx(x1);
+      }
       if (t > 0) {
         mbar_wait(o_ready, (t - 1) & 1);  // PV(t-1) retired: P and O are free again
         tcgen05_fence_after();
@@ -345,7 +368,7 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         pk.z = pack_bf16x2(sv[c * 8 + 4], sv[c * 8 + 5]);
         pk.w = pack_bf16x2(sv[c * 8 + 6], sv[c * 8 + 7]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ps[j] += sv[c * 8 + j];
+        for (int j = 0; j < 8; j += 2) add2(ps[j], ps[j + 1], ps[j], ps[j + 1], sv[c * 8 + j], sv[c * 8 + j + 1]);
         *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
       }
       l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
@@ -660,11 +683,11 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
             tmem_ld_32x32b_x32(tl + WCOL_S + hf * 32, a);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              constexpr int dummy = 0;
-              (void)dummy;
+            for (int j = 0; j < 32; j += 2) {
               const int k = KT * 64 + hf * 32 + j;
-              sv[hf * 32 + j] = fmaf(__uint_as_float(a[j]), scale_l2, bh[k / WIN] + bw[k % WIN]);
+              float b0, b1;
+              add2(b0, b1, bh[k / WIN], bh[(k + 1) / WIN], bw[k % WIN], bw[(k + 1) % WIN]);
+              fma2(sv[hf * 32 + j], sv[hf * 32 + j + 1], __uint_as_float(a[j]), __uint_as_float(a[j + 1]), scale_l2, b0, b1);
             }
           }
         } else {
@@ -689,7 +712,12 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
         const float m_new = (mt_ > m_run + LAZY_RESCALE) ? mt_ : m_run;
         const float corr = ex2_approx(m_run - m_new);
 #pragma unroll
-        for (int j = 0; j < NK; ++j) sv[j] = ex2_approx(sv[j] - m_new);
+        for (int j = 0; j < NK; j += 2) {
+          float x0, x1;
+          add2(x0, x1, sv[j], sv[j + 1], -m_new, -m_new);
+          sv[j] = ex2_approx(x0);
+          sv[j + 1] = ex2_approx(x1);
+        }
         if (g > 0) {
           mbar_wait(o_ready, (g - 1) & 1);  // previous PV retired: P (and O) are free again
           tcgen05_fence_after();
@@ -717,7 +745,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
           pk.z = pack_bf16x2(sv[c * 8 + 4], sv[c * 8 + 5]);
           pk.w = pack_bf16x2(sv[c * 8 + 6], sv[c * 8 + 7]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ps[j] += sv[c * 8 + j];
+          for (int j = 0; j < 8; j += 2) add2(ps[j], ps[j + 1], ps[j], ps[j + 1], sv[c * 8 + j], sv[c * 8 + j + 1]);
           *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = pk;
         }
         l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
