@@ -159,9 +159,10 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs p) {
       const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < RM; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < RM; ++i) {  // packed pairs: same products and rounding as four fmaf, half the issue slots
+        fma2_s(acc[i][0], acc[i][1], av[i], bv[0], bv[1], acc[i][0], acc[i][1]);
+        fma2_s(acc[i][2], acc[i][3], av[i], bv[2], bv[3], acc[i][2], acc[i][3]);
+      }
     }
     if (kt + 1 < nk) {
       sstore(buf ^ 1);
@@ -396,8 +397,8 @@ __global__ void __launch_bounds__(256) attn_fewq_long_kernel(const float* __rest
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const float4 a = *reinterpret_cast<const float4*>(&vs[kk][c4 * 4]);
-          acc[c4 * 4] = fmaf(pw, a.x, acc[c4 * 4]); acc[c4 * 4 + 1] = fmaf(pw, a.y, acc[c4 * 4 + 1]);
-          acc[c4 * 4 + 2] = fmaf(pw, a.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(pw, a.w, acc[c4 * 4 + 3]);
+          fma2_s(acc[c4 * 4], acc[c4 * 4 + 1], pw, a.x, a.y, acc[c4 * 4], acc[c4 * 4 + 1]);
+          fma2_s(acc[c4 * 4 + 2], acc[c4 * 4 + 3], pw, a.z, a.w, acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
         }
       }
     }
@@ -519,8 +520,8 @@ __global__ void __launch_bounds__(256) attn_fewk_kernel(const float* __restrict_
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         const float4 vv = *reinterpret_cast<const float4*>(&vs[t][h][c4 * 4]);
-        o[c4 * 4] = fmaf(pw, vv.x, o[c4 * 4]); o[c4 * 4 + 1] = fmaf(pw, vv.y, o[c4 * 4 + 1]);
-        o[c4 * 4 + 2] = fmaf(pw, vv.z, o[c4 * 4 + 2]); o[c4 * 4 + 3] = fmaf(pw, vv.w, o[c4 * 4 + 3]);
+        fma2_s(o[c4 * 4], o[c4 * 4 + 1], pw, vv.x, vv.y, o[c4 * 4], o[c4 * 4 + 1]);
+        fma2_s(o[c4 * 4 + 2], o[c4 * 4 + 3], pw, vv.z, vv.w, o[c4 * 4 + 2], o[c4 * 4 + 3]);
       }
     }
   }
