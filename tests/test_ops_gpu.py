@@ -110,7 +110,7 @@ def _attention_reference(qkv, bias16, rel_h, rel_w, heads, hd, window):
     return o.reshape(B * 4096, D)
 
 
-@pytest.mark.parametrize("heads,hd,glob", [(16, 80, 0), (12, 64, 0), (4, 80, 1), (3, 64, 1), (2, 80, 2), (2, 64, 2), (3, 80, 3), (2, 64, 3), (16, 80, 4), (5, 64, 4)])
+@pytest.mark.parametrize("heads,hd,glob", [(16, 80, 0), (12, 64, 0), (4, 80, 1), (3, 64, 1), (2, 80, 2), (2, 64, 2), (3, 80, 3), (2, 64, 3), (16, 80, 4), (5, 64, 4), (16, 80, 5), (5, 64, 5)])
 def test_encoder_attention(heads, hd, glob):
     g = torch.Generator(device="cpu").manual_seed(heads * 100 + hd + glob)
     D = heads * hd

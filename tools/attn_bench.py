@@ -18,7 +18,7 @@ qkv = torch.randn((B * 4096, 3 * D), device=dev).bfloat16()
 bias = torch.randn((3 * D,), device=dev).bfloat16()
 out = torch.empty((B * 4096, D), dtype=torch.bfloat16, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name, glob, S, flop in (("window (tcgen05)", 0, 14, 4 * heads * 4096 * 210 * hd), ("window (tcgen05 v2)", 4, 14, 4 * heads * 4096 * 210 * hd), ("window (mma.sync)", 3, 14, 4 * heads * 4096 * 210 * hd), ("global (tcgen05)", 1, 64, 4 * heads * 4096 * 4160 * hd),
+for name, glob, S, flop in (("window (tcgen05)", 0, 14, 4 * heads * 4096 * 210 * hd), ("window (tcgen05 v2)", 4, 14, 4 * heads * 4096 * 210 * hd), ("window (tcgen05 v3)", 5, 14, 4 * heads * 4096 * 210 * hd), ("window (mma.sync)", 3, 14, 4 * heads * 4096 * 210 * hd), ("global (tcgen05)", 1, 64, 4 * heads * 4096 * 4160 * hd),
                             ("global (mma.sync)", 2, 64, 4 * heads * 4096 * 4160 * hd)):
     rel_h = (0.02 * torch.randn((2 * S - 1, hd), device=dev)).bfloat16()
     rel_w = (0.02 * torch.randn((2 * S - 1, hd), device=dev)).bfloat16()
