@@ -125,7 +125,8 @@ B200SAM_API int b200sam_gemm_bf16(const void* A, const void* W, void* out, const
 B200SAM_API int b200sam_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
                       int out_bf16, void* stream);
 /* qkv: [B*4096, 3*heads*hd] bf16; out: [B*4096, heads*hd] bf16; global_attn: 0 = 14x14 windows, 1 = global
- * (tcgen05 path used by the encoder), 2 = global on the legacy mma.sync path (kept for A/B measurements) */
+ * (the tcgen05 paths used by the encoder); A/B variants kept for measurements: 2 / 3 = global / windows on the legacy
+ * mma.sync path, 4 / 5 = second / third generation windowed tcgen05 kernels (attention_win2.cu, attention_win3.cu) */
 B200SAM_API int b200sam_encoder_attention(const void* qkv, const void* qkv_bias_bf16, const void* rel_h_bf16,
                               const void* rel_w_bf16, void* out, int batch, int heads, int hd, int global_attn,
                               void* stream);

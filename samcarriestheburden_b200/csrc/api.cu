@@ -177,6 +177,7 @@ int b200sam_encoder_attention(const void* qkv, const void* qkv_bias_bf16, const 
   if (global_attn == 2) return global_attention(a, static_cast<cudaStream_t>(stream));
   if (global_attn == 3) return window_attention(a, static_cast<cudaStream_t>(stream));
   if (global_attn == 4) return window_attention_tc2(a, static_cast<cudaStream_t>(stream));
+  if (global_attn == 5) return window_attention_tc3(a, static_cast<cudaStream_t>(stream));
   return window_attention_tc(a, static_cast<cudaStream_t>(stream));
 }
 int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, int w, const float* mean3,

@@ -78,7 +78,9 @@ int window_attention(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows 
 int global_attention(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096, mma.sync path (A/B reference)
 int window_attention_tc(const AttnArgs& a, cudaStream_t stream);
 // second generation: both query tiles of a window concurrently, P as a TMEM A-operand (attention_win2.cu)
-int window_attention_tc2(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows on tcgen05 / TMEM (attention_tc.cu)
+int window_attention_tc2(const AttnArgs& a, cudaStream_t stream);
+// third generation: two large softmax rounds per query tile (two-pass TMEM softmax), attention_win3.cu
+int window_attention_tc3(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows on tcgen05 / TMEM (attention_tc.cu)
 int global_attention_tc(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096 on tcgen05 / TMEM (attention_tc.cu)
 
 // ---- prompt_extract.cu -----------------------------------------------------------------------
