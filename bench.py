@@ -324,6 +324,7 @@ def main():
                                      "ms": round(v["ms"], 4), "bytes": v["bytes"]}
                                  for k, v in stage_bench.run(peaks["hbm"]).items()}
             out["pipeline"] = pipeline_throughput(sam, dev)
+            out["unet"] = unet_throughput(dev)
         if world == 1 and not args.no_cpu_baseline:
             v, cores, times = cpu_encoder_images_per_s(args.model, 1)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
@@ -385,6 +386,28 @@ def refine_throughput(sam, dev, n_images: int = 32, batch: int = 8):
             "value": nb / (msb / 1e3), "unit": "masks/s", "images": n_images, "masks": nb,
             "ms_per_image": msb / n_images,
             "per_image_api": {"value": n1 / (ms1 / 1e3), "unit": "masks/s", "ms_per_image": ms1 / min(n_images, 8)}}
+
+
+def unet_throughput(dev, batch: int = 8, reps: int = 5):
+    """the U-Net that produces the masks (17 classes, 384 x 224), random-init weights, batch 8."""
+    import torch
+    from oracle import unet_oracle as U
+    from samcarriestheburden_b200.custom_arcitecture.classic_u_net import UNet
+    m = UNet(1, 17)
+    m.load_state_dict(U.random_unet_state_dict(0), strict=True)
+    m = m.to(dev)
+    x = torch.cat([U.synthetic_radiograph_small(i) for i in range(batch)]).to(dev)
+    m.predict_proba(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        m.predict_proba(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"metric": "U-Net probability maps/s (1 x 384 x 224 -> 17 x 384 x 224, ~130 GFLOP per image, fp32-grade split GEMMs)",
+            "images_per_s": batch / (ms / 1e3), "ms_per_image": ms / batch, "batch": batch}
 
 
 def pipeline_throughput(sam, dev, n_images: int = 32, batch: int = 8):

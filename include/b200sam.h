@@ -117,6 +117,23 @@ B200SAM_API int b200sam_ccl_select(const float* prob, int n_planes, int H, int W
 B200SAM_API int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw,
                        int origin_y, int origin_x, int dilate, float* out, void* stream);
 
+/* ---------------------------------------------------------------- U-Net inference
+ * Replaces UNet.forward (custom_arcitecture/classic_u_net.py:81-119, bilinear = False) as called from
+ * scripts/save_refined_segmentations.py:67-69 (+ the torch.sigmoid that follows).  Weight table like the SAM handles:
+ * "state_dict key|packing" with packing conv3x3_tap (fp32 [Cout, Kp], column (ky*3+kx)*Cin + c, zero padded to
+ * Kp = b200sam_unet_conv_kp(Cin)), convT, repeat4, pad_rows8 / pad8 (rows / elements zero padded to a multiple of 8).
+ * image: [batch,1,H,W] float32, already normalised, H and W multiples of 16; outputs [batch,n_classes,H,W]. */
+typedef struct b200sam_unet b200sam_unet;
+B200SAM_API int b200sam_unet_weight_count(void);
+B200SAM_API const char* b200sam_unet_weight_name(int i);
+B200SAM_API int b200sam_unet_conv_kp(int cin);
+B200SAM_API int b200sam_unet_create(int n_channels, int n_classes, int n_last_channel, const void* const* weights,
+                        int n_weights, b200sam_unet** out, void* stream);
+B200SAM_API void b200sam_unet_destroy(b200sam_unet* u);
+B200SAM_API size_t b200sam_unet_workspace_bytes(const b200sam_unet* u, int batch, int H, int W);
+B200SAM_API int b200sam_unet_forward(const b200sam_unet* u, const float* image, int batch, int H, int W, float* logits_out,
+                         float* probs_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- building blocks (exposed for parity tests)
  * D[M,N] = A[M,K] W[N,K]^T (+bias) (+GELU) (+residual[row % res_row_mod]); bf16 operands, fp32 accumulate (tcgen05). */
 B200SAM_API int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M,

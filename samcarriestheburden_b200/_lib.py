@@ -46,6 +46,13 @@ _PROTOTYPES = {
     "b200sam_decoder_workspace_bytes_batch": (_sz, [_i, _i, _i]),
     "b200sam_decode_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200sam_upscale_threshold": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
+    "b200sam_unet_weight_count": (_i, []),
+    "b200sam_unet_weight_name": (C.c_char_p, [_i]),
+    "b200sam_unet_conv_kp": (_i, [_i]),
+    "b200sam_unet_create": (_i, [_i, _i, _i, C.POINTER(_vp), _i, C.POINTER(_vp), _vp]),
+    "b200sam_unet_destroy": (None, [_vp]),
+    "b200sam_unet_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "b200sam_unet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200sam_ccl_scratch_bytes": (_sz, [_i, _i, _i]),
     "b200sam_ccl_select": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "b200sam_morph_flat": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -23,6 +23,7 @@ using namespace b200sam;
 
 struct b200sam_encoder { Encoder* impl; };
 struct b200sam_decoder { Decoder* impl; };
+struct b200sam_unet { UNetCtx* impl; };
 
 static EncoderConfig to_cfg(const b200sam_encoder_config* c) {
   EncoderConfig e;
@@ -135,6 +136,33 @@ int b200sam_upscale_threshold(const float* low_res, int n, int low, int img_size
   if (n > 0 && !low_res) { set_last_error("upscale: null input"); return 2; }
   return upscale_threshold(low_res, n, low, img_size, in_h, in_w, out_h, out_w, threshold, mask_out, logits_out,
                            small_out, small_h, small_w, static_cast<cudaStream_t>(stream));
+}
+
+int b200sam_unet_weight_count(void) { return unet_weight_count(); }
+const char* b200sam_unet_weight_name(int i) { return unet_weight_name(i); }
+int b200sam_unet_conv_kp(int cin) { return unet_conv_kp(cin); }
+int b200sam_unet_create(int n_channels, int n_classes, int n_last_channel, const void* const* weights, int n_weights,
+                        b200sam_unet** out, void* stream) {
+  if (!weights || !out) { set_last_error("unet_create: null argument"); return 2; }
+  UNetCtx* u = nullptr;
+  if (int rc = unet_create(n_channels, n_classes, n_last_channel, weights, n_weights, &u, static_cast<cudaStream_t>(stream)))
+    return rc;
+  *out = new b200sam_unet{u};
+  return 0;
+}
+void b200sam_unet_destroy(b200sam_unet* u) {
+  if (!u) return;
+  unet_destroy(u->impl);
+  delete u;
+}
+size_t b200sam_unet_workspace_bytes(const b200sam_unet* u, int batch, int H, int W) {
+  return u ? unet_workspace_bytes(u->impl, batch, H, W) : 0;
+}
+int b200sam_unet_forward(const b200sam_unet* u, const float* image, int batch, int H, int W, float* logits_out,
+                         float* probs_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!u) { set_last_error("unet_forward: null handle"); return 2; }
+  return unet_forward(u->impl, image, batch, H, W, logits_out, probs_out, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream));
 }
 
 size_t b200sam_ccl_scratch_bytes(int n_planes, int H, int W) {

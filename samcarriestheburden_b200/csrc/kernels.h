@@ -102,4 +102,17 @@ int ccl_select(const float* prob, int n_planes, int H, int W, float threshold, i
 int morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw, int origin_y,
                int origin_x, int dilate, float* out, cudaStream_t stream);
 
+// ---- unet.cu -----------------------------------------------------------------------------------
+struct UNetCtx;
+int unet_weight_count();
+const char* unet_weight_name(int i);
+int unet_conv_kp(int cin);  // padded K of a 3x3 convolution with cin input channels
+int unet_create(int n_channels, int n_classes, int n_last, const void* const* weights, int n, UNetCtx** out,
+                cudaStream_t stream);
+void unet_destroy(UNetCtx* u);
+size_t unet_workspace_bytes(const UNetCtx* u, int B, int H, int W);
+// image [B, 1, H, W] fp32 (already normalised) -> logits / sigmoid probabilities [B, n_classes, H, W] (either may be null)
+int unet_forward(const UNetCtx* u, const float* image, int B, int H, int W, float* logits_out, float* probs_out,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace b200sam

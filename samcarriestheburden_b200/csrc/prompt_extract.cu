@@ -16,6 +16,7 @@ namespace {
 constexpr int SLOT = 12;  // int32 words per (image, class) accumulator, 48 B (keeps the u64 sums aligned)
 // [0,1] sum_r (u64)  [2,3] sum_c (u64)  [4] n_seed  [5] n_all  [6] min_r  [7] max_r  [8] min_c  [9] max_c
 constexpr int MAX_C = 64;
+constexpr int PE_ITEM_GROUPS = 1024;  // 16-pixel groups per work item of the fast path (4 per thread)
 
 __global__ void prompt_init_kernel(int32_t* scratch, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,7 +130,7 @@ B200SAM_DEVINL uint32_t norm01(uint32_t w) {  // every non-zero byte -> 1
   return (w | (w >> 1)) & 0x01010101u;
 }
 
-// Work item = (image, chunk of 256 groups = 4096 pixels x C classes); a fixed grid of CTAs walks the items of the
+// Work item = (image, chunk of 1024 groups = 16384 pixels x C classes); a fixed grid of CTAs walks the items of the
 // whole batch with a grid stride (balanced: every CTA gets the same number of items), accumulating one item in shared
 // memory and flushing it to the image's global slots with a handful of atomics.
 __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* __restrict__ masks, int C, int H, int W,
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
       s_mm[c][0] = INT_MAX; s_mm[c][1] = -1; s_mm[c][2] = INT_MAX; s_mm[c][3] = -1;
     }
     __syncthreads();
-    const int g = chunk * 256 + threadIdx.x;
-    if (g < groups) {
+    const int gend = min(groups, (chunk + 1) * PE_ITEM_GROUPS);
+    for (int g = chunk * PE_ITEM_GROUPS + threadIdx.x; g < gend; g += 256) {
       const int p0 = g * 16;
       const int r = p0 / W, c0 = p0 - r * W;
       const uint8_t* base = masks + static_cast<size_t>(img) * C * HW + p0;
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
           if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) any |= 1ull << (cb + j);
         }
       }
-      if (any != 0ull) {
+      if (any == 0ull) continue;
+      {
         if (((odd.x | odd.y | odd.z | odd.w) & 0xfefefefeu) != 0u) {  // bytes other than 0/1: recount normalised
           cov = make_uint4(0, 0, 0, 0);
           for (unsigned long long t = any; t; t &= t - 1) {
@@ -271,7 +273,7 @@ int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t
   if (HW > 0) {
     const bool fast = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && (HW % 16 == 0);
     if (fast) {
-      const int chunks = (HW / 16 + 255) / 256;
+      const int chunks = (HW / 16 + PE_ITEM_GROUPS - 1) / PE_ITEM_GROUPS;
       const long long items = static_cast<long long>(n_img) * chunks;
       B200SAM_REQUIRE(items < (1ll << 31), "prompt_extract: batch too large");
       const int max_ctas = 148 * 4;  // all CTAs resident (4 x 256 threads per SM): a persistent, balanced grid

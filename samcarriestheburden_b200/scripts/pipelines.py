@@ -60,6 +60,27 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
 
 
 @torch.no_grad()
+def predict_unet_probabilities(unet, images: Sequence[np.ndarray], size=(384, 224), batch: int = 8,
+                               mean: float = 0.3505533917353781, std: float = 0.22763733675869177) -> List[torch.Tensor]:
+    """The U-Net stage of save_refined_segmentations.py:61-69 for the local shard: grey uint8 images -> bilinear
+    resize to (H, W) (cv2.INTER_LINEAR == half-pixel bilinear without antialiasing) -> / 255 -> normalise -> U-Net ->
+    sigmoid.  Returns one [C, H, W] probability map per input image (on the model's device)."""
+    dev = unet.outc.conv.weight.device
+    H, W = size
+    out: List[torch.Tensor] = []
+    for j in range(0, len(images), batch):
+        xs = []
+        for img in images[j:j + batch]:
+            g = torch.from_numpy(np.ascontiguousarray(img if img.ndim == 2 else img[..., 0])).to(dev).float()[None, None]
+            if tuple(g.shape[-2:]) != (H, W):
+                g = torch.nn.functional.interpolate(g, size=(H, W), mode="bilinear", align_corners=False)
+            xs.append((g / 255.0 - mean) / std)
+        probs = unet.predict_proba(torch.cat(xs))
+        out.extend(probs[k] for k in range(probs.shape[0]))
+    return out
+
+
+@torch.no_grad()
 def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor], names: Sequence[str],
                          prompts2use=(("box",), ("pos_points", "neg_points")), gather: bool = False,
                          batch: int = 8, ccl_selection: str | None = None):
