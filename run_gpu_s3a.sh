@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q --tb=short -x -k "upscale or prompt" > gpurun_out/pytest_ops.log 2>&1; echo "pytest exit=$?"; tail -3 gpurun_out/pytest_ops.log | cut -c1-300
+timeout 300 python tools/stage_bench.py > gpurun_out/stage.json 2> gpurun_out/stage.err; echo "stage exit=$?"; cat gpurun_out/stage.json

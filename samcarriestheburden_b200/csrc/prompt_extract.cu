@@ -16,7 +16,6 @@ namespace {
 constexpr int SLOT = 12;  // int32 words per (image, class) accumulator, 48 B (keeps the u64 sums aligned)
 // [0,1] sum_r (u64)  [2,3] sum_c (u64)  [4] n_seed  [5] n_all  [6] min_r  [7] max_r  [8] min_c  [9] max_c
 constexpr int MAX_C = 64;
-constexpr int PE_ITEM_GROUPS = 1024;  // 16-pixel groups per work item of the fast path (4 per thread)
 
 __global__ void prompt_init_kernel(int32_t* scratch, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,30 +129,47 @@ B200SAM_DEVINL uint32_t norm01(uint32_t w) {  // every non-zero byte -> 1
   return (w | (w >> 1)) & 0x01010101u;
 }
 
-// Work item = (image, chunk of 1024 groups = 16384 pixels x C classes); a fixed grid of CTAs walks the items of the
-// whole batch with a grid stride (balanced: every CTA gets the same number of items), accumulating one item in shared
-// memory and flushing it to the image's global slots with a handful of atomics.
+// sum of the positions of the set bits of a 16-bit mask
+B200SAM_DEVINL int bitpos_sum16(uint32_t m) {
+  return __popc(m & 0xaaaau) + 2 * __popc(m & 0xccccu) + 4 * __popc(m & 0xf0f0u) + 8 * __popc(m & 0xff00u);
+}
+
+// The batch is one flat sequence of 16-pixel groups ([image][group]); every CTA of a fully resident grid owns one
+// contiguous, equally long slice of it (balanced to within one warp iteration) and walks the (at most two or three)
+// images its slice touches.  Within an image segment the per-class accumulators live in shared memory and are flushed
+// to the image's global slots with a handful of atomics.  A warp reads 512 consecutive pixels of each class plane per
+// iteration; the contributions of its 32 lanes are combined with warp reductions (redux.sync / ballot) first, so one
+// lane issues the shared-memory atomics: neighbouring lanes almost always hit the SAME class, and per-lane atomics
+// on one address serialise 32-fold.
 __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* __restrict__ masks, int C, int H, int W,
-                                                             int32_t* __restrict__ scratch, int n_items,
-                                                             int chunks_per_img) {
+                                                             int32_t* __restrict__ scratch, long long total_groups,
+                                                             int groups_per_cta) {
   __shared__ unsigned long long s_sum[MAX_C][2];
   __shared__ int s_cnt[MAX_C][2];
   __shared__ int s_mm[MAX_C][4];
+  constexpr unsigned FULL = 0xffffffffu;
   const int HW = H * W;
   const int groups = HW / 16;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int img = item / chunks_per_img, chunk = item - img * chunks_per_img;
+  const long long start = static_cast<long long>(blockIdx.x) * groups_per_cta;
+  const long long end = min(total_groups, start + groups_per_cta);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int img = static_cast<int>(start / groups); static_cast<long long>(img) * groups < end; ++img) {
+    const long long ibase = static_cast<long long>(img) * groups;
+    const int lo = static_cast<int>(max(start, ibase) - ibase);
+    const int hi = static_cast<int>(min(end, ibase + groups) - ibase);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       s_sum[c][0] = s_sum[c][1] = 0ull;
       s_cnt[c][0] = s_cnt[c][1] = 0;
       s_mm[c][0] = INT_MAX; s_mm[c][1] = -1; s_mm[c][2] = INT_MAX; s_mm[c][3] = -1;
     }
     __syncthreads();
-    const int gend = min(groups, (chunk + 1) * PE_ITEM_GROUPS);
-    for (int g = chunk * PE_ITEM_GROUPS + threadIdx.x; g < gend; g += 256) {
-      const int p0 = g * 16;
+    const uint8_t* ibytes = masks + static_cast<size_t>(img) * C * HW;
+    for (int gb = lo + warp * 32; gb < hi; gb += 256) {  // warp-uniform trip count
+      const int g = gb + lane;
+      const bool valid = g < hi;
+      const int p0 = (valid ? g : gb) * 16;
       const int r = p0 / W, c0 = p0 - r * W;
-      const uint8_t* base = masks + static_cast<size_t>(img) * C * HW + p0;
+      const uint8_t* base = ibytes + p0;
       // pass 1: 8 independent 16-byte loads in flight per thread; bool bytes are 0/1, so the per-pixel cover count is
       // a plain packed byte add (anything else is detected through `odd` and recounted below)
       uint4 cov = make_uint4(0, 0, 0, 0), odd = make_uint4(0, 0, 0, 0);
@@ -162,8 +178,8 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
         uint4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          v[j] = cb + j < C ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(cb + j) * HW))
-                            : make_uint4(0, 0, 0, 0);
+          v[j] = (cb + j < C && valid) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(cb + j) * HW))
+                                       : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           cov.x += v[j].x; cov.y += v[j].y; cov.z += v[j].z; cov.w += v[j].w;
@@ -171,43 +187,59 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
           if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) any |= 1ull << (cb + j);
         }
       }
-      if (any == 0ull) continue;
-      {
-        if (((odd.x | odd.y | odd.z | odd.w) & 0xfefefefeu) != 0u) {  // bytes other than 0/1: recount normalised
-          cov = make_uint4(0, 0, 0, 0);
-          for (unsigned long long t = any; t; t &= t - 1) {
-            const int c = __ffsll(static_cast<long long>(t)) - 1;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW));
-            cov.x += norm01(v.x); cov.y += norm01(v.y); cov.z += norm01(v.z); cov.w += norm01(v.w);
-          }
-        }
-        // pixels covered by fewer than two classes; per-byte test without cross-byte carries: byte < 2 <=> byte >> 1 == 0
-        auto lt2 = [](uint32_t w) {
-          const uint32_t hi = (w >> 1) & 0x7f7f7f7fu;                   // byte >> 1
-          const uint32_t nz = ((hi + 0x7f7f7f7fu) | hi) & 0x80808080u;  // 0x80 where byte >> 1 != 0
-          return (~nz & 0x80808080u) >> 7;                              // 1 where byte < 2
-        };
-        uint4 single;
-        single.x = lt2(cov.x); single.y = lt2(cov.y); single.z = lt2(cov.z); single.w = lt2(cov.w);
-        const uint32_t smask = bytes_to_mask16(single);
-        // pass 2 revisits only the classes with a set pixel in this group (L1 hits): bytes -> 16-bit masks so count /
-        // min / max / sum come from popc / ffs / clz instead of per-pixel branches
-        while (any) {
-          const int c = __ffsll(static_cast<long long>(any)) - 1;
-          any &= any - 1;
+      // classes with a set pixel anywhere in the warp's 512 pixels
+      const uint32_t any_lo = __reduce_or_sync(FULL, static_cast<uint32_t>(any));
+      const uint32_t any_hi = C > 32 ? __reduce_or_sync(FULL, static_cast<uint32_t>(any >> 32)) : 0u;
+      if ((any_lo | any_hi) == 0u) continue;
+      if (((odd.x | odd.y | odd.z | odd.w) & 0xfefefefeu) != 0u) {  // bytes other than 0/1: recount normalised
+        cov = make_uint4(0, 0, 0, 0);
+        for (unsigned long long t = any; t; t &= t - 1) {
+          const int c = __ffsll(static_cast<long long>(t)) - 1;
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW));
-          const uint32_t m = bytes_to_mask16(v);
+          cov.x += norm01(v.x); cov.y += norm01(v.y); cov.z += norm01(v.z); cov.w += norm01(v.w);
+        }
+      }
+      // pixels covered by fewer than two classes; per-byte test without cross-byte carries: byte < 2 <=> byte >> 1 == 0
+      auto lt2 = [](uint32_t w) {
+        const uint32_t hi7 = (w >> 1) & 0x7f7f7f7fu;                    // byte >> 1
+        const uint32_t nz = ((hi7 + 0x7f7f7f7fu) | hi7) & 0x80808080u;  // 0x80 where byte >> 1 != 0
+        return (~nz & 0x80808080u) >> 7;                                // 1 where byte < 2
+      };
+      uint4 single;
+      single.x = lt2(cov.x); single.y = lt2(cov.y); single.z = lt2(cov.z); single.w = lt2(cov.w);
+      const uint32_t smask = bytes_to_mask16(single);
+      // pass 2 (warp-uniform loop over the classes present in the warp; re-loads are L1 hits): bytes -> 16-bit masks so
+      // count / min / max / sum come from popc / ffs / clz, then one warp reduction per quantity
+      for (int half = 0; half < 2; ++half) {
+        uint32_t todo = half == 0 ? any_lo : any_hi;
+        while (todo) {
+          const int c = __ffs(todo) - 1 + 32 * half;
+          todo &= todo - 1;
+          uint32_t m = 0u;
+          if ((any >> c) & 1ull)
+            m = bytes_to_mask16(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW)));
           const uint32_t sd = m & smask;
-          atomicAdd(&s_cnt[c][1], __popc(m));
-          atomicMin(&s_mm[c][0], r); atomicMax(&s_mm[c][1], r);
-          atomicMin(&s_mm[c][2], c0 + __ffs(m) - 1); atomicMax(&s_mm[c][3], c0 + 31 - __clz(m));
-          if (sd) {
+          const int n_all = __reduce_add_sync(FULL, __popc(m));
+          const int mn_r = __reduce_min_sync(FULL, m ? r : INT_MAX), mx_r = __reduce_max_sync(FULL, m ? r : -1);
+          const int mn_c = __reduce_min_sync(FULL, m ? c0 + __ffs(m) - 1 : INT_MAX);
+          const int mx_c = __reduce_max_sync(FULL, m ? c0 + 31 - __clz(m) : -1);
+          const bool seeds = __any_sync(FULL, sd != 0u);
+          int n_seed = 0, sr = 0, sc = 0;
+          if (seeds) {  // per warp: <= 512 pixels, rows / columns < 2^16 -> the 32-bit partial sums cannot overflow
             const int ns = __popc(sd);
-            int pos = 0;
-            for (uint32_t t = sd; t; t &= t - 1) pos += __ffs(t) - 1;
-            atomicAdd(&s_cnt[c][0], ns);
-            atomicAdd(&s_sum[c][0], static_cast<unsigned long long>(ns) * r);
-            atomicAdd(&s_sum[c][1], static_cast<unsigned long long>(ns) * c0 + pos);
+            n_seed = __reduce_add_sync(FULL, ns);
+            sr = __reduce_add_sync(FULL, ns * r);
+            sc = __reduce_add_sync(FULL, ns * c0 + bitpos_sum16(sd));
+          }
+          if (lane == 0) {
+            atomicAdd(&s_cnt[c][1], n_all);
+            atomicMin(&s_mm[c][0], mn_r); atomicMax(&s_mm[c][1], mx_r);
+            atomicMin(&s_mm[c][2], mn_c); atomicMax(&s_mm[c][3], mx_c);
+            if (n_seed) {
+              atomicAdd(&s_cnt[c][0], n_seed);
+              atomicAdd(&s_sum[c][0], static_cast<unsigned long long>(sr));
+              atomicAdd(&s_sum[c][1], static_cast<unsigned long long>(sc));
+            }
           }
         }
       }
@@ -225,7 +257,7 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
         atomicAdd(reinterpret_cast<unsigned long long*>(s + 2), s_sum[c][1]);
       }
     }
-    __syncthreads();  // the accumulators are re-initialised at the top of the next item
+    __syncthreads();  // the accumulators are re-initialised at the top of the next segment
   }
 }
 
@@ -273,13 +305,13 @@ int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t
   if (HW > 0) {
     const bool fast = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && (HW % 16 == 0);
     if (fast) {
-      const int chunks = (HW / 16 + PE_ITEM_GROUPS - 1) / PE_ITEM_GROUPS;
-      const long long items = static_cast<long long>(n_img) * chunks;
-      B200SAM_REQUIRE(items < (1ll << 31), "prompt_extract: batch too large");
+      const long long total = static_cast<long long>(n_img) * (HW / 16);
       const int max_ctas = 148 * 4;  // all CTAs resident (4 x 256 threads per SM): a persistent, balanced grid
-      const int iters = static_cast<int>((items + max_ctas - 1) / max_ctas);
-      const int ctas = static_cast<int>((items + iters - 1) / iters);  // every CTA walks `iters` (or iters - 1) items
-      prompt_accum16_kernel<<<ctas, 256, 0, stream>>>(masks, C, H, W, scratch, static_cast<int>(items), chunks);
+      long long gpc = (total + max_ctas - 1) / max_ctas;
+      gpc = (gpc + 31) / 32 * 32;  // whole warps
+      B200SAM_REQUIRE(gpc < (1ll << 30), "prompt_extract: batch too large");
+      const int ctas = static_cast<int>((total + gpc - 1) / gpc);
+      prompt_accum16_kernel<<<ctas, 256, 0, stream>>>(masks, C, H, W, scratch, total, static_cast<int>(gpc));
     } else {
       dim3 grid((HW + 1023) / 1024, n_img);
       prompt_accum_kernel<<<grid, 256, 0, stream>>>(masks, C, H, W, scratch);

@@ -9,6 +9,7 @@
 // (L1/L2 resident), so HBM sees 256 KiB in and 1 byte per output pixel out.
 #include "common.cuh"
 #include "kernels.h"
+#include <type_traits>
 
 namespace b200sam {
 
@@ -112,17 +113,20 @@ __global__ void __launch_bounds__(256) nearest_exact_kernel(UpParams p, uint8_t*
 constexpr int UP_PX = 8;         // output pixels per thread
 constexpr int UP_THREADS = 128;
 constexpr int UP_MAXROWS = 128;  // output rows per block (upper bound; the launch picks rows_per_block)
-constexpr int UP_LOWROWS = 40;   // low-res rows staged per block
+constexpr int UP_LOWROWS = 38;   // low-res rows staged per block
 constexpr int UP_MAXS = 3;       // nearest-exact taps per thread and row
 
-// three-tap form of one axis: base index (<= L-3) and the coefficients of low[base .. base+2]
+// three-tap form of one axis: base index and the coefficients of low[base .. base+2].  CLAMP: base <= L-3, so all three
+// samples exist (columns); otherwise base is the first contributing sample and the taps that would fall beyond L-1
+// carry zero weight (rows: the caller clamps the row index when it loads them).
+template <bool CLAMP>
 B200SAM_DEVINL void taps3(float scale2, int in2, float s1, int L, int o, int& base, float& c0, float& c1, float& c2) {
   int i0, i1, a0, a1, b0, b1;
   float w0, w1, u0, u1, v0, v1;
   src_index(scale2, o, in2, i0, i1, w0, w1);
   src_index(s1, i0, L, a0, a1, u0, u1);
   src_index(s1, i1, L, b0, b1, v0, v1);
-  base = min(a0, L - 3);
+  base = CLAMP ? min(a0, L - 3) : a0;
   c0 = c1 = c2 = 0.0f;
   auto put = [&](int idx, float w) {
     const int sl = idx - base;
@@ -142,17 +146,16 @@ B200SAM_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
-// 4 results -> 4 mask bytes (0/1).  ZERO_THR: v > 0 <=> the int32 pattern of v is in [1, 0x7fffffff]; v is produced
-// by an FMA chain that starts from +0.0, which can never yield -0.0, so `bits - 1` has its sign bit set exactly for
-// v <= 0 and PRMT's sign-replicate mode turns the four sign bits into four bytes.
+// 4 results -> 4 mask bytes (0/1).  ZERO_THR: the caller hands in u = -v (negated row coefficients, FMA chain started
+// from +0.0).  In round-to-nearest an exact zero sum is +0.0 unless both addends are -0.0, so u is never -0.0 and
+// its sign bit is set exactly for v > 0; PRMT's sign-replicate mode turns the four sign bits into four bytes.
+// (A product below the smallest subnormal, |c * low| < 2^-150, would round to -0.0: not reachable from logits.)
 template <bool ZERO_THR>
 B200SAM_DEVINL uint32_t pack4(float a, float b, float c, float d, float thr) {
   if (ZERO_THR) {
-    const uint32_t ia = __float_as_uint(a) - 1u, ib = __float_as_uint(b) - 1u;
-    const uint32_t ic = __float_as_uint(c) - 1u, id = __float_as_uint(d) - 1u;
-    const uint32_t t01 = prmt(ia, ib, 0x00fbu);  // byte0 = sign(a) x 8, byte1 = sign(b) x 8
-    const uint32_t t23 = prmt(ic, id, 0x00fbu);
-    return ~prmt(t01, t23, 0x5410u) & 0x01010101u;
+    const uint32_t t01 = prmt(__float_as_uint(a), __float_as_uint(b), 0x00fbu);  // byte0 = sign(a) x 8, byte1 = sign(b) x 8
+    const uint32_t t23 = prmt(__float_as_uint(c), __float_as_uint(d), 0x00fbu);
+    return prmt(t01, t23, 0x5410u) & 0x01010101u;
   }
   const uint32_t ma = a > thr ? 1u : 0u, mb = b > thr ? 1u : 0u, mc = c > thr ? 1u : 0u, md = d > thr ? 1u : 0u;
   return ma | (mb << 8) | (mc << 16) | (md << 24);
@@ -188,103 +191,151 @@ B200SAM_DEVINL void store8(uint8_t* ptr, uint2 w, int al) {
 
 // ALIGNED: out_w % 8 == 0 and an 8-byte aligned output -> one 64-bit store per thread and row.  Otherwise the row's
 // (warp-uniform) misalignment picks the store pattern; only the last, partial thread of a row writes single bytes.
-template <bool ALIGNED, bool ZERO_THR>
-__global__ void __launch_bounds__(UP_THREADS) upscale_mask_fast_kernel(UpParams p, uint8_t* __restrict__ mask_out,
-                                                                       int rows_per_block, SmallOut sm) {
-  __shared__ float4 rowtab[UP_MAXROWS];  // c0, c1, c2, bits(m | (small_row + 1) << 12)
+//
+// Staged low-res rows live in shared memory in groups of 32 words followed by 3 pad words that repeat the first
+// words of the next group (row pitch 35 * ceil(L / 32)): a thread's three taps stay contiguous, and the lanes of a
+// warp, whose tap bases advance by ~2 words per lane at 4x up-scaling, fall into distinct banks (the un-padded layout
+// is a 2-way conflict on every tap load).
+constexpr int UP_GRP = 35;
+B200SAM_DEVINL int up_pos(int i) { return UP_GRP * (i >> 5) + (i & 31); }
+constexpr int UP_SAME_NEXT = 1 << 24;  // rowtab flag: the next row of the block uses the same low-res window
+constexpr int UP_SAMPLED = 1 << 25;    // rowtab flag: the nearest-exact grid samples this native row
+
+template <bool ALIGNED, bool ZERO_THR, bool THREE>
+__global__ void __launch_bounds__(UP_THREADS, 5) upscale_mask_fast_kernel(UpParams p, uint8_t* __restrict__ mask_out,
+                                                                          int rows_per_block, SmallOut sm) {
+  __shared__ float4 rowtab[UP_MAXROWS + 2];  // (+2: the row loop reads two entries ahead)  // c0, c1, c2, bits(m | UP_SAMPLED | UP_SAME_NEXT)
   extern __shared__ __align__(16) uint8_t dyn[];
-  float* lowst = reinterpret_cast<float*>(dyn);  // [UP_LOWROWS][L] staged low-res rows
+  float* lowst = reinterpret_cast<float*>(dyn);  // [UP_LOWROWS][pitch] staged low-res rows
+  const int pitch = UP_GRP * ((p.L + 31) >> 5);
   const int n = blockIdx.z;
   const float* plane = p.low + static_cast<size_t>(n) * p.L * p.L;
   const int r0 = blockIdx.y * rows_per_block;
   const int nrows = min(rows_per_block, p.out_h - r0);
   const int tid = threadIdx.x;
   for (int i = tid; i < nrows; i += UP_THREADS) {
-    int m;
-    float c0, c1, c2;
+    int m, m_next;
+    float c0, c1, c2, e0, e1, e2;
     const int oy = r0 + i;
-    taps3(p.sy2, p.in_h, p.s1, p.L, oy, m, c0, c1, c2);
-    int srow = -1;
-    if (sm.out != nullptr) {  // the (at most one, ny >= 1) nearest-exact row that samples native row oy
+    taps3<false>(p.sy2, p.in_h, p.s1, p.L, oy, m, c0, c1, c2);
+    taps3<false>(p.sy2, p.in_h, p.s1, p.L, min(oy + 1, p.out_h - 1), m_next, e0, e1, e2);
+    int sampled = 0;
+    if (sm.out != nullptr) {  // is native row oy sampled by the (at most one, ny >= 1) nearest-exact row?
       const int y0 = max(0, static_cast<int>(static_cast<float>(oy) / sm.ny) - 1);
       for (int y = y0; y < min(sm.sh, y0 + 4); ++y)
-        if (nearest_src(y, sm.ny, p.out_h) == oy) srow = y;
+        if (nearest_src(y, sm.ny, p.out_h) == oy) sampled = UP_SAMPLED;
     }
-    rowtab[i] = make_float4(c0, c1, c2, __int_as_float(m | ((srow + 1) << 12)));
+    const int same = (i + 1 < nrows && m_next == m) ? UP_SAME_NEXT : 0;
+    if (ZERO_THR) { c0 = -c0; c1 = -c1; c2 = -c2; }  // the row loop evaluates -v (see pack4)
+    rowtab[i] = make_float4(c0, c1, c2, __int_as_float(m | sampled | same));
   }
   const int ox0 = (blockIdx.x * UP_THREADS + tid) * UP_PX;
   const bool mine = ox0 < p.out_w;  // this thread owns at least one output column
-  int lb[UP_PX];
+  int lb[UP_PX];                    // tap base as a position in the padded shared-memory row
   float d0[UP_PX], d1[UP_PX], d2[UP_PX];
 #pragma unroll
-  for (int k = 0; k < UP_PX; ++k) taps3(p.sx2, p.in_w, p.s1, p.L, min(ox0 + k, p.out_w - 1), lb[k], d0[k], d1[k], d2[k]);
-  // nearest-exact columns that sample one of this thread's 8 native columns: x = sx0 + j, byte off[j] of the row word
-  int sx0 = 0;
-  uint32_t soff[UP_MAXS];
-#pragma unroll
-  for (int j = 0; j < UP_MAXS; ++j) soff[j] = 0xffu;
+  for (int k = 0; k < UP_PX; ++k) {
+    taps3<true>(p.sx2, p.in_w, p.s1, p.L, min(ox0 + k, p.out_w - 1), lb[k], d0[k], d1[k], d2[k]);
+    lb[k] = up_pos(lb[k]);
+  }
+  // nearest-exact columns that sample one of this thread's 8 native columns: x = sx0 + j for j < snv; one PRMT with
+  // selector ssel gathers their mask bytes.  The sampled native rows of a block map to consecutive nearest-exact rows,
+  // so the thread's output pointer just advances by one row per sampled native row.
+  int snv = 0;
+  uint32_t ssel = 0u;
+  uint8_t* sptr = nullptr;
   if (sm.out != nullptr && mine) {
-    sx0 = max(0, static_cast<int>(static_cast<float>(ox0) / sm.nx) - 1);
+    int sx0 = max(0, static_cast<int>(static_cast<float>(ox0) / sm.nx) - 1);
     while (sx0 < sm.sw && nearest_src(sx0, sm.nx, p.out_w) < ox0) ++sx0;
 #pragma unroll
     for (int j = 0; j < UP_MAXS; ++j) {
       if (sx0 + j < sm.sw) {
         const int o = nearest_src(sx0 + j, sm.nx, p.out_w) - ox0;
-        if (o < UP_PX) soff[j] = static_cast<uint32_t>(o);
+        if (o < UP_PX && snv == j) { ssel |= static_cast<uint32_t>(o) << (4 * j); snv = j + 1; }
       }
     }
+    int sy0 = max(0, static_cast<int>(static_cast<float>(r0) / sm.ny) - 1);  // first nearest-exact row at or below r0
+    while (sy0 < sm.sh && nearest_src(sy0, sm.ny, p.out_h) < r0) ++sy0;
+    sptr = sm.out + (static_cast<size_t>(n) * sm.sh + sy0) * sm.sw + sx0;
   }
-  uint8_t* const srp = sm.out != nullptr ? sm.out + static_cast<size_t>(n) * sm.sh * sm.sw + sx0 : nullptr;
   __syncthreads();
   // stage the low-res rows this block touches: m(first row) .. m(last row) + 2
   const int mlo = __float_as_int(rowtab[0].w) & 0xfff;
-  const int mhi = min((__float_as_int(rowtab[nrows - 1].w) & 0xfff) + 2, mlo + UP_LOWROWS - 1);
+  const int mhi = min((__float_as_int(rowtab[nrows - 1].w) & 0xfff) + 2, p.L - 1);
+  if (mhi - mlo >= UP_LOWROWS) __trap();  // the launch sizes rows_per_block so that this cannot happen
   {
     const float* src = plane + static_cast<size_t>(mlo) * p.L;
-    const int cnt = (mhi - mlo + 1) * p.L;
-    if ((p.L & 3) == 0) {
-      for (int i = tid; i < cnt / 4; i += UP_THREADS)
-        reinterpret_cast<float4*>(lowst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    const int rows = mhi - mlo + 1;
+    if ((p.L & 31) == 0) {  // float4 loads; the 4 words stay inside one 32-word group (no division in the loop)
+      const int q4 = p.L >> 2;
+      int rr = tid / q4, c = tid - rr * q4;
+      const int drr = UP_THREADS / q4, dc = UP_THREADS - drr * q4;
+      while (rr < rows) {  // four independent 16-byte loads in flight per thread
+        float4 v[4];
+        int vr[4], vc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          vr[j] = rr; vc[j] = c;
+          if (rr < rows) v[j] = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(rr) * p.L) + c);
+          rr += drr; c += dc;
+          if (c >= q4) { c -= q4; ++rr; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (vr[j] < rows) {
+            float* row = lowst + vr[j] * pitch;
+            float* dst = row + UP_GRP * (vc[j] >> 3) + 4 * (vc[j] & 7);
+            dst[0] = v[j].x; dst[1] = v[j].y; dst[2] = v[j].z; dst[3] = v[j].w;
+            if ((vc[j] & 7) == 0 && vc[j] >= 8) {  // first words of a group: repeat them in the previous group's pad
+              float* pad = row + UP_GRP * ((vc[j] >> 3) - 1) + 32;
+              pad[0] = v[j].x; pad[1] = v[j].y; pad[2] = v[j].z;
+            }
+          }
+        }
+      }
     } else {
-      for (int i = tid; i < cnt; i += UP_THREADS) lowst[i] = __ldg(src + i);
+      for (int rr = 0; rr < rows; ++rr) {
+        float* row = lowst + rr * pitch;
+        for (int i = tid; i < p.L; i += UP_THREADS) {
+          const float v = __ldg(src + static_cast<size_t>(rr) * p.L + i);
+          row[up_pos(i)] = v;
+          if (i >= 32 && (i & 31) < UP_GRP - 32) row[UP_GRP * ((i >> 5) - 1) + 32 + (i & 31)] = v;
+        }
+      }
     }
   }
   __syncthreads();
   if (!mine) return;
   float g0[UP_PX], g1[UP_PX], g2[UP_PX];
-  auto load_row = [&](int r, float (&g)[UP_PX]) {
-    if (r <= mhi) {  // block-uniform
-      const float* rp = lowst + (r - mlo) * p.L;
+  auto load_row = [&](int r, float (&g)[UP_PX]) {  // r > L-1: a zero-weight tap, any staged row will do
+    const float* rp = lowst + (min(r, mhi) - mlo) * pitch;
 #pragma unroll
-      for (int k = 0; k < UP_PX; ++k) {
-        const float* q = rp + lb[k];
-        g[k] = __fmaf_rn(d2[k], q[2], __fmaf_rn(d1[k], q[1], d0[k] * q[0]));
-      }
-    } else {  // beyond the staged window (only for extreme down-scaling): straight from global / L1
-      const float* rp = plane + static_cast<size_t>(r) * p.L;
-#pragma unroll
-      for (int k = 0; k < UP_PX; ++k) {
-        const float* q = rp + lb[k];
-        g[k] = __fmaf_rn(d2[k], __ldg(q + 2), __fmaf_rn(d1[k], __ldg(q + 1), d0[k] * __ldg(q)));
-      }
+    for (int k = 0; k < UP_PX; k += 2) {
+      const float* q = rp + lb[k];
+      const float* q2 = rp + lb[k + 1];
+      fma2_v(g[k], g[k + 1], d0[k], d0[k + 1], q[0], q2[0], 0.0f, 0.0f);
+      fma2_v(g[k], g[k + 1], d1[k], d1[k + 1], q[1], q2[1], g[k], g[k + 1]);
+      fma2_v(g[k], g[k + 1], d2[k], d2[k + 1], q[2], q2[2], g[k], g[k + 1]);
     }
   };
   uint8_t* optr = mask_out + (static_cast<size_t>(n) * p.out_h + r0) * p.out_w + ox0;  // this thread's bytes of row i
   const int valid = min(UP_PX, p.out_w - ox0);
-  // one output row from the window (A, B, C) = G rows (m, m+1, m+2)
-  auto emit = [&](const float4& rt, int packed, const float (&A)[UP_PX], const float (&B)[UP_PX],
-                  const float (&C)[UP_PX]) {
+  // one output row from the window (A, B, C) = G rows (m, m+1, m+2); rt holds the (ZERO_THR: negated) row taps
+  auto compute = [&](const float4& rt, const float (&A)[UP_PX], const float (&B)[UP_PX],
+                     const float (&C)[UP_PX]) -> uint2 {
     float v[UP_PX];
-    if (rt.z == 0.0f) {  // block-uniform: only two low-res rows contribute (always so for an identity stage 2)
 #pragma unroll
-      for (int k = 0; k < UP_PX; ++k) v[k] = __fmaf_rn(rt.y, B[k], __fmaf_rn(rt.x, A[k], 0.0f));
-    } else {
-#pragma unroll
-      for (int k = 0; k < UP_PX; ++k) v[k] = __fmaf_rn(rt.z, C[k], __fmaf_rn(rt.y, B[k], __fmaf_rn(rt.x, A[k], 0.0f)));
+    for (int k = 0; k < UP_PX; k += 2) {  // packed FFMA2: two pixels per issue slot
+      fma2_s(v[k], v[k + 1], rt.x, A[k], A[k + 1], 0.0f, 0.0f);
+      fma2_s(v[k], v[k + 1], rt.y, B[k], B[k + 1], v[k], v[k + 1]);
+      if (THREE) fma2_s(v[k], v[k + 1], rt.z, C[k], C[k + 1], v[k], v[k + 1]);  // rt.z == 0: an exact no-op
     }
     uint2 w;
     w.x = pack4<ZERO_THR>(v[0], v[1], v[2], v[3], p.thr);
     w.y = pack4<ZERO_THR>(v[4], v[5], v[6], v[7], p.thr);
+    return w;
+  };
+  auto store = [&](const uint2& w, int flags) {
     if (ALIGNED) {
       *reinterpret_cast<uint2*>(optr) = w;
     } else if (valid == UP_PX) {
@@ -293,44 +344,55 @@ __global__ void __launch_bounds__(UP_THREADS) upscale_mask_fast_kernel(UpParams 
       for (int k = 0; k < valid; ++k) optr[k] = static_cast<uint8_t>(prmt(w.x, w.y, k));
     }
     optr += p.out_w;
-    const int srow = (packed >> 12) - 1;
-    if (srow >= 0) {  // block-uniform: this native row is sampled by the nearest-exact grid
-      uint8_t* q = srp + srow * sm.sw;
-#pragma unroll
-      for (int j = 0; j < UP_MAXS; ++j)
-        if (soff[j] != 0xffu) q[j] = static_cast<uint8_t>(prmt(w.x, w.y, soff[j]));
+    if (flags & UP_SAMPLED) {  // block-uniform: this native row is sampled by the nearest-exact grid
+      const uint32_t t = prmt(w.x, w.y, ssel);
+      if (snv > 0) sptr[0] = static_cast<uint8_t>(t);
+      if (snv > 1) sptr[1] = static_cast<uint8_t>(t >> 8);
+      if (snv > 2) sptr[2] = static_cast<uint8_t>(t >> 16);
+      sptr += sm.sw;
     }
   };
   // Row loop as a three-state machine: the roles of (g0, g1, g2) rotate when m advances by one, so the window
-  // shifts without moving registers.  All branches are block-uniform.
-  int i = 0, state = 3, mcur = 0;
-  float4 rt = rowtab[0];
-  int packed = __float_as_int(rt.w);
-  while (i < nrows) {
-    const int m = packed & 0xfff;
-    if (state == 3 || (m != mcur && m != mcur + 1)) {
-      load_row(m, g0);
-      load_row(m + 1, g1);
-      load_row(m + 2, g2);
-      state = 0;
-    } else if (m == mcur + 1) {
-      if (state == 0) load_row(m + 2, g0);
-      else if (state == 1) load_row(m + 2, g1);
-      else load_row(m + 2, g2);
-      state = state == 2 ? 0 : state + 1;
-    }
-    mcur = m;
+  // shifts without moving registers.  Rows that share a window are emitted in pairs (two independent FMA / pack
+  // chains in flight, one loop test per pair).  All branches are block-uniform.
+  {
+    int i = 0, state = 3, mcur = 0;
+    float4 rt = rowtab[0];
+    while (i < nrows) {
+      const int m = __float_as_int(rt.w) & 0xfff;
+      if (state == 3 || (m != mcur && m != mcur + 1)) {
+        load_row(m, g0);
+        load_row(m + 1, g1);
+        load_row(m + 2, g2);
+        state = 0;
+      } else if (m == mcur + 1) {
+        if (state == 0) load_row(m + 2, g0);
+        else if (state == 1) load_row(m + 2, g1);
+        else load_row(m + 2, g2);
+        state = state == 2 ? 0 : state + 1;
+      }
+      mcur = m;
 #define B200SAM_UP_RUN(A, B, C)                                            \
-    do {                                                                   \
-      emit(rt, packed, A, B, C);                                           \
-      if (++i >= nrows) break;                                             \
-      rt = rowtab[i];                                                      \
-      packed = __float_as_int(rt.w);                                       \
-    } while ((packed & 0xfff) == mcur)
-    if (state == 0) B200SAM_UP_RUN(g0, g1, g2);
-    else if (state == 1) B200SAM_UP_RUN(g1, g2, g0);
-    else B200SAM_UP_RUN(g2, g0, g1);
+      do {                                                                 \
+        const float4 rt2 = rowtab[i + 1], rt3 = rowtab[i + 2];             \
+        if (__float_as_int(rt.w) & UP_SAME_NEXT) {                         \
+          const uint2 wa = compute(rt, A, B, C);                           \
+          const uint2 wb = compute(rt2, A, B, C);                          \
+          store(wa, __float_as_int(rt.w));                                 \
+          store(wb, __float_as_int(rt2.w));                                \
+          rt = rt3;                                                        \
+          i += 2;                                                          \
+        } else {                                                           \
+          store(compute(rt, A, B, C), __float_as_int(rt.w));               \
+          rt = rt2;                                                        \
+          i += 1;                                                          \
+        }                                                                  \
+      } while (i < nrows && (__float_as_int(rt.w) & 0xfff) == mcur)
+      if (state == 0) B200SAM_UP_RUN(g0, g1, g2);
+      else if (state == 1) B200SAM_UP_RUN(g1, g2, g0);
+      else B200SAM_UP_RUN(g2, g0, g1);
 #undef B200SAM_UP_RUN
+    }
   }
 }
 
@@ -371,11 +433,14 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
   if (small_out != nullptr)
     B200SAM_REQUIRE(small_h > 0 && small_w > 0, "upscale: bad nearest-exact size (%d,%d)", small_h, small_w);
   // masks only, stage 1 upsampling (L <= S): the separable three-tap kernel; logits keep the literal nested form
-  const bool fast = mask_out != nullptr && logits_out == nullptr && low >= 3 && low <= img_size;
+  // (a block of >= 8 output rows must fit its low-res rows into the staged window: not for > 4x vertical down-scaling)
+  const float lowrows_per_row = p.s1 * p.sy2;
+  const bool fast = mask_out != nullptr && logits_out == nullptr && low >= 3 && low <= img_size &&
+                    lowrows_per_row * 8.0f + 6.0f <= static_cast<float>(UP_LOWROWS);
   if (fast) {
-    // rows per block: as many as the staged low-res window (UP_LOWROWS rows) covers, at most UP_MAXROWS
-    const float lowrows_per_row = p.s1 * p.sy2;
-    int rpb = static_cast<int>(static_cast<float>(UP_LOWROWS - 4) / (lowrows_per_row > 1e-6f ? lowrows_per_row : 1e-6f));
+    // rows per block: as many as the staged low-res window covers (the two floors of the composed source index add up
+    // to 2 rows of slack, the three-tap window 3 more), at most UP_MAXROWS
+    int rpb = static_cast<int>(static_cast<float>(UP_LOWROWS - 6) / (lowrows_per_row > 1e-6f ? lowrows_per_row : 1e-6f));
     rpb = rpb > UP_MAXROWS ? UP_MAXROWS : (rpb < 8 ? 8 : (rpb & ~7));
     // small batches: keep at least ~4 CTAs per SM in flight
     while (rpb > 32 && static_cast<long long>((out_h + rpb - 1) / rpb) * n * ((out_w + UP_THREADS * UP_PX - 1) / (UP_THREADS * UP_PX)) < 592)
@@ -383,23 +448,27 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
     const bool aligned = (out_w % 8 == 0) && (reinterpret_cast<uintptr_t>(mask_out) % 8 == 0);
     dim3 grid((out_w + UP_THREADS * UP_PX - 1) / (UP_THREADS * UP_PX), (out_h + rpb - 1) / rpb, n);
     // the fused nearest-exact tap needs <= 1 sampled row per native row and <= UP_MAXS sampled columns per 8 pixels
-    const bool fuse_small = small_out != nullptr && ny >= 1.0f && nx >= 8.0f / UP_MAXS + 0.01f;
+    const bool fuse_small = small_out != nullptr && ny >= 1.0f && nx >= 8.0f / UP_MAXS + 0.01f && small_h < 4095;
     SmallOut so;
     so.out = fuse_small ? small_out : nullptr;
     so.sh = small_h; so.sw = small_w; so.ny = ny; so.nx = nx;
-    const size_t low_bytes = static_cast<size_t>(UP_LOWROWS) * low * sizeof(float);
+    const size_t low_bytes = static_cast<size_t>(UP_LOWROWS) * 35 * ((low + 31) / 32) * sizeof(float);
     const size_t smem = low_bytes;
     B200SAM_REQUIRE(low < 4096 && smem <= 200 * 1024, "upscale: low-res size %d not supported by the fast path", low);
+    // THREE: a third low-res row can contribute to an output row unless stage 2 is the identity (in_h == out_h)
+    using KernelFn = void (*)(UpParams, uint8_t*, int, SmallOut);
+    static const KernelFn kernels[8] = {
+        upscale_mask_fast_kernel<false, false, false>, upscale_mask_fast_kernel<false, false, true>,
+        upscale_mask_fast_kernel<false, true, false>,  upscale_mask_fast_kernel<false, true, true>,
+        upscale_mask_fast_kernel<true, false, false>,  upscale_mask_fast_kernel<true, false, true>,
+        upscale_mask_fast_kernel<true, true, false>,   upscale_mask_fast_kernel<true, true, true>};
     static bool attr_set = false;
     if (!attr_set) {
-      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      B200SAM_CHECK_CUDA(cudaFuncSetAttribute(upscale_mask_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      for (KernelFn k : kernels)
+        B200SAM_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    auto kernel = thresh == 0.0f ? (aligned ? upscale_mask_fast_kernel<true, true> : upscale_mask_fast_kernel<false, true>)
-                                 : (aligned ? upscale_mask_fast_kernel<true, false> : upscale_mask_fast_kernel<false, false>);
+    const KernelFn kernel = kernels[(aligned ? 4 : 0) | (thresh == 0.0f ? 2 : 0) | (in_h != out_h ? 1 : 0)];
     kernel<<<grid, UP_THREADS, smem, stream>>>(p, mask_out, rpb, so);
     if (small_out != nullptr && !fuse_small) {
       dim3 block(32, 8);
