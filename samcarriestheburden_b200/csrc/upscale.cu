@@ -203,17 +203,20 @@ constexpr int UP_SAMPLED = 1 << 25;    // rowtab flag: the nearest-exact grid sa
 
 template <bool ALIGNED, bool ZERO_THR, bool THREE>
 __global__ void __launch_bounds__(UP_THREADS, 5) upscale_mask_fast_kernel(UpParams p, uint8_t* __restrict__ mask_out,
-                                                                          int rows_per_block, SmallOut sm) {
-  __shared__ float4 rowtab[UP_MAXROWS + 2];  // (+2: the row loop reads two entries ahead)  // c0, c1, c2, bits(m | UP_SAMPLED | UP_SAME_NEXT)
+                                                                          int rows_per_block, int col_groups,
+                                                                          SmallOut sm) {
+  // c0, c1, c2, bits(m | UP_SAMPLED | UP_SAME_NEXT); +2: the row loop reads two entries ahead
+  __shared__ float4 rowtab[UP_MAXROWS + 2];
   extern __shared__ __align__(16) uint8_t dyn[];
-  float* lowst = reinterpret_cast<float*>(dyn);  // [UP_LOWROWS][pitch] staged low-res rows
-  const int pitch = UP_GRP * ((p.L + 31) >> 5);
+  float* lowst = reinterpret_cast<float*>(dyn);  // [UP_LOWROWS][pitch] staged low-res rows (this block's columns only)
+  const int pitch = UP_GRP * col_groups;
+  const int nthreads = blockDim.x;  // a multiple of 32 chosen by the launch so that few lanes fall beyond out_w
   const int n = blockIdx.z;
   const float* plane = p.low + static_cast<size_t>(n) * p.L * p.L;
   const int r0 = blockIdx.y * rows_per_block;
   const int nrows = min(rows_per_block, p.out_h - r0);
   const int tid = threadIdx.x;
-  for (int i = tid; i < nrows; i += UP_THREADS) {
+  for (int i = tid; i < nrows; i += nthreads) {
     int m, m_next;
     float c0, c1, c2, e0, e1, e2;
     const int oy = r0 + i;
@@ -229,14 +232,25 @@ __global__ void __launch_bounds__(UP_THREADS, 5) upscale_mask_fast_kernel(UpPara
     if (ZERO_THR) { c0 = -c0; c1 = -c1; c2 = -c2; }  // the row loop evaluates -v (see pack4)
     rowtab[i] = make_float4(c0, c1, c2, __int_as_float(m | sampled | same));
   }
-  const int ox0 = (blockIdx.x * UP_THREADS + tid) * UP_PX;
+  const int ox0 = (blockIdx.x * nthreads + tid) * UP_PX;
   const bool mine = ox0 < p.out_w;  // this thread owns at least one output column
+  // low-res columns this block touches: [lc0, lc0 + 32 * ngroups), lc0 a multiple of 32
+  int lc0, ngroups;
+  {
+    int b0, b1;
+    float t0, t1, t2;
+    taps3<true>(p.sx2, p.in_w, p.s1, p.L, min(blockIdx.x * nthreads * UP_PX, p.out_w - 1), b0, t0, t1, t2);
+    taps3<true>(p.sx2, p.in_w, p.s1, p.L, min((blockIdx.x + 1) * nthreads * UP_PX, p.out_w) - 1, b1, t0, t1, t2);
+    lc0 = b0 & ~31;
+    ngroups = ((b1 + 2 - lc0) >> 5) + 1;
+    if (ngroups > col_groups) __trap();  // the launch sizes col_groups so that this cannot happen
+  }
   int lb[UP_PX];                    // tap base as a position in the padded shared-memory row
   float d0[UP_PX], d1[UP_PX], d2[UP_PX];
 #pragma unroll
   for (int k = 0; k < UP_PX; ++k) {
     taps3<true>(p.sx2, p.in_w, p.s1, p.L, min(ox0 + k, p.out_w - 1), lb[k], d0[k], d1[k], d2[k]);
-    lb[k] = up_pos(lb[k]);
+    lb[k] = up_pos(lb[k] - lc0);
   }
   // nearest-exact columns that sample one of this thread's 8 native columns: x = sx0 + j for j < snv; one PRMT with
   // selector ssel gathers their mask bytes.  The sampled native rows of a block map to consecutive nearest-exact rows,
@@ -264,12 +278,13 @@ __global__ void __launch_bounds__(UP_THREADS, 5) upscale_mask_fast_kernel(UpPara
   const int mhi = min((__float_as_int(rowtab[nrows - 1].w) & 0xfff) + 2, p.L - 1);
   if (mhi - mlo >= UP_LOWROWS) __trap();  // the launch sizes rows_per_block so that this cannot happen
   {
-    const float* src = plane + static_cast<size_t>(mlo) * p.L;
+    const float* src = plane + static_cast<size_t>(mlo) * p.L + lc0;
     const int rows = mhi - mlo + 1;
+    const int ncols = min(32 * ngroups, p.L - lc0);
     if ((p.L & 31) == 0) {  // float4 loads; the 4 words stay inside one 32-word group (no division in the loop)
-      const int q4 = p.L >> 2;
+      const int q4 = ncols >> 2;
       int rr = tid / q4, c = tid - rr * q4;
-      const int drr = UP_THREADS / q4, dc = UP_THREADS - drr * q4;
+      const int drr = nthreads / q4, dc = nthreads - drr * q4;
       while (rr < rows) {  // four independent 16-byte loads in flight per thread
         float4 v[4];
         int vr[4], vc[4];
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(UP_THREADS, 5) upscale_mask_fast_kernel(UpPara
     } else {
       for (int rr = 0; rr < rows; ++rr) {
         float* row = lowst + rr * pitch;
-        for (int i = tid; i < p.L; i += UP_THREADS) {
+        for (int i = tid; i < ncols; i += nthreads) {
           const float v = __ldg(src + static_cast<size_t>(rr) * p.L + i);
           row[up_pos(i)] = v;
           if (i >= 32 && (i & 31) < UP_GRP - 32) row[UP_GRP * ((i >> 5) - 1) + 32 + (i & 31)] = v;
@@ -445,18 +460,28 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
     // small batches: keep at least ~4 CTAs per SM in flight
     while (rpb > 32 && static_cast<long long>((out_h + rpb - 1) / rpb) * n * ((out_w + UP_THREADS * UP_PX - 1) / (UP_THREADS * UP_PX)) < 592)
       rpb >>= 1;
+    // even out the rows over the row blocks (no nearly empty last block)
+    rpb = min(rpb, (((out_h + (out_h + rpb - 1) / rpb - 1) / ((out_h + rpb - 1) / rpb)) + 7) & ~7);
     const bool aligned = (out_w % 8 == 0) && (reinterpret_cast<uintptr_t>(mask_out) % 8 == 0);
-    dim3 grid((out_w + UP_THREADS * UP_PX - 1) / (UP_THREADS * UP_PX), (out_h + rpb - 1) / rpb, n);
+    // block width: as few x-blocks as possible, whole warps, few lanes beyond out_w (754 px -> 96 threads, not 128)
+    const int groups8 = (out_w + UP_PX - 1) / UP_PX;
+    const int nbx = (groups8 + UP_THREADS - 1) / UP_THREADS;
+    const int bt = min(UP_THREADS, (((groups8 + nbx - 1) / nbx) + 31) & ~31);
+    dim3 grid((groups8 + bt - 1) / bt, (out_h + rpb - 1) / rpb, n);
+    // staged low-res columns per block, in 32-word groups (+1 for the 32-alignment of the first one)
+    const float lowcols = static_cast<float>(bt * UP_PX) * p.s1 * p.sx2;
+    int col_groups = grid.x == 1 ? static_cast<int>(lowcols + 4.0f) / 32 + 1   // first column group is group 0
+                                 : static_cast<int>(lowcols + 6.0f) / 32 + 2;
+    col_groups = min(col_groups, (low + 31) / 32);
     // the fused nearest-exact tap needs <= 1 sampled row per native row and <= UP_MAXS sampled columns per 8 pixels
     const bool fuse_small = small_out != nullptr && ny >= 1.0f && nx >= 8.0f / UP_MAXS + 0.01f && small_h < 4095;
     SmallOut so;
     so.out = fuse_small ? small_out : nullptr;
     so.sh = small_h; so.sw = small_w; so.ny = ny; so.nx = nx;
-    const size_t low_bytes = static_cast<size_t>(UP_LOWROWS) * 35 * ((low + 31) / 32) * sizeof(float);
-    const size_t smem = low_bytes;
+    const size_t smem = static_cast<size_t>(UP_LOWROWS) * UP_GRP * col_groups * sizeof(float);
     B200SAM_REQUIRE(low < 4096 && smem <= 200 * 1024, "upscale: low-res size %d not supported by the fast path", low);
     // THREE: a third low-res row can contribute to an output row unless stage 2 is the identity (in_h == out_h)
-    using KernelFn = void (*)(UpParams, uint8_t*, int, SmallOut);
+    using KernelFn = void (*)(UpParams, uint8_t*, int, int, SmallOut);
     static const KernelFn kernels[8] = {
         upscale_mask_fast_kernel<false, false, false>, upscale_mask_fast_kernel<false, false, true>,
         upscale_mask_fast_kernel<false, true, false>,  upscale_mask_fast_kernel<false, true, true>,
@@ -469,7 +494,7 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
       attr_set = true;
     }
     const KernelFn kernel = kernels[(aligned ? 4 : 0) | (thresh == 0.0f ? 2 : 0) | (in_h != out_h ? 1 : 0)];
-    kernel<<<grid, UP_THREADS, smem, stream>>>(p, mask_out, rpb, so);
+    kernel<<<grid, bt, smem, stream>>>(p, mask_out, rpb, col_groups, so);
     if (small_out != nullptr && !fuse_small) {
       dim3 block(32, 8);
       dim3 g2((small_w + 31) / 32, (small_h + 7) / 8, n);
