@@ -123,6 +123,11 @@ B200SAM_DEVINL uint32_t bytes_to_mask4(uint32_t w) {  // 4 bytes (0 or !=0) -> 4
 B200SAM_DEVINL uint32_t bytes_to_mask16(const uint4& v) {
   return bytes_to_mask4(v.x) | (bytes_to_mask4(v.y) << 4) | (bytes_to_mask4(v.z) << 8) | (bytes_to_mask4(v.w) << 12);
 }
+// the same for bytes known to be 0 / 1 (torch.bool storage): one multiply + shift per word
+B200SAM_DEVINL uint32_t bool_bytes_to_mask16(const uint4& v) {
+  return ((v.x * 0x01020408u) >> 24) | (((v.y * 0x01020408u) >> 24) << 4) | (((v.z * 0x01020408u) >> 24) << 8) |
+         (((v.w * 0x01020408u) >> 24) << 12);
+}
 B200SAM_DEVINL uint32_t norm01(uint32_t w) {  // every non-zero byte -> 1
   w = (w | (w >> 4)) & 0x0f0f0f0fu;
   w = (w | (w >> 2)) & 0x03030303u;
@@ -191,7 +196,9 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
       const uint32_t any_lo = __reduce_or_sync(FULL, static_cast<uint32_t>(any));
       const uint32_t any_hi = C > 32 ? __reduce_or_sync(FULL, static_cast<uint32_t>(any >> 32)) : 0u;
       if ((any_lo | any_hi) == 0u) continue;
-      if (((odd.x | odd.y | odd.z | odd.w) & 0xfefefefeu) != 0u) {  // bytes other than 0/1: recount normalised
+      const bool nonbool = ((odd.x | odd.y | odd.z | odd.w) & 0xfefefefeu) != 0u;
+      const bool warp_bool = !__any_sync(FULL, nonbool);  // the usual case: every byte the warp saw is 0 / 1
+      if (nonbool) {  // bytes other than 0/1: recount normalised
         cov = make_uint4(0, 0, 0, 0);
         for (unsigned long long t = any; t; t &= t - 1) {
           const int c = __ffsll(static_cast<long long>(t)) - 1;
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
       };
       uint4 single;
       single.x = lt2(cov.x); single.y = lt2(cov.y); single.z = lt2(cov.z); single.w = lt2(cov.w);
-      const uint32_t smask = bytes_to_mask16(single);
+      const uint32_t smask = bool_bytes_to_mask16(single);
       // pass 2 (warp-uniform loop over the classes present in the warp; re-loads are L1 hits): bytes -> 16-bit masks so
       // count / min / max / sum come from popc / ffs / clz, then one warp reduction per quantity
       for (int half = 0; half < 2; ++half) {
@@ -216,8 +223,10 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
           const int c = __ffs(todo) - 1 + 32 * half;
           todo &= todo - 1;
           uint32_t m = 0u;
-          if ((any >> c) & 1ull)
-            m = bytes_to_mask16(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW)));
+          if ((any >> c) & 1ull) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(c) * HW));
+            m = warp_bool ? bool_bytes_to_mask16(v) : bytes_to_mask16(v);
+          }
           const uint32_t sd = m & smask;
           const int n_all = __reduce_add_sync(FULL, __popc(m));
           const int mn_r = __reduce_min_sync(FULL, m ? r : INT_MAX), mx_r = __reduce_max_sync(FULL, m ? r : -1);
