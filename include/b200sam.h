@@ -117,6 +117,21 @@ B200SAM_API int b200sam_ccl_select(const float* prob, int n_planes, int H, int W
 B200SAM_API int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw,
                        int origin_y, int origin_x, int dilate, float* out, void* stream);
 
+/* ---------------------------------------------------------------- image ingest
+ * Replaces ResizeLongestSide.apply_image (segment_anything/utils/transforms.py:26-31: torchvision `resize` of a PIL
+ * image = Pillow's antialiased bilinear ImagingResample in 22-bit fixed point) as called from SamPredictor.set_image
+ * (predictor.py:54-57) and scripts/generate_img_embeddings.py:43-45.  Bit-exact with Pillow.
+ * b200sam_resize_coeffs_host is a pure HOST function: it fills bounds_host [out_size,2] (first tap, tap count) and
+ * kk_host [out_size, b200sam_resize_ksize(in,out)] (fixed-point weights); the caller uploads them once per size pair.
+ * b200sam_resize_u8: image [H,W,C] uint8 -> out [out_h,out_w,C] (out_chw = 0) or [C,out_h,out_w] (out_chw = 1, the
+ * layout b200sam_encoder_forward reads).  A NULL bounds table skips that pass (size unchanged on that axis);
+ * tmp [H,out_w,C] is needed when the horizontal pass is followed by the vertical one. */
+B200SAM_API int b200sam_resize_ksize(int in_size, int out_size);
+B200SAM_API int b200sam_resize_coeffs_host(int in_size, int out_size, int32_t* bounds_host, int32_t* kk_host);
+B200SAM_API int b200sam_resize_u8(const uint8_t* image, int H, int W, int C, const int32_t* xbounds, const int32_t* xkk,
+                      int xksize, const int32_t* ybounds, const int32_t* ykk, int yksize, int out_h, int out_w,
+                      uint8_t* tmp, uint8_t* out, int out_chw, void* stream);
+
 /* ---------------------------------------------------------------- U-Net inference
  * Replaces UNet.forward (custom_arcitecture/classic_u_net.py:81-119, bilinear = False) as called from
  * scripts/save_refined_segmentations.py:67-69 (+ the torch.sigmoid that follows).  Weight table like the SAM handles:

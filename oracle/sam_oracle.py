@@ -284,6 +284,76 @@ def get_preprocess_shape(oldh: int, oldw: int, long_side: int = 1024) -> Tuple[i
     return int(oldh * scale + 0.5), int(oldw * scale + 0.5)
 
 
+# ----------------------------------------------------------------------------------------------- image ingest
+_PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_resize_coeffs(in_size: int, out_size: int):
+    """Pillow src/libImaging/Resample.c `precompute_coeffs` + `normalize_coeffs_8bpc` with the bilinear (triangle)
+    filter (support 1.0), full-image box: -> (bounds int32 [out, 2] = (first tap, tap count), kk int32 [out, ksize]).
+    Pillow is the un-vendored dependency behind utils/transforms.py:26-31 (torchvision `resize(to_pil_image(img))`);
+    this restates its published algorithm in float64 / integers and is pinned against Pillow itself
+    (tests/golden/make_golden_resize.py -> tests/golden/resize_golden.npz, tests/test_resize_oracle.py)."""
+    scale = float(np.float32(in_size)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)  # C (int) cast truncates toward zero, like int()
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [0.0] * ksize
+        ww = 0.0
+        for x in range(xmax):
+            a = abs((x + xmin - center + 0.5) * ss)
+            w[x] = 1.0 - a if a < 1.0 else 0.0
+            ww += w[x]
+        for x in range(xmax):
+            if ww != 0.0:
+                w[x] /= ww
+        bounds[xx] = (xmin, xmax)
+        for x in range(ksize):
+            v = w[x] * (1 << _PIL_PRECISION_BITS)
+            kk[xx, x] = int(-0.5 + v) if w[x] < 0 else int(0.5 + v)
+    return bounds, kk
+
+
+def _pil_resample_axis0(img: np.ndarray, bounds: np.ndarray, kk: np.ndarray) -> np.ndarray:
+    """One 8-bit pass along axis 0: clip8((2^21 + sum_k px_k * kk_k) >> 22)."""
+    out = np.empty((bounds.shape[0],) + img.shape[1:], np.uint8)
+    src = img.astype(np.int64)
+    for o in range(bounds.shape[0]):
+        lo, n = int(bounds[o, 0]), int(bounds[o, 1])
+        acc = np.full(img.shape[1:], 1 << (_PIL_PRECISION_BITS - 1), np.int64)
+        for t in range(n):
+            acc += src[lo + t] * int(kk[o, t])
+        out[o] = np.clip(acc >> _PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+    return out
+
+
+def resize_bilinear_u8(image: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """`PIL.Image.resize((out_w, out_h), BILINEAR)` of an HxWxC (or HxW) uint8 image: horizontal pass first, its uint8
+    result feeds the vertical pass; a pass whose size does not change is skipped (Resample.c ImagingResample)."""
+    img = np.ascontiguousarray(image)
+    H, W = img.shape[:2]
+    if out_w != W:
+        b, k = pil_resize_coeffs(W, out_w)
+        img = np.swapaxes(_pil_resample_axis0(np.swapaxes(img, 0, 1), b, k), 0, 1)
+    if out_h != H:
+        b, k = pil_resize_coeffs(H, out_h)
+        img = _pil_resample_axis0(img, b, k)
+    return np.ascontiguousarray(img)
+
+
+def apply_image(image: np.ndarray, long_side: int = 1024) -> np.ndarray:
+    """utils/transforms.py:26-31 (ResizeLongestSide.apply_image)."""
+    newh, neww = get_preprocess_shape(image.shape[0], image.shape[1], long_side)
+    return resize_bilinear_u8(image, newh, neww)
+
+
 # ----------------------------------------------------------------------------------------------- prompt extraction
 @dataclass
 class OraclePrompt:

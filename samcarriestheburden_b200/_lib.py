@@ -53,6 +53,9 @@ _PROTOTYPES = {
     "b200sam_unet_destroy": (None, [_vp]),
     "b200sam_unet_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "b200sam_unet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200sam_resize_ksize": (_i, [_i, _i]),
+    "b200sam_resize_coeffs_host": (_i, [_i, _i, _vp, _vp]),
+    "b200sam_resize_u8": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "b200sam_ccl_scratch_bytes": (_sz, [_i, _i, _i]),
     "b200sam_ccl_select": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "b200sam_morph_flat": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

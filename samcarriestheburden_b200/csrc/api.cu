@@ -165,6 +165,17 @@ int b200sam_unet_forward(const b200sam_unet* u, const float* image, int batch, i
                       static_cast<cudaStream_t>(stream));
 }
 
+int b200sam_resize_ksize(int in_size, int out_size) { return resize_ksize(in_size, out_size); }
+int b200sam_resize_coeffs_host(int in_size, int out_size, int32_t* bounds_host, int32_t* kk_host) {
+  return resize_coeffs_host(in_size, out_size, bounds_host, kk_host);
+}
+int b200sam_resize_u8(const uint8_t* image, int H, int W, int C, const int32_t* xbounds, const int32_t* xkk, int xksize,
+                      const int32_t* ybounds, const int32_t* ykk, int yksize, int out_h, int out_w, uint8_t* tmp,
+                      uint8_t* out, int out_chw, void* stream) {
+  return resize_u8(image, H, W, C, xbounds, xkk, xksize, ybounds, ykk, yksize, out_h, out_w, tmp, out, out_chw,
+                   static_cast<cudaStream_t>(stream));
+}
+
 size_t b200sam_ccl_scratch_bytes(int n_planes, int H, int W) {
   if (n_planes < 0 || H <= 0 || W <= 0) return 0;
   return ccl_scratch_bytes(n_planes, H, W);

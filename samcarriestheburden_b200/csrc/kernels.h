@@ -102,6 +102,14 @@ int ccl_select(const float* prob, int n_planes, int H, int W, float threshold, i
 int morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw, int origin_y,
                int origin_x, int dilate, float* out, cudaStream_t stream);
 
+// ---- resize.cu -------------------------------------------------------------------------------
+// Pillow-exact antialiased bilinear uint8 resize (ResizeLongestSide.apply_image); coefficient tables built on the host
+int resize_ksize(int in_size, int out_size);
+int resize_coeffs_host(int in_size, int out_size, int32_t* bounds, int32_t* kk);
+int resize_u8(const uint8_t* in, int H, int W, int C, const int32_t* xbounds, const int32_t* xkk, int xksize,
+              const int32_t* ybounds, const int32_t* ykk, int yksize, int out_h, int out_w, uint8_t* tmp, uint8_t* out,
+              int out_chw, cudaStream_t stream);
+
 // ---- unet.cu -----------------------------------------------------------------------------------
 struct UNetCtx;
 int unet_weight_count();

@@ -39,7 +39,7 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
 
     def flush(key):
         items = pending.pop(key)
-        x = torch.stack([t for _, t, _ in items]).to(dev, non_blocking=True)
+        x = torch.stack([t.to(dev, non_blocking=True) for _, t, _ in items])
         emb = sam.encode_image(x)
         for j, (slot, _, orig) in enumerate(items):
             local[slot] = emb[j]
@@ -47,8 +47,11 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
 
     for slot, i in enumerate(mine):
         img = images[i]
-        resized = pred.transform.apply_image(img)
-        t = torch.from_numpy(np.ascontiguousarray(resized)).permute(2, 0, 1).contiguous()
+        target = pred.transform.get_preprocess_shape(img.shape[0], img.shape[1], pred.transform.target_length)
+        if target == tuple(img.shape[:2]):  # already at the encoder's size: upload as is
+            t = torch.from_numpy(np.ascontiguousarray(img)).permute(2, 0, 1).contiguous()
+        else:  # native-resolution radiograph: upload the uint8 pixels once, Pillow-exact resize on the GPU
+            t = pred.transform.apply_image_cuda(img, device=dev, chw=True)
         key = tuple(t.shape[-2:])
         pending.setdefault(key, []).append((slot, t, tuple(img.shape[:2])))
         if len(pending[key]) == batch:

@@ -21,9 +21,9 @@ class SamPredictor:
         assert image_format in ["RGB", "BGR"], f"image_format must be in ['RGB', 'BGR'], is {image_format}."
         if image_format != self.model.image_format:
             image = image[..., ::-1]
-        input_image = self.transform.apply_image(image)
-        input_image_torch = torch.as_tensor(np.ascontiguousarray(input_image), device=self.device)
-        input_image_torch = input_image_torch.permute(2, 0, 1).contiguous()[None, :, :, :]
+        # ResizeLongestSide.apply_image on the GPU (Pillow-exact fixed-point resample, csrc/resize.cu): the native
+        # uint8 pixels are uploaded once and resized / transposed to CHW there (bit-identical to the host path)
+        input_image_torch = self.transform.apply_image_cuda(np.ascontiguousarray(image), device=self.device)[None]
         self.set_torch_image(input_image_torch, image.shape[:2])
 
     @torch.no_grad()

@@ -1,11 +1,58 @@
-"""Host-side resize helpers (reference: segment_anything/utils/transforms.py).  Semantics kept: PIL bilinear
-(antialiased) uint8 resize so the long side is `target_length`, `int(x * scale + 0.5)` rounding."""
+"""Resize helpers (reference: segment_anything/utils/transforms.py).  Semantics kept: PIL bilinear (antialiased)
+uint8 resize so the long side is `target_length`, `int(x * scale + 0.5)` rounding.  `apply_image` is the reference's
+host path; `apply_image_cuda` / `resize_u8_cuda` run the same arithmetic (Pillow's 22-bit fixed-point resample,
+bit-exact) on the GPU through `b200sam_resize_u8` so that native-resolution radiographs are uploaded once as uint8
+and never resized on the host."""
+import ctypes as C
 from copy import deepcopy
-from typing import Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 import torch
 from torch.nn import functional as F
+
+_TABLES: Dict[Tuple[int, int, str], Tuple[torch.Tensor, torch.Tensor, int]] = {}
+
+
+def _resize_tables(in_size: int, out_size: int, device: torch.device):
+    """Fixed-point coefficient tables of one axis, built by the library's host function and cached on the device."""
+    from ... import _lib
+    key = (in_size, out_size, str(device))
+    hit = _TABLES.get(key)
+    if hit is None:
+        lib = _lib.load()
+        ksize = lib.b200sam_resize_ksize(in_size, out_size)
+        bounds = np.zeros((out_size, 2), np.int32)
+        kk = np.zeros((out_size, ksize), np.int32)
+        _lib.check(lib.b200sam_resize_coeffs_host(in_size, out_size, bounds.ctypes.data_as(C.c_void_p),
+                                                  kk.ctypes.data_as(C.c_void_p)), "resize_coeffs_host")
+        hit = (torch.from_numpy(bounds).to(device), torch.from_numpy(kk).to(device), ksize)
+        _TABLES[key] = hit
+    return hit
+
+
+def resize_u8_cuda(image: torch.Tensor, out_h: int, out_w: int, chw: bool = False) -> torch.Tensor:
+    """image: [H, W, C] uint8 CUDA tensor -> `PIL.Image.resize((out_w, out_h), BILINEAR)` of it, bit-exact, as
+    [out_h, out_w, C] (chw=False) or [C, out_h, out_w] (chw=True, the encoder's input layout)."""
+    from ... import _lib
+    assert image.is_cuda and image.dtype == torch.uint8 and image.dim() == 3, "expected a [H, W, C] uint8 CUDA tensor"
+    image = image.contiguous()
+    H, W, Cc = image.shape
+    lib = _lib.load()
+    xb = xk = yb = yk = None
+    kx = ky = 0
+    if out_w != W:
+        xb, xk, kx = _resize_tables(W, out_w, image.device)
+    if out_h != H:
+        yb, yk, ky = _resize_tables(H, out_h, image.device)
+    out = torch.empty((Cc, out_h, out_w) if chw else (out_h, out_w, Cc), dtype=torch.uint8, device=image.device)
+    tmp = None
+    if xb is not None and (yb is not None or chw):
+        tmp = torch.empty((H, out_w, Cc), dtype=torch.uint8, device=image.device)
+    _lib.check(lib.b200sam_resize_u8(_lib.ptr(image), H, W, Cc, _lib.ptr(xb), _lib.ptr(xk), kx, _lib.ptr(yb),
+                                     _lib.ptr(yk), ky, out_h, out_w, _lib.ptr(tmp), _lib.ptr(out), int(chw),
+                                     _lib.current_stream()), "resize_u8")
+    return out
 
 
 class ResizeLongestSide:
@@ -19,6 +66,17 @@ class ResizeLongestSide:
         if (newh, neww) == image.shape[:2]:
             return np.array(image)
         return np.array(Image.fromarray(image).resize((neww, newh), resample=Image.BILINEAR))
+
+    def apply_image_cuda(self, image, device=None, chw: bool = True) -> torch.Tensor:
+        """`apply_image` on the GPU: HxWxC uint8 (numpy array, pinned / pageable host tensor or CUDA tensor) ->
+        resized uint8 CUDA tensor ([C, h, w] for chw=True).  Bit-identical to the host path."""
+        from ... import _lib
+        if isinstance(image, np.ndarray):
+            image = torch.from_numpy(np.ascontiguousarray(image))
+        if not image.is_cuda:
+            image = image.to(_lib.require_cuda(device), non_blocking=True)
+        newh, neww = self.get_preprocess_shape(image.shape[0], image.shape[1], self.target_length)
+        return resize_u8_cuda(image, newh, neww, chw=chw)
 
     def apply_coords(self, coords: np.ndarray, original_size: Tuple[int, ...]) -> np.ndarray:
         old_h, old_w = original_size

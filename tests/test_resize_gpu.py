@@ -1,0 +1,80 @@
+"""GPU image ingest: b200sam_resize_u8 through the Python mirror against the oracle restatement of
+Pillow's antialiased bilinear resample and the committed Pillow golden vectors.  Integer arithmetic: bit-exact."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sam_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(Path(__file__).parent / "golden" / "resize_golden.npz")
+N_CASES = sum(1 for k in GOLD.files if k.startswith("in"))
+
+
+def _resize(img: np.ndarray, oh: int, ow: int, chw: bool) -> np.ndarray:
+    from samcarriestheburden_b200.segment_anything.utils.transforms import resize_u8_cuda
+    out = resize_u8_cuda(torch.from_numpy(img).cuda(), oh, ow, chw=chw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("i", range(N_CASES))
+def test_resize_matches_pillow_golden(i):
+    img, want = GOLD[f"in{i}"], GOLD[f"out{i}"]
+    got = _resize(img, want.shape[0], want.shape[1], chw=False)
+    assert np.array_equal(got, want)
+    got_chw = _resize(img, want.shape[0], want.shape[1], chw=True)
+    assert np.array_equal(got_chw, np.transpose(want, (2, 0, 1)))
+
+
+@pytest.mark.parametrize("shape", [(1182, 754), (881, 578), (2570, 2040), (640, 1024), (300, 300), (1024, 1024)])
+def test_apply_image_cuda_native_sizes_bit_exact(shape):
+    """ResizeLongestSide.apply_image_cuda == the oracle (== Pillow) on CVAT-like native radiograph sizes."""
+    from samcarriestheburden_b200.segment_anything.utils.transforms import ResizeLongestSide
+    H, W = shape
+    img = O.synthetic_radiograph(3, H, W)
+    img[::7, ::5] = np.random.default_rng(0).integers(0, 256, size=img[::7, ::5].shape, dtype=np.uint8)  # sharp detail
+    tr = ResizeLongestSide(1024)
+    want = O.apply_image(img, 1024)
+    got = tr.apply_image_cuda(img, chw=False).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert np.array_equal(tr.apply_image(img), want)  # the host path (Pillow itself) agrees as well
+
+
+def test_resize_identity_and_single_channel_and_errors():
+    from samcarriestheburden_b200 import _lib
+    from samcarriestheburden_b200.segment_anything.utils.transforms import resize_u8_cuda
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, size=(37, 53, 1), dtype=np.uint8)
+    same = _resize(img, 37, 53, chw=True)  # no pass needed: layout conversion only
+    assert np.array_equal(same, np.transpose(img, (2, 0, 1)))
+    assert np.array_equal(_resize(img, 37, 53, chw=False), img)
+    up = _resize(img, 80, 53, chw=False)  # height only
+    assert np.array_equal(up, O.resize_bilinear_u8(img, 80, 53))
+    with pytest.raises(AssertionError):
+        resize_u8_cuda(torch.zeros((4, 4), dtype=torch.uint8, device="cuda"), 2, 2)
+    lib = _lib.load()
+    x = torch.zeros((4, 4, 3), dtype=torch.uint8, device="cuda")
+    y = torch.zeros((2, 4, 3), dtype=torch.uint8, device="cuda")
+    # height changes but no vertical table: loud error, no silent fallback
+    rc = lib.b200sam_resize_u8(x.data_ptr(), 4, 4, 3, None, None, 0, None, None, 0, 2, 4, None, y.data_ptr(), 0, None)
+    assert rc != 0 and b"vertical" in lib.b200sam_last_error()
+
+
+def test_set_image_uses_gpu_resize_and_matches_host_resize():
+    """SamPredictor.set_image on a non-square native image == set_torch_image of the Pillow-resized image."""
+    from samcarriestheburden_b200.segment_anything import SamPredictor, sam_model_registry
+    sam = sam_model_registry["vit_b"]()
+    sam.load_state_dict(O.random_state_dict("vit_b", seed=0), strict=True)
+    sam = sam.to("cuda")
+    pred = SamPredictor(sam)
+    img = O.synthetic_radiograph(11, 591, 377)
+    pred.set_image(img)
+    a = pred.get_image_embedding().clone()
+    assert pred.original_size == (591, 377) and pred.input_size == (1024, 653)
+    host = torch.from_numpy(O.apply_image(img, 1024)).permute(2, 0, 1).contiguous()[None].cuda()
+    pred.set_torch_image(host, (591, 377))
+    assert torch.equal(a, pred.get_image_embedding())
