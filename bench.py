@@ -48,6 +48,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
@@ -56,7 +57,17 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def _lines(self):
+        try:
+            return [r for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        except Exception:
+            return []
+
+    def mark(self) -> int:
+        """Number of samples taken so far (nvidia-smi is up once this is > 0)."""
+        return len(self._lines())
+
+    def stop(self, since: int = 0):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -66,16 +77,23 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        rows = [r.split(",") for r in self._lines()]
         os.unlink(self.f.name)
         if not rows:
             return out
+        rows = rows[since:] or rows  # the samples taken during the timed region
         sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
         busy = [v for v in sm if v > 0.5 * max(sm)] or sm
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows)]
         out.update(sm_mhz=statistics.median(busy), sm_max_mhz=float(rows[0][2]), reasons=reasons,
                    power_w_max=max(float(r[3]) for r in rows), samples=len(rows))
+        try:  # the board's enforced power limit explains a sw_power_cap clock (the peaks file may come from another box)
+            lim = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", "--query-gpu=enforced.power.limit",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            out["power_limit_w"] = float(lim.strip().splitlines()[0])
+        except Exception:
+            pass
         return out
 
 
@@ -274,11 +292,21 @@ def main():
         host_out.copy_(emb, non_blocking=True)
         return emb
 
+    # nvidia-smi's start-up takes a driver-wide lock for tens of milliseconds: launch the sampler BEFORE the warm-up and
+    # keep warming up (bounded) until its first sample has arrived, so that the timed region only sees steady polling
+    sampler = ClockSampler(local) if rank == 0 else None
     for s in range(W):
         step_resident(s)
-    sampler = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize()
+    mark = 0
+    if sampler is not None and sampler.p is not None:
+        t_wait = time.perf_counter()
+        while sampler.mark() == 0 and time.perf_counter() - t_wait < 5.0:
+            step_resident(0)
+            torch.cuda.synchronize()
+        mark = sampler.mark()
     ms = timed(step_resident, K)
-    clocks = sampler.stop() if sampler else {}
+    clocks = sampler.stop(since=mark) if sampler else {}
     for s in range(2):
         step_e2e(s)
     ms_e2e = timed(step_e2e, K)

@@ -39,7 +39,11 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
 
     def flush(key):
         items = pending.pop(key)
-        x = torch.stack([t.to(dev, non_blocking=True) for _, t, _ in items])
+        ts = [t for _, t, _ in items]
+        if all(not t.is_cuda for t in ts):  # one stacked upload instead of one copy per image
+            x = torch.stack(ts).to(dev, non_blocking=True)
+        else:
+            x = torch.stack([t.to(dev, non_blocking=True) for t in ts])
         emb = sam.encode_image(x)
         for j, (slot, _, orig) in enumerate(items):
             local[slot] = emb[j]

@@ -31,6 +31,9 @@ refiner = SAMSegRefiner("SAM", str(dev), [["box"], ["pos_points", "neg_points"]]
 batch = torch.stack(segs)
 low = torch.randn((256, 1, 256, 256), device=dev)
 masks = torch.from_numpy(np.stack([O.synthetic_unet_masks(i % 16) for i in range(256)])).to(dev)
+from samcarriestheburden_b200.segment_anything.utils.transforms import ResizeLongestSide  # noqa: E402
+native = torch.randint(0, 256, (2570, 2040, 3), dtype=torch.uint8, device=dev)
+ingest = ResizeLongestSide(1024)
 
 
 def roi():
@@ -40,6 +43,7 @@ def roi():
         upscale_masks(low, (1024, 1024), (1024, 1024), small_size=(384, 224))
         upscale_masks(low, (1024, 653), (1182, 754), small_size=(384, 224))
         extract_seeds_boxes(masks)
+        ingest.apply_image_cuda(native)
 
 
 roi()

@@ -44,6 +44,17 @@ def run(peak_gbs=6545.9):
         by = n * (256 * 256 * 4 + oh * ow + 384 * 224)
         out[f"upscale_threshold_{oh}x{ow}"] = {"masks": n, "ms": t, "bytes": by, "gbs": by / t / 1e6,
                                                "frac_hbm": by / t / 1e6 / peak_gbs}
+    # image ingest: native-resolution uint8 radiographs (largest CVAT size) -> encoder input size, Pillow-exact resize
+    from samcarriestheburden_b200.segment_anything.utils.transforms import ResizeLongestSide
+    tr = ResizeLongestSide(1024)
+    H, W = 2570, 2040
+    n = 16
+    imgs = [torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    oh, ow = tr.get_preprocess_shape(H, W, 1024)
+    t = timed(lambda: [tr.apply_image_cuda(im) for im in imgs])
+    by = n * (H * W * 3 + oh * ow * 3)
+    out[f"ingest_resize_{H}x{W}"] = {"images": n, "ms": t, "bytes": by, "gbs": by / t / 1e6,
+                                      "frac_hbm": by / t / 1e6 / peak_gbs}
     return out
 
 
