@@ -82,26 +82,50 @@ __global__ void __launch_bounds__(256) unet_im2col3x3_split_kernel(const float* 
   }
 }
 
-// per-(image, channel) sum and sum of squares over the H*W rows of x [B*HW, C] (fp64 accumulators, pre-zeroed)
+// per-(image, channel) sum and sum of squares over the H*W rows of x [B*HW, C] (fp64 accumulators, pre-zeroed).
+// A block covers rows [r0, r1) of one image and 4 * min(C / 4, 256) channels: thread = (float4 channel group, row
+// sub-sequence), so all 256 threads stream 16-byte loads whatever C is (C = 64: 16 groups x 16 row sub-sequences);
+// short fp32 runs, fp64 across runs, shared-memory tree over the row sub-sequences, one fp64 atomic pair per channel.
 __global__ void __launch_bounds__(256) unet_in_stats_kernel(const float* __restrict__ x, int HW, int C, int rows_per_block,
                                                             double* __restrict__ stats /*[B, C, 2]*/) {
+  __shared__ double sh[256][8];
   const int b = blockIdx.z;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    float s = 0.0f, q = 0.0f;
-    double ds = 0.0, dq = 0.0;
+  const int c4n = C >> 2;                  // float4 groups per row
+  const int gpb = min(c4n, 256);           // groups handled by this block
+  const int nsub = 256 / gpb;              // row sub-sequences
+  const int g = threadIdx.x % gpb, sub = threadIdx.x / gpb;
+  const int c4 = blockIdx.x * gpb + g;
+  double ds[4] = {0.0, 0.0, 0.0, 0.0}, dq[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c4 < c4n && sub < nsub) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
     int n = 0;
-    for (int r = r0; r < r1; ++r) {
-      const float v = x[(static_cast<size_t>(b) * HW + r) * C + c];
-      s += v;
-      q = fmaf(v, v, q);
-      if (++n == 64) { ds += s; dq += q; s = q = 0.0f; n = 0; }  // short fp32 runs, fp64 across runs
+    const float* px = x + (static_cast<size_t>(b) * HW) * C + 4 * c4;
+    for (int r = r0 + sub; r < r1; r += nsub) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(px + static_cast<size_t>(r) * C));
+      s4[0] += v.x; s4[1] += v.y; s4[2] += v.z; s4[3] += v.w;
+      q4[0] = fmaf(v.x, v.x, q4[0]); q4[1] = fmaf(v.y, v.y, q4[1]);
+      q4[2] = fmaf(v.z, v.z, q4[2]); q4[3] = fmaf(v.w, v.w, q4[3]);
+      if (++n == 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ds[i] += s4[i]; dq[i] += q4[i]; s4[i] = q4[i] = 0.0f; }
+        n = 0;
+      }
     }
-    ds += s;
-    dq += q;
-    atomicAdd(&stats[(static_cast<size_t>(b) * C + c) * 2 + 0], ds);
-    atomicAdd(&stats[(static_cast<size_t>(b) * C + c) * 2 + 1], dq);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ds[i] += s4[i]; dq[i] += q4[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sh[threadIdx.x][i] = ds[i]; sh[threadIdx.x][4 + i] = dq[i]; }
+  __syncthreads();
+  // threads 0 .. gpb*8-1: one (group, component) each, summing over the row sub-sequences
+  for (int t = threadIdx.x; t < gpb * 8; t += 256) {
+    const int gg = t >> 3, comp = t & 7;
+    double acc = 0.0;
+    for (int k = 0; k < nsub; ++k) acc += sh[k * gpb + gg][comp];
+    const int cc = 4 * (blockIdx.x * gpb + gg) + (comp & 3);
+    if (cc < C) atomicAdd(&stats[(static_cast<size_t>(b) * C + cc) * 2 + (comp >> 2)], acc);
   }
 }
 
@@ -388,8 +412,8 @@ int conv_in_lrelu(const UNetCtx* u, const UWork& w, const float* in, int ld_in, 
   unet_im2col3x3_split_kernel<<<grid_for(M * (Kp / 8)), 256, 0, s>>>(in, B, H, W, cin, ld_in, Kp, w.col);
   TRY(split_gemm(w.col, ws, nullptr, tmp, M, cout, Kp, s));
   B200SAM_CHECK_CUDA(cudaMemsetAsync(w.stats, 0, static_cast<size_t>(B) * cout * 2 * sizeof(double), s));
-  const int rpb = 256;
-  dim3 gs((cout + 255) / 256, static_cast<unsigned>((HW + rpb - 1) / rpb), B);
+  const int rpb = static_cast<int>(std::min<size_t>(512, std::max<size_t>(64, HW / 32)));  // >= ~250 blocks per launch
+  dim3 gs((cout / 4 + 255) / 256, static_cast<unsigned>((HW + rpb - 1) / rpb), B);
   unet_in_stats_kernel<<<gs, 256, 0, s>>>(tmp, static_cast<int>(HW), cout, rpb, w.stats);
   const size_t total4 = M * (cout / 4);
   unet_in_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tmp, w.stats, gamma, beta, static_cast<int>(HW), cout, total4, out,

@@ -65,7 +65,12 @@ class SAMMaskDecoderHead:
             sam_checkpoint = Path(sam_checkpoint)
             assert attrs["checkpoint"] == sam_checkpoint.name, "SAM checkpoint mismatch"
             sam_model = sam_model_registry[model_type](checkpoint=sam_checkpoint)
-        self.sam = sam_model.to(device=self.device)
+        # `.to()` re-packs the weights of the CUDA engines: only move the model if it is not on the device already
+        cur = sam_model.device
+        same = cur.type == self.device.type and (
+            self.device.index is None or cur.index == self.device.index or
+            (cur.index is None and self.device.index == torch.cuda.current_device()))
+        self.sam = sam_model if same else sam_model.to(device=self.device)
         self.prompt_encoder = self.sam.prompt_encoder
         self.mask_decoder = self.sam.mask_decoder
         self.mask_threshold = self.sam.mask_threshold
