@@ -129,8 +129,20 @@ __global__ void __launch_bounds__(256) unet_in_stats_kernel(const float* __restr
   }
 }
 
-// y = LeakyReLU_0.01((x - mean) * rstd * gamma + beta); biased variance, eps 1e-5 (nn.InstanceNorm2d defaults)
-__global__ void __launch_bounds__(256) unet_in_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+// (sum, sum of squares) -> (mean, 1 / sqrt(var + eps)) in fp64, rounded to fp32 once per (image, channel);
+// biased variance, eps 1e-5 (nn.InstanceNorm2d defaults)
+__global__ void __launch_bounds__(256) unet_in_finalize_kernel(const double* __restrict__ stats, int HW, int n,
+                                                               float2* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = stats[2 * i] / HW;
+  double var = stats[2 * i + 1] / HW - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  mr[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + 1e-5)));
+}
+
+// y = LeakyReLU_0.01((x - mean) * rstd * gamma + beta)
+__global__ void __launch_bounds__(256) unet_in_apply_kernel(const float* __restrict__ x, const float2* __restrict__ mr,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int HW, int C, size_t total4, float* __restrict__ y, int ld_y) {
   const int c4n = C / 4;
@@ -140,16 +152,14 @@ __global__ void __launch_bounds__(256) unet_in_apply_kernel(const float* __restr
     const size_t m = idx / c4n;
     const size_t b = m / HW;
     const float4 v = *reinterpret_cast<const float4*>(x + m * C + c);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
     const float in[4] = {v.x, v.y, v.z, v.w};
+    const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
     float o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double s = stats[(b * C + c + i) * 2], q = stats[(b * C + c + i) * 2 + 1];
-      const double mean = s / HW;
-      double var = q / HW - mean * mean;
-      var = var < 0.0 ? 0.0 : var;
-      const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
-      const float t = (in[i] - static_cast<float>(mean)) * rstd * gamma[c + i] + beta[c + i];
+      const float2 s = __ldg(mr + b * C + c + i);
+      const float t = (in[i] - s.x) * s.y * gm[i] + bt[i];
       o[i] = t >= 0.0f ? t : 0.01f * t;
     }
     *reinterpret_cast<float4*>(y + m * ld_y + c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -349,6 +359,7 @@ struct UWork {
   float *t0, *t1;    // conv outputs / pooled inputs (largest: [B*HW, 64] and [B*HW/4, 128] ...)
   __nv_bfloat16* col;  // im2col / split operand
   double* stats;     // [B, 1024, 2]
+  float2* mr;        // [B, 1024] (mean, rstd)
   size_t total;
 };
 
@@ -385,6 +396,7 @@ UWork carve_unet(uint8_t* base, const UNetCtx* u, int B, int H, int W) {
   w.t1 = reinterpret_cast<float*>(take(tmax * sizeof(float)));
   w.col = reinterpret_cast<__nv_bfloat16*>(take(cmax * sizeof(__nv_bfloat16)));
   w.stats = reinterpret_cast<double*>(take(static_cast<size_t>(B) * 1024 * 2 * sizeof(double)));
+  w.mr = reinterpret_cast<float2*>(take(static_cast<size_t>(B) * 1024 * sizeof(float2)));
   w.total = off;
   return w;
 }
@@ -416,7 +428,8 @@ int conv_in_lrelu(const UNetCtx* u, const UWork& w, const float* in, int ld_in, 
   dim3 gs((cout / 4 + 255) / 256, static_cast<unsigned>((HW + rpb - 1) / rpb), B);
   unet_in_stats_kernel<<<gs, 256, 0, s>>>(tmp, static_cast<int>(HW), cout, rpb, w.stats);
   const size_t total4 = M * (cout / 4);
-  unet_in_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tmp, w.stats, gamma, beta, static_cast<int>(HW), cout, total4, out,
+  unet_in_finalize_kernel<<<(B * cout + 255) / 256, 256, 0, s>>>(w.stats, static_cast<int>(HW), B * cout, w.mr);
+  unet_in_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tmp, w.mr, gamma, beta, static_cast<int>(HW), cout, total4, out,
                                                        ld_out);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
