@@ -44,10 +44,15 @@ constexpr uint32_t TMEM_COLS = 512;
 // same 8 epilogue warps (the `half` index selects the row block instead of the column block).
 // a_wrap > 0: the A operand is stored with only a_wrap columns and k-blocks past it wrap around to column
 // kb*BK - a_wrap (the [hi | lo | hi] split operand of the decoder is stored as [hi | lo]).
+// conv_cin > 0: implicit 3x3 convolution (U-Net).  A is the [hi | lo] split activation on a zero-BORDERED pixel grid
+// ([B * (H+2) * (W+2), 2 * conv_cin], conv_wp = W + 2) and the GEMM runs over that padded grid too, so the A tile of tap
+// (ky, kx) is the SAME 2-D box shifted by (ky-1) * conv_wp + (kx-1) rows: no im2col matrix is ever written.  K runs over
+// (segment hi|lo|hi, tap, channel block) to match the [hi | hi | lo] tap-major weights; rows outside the tensor are
+// zero-filled by TMA (they only feed border rows, which the consumers skip).
 template <bool OUT_BF16, int BN_EFF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    EpiParams ep, int M, int N, int K, int a_wrap) {
+                    EpiParams ep, int M, int N, int K, int a_wrap, int conv_cin, int conv_wp) {
   // SWIZZLE_128B tiles need 1024 B alignment.  The alignment is requested on the symbol (not by rounding the
   // pointer through an integer): pointer arithmetic through uintptr_t makes the compiler lose the shared
   // state space and emit generic LD/ST (L1TEX path, long-scoreboard latency) for every staging access.
@@ -108,8 +113,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int ka = kb * BK;
-          tma_load_2d(sa, &tma_a, &full_bar[stage], (a_wrap > 0 && ka >= a_wrap) ? ka - a_wrap : ka, m0);
+          int a_col = kb * BK, a_row = m0;
+          if (conv_cin > 0) {
+            const int cb = conv_cin / BK, per_seg = 9 * cb;
+            const int seg = kb / per_seg, r = kb - seg * per_seg;
+            const int tap = r / cb, cblk = r - tap * cb;
+            a_col = (seg == 1 ? conv_cin : 0) + cblk * BK;
+            a_row = m0 + (tap / 3 - 1) * conv_wp + (tap % 3 - 1);
+          } else if (a_wrap > 0 && a_col >= a_wrap) {
+            a_col -= a_wrap;
+          }
+          tma_load_2d(sa, &tma_a, &full_bar[stage], a_col, a_row);
           tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -206,9 +220,13 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
                   "gemm: A and B must be 16-byte aligned");
   B200SAM_REQUIRE(g.a_wrap == 0 || (g.a_wrap % BK == 0 && g.a_wrap > 0 && g.K <= 2 * g.a_wrap),
                   "gemm: a_wrap=%d must be a positive multiple of %d with K <= 2 a_wrap", g.a_wrap, BK);
+  B200SAM_REQUIRE(g.conv_cin == 0 || (g.conv_cin % BK == 0 && g.K == 27 * g.conv_cin && g.conv_wp >= 3 &&
+                                      g.lda >= 2 * g.conv_cin && g.a_wrap == 0),
+                  "gemm: bad implicit-convolution configuration (cin=%d, K=%d, wp=%d)", g.conv_cin, g.K, g.conv_wp);
   const bool narrow = g.N <= 128;
   CUtensorMap ta, tb;
-  if (make_tmap_bf16(&ta, g.A, g.M, g.a_wrap > 0 ? g.a_wrap : g.K, g.lda, narrow ? 2 * BM : BM, BK,
+  const int a_cols = g.conv_cin > 0 ? 2 * g.conv_cin : (g.a_wrap > 0 ? g.a_wrap : g.K);
+  if (make_tmap_bf16(&ta, g.A, g.M, a_cols, g.lda, narrow ? 2 * BM : BM, BK,
                      CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, narrow ? 128 : BN, BK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   EpiParams ep;
@@ -241,7 +259,7 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   }
   auto kernel = g.out_bf16 ? (narrow ? gemm_bf16_tn_kernel<true, 128> : gemm_bf16_tn_kernel<true, 256>)
                            : (narrow ? gemm_bf16_tn_kernel<false, 128> : gemm_bf16_tn_kernel<false, 256>);
-  kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K, g.a_wrap);
+  kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K, g.a_wrap, g.conv_cin, g.conv_wp);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

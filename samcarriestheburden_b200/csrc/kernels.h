@@ -43,6 +43,8 @@ struct GemmArgs {
   int out_bf16;     // 1: bf16 output, 0: fp32 output
   int max_ctas;     // <= 0: one CTA per SM; > 0 caps the persistent grid
   int a_wrap = 0;   // > 0: A has only a_wrap columns; k >= a_wrap reads column k - a_wrap ([hi|lo|hi] stored as [hi|lo])
+  int conv_cin = 0;  // > 0: implicit 3x3 convolution over a zero-bordered pixel grid (see gemm_tcgen05.cu); K = 27 * conv_cin
+  int conv_wp = 0;   //      padded row length W + 2
   // fused mask-decoder upscaler epilogues (gemm_epilogue.cuh): 0 none, 1 LN2d(64)+GELU+split (N = 256), 2 GELU+hyper dot (N = 128)
   int epi_mode = 0;
   const float* aux0 = nullptr;  // mode 1: LN gamma [64]; mode 2: hyper [prompts, 4, 32]

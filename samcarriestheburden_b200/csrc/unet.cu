@@ -82,12 +82,41 @@ __global__ void __launch_bounds__(256) unet_im2col3x3_split_kernel(const float* 
   }
 }
 
+// Operand of the implicit 3x3 convolution (gemm_tcgen05.cu, conv mode): in fp32 [B, H, W, *] (row pitch ld_in floats,
+// C channels, C % 8 == 0) -> out bf16 [B * (H+2) * (W+2), 2*C] = [hi | lo] on a pixel grid with a one-pixel ZERO border.
+// 4*C bytes written per pixel instead of the 36*C of the explicit im2col matrix.
+__global__ void __launch_bounds__(256) unet_pad_split_kernel(const float* __restrict__ in, int B, int H, int W, int C,
+                                                             int ld_in, __nv_bfloat16* __restrict__ out) {
+  const int vec_per_row = C / 8;
+  const int Hp = H + 2, Wp = W + 2;
+  const size_t total = static_cast<size_t>(B) * Hp * Wp * vec_per_row;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % vec_per_row);
+    const size_t pm = idx / vec_per_row;
+    const int xp = static_cast<int>(pm % Wp);
+    const int yp = static_cast<int>((pm / Wp) % Hp);
+    const size_t bimg = pm / (static_cast<size_t>(Wp) * Hp);
+    uint4 Hh = make_uint4(0, 0, 0, 0), Lo = make_uint4(0, 0, 0, 0);
+    if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) {
+      const float4* src = reinterpret_cast<const float4*>(in + ((bimg * H + (yp - 1)) * W + (xp - 1)) * ld_in + 8 * v);
+      const float4 a = src[0], b = src[1];
+      const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      split8(f, Hh, Lo);
+    }
+    __nv_bfloat16* o = out + pm * (2 * static_cast<size_t>(C)) + 8 * v;
+    *reinterpret_cast<uint4*>(o) = Hh;
+    *reinterpret_cast<uint4*>(o + C) = Lo;
+  }
+}
+
 // per-(image, channel) sum and sum of squares over the H*W rows of x [B*HW, C] (fp64 accumulators, pre-zeroed).
+// W > 0: x lives on the zero-bordered (H+2) x (W+2) grid of the implicit convolution; only interior rows count.
 // A block covers rows [r0, r1) of one image and 4 * min(C / 4, 256) channels: thread = (float4 channel group, row
 // sub-sequence), so all 256 threads stream 16-byte loads whatever C is (C = 64: 16 groups x 16 row sub-sequences);
 // short fp32 runs, fp64 across runs, shared-memory tree over the row sub-sequences, one fp64 atomic pair per channel.
 __global__ void __launch_bounds__(256) unet_in_stats_kernel(const float* __restrict__ x, int HW, int C, int rows_per_block,
-                                                            double* __restrict__ stats /*[B, C, 2]*/) {
+                                                            double* __restrict__ stats /*[B, C, 2]*/, int W) {
   __shared__ double sh[256][8];
   const int b = blockIdx.z;
   const int r0 = blockIdx.y * rows_per_block;
@@ -101,9 +130,19 @@ __global__ void __launch_bounds__(256) unet_in_stats_kernel(const float* __restr
   if (c4 < c4n && sub < nsub) {
     float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
     int n = 0;
-    const float* px = x + (static_cast<size_t>(b) * HW) * C + 4 * c4;
+    const int Wp = W + 2;
+    const size_t img_rows = W > 0 ? static_cast<size_t>(HW / W + 2) * Wp : static_cast<size_t>(HW);
+    const float* px = x + (static_cast<size_t>(b) * img_rows) * C + 4 * c4;
+    int yy = 0, xx = 0;
+    if (W > 0) { yy = (r0 + sub) / W; xx = (r0 + sub) - yy * W; }
     for (int r = r0 + sub; r < r1; r += nsub) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(px + static_cast<size_t>(r) * C));
+      size_t row = static_cast<size_t>(r);
+      if (W > 0) {
+        row = static_cast<size_t>(yy + 1) * Wp + (xx + 1);
+        xx += nsub;
+        while (xx >= W) { xx -= W; ++yy; }
+      }
+      const float4 v = __ldg(reinterpret_cast<const float4*>(px + row * C));
       s4[0] += v.x; s4[1] += v.y; s4[2] += v.z; s4[3] += v.w;
       q4[0] = fmaf(v.x, v.x, q4[0]); q4[1] = fmaf(v.y, v.y, q4[1]);
       q4[2] = fmaf(v.z, v.z, q4[2]); q4[3] = fmaf(v.w, v.w, q4[3]);
@@ -144,14 +183,21 @@ __global__ void __launch_bounds__(256) unet_in_finalize_kernel(const double* __r
 // y = LeakyReLU_0.01((x - mean) * rstd * gamma + beta)
 __global__ void __launch_bounds__(256) unet_in_apply_kernel(const float* __restrict__ x, const float2* __restrict__ mr,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            int HW, int C, size_t total4, float* __restrict__ y, int ld_y) {
+                                                            int HW, int C, size_t total4, float* __restrict__ y, int ld_y,
+                                                            int W /* > 0: x on the zero-bordered grid */) {
   const int c4n = C / 4;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total4;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(idx % c4n) * 4;
     const size_t m = idx / c4n;
     const size_t b = m / HW;
-    const float4 v = *reinterpret_cast<const float4*>(x + m * C + c);
+    size_t xrow = m;
+    if (W > 0) {
+      const int rem = static_cast<int>(m - b * HW);
+      const int yy = rem / W, xx = rem - yy * W;
+      xrow = (b * (HW / W + 2) + yy + 1) * (W + 2) + xx + 1;
+    }
+    const float4 v = *reinterpret_cast<const float4*>(x + xrow * C + c);
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
     const float in[4] = {v.x, v.y, v.z, v.w};
     const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -380,8 +426,10 @@ UWork carve_unet(uint8_t* base, const UNetCtx* u, int B, int H, int W) {
   for (int i = 0; i < 9; ++i) {
     const int lvl = i < 5 ? i : 8 - i;  // resolution level of the DoubleConv
     const size_t M = B * (HW >> (2 * lvl));
+    const size_t Mp = static_cast<size_t>(B) * ((H >> lvl) + 2) * ((W >> lvl) + 2);  // implicit-conv outputs: padded grid
     for (int j = 0; j < 2; ++j) {
-      tmax = std::max(tmax, M * u->arch.dc[i][j].cout);
+      tmax = std::max(tmax, Mp * u->arch.dc[i][j].cout);
+      cmax = std::max(cmax, Mp * 2 * static_cast<size_t>(u->arch.dc[i][j].cin));
       cmax = std::max(cmax, M * 2 * static_cast<size_t>(unet_conv_kp(u->arch.dc[i][j].cin)));
     }
   }
@@ -421,16 +469,30 @@ int conv_in_lrelu(const UNetCtx* u, const UWork& w, const float* in, int ld_in, 
   (void)u;
   const size_t HW = static_cast<size_t>(H) * W, M = B * HW;
   const int Kp = unet_conv_kp(cin);
-  unet_im2col3x3_split_kernel<<<grid_for(M * (Kp / 8)), 256, 0, s>>>(in, B, H, W, cin, ld_in, Kp, w.col);
-  TRY(split_gemm(w.col, ws, nullptr, tmp, M, cout, Kp, s));
+  const bool implicit = cin % 64 == 0;  // every convolution but the first (cin = n_channels = 1)
+  if (implicit) {
+    // zero-bordered [hi | lo] operand + implicit-convolution GEMM over the padded grid (no im2col matrix)
+    const size_t Mp = static_cast<size_t>(B) * (H + 2) * (W + 2);
+    B200SAM_REQUIRE(Mp < (1ull << 31) && Kp == 9 * cin, "unet: bad implicit convolution shape");
+    unet_pad_split_kernel<<<grid_for(Mp * (cin / 8)), 256, 0, s>>>(in, B, H, W, cin, ld_in, w.col);
+    GemmArgs g;
+    g.A = w.col; g.B = ws; g.out = tmp; g.bias = nullptr; g.residual = nullptr;
+    g.M = static_cast<int>(Mp); g.N = cout; g.K = 27 * cin; g.lda = 2 * cin; g.ldb = 27 * cin; g.ldo = cout; g.ldr = 0;
+    g.res_row_mod = 0; g.gelu = 0; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 0; g.conv_cin = cin; g.conv_wp = W + 2;
+    TRY(gemm_bf16_tn(g, s));
+  } else {
+    unet_im2col3x3_split_kernel<<<grid_for(M * (Kp / 8)), 256, 0, s>>>(in, B, H, W, cin, ld_in, Kp, w.col);
+    TRY(split_gemm(w.col, ws, nullptr, tmp, M, cout, Kp, s));
+  }
+  const int Wg = implicit ? W : 0;
   B200SAM_CHECK_CUDA(cudaMemsetAsync(w.stats, 0, static_cast<size_t>(B) * cout * 2 * sizeof(double), s));
   const int rpb = static_cast<int>(std::min<size_t>(512, std::max<size_t>(64, HW / 32)));  // >= ~250 blocks per launch
   dim3 gs((cout / 4 + 255) / 256, static_cast<unsigned>((HW + rpb - 1) / rpb), B);
-  unet_in_stats_kernel<<<gs, 256, 0, s>>>(tmp, static_cast<int>(HW), cout, rpb, w.stats);
+  unet_in_stats_kernel<<<gs, 256, 0, s>>>(tmp, static_cast<int>(HW), cout, rpb, w.stats, Wg);
   const size_t total4 = M * (cout / 4);
   unet_in_finalize_kernel<<<(B * cout + 255) / 256, 256, 0, s>>>(w.stats, static_cast<int>(HW), B * cout, w.mr);
   unet_in_apply_kernel<<<grid_for(total4), 256, 0, s>>>(tmp, w.mr, gamma, beta, static_cast<int>(HW), cout, total4, out,
-                                                       ld_out);
+                                                       ld_out, Wg);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
