@@ -4,11 +4,16 @@
 //   DoubleConv = (conv3x3 pad 1, no bias -> InstanceNorm2d(affine, eps 1e-5) -> LeakyReLU(0.01)) x 2
 //   Down = MaxPool2d(2) + DoubleConv;  Up = ConvTranspose2d(k2, s2) + cat([skip, up]) + DoubleConv;  OutConv = conv1x1
 //
-// Activations are NHWC fp32 ([B*H*W, C] row-major, optionally a channel slice of a wider concat buffer).  Every
-// convolution is an im2col + tcgen05 GEMM on 3-way bf16 split operands (x = hi + lo; [hi|lo|hi] x [hi|hi|lo], fp32
-// accumulate, ~2^-17 relative error - the same fp32-grade path as the mask decoder): the im2col kernel writes the
-// [hi | lo] operand directly, the weights are split once at create time.  InstanceNorm statistics are two plain
-// passes (per-(image, channel) sum / sum of squares in fp64, then normalise + LeakyReLU into the consumer's buffer).
+// Activations are NHWC fp32 ([B*H*W, C] row-major, optionally a channel slice of a wider concat buffer).  Every 3x3
+// convolution with Cin % 64 == 0 is an IMPLICIT GEMM on the tcgen05 kernel: the input is written once as a [hi | lo] bf16
+// split operand on a pixel grid with a one-pixel zero border (unet_pad_split_kernel, 4*Cin bytes per pixel), the GEMM runs
+// over that padded grid and its TMA producer fetches the A tile of tap (ky, kx) as the same 2-D box shifted by
+// (ky-1)*(W+2) + (kx-1) rows (gemm_tcgen05.cu, conv mode) - no im2col matrix (36*Cin bytes per pixel) is ever written.
+// 3-way bf16 split operands (x = hi + lo; [hi|lo|hi] x [hi|hi|lo], fp32 accumulate, ~2^-17 relative error - the same
+// fp32-grade path as the mask decoder); the weights are split once at create time.  The first convolution (one input
+// channel, 9 MACs per output) is a direct fp32 kernel.  InstanceNorm: per-(image, channel) sum / sum of squares in fp64
+// over the interior rows of the padded grid, (mean, rstd) finalised once per channel, normalise + LeakyReLU written into
+// the consumer's (un-padded) buffer.  ConvTranspose2d(k2, s2) = GEMM + depth-to-space; OutConv = 1x1 GEMM + sigmoid.
 #include "common.cuh"
 #include "kernels.h"
 #include "decoder_ops.h"
@@ -79,6 +84,39 @@ __global__ void __launch_bounds__(256) unet_im2col3x3_split_kernel(const float* 
     __nv_bfloat16* o = out + m * (2 * static_cast<size_t>(Kp)) + k0;
     *reinterpret_cast<uint4*>(o) = Hh;
     *reinterpret_cast<uint4*>(o + Kp) = Lo;
+  }
+}
+
+// First convolution (one input channel): direct fp32 FMAs, one thread per (pixel, 4 output channels); wt fp32 [Cout, Kp]
+// tap-major.  The grid stride is a multiple of Cout / 4, so a thread keeps its 4 x 9 weights in registers for all its
+// pixels.  9 MACs per output: HBM-bound on the output write.
+__global__ void __launch_bounds__(256) unet_conv3x3_direct_kernel(const float* __restrict__ in, int B, int H, int W,
+                                                                  int ld_in, const float* __restrict__ wt, int Kp, int Cout,
+                                                                  float* __restrict__ out) {
+  const int q = Cout / 4;
+  const size_t total = static_cast<size_t>(B) * H * W * q;
+  const size_t first = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const int co = static_cast<int>(first % q) * 4;  // invariant: the stride below is a multiple of q
+  float wr[4][9];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[i][t] = __ldg(wt + static_cast<size_t>(co + i) * Kp + t);
+  for (size_t idx = first; idx < total; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t m = idx / q;
+    const int x = static_cast<int>(m % W);
+    const int y = static_cast<int>((m / W) % H);
+    const size_t bimg = m / (static_cast<size_t>(W) * H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const float v = ok ? __ldg(in + ((bimg * H + (ok ? yy : y)) * W + (ok ? xx : x)) * ld_in) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(v, wr[i][t], acc[i]);
+    }
+    *reinterpret_cast<float4*>(out + m * Cout + co) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
@@ -464,8 +502,8 @@ int split_gemm(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* bi
 
 // conv3x3 (no bias) + InstanceNorm + LeakyReLU: in [B,H,W,cin] (pitch ld_in) -> out [B,H,W,cout] (pitch ld_out)
 int conv_in_lrelu(const UNetCtx* u, const UWork& w, const float* in, int ld_in, int B, int H, int W, int cin, int cout,
-                  const __nv_bfloat16* ws, const float* gamma, const float* beta, float* tmp, float* out, int ld_out,
-                  cudaStream_t s) {
+                  const __nv_bfloat16* ws, const float* wf32, const float* gamma, const float* beta, float* tmp, float* out,
+                  int ld_out, cudaStream_t s) {
   (void)u;
   const size_t HW = static_cast<size_t>(H) * W, M = B * HW;
   const int Kp = unet_conv_kp(cin);
@@ -480,6 +518,8 @@ int conv_in_lrelu(const UNetCtx* u, const UWork& w, const float* in, int ld_in, 
     g.M = static_cast<int>(Mp); g.N = cout; g.K = 27 * cin; g.lda = 2 * cin; g.ldb = 27 * cin; g.ldo = cout; g.ldr = 0;
     g.res_row_mod = 0; g.gelu = 0; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 0; g.conv_cin = cin; g.conv_wp = W + 2;
     TRY(gemm_bf16_tn(g, s));
+  } else if (cin == 1 && wf32 != nullptr && 256 % (cout / 4) == 0) {
+    unet_conv3x3_direct_kernel<<<grid_for(M * (cout / 4)), 256, 0, s>>>(in, B, H, W, ld_in, wf32, Kp, cout, tmp);
   } else {
     unet_im2col3x3_split_kernel<<<grid_for(M * (Kp / 8)), 256, 0, s>>>(in, B, H, W, cin, ld_in, Kp, w.col);
     TRY(split_gemm(w.col, ws, nullptr, tmp, M, cout, Kp, s));
@@ -518,9 +558,9 @@ int unet_forward(const UNetCtx* u, const float* image, int B, int H, int W, floa
   auto dc = [&](int i, const float* in, int ld_in, int h, int wd, float* out, int ld_out) -> int {
     const float* const* P = Wt + W_DC + i * 6;
     // conv a -> t1 (pitch = mid channels), conv b -> out
-    TRY(conv_in_lrelu(u, w, in, ld_in, B, h, wd, a.dc[i][0].cin, a.dc[i][0].cout, u->ws_dc[i][0], P[1], P[2], w.t0, w.t1,
+    TRY(conv_in_lrelu(u, w, in, ld_in, B, h, wd, a.dc[i][0].cin, a.dc[i][0].cout, u->ws_dc[i][0], P[0], P[1], P[2], w.t0, w.t1,
                       a.dc[i][0].cout, s));
-    TRY(conv_in_lrelu(u, w, w.t1, a.dc[i][0].cout, B, h, wd, a.dc[i][1].cin, a.dc[i][1].cout, u->ws_dc[i][1], P[4], P[5],
+    TRY(conv_in_lrelu(u, w, w.t1, a.dc[i][0].cout, B, h, wd, a.dc[i][1].cin, a.dc[i][1].cout, u->ws_dc[i][1], P[3], P[4], P[5],
                       w.t0, out, ld_out, s));
     return 0;
   };
