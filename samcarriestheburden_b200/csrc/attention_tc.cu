@@ -76,6 +76,7 @@ B200SAM_DEVINL void add2(float& d0, float& d1, float a0, float a1, float b0, flo
 struct TcParams {
   __nv_bfloat16* out;
   int heads;
+  int reverse;  // 1: images last-to-first (the qkv GEMM that ran forward left the last images in L2)
 };
 
 template <int HD>
@@ -105,7 +106,8 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   float* th_t = reinterpret_cast<float*>(smem + L::OFF_TH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x, head = blockIdx.y;
+  const int b = prm.reverse ? static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z) : static_cast<int>(blockIdx.z);
   const int D = prm.heads * HD;
   const int q0 = qt * TQ;
   const int qh0 = q0 >> 6;
@@ -447,6 +449,7 @@ struct WinParams {
   __nv_bfloat16* out;
   const __nv_bfloat16* qkv_bias;
   int heads;
+  int reverse;  // 1: images last-to-first
 };
 
 template <int HD>
@@ -475,7 +478,8 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int win = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int win = blockIdx.x, head = blockIdx.y;
+  const int b = prm.reverse ? static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z) : static_cast<int>(blockIdx.z);
   const int wy = win / 5, wx = win % 5;
   const int D = prm.heads * HD;
   const int wrows = min(WIN, 64 - wy * WIN);
@@ -819,6 +823,7 @@ int launch_win_tc(const AttnArgs& a, cudaStream_t stream) {
   p.out = a.out;
   p.qkv_bias = a.qkv_bias;
   p.heads = a.heads;
+  p.reverse = a.reverse;
   dim3 grid(25, a.heads, a.B);
   window_attn_tc_kernel<HD><<<grid, TC_THREADS, L::BYTES, stream>>>(m1414, m0814, m1408, m0808, mrh, mrw, p);
   B200SAM_CHECK_CUDA(cudaGetLastError());
@@ -844,6 +849,7 @@ int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   TcParams p;
   p.out = a.out;
   p.heads = a.heads;
+  p.reverse = a.reverse;
   dim3 grid(4096 / TQ, a.heads, a.B);
   global_attn_tc_kernel<HD><<<grid, TC_THREADS, L::BYTES, stream>>>(mq, mkv, mrh, mrw, p);
   B200SAM_CHECK_CUDA(cudaGetLastError());

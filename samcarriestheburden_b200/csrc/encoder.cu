@@ -79,11 +79,11 @@ Workspace carve(uint8_t* base, const EncoderConfig& c, int B) {
 }
 
 int gemm(const __nv_bfloat16* A, const void* W, void* out, const float* bias, const float* res, int M, int N, int K,
-         int ldr, int res_mod, int gelu, int out_bf16, cudaStream_t s) {
+         int ldr, int res_mod, int gelu, int out_bf16, cudaStream_t s, int reverse_m = 0) {
   GemmArgs g;
   g.A = A; g.B = reinterpret_cast<const __nv_bfloat16*>(W); g.out = out; g.bias = bias; g.residual = res;
   g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldo = N; g.ldr = ldr; g.res_row_mod = res_mod;
-  g.gelu = gelu; g.out_bf16 = out_bf16; g.max_ctas = 0;
+  g.gelu = gelu; g.out_bf16 = out_bf16; g.max_ctas = 0; g.reverse_m = reverse_m;
   return gemm_bf16_tn(g, s);
 }
 
@@ -145,17 +145,29 @@ int encoder_forward(const Encoder* e, const void* img, int is_u8, int B, int h, 
 
   AttnArgs at;
   at.qkv = ws.qkv; at.out = ws.att; at.B = B; at.heads = c.num_heads; at.hd = D / c.num_heads;
+  // Traversal direction ("boustrophedon"): the residual stream (4*D bytes per token, 168 MB at batch 8) and the MLP
+  // hidden (8*D) are larger than the 126 MB L2, so a consumer that walks the rows in the SAME order as its producer finds
+  // its first rows already evicted.  Each LayerNorm / GEMM below therefore starts at the end its producer finished at
+  // (results are identical; only the order of the row blocks changes).  B200SAM_FORWARD_ONLY=1 disables it (A/B timing).
+  static const bool kBoustrophedon = std::getenv("B200SAM_FORWARD_ONLY") == nullptr;
+  int x_dir = 0;  // direction in which ws.x was last written (patch embedding: forward)
   for (int b = 0; b < c.depth; ++b) {
     const int o = G_BLOCK0 + b * B_STRIDE;
-    TRY(layernorm_rows(ws.x, F(o + B_N1W), F(o + B_N1B), 1e-6f, M, D, ws.xn, 1, s));
-    TRY(gemm(ws.xn, W[o + B_QKVW], ws.qkv, F(o + B_QKVB), nullptr, M, 3 * D, D, 0, 0, 0, 1, s));
+    const int ln1_dir = kBoustrophedon ? !x_dir : 0;
+    const int qkv_dir = kBoustrophedon ? !ln1_dir : 0;
+    TRY(layernorm_rows(ws.x, F(o + B_N1W), F(o + B_N1B), 1e-6f, M, D, ws.xn, 1, s, ln1_dir));
+    TRY(gemm(ws.xn, W[o + B_QKVW], ws.qkv, F(o + B_QKVB), nullptr, M, 3 * D, D, 0, 0, 0, 1, s, qkv_dir));
     at.qkv_bias = H(o + B_QKVB16); at.rel_h = H(o + B_RELH); at.rel_w = H(o + B_RELW);
+    at.reverse = kBoustrophedon ? !qkv_dir : 0;
     if ((c.global_mask_lo >> b) & 1) TRY(global_attention_tc(at, s));
     else TRY(window_attention_tc(at, s));
     TRY(gemm(ws.att, W[o + B_PROJW], ws.x, F(o + B_PROJB), ws.x, M, D, D, D, 0, 0, 0, s));
-    TRY(layernorm_rows(ws.x, F(o + B_N2W), F(o + B_N2B), 1e-6f, M, D, ws.xn, 1, s));
-    TRY(gemm(ws.xn, W[o + B_L1W], ws.h, F(o + B_L1B), nullptr, M, 4 * D, D, 0, 0, 1, 1, s));
-    TRY(gemm(ws.h, W[o + B_L2W], ws.x, F(o + B_L2B), ws.x, M, D, 4 * D, D, 0, 0, 0, s));
+    // proj runs forward (its A operand, the 2*D-byte attention output, fits the L2 either way)
+    const int ln2_dir = kBoustrophedon ? 1 : 0, l1_dir = kBoustrophedon ? !ln2_dir : 0, l2_dir = kBoustrophedon ? !l1_dir : 0;
+    TRY(layernorm_rows(ws.x, F(o + B_N2W), F(o + B_N2B), 1e-6f, M, D, ws.xn, 1, s, ln2_dir));
+    TRY(gemm(ws.xn, W[o + B_L1W], ws.h, F(o + B_L1B), nullptr, M, 4 * D, D, 0, 0, 1, 1, s, l1_dir));
+    TRY(gemm(ws.h, W[o + B_L2W], ws.x, F(o + B_L2B), ws.x, M, D, 4 * D, D, 0, 0, 0, s, l2_dir));
+    x_dir = l2_dir;
   }
 
   // neck: conv1x1 -> LayerNorm2d -> conv3x3(pad 1) -> LayerNorm2d (image_encoder.py:88-104), NCHW fp32 out

@@ -63,10 +63,12 @@ template <int NV, bool OUT_BF16>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int M, int D,
-                                                             void* __restrict__ y) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                             void* __restrict__ y, int reverse) {
+  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  if (w0 >= M) return;
+  // reverse: the first blocks take the LAST rows - the ones the producing GEMM wrote most recently (L2 resident)
+  const int warp = reverse ? M - 1 - w0 : w0;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * D);
   float4 v[NV];
   float s = 0.0f;
@@ -109,13 +111,13 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 
 template <int NV>
 int launch_ln(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y, int out_bf16,
-              cudaStream_t stream) {
+              cudaStream_t stream, int reverse) {
   const int warps_per_block = 8;
   const int blocks = (M + warps_per_block - 1) / warps_per_block;
   if (out_bf16)
-    layernorm_rows_kernel<NV, true><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y);
+    layernorm_rows_kernel<NV, true><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y, reverse);
   else
-    layernorm_rows_kernel<NV, false><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y);
+    layernorm_rows_kernel<NV, false><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y, reverse);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -208,15 +210,15 @@ int preprocess_patchify(const void* img, int is_u8, int B, int h, int w, const f
 }
 
 int layernorm_rows(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
-                   int out_bf16, cudaStream_t stream) {
+                   int out_bf16, cudaStream_t stream, int reverse) {
   B200SAM_REQUIRE(M > 0 && D % 128 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 128 and <= 2048", D);
   switch (D / 128) {
-    case 1: return launch_ln<1>(x, gamma, beta, eps, M, D, y, out_bf16, stream);
-    case 2: return launch_ln<2>(x, gamma, beta, eps, M, D, y, out_bf16, stream);
-    case 6: return launch_ln<6>(x, gamma, beta, eps, M, D, y, out_bf16, stream);
-    case 8: return launch_ln<8>(x, gamma, beta, eps, M, D, y, out_bf16, stream);
-    case 10: return launch_ln<10>(x, gamma, beta, eps, M, D, y, out_bf16, stream);
-    case 16: return launch_ln<16>(x, gamma, beta, eps, M, D, y, out_bf16, stream);
+    case 1: return launch_ln<1>(x, gamma, beta, eps, M, D, y, out_bf16, stream, reverse);
+    case 2: return launch_ln<2>(x, gamma, beta, eps, M, D, y, out_bf16, stream, reverse);
+    case 6: return launch_ln<6>(x, gamma, beta, eps, M, D, y, out_bf16, stream, reverse);
+    case 8: return launch_ln<8>(x, gamma, beta, eps, M, D, y, out_bf16, stream, reverse);
+    case 10: return launch_ln<10>(x, gamma, beta, eps, M, D, y, out_bf16, stream, reverse);
+    case 16: return launch_ln<16>(x, gamma, beta, eps, M, D, y, out_bf16, stream, reverse);
     default: break;
   }
   set_last_error("layernorm: unsupported D=%d (supported: 128,256,768,1024,1280,2048)", D);

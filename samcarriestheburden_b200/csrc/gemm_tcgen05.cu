@@ -44,6 +44,8 @@ constexpr uint32_t TMEM_COLS = 512;
 // same 8 epilogue warps (the `half` index selects the row block instead of the column block).
 // a_wrap > 0: the A operand is stored with only a_wrap columns and k-blocks past it wrap around to column
 // kb*BK - a_wrap (the [hi | lo | hi] split operand of the decoder is stored as [hi | lo]).
+// reverse_m: the persistent grid walks the row blocks from the LAST to the first.  A kernel that consumes a tensor larger
+// than the 126 MB L2 right after its producer starts with the rows the producer wrote last (still L2 resident).
 // conv_cin > 0: implicit 3x3 convolution (U-Net).  A is the [hi | lo] split activation on a zero-BORDERED pixel grid
 // ([B * (H+2) * (W+2), 2 * conv_cin], conv_wp = W + 2) and the GEMM runs over that padded grid too, so the A tile of tap
 // (ky, kx) is the SAME 2-D box shifted by (ky-1) * conv_wp + (kx-1) rows: no im2col matrix is ever written.  K runs over
@@ -52,7 +54,7 @@ constexpr uint32_t TMEM_COLS = 512;
 template <bool OUT_BF16, int BN_EFF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    EpiParams ep, int M, int N, int K, int a_wrap, int conv_cin, int conv_wp) {
+                    EpiParams ep, int M, int N, int K, int a_wrap, int conv_cin, int conv_wp, int reverse_m) {
   // SWIZZLE_128B tiles need 1024 B alignment.  The alignment is requested on the symbol (not by rounding the
   // pointer through an integer): pointer arithmetic through uintptr_t makes the compiler lose the shared
   // state space and emit generic LD/ST (L1TEX path, long-scoreboard latency) for every staging access.
@@ -106,7 +108,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM_T;
+        const int mb = tile / num_n;
+        const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM_T;
         const int n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -177,7 +180,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * BM_T + (TALL ? half * 128 : 0);
+      const int mb = tile / num_n;
+      const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM_T + (TALL ? half * 128 : 0);
       const int n0 = (tile % num_n) * BN + (TALL ? 0 : half * 128);
       const int row_base = m0 + quad * 32;
       epilogue_prefetch<OUT_BF16>(ep, M, N, row_base, n0, sbias, lane);
@@ -259,7 +263,7 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   }
   auto kernel = g.out_bf16 ? (narrow ? gemm_bf16_tn_kernel<true, 128> : gemm_bf16_tn_kernel<true, 256>)
                            : (narrow ? gemm_bf16_tn_kernel<false, 128> : gemm_bf16_tn_kernel<false, 256>);
-  kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K, g.a_wrap, g.conv_cin, g.conv_wp);
+  kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K, g.a_wrap, g.conv_cin, g.conv_wp, g.reverse_m);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -45,6 +45,7 @@ struct GemmArgs {
   int a_wrap = 0;   // > 0: A has only a_wrap columns; k >= a_wrap reads column k - a_wrap ([hi|lo|hi] stored as [hi|lo])
   int conv_cin = 0;  // > 0: implicit 3x3 convolution over a zero-bordered pixel grid (see gemm_tcgen05.cu); K = 27 * conv_cin
   int conv_wp = 0;   //      padded row length W + 2
+  int reverse_m = 0; // 1: walk the row blocks last-to-first (start with what the producer kernel left in L2)
   // fused mask-decoder upscaler epilogues (gemm_epilogue.cuh): 0 none, 1 LN2d(64)+GELU+split (N = 256), 2 GELU+hyper dot (N = 128)
   int epi_mode = 0;
   const float* aux0 = nullptr;  // mode 1: LN gamma [64]; mode 2: hyper [prompts, 4, 32]
@@ -59,7 +60,7 @@ int preprocess_patchify(const void* img, int is_u8, int B, int h, int w, const f
                         __nv_bfloat16* out, cudaStream_t stream);
 // y = LN(x) over the last dim (fp32 statistics, biased variance); x fp32 [M,D]; y bf16 or fp32
 int layernorm_rows(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
-                   int out_bf16, cudaStream_t stream);
+                   int out_bf16, cudaStream_t stream, int reverse = 0);
 // 3x3/pad1 im2col over a 64x64 token grid: in bf16 [B*4096, C] -> out bf16 [B*4096, 9*C] (tap-major)
 int im2col3x3_tokens(const __nv_bfloat16* in, int B, int C, __nv_bfloat16* out, cudaStream_t stream);
 // LayerNorm2d over channels + token-major -> NCHW transpose: in fp32 [B*4096, C] -> out fp32 [B,C,64,64]
@@ -75,6 +76,7 @@ struct AttnArgs {
   const __nv_bfloat16* rel_w;     // [2S-1, hd] bf16
   __nv_bfloat16* out;             // [B*4096, D] bf16
   int B, heads, hd;
+  int reverse = 0;  // tcgen05 kernels: walk the images last-to-first (start with what the qkv GEMM left in L2)
 };
 int window_attention(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows over the 64x64 grid
 int global_attention(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096, mma.sync path (A/B reference)
