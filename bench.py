@@ -67,7 +67,7 @@ class ClockSampler:
         """Number of samples taken so far (nvidia-smi is up once this is > 0)."""
         return len(self._lines())
 
-    def stop(self, since: int = 0):
+    def stop(self, since: int = 0, until: int | None = None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -81,7 +81,7 @@ class ClockSampler:
         os.unlink(self.f.name)
         if not rows:
             return out
-        rows = rows[since:] or rows  # the samples taken during the timed region
+        rows = rows[since:until] or rows[since:] or rows  # the samples taken during the timed region
         sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
         busy = [v for v in sm if v > 0.5 * max(sm)] or sm
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -306,7 +306,7 @@ def main():
             torch.cuda.synchronize()
         mark = sampler.mark()
     ms = timed(step_resident, K)
-    clocks = sampler.stop(since=mark) if sampler else {}
+    clocks = sampler.stop(since=mark, until=max(sampler.mark(), mark + 1)) if sampler else {}
     for s in range(2):
         step_e2e(s)
     ms_e2e = timed(step_e2e, K)
