@@ -49,6 +49,20 @@ def test_unet_full_size_batch_masks(unet):
     assert torch.equal(one, logits[1:2])
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 32), (1, 64, 48), (2, 96, 160), (5, 32, 272)])
+def test_unet_other_geometries(unet, shape):
+    """Sizes whose zero-bordered pixel grid (implicit convolution) does not line up with the GEMM's 128 / 256 row tiles,
+    down to a 2 x 2 bottleneck (32 x 32; the reference rejects 16 x 16: InstanceNorm over a single element)."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(100 + H + W)
+    x = torch.randn((B, 1, H, W), generator=g)
+    ref = U.unet_forward(U.random_unet_state_dict(0), x)
+    y = unet(x.to(DEV)).cpu()
+    err = float((y - ref).abs().max())
+    print(f"unet {B}x{H}x{W}: max |dlogit| {err:.2e} (max |logit| {float(ref.abs().max()):.2f})")
+    assert err < 5e-3, err
+
+
 def test_unet_feeds_the_refinement_pipeline(unet):
     """U-Net probabilities -> SegEnhance (CCL) -> SAM refinement, all on the device."""
     from samcarriestheburden_b200.segment_anything import sam_model_registry
