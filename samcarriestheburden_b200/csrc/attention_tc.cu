@@ -51,11 +51,21 @@ struct TcLayout {
   static_assert(2 * KV_TILE == NS * Q_SLAB, "each rel-pos table aliases one of the K / V rings exactly");
 };
 
+constexpr int GLOBAL_POLY_EVERY = 4;  // global attention: one pair in four takes the polynomial exp2
+
 B200SAM_DEVINL float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// exp2 of a pair on the FMA pipe (no MUFU): Cody-Waite split x = n + f with the 1.5 * 2^23 magic add, a degree-3
+// polynomial for 2^f (max relative error 8.8e-5, far below the bf16 rounding of P that follows), 2^n applied by adding
+// n << 23 to the exponent bits.  The caller passes xh = x - 0.5 (so that round-to-nearest of the magic add is
+// floor(x)); the polynomial is expressed in g = xh - n in [-0.5, 0.5].  Arguments below -126 are clamped (result ~1e-38,
+// where ex2.approx.ftz returns 0).  The global kernel's softmax is MUFU bound (64 exponentials per row and key tile
+// against 4 MUFU lanes per SM sub-partition): moving a quarter of them here balances the two pipes.
+B200SAM_DEVINL void ex2_poly2(float& y0, float& y1, float xh0, float xh1);
 
 // packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot per two elements in the softmax inner loops
 B200SAM_DEVINL void fma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
@@ -71,6 +81,20 @@ B200SAM_DEVINL void add2(float& d0, float& d1, float a0, float a1, float b0, flo
       "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+B200SAM_DEVINL void ex2_poly2(float& y0, float& y1, float xh0, float xh1) {
+  constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
+  xh0 = fmaxf(xh0, -126.0f);
+  xh1 = fmaxf(xh1, -126.0f);
+  float t0, t1, n0, n1, g0, g1, p0, p1;
+  add2(t0, t1, xh0, xh1, MAGIC, MAGIC);        // low mantissa bits of t = n = round(xh) = floor(x)
+  add2(n0, n1, t0, t1, -MAGIC, -MAGIC);
+  fma2(g0, g1, n0, n1, -1.0f, xh0, xh1);       // g = xh - n in [-0.5, 0.5]
+  fma2(p0, p1, g0, g1, 0.07711908966302872f, 0.3432430326938629f, 0.3432430326938629f);
+  fma2_v(p0, p1, p0, p1, g0, g1, 0.9805498719215393f, 0.9805498719215393f);
+  fma2_v(p0, p1, p0, p1, g0, g1, 1.4141041040420532f, 1.4141041040420532f);  // sqrt(2) * 2^g = 2^f
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 struct TcParams {
@@ -335,13 +359,18 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // lazy rescale: keep the old reference maximum unless the new one exceeds it by more than 2^8
       const float m_new = (mt > m_run + LAZY_RESCALE) ? mt : m_run;
       const float corr = ex2_approx(m_run - m_new);  // 1 when unchanged, 0 on the first tile
-      const float noff = th - m_new;
+      const float noff = th - m_new, noff_h = noff - 0.5f;
 #pragma unroll
       for (int j = 0; j < 64; j += 2) {
         float x0, x1;
-        add2(x0, x1, sv[j], sv[j + 1], noff, noff);
-        sv[j] = ex2_approx(x0);
-        sv[j + 1] = ex2_approx(x1);
+        if ((j / 2) % GLOBAL_POLY_EVERY == GLOBAL_POLY_EVERY - 1) {  // every 4th pair on the FMA pipe (see ex2_poly2)
+          add2(x0, x1, sv[j], sv[j + 1], noff_h, noff_h);
+          ex2_poly2(sv[j], sv[j + 1], x0, x1);
+        } else {
+          add2(x0, x1, sv[j], sv[j + 1], noff, noff);
+          sv[j] = ex2_approx(x0);
+          sv[j + 1] = ex2_approx(x1);
+        }
       }
       if (t > 0) {
         mbar_wait(o_ready, (t - 1) & 1);  // PV(t-1) retired: P and O are free again
