@@ -82,8 +82,18 @@ class ClockSampler:
         if not rows:
             return out
         rows = rows[since:until] or rows[since:] or rows  # the samples taken during the timed region
-        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
-        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        pairs = [(num(r[1]), num(r[3])) for r in rows]
+        pairs = [(c, w) for c, w in pairs if c is not None]
+        sm = [c for c, _ in pairs]
+        # "under load" = samples drawing at least 60 % of the highest power seen: an idle GPU (waiting in a barrier)
+        # reports its maximum clock and would otherwise hide the power-capped clock of the timed loop
+        pmax = max((w for _, w in pairs if w is not None), default=None)
+        busy = [c for c, w in pairs if pmax is not None and w is not None and w >= 0.6 * pmax] or sm
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows)]
         out.update(sm_mhz=statistics.median(busy), sm_max_mhz=float(rows[0][2]), reasons=reasons,
