@@ -117,6 +117,15 @@ B200SAM_API int b200sam_ccl_select(const float* prob, int n_planes, int H, int W
 B200SAM_API int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw,
                        int origin_y, int origin_x, int dilate, float* out, void* stream);
 
+/* ---------------------------------------------------------------- mask statistics
+ * Replace calculate_stability_score (segment_anything/utils/amg.py:154-176; logits [n,H,W] float32 -> score [n] =
+ * count(x > threshold_hi) / count(x > threshold_lo) with threshold_hi/lo = mask_threshold +/- threshold_offset formed
+ * by the caller, int32 counts divided in fp32) and batched_mask_to_box (amg.py:303-346;
+ * masks [n,H,W] 0/1 bytes -> int64 XYXY boxes [n,4], zeros for an empty mask).  scratch: int32 [n,2] / [n,4]. */
+B200SAM_API int b200sam_stability_score(const float* logits, int n, int H, int W, float threshold_hi, float threshold_lo,
+                            float* score_out, int32_t* scratch, void* stream);
+B200SAM_API int b200sam_mask_to_box(const uint8_t* masks, int n, int H, int W, int64_t* boxes_out, int32_t* scratch, void* stream);
+
 /* ---------------------------------------------------------------- image ingest
  * Replaces ResizeLongestSide.apply_image (segment_anything/utils/transforms.py:26-31: torchvision `resize` of a PIL
  * image = Pillow's antialiased bilinear ImagingResample in 22-bit fixed point) as called from SamPredictor.set_image

@@ -284,6 +284,31 @@ def get_preprocess_shape(oldh: int, oldw: int, long_side: int = 1024) -> Tuple[i
     return int(oldh * scale + 0.5), int(oldw * scale + 0.5)
 
 
+# ----------------------------------------------------------------------------------------------- mask statistics
+def stability_score(masks: np.ndarray, mask_threshold: float, threshold_offset: float) -> np.ndarray:
+    """utils/amg.py:154-176: count(x > thr + off) / count(x > thr - off) over the last two axes.  torch compares the fp32
+    tensor with the Python scalar rounded to fp32 and divides the two int32 counts as fp32 (0 / 0 -> NaN)."""
+    x = np.asarray(masks, np.float32)
+    hi, lo = np.float32(mask_threshold + threshold_offset), np.float32(mask_threshold - threshold_offset)
+    inter = (x > hi).sum(axis=(-2, -1)).astype(np.int32)
+    union = (x > lo).sum(axis=(-2, -1)).astype(np.int32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return inter.astype(np.float32) / union.astype(np.float32)
+
+
+def mask_to_box(masks: np.ndarray) -> np.ndarray:
+    """utils/amg.py:303-346: XYXY box of the set pixels of every [..., H, W] mask (int64), zeros for an empty mask."""
+    m = np.asarray(masks).astype(bool)
+    lead = m.shape[:-2]
+    flat = m.reshape((-1,) + m.shape[-2:])
+    out = np.zeros((flat.shape[0], 4), np.int64)
+    for i, one in enumerate(flat):
+        ys, xs = np.nonzero(one)
+        if ys.size:
+            out[i] = (xs.min(), ys.min(), xs.max(), ys.max())
+    return out.reshape(lead + (4,))
+
+
 # ----------------------------------------------------------------------------------------------- image ingest
 _PIL_PRECISION_BITS = 32 - 8 - 2
 

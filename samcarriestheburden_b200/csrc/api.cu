@@ -176,6 +176,15 @@ int b200sam_resize_u8(const uint8_t* image, int H, int W, int C, const int32_t* 
                    static_cast<cudaStream_t>(stream));
 }
 
+int b200sam_stability_score(const float* logits, int n, int H, int W, float threshold_hi, float threshold_lo,
+                            float* score_out, int32_t* scratch, void* stream) {
+  return stability_score(logits, n, H, W, threshold_hi, threshold_lo, score_out, scratch,
+                         static_cast<cudaStream_t>(stream));
+}
+int b200sam_mask_to_box(const uint8_t* masks, int n, int H, int W, int64_t* boxes_out, int32_t* scratch, void* stream) {
+  return mask_to_box(masks, n, H, W, reinterpret_cast<long long*>(boxes_out), scratch, static_cast<cudaStream_t>(stream));
+}
+
 size_t b200sam_ccl_scratch_bytes(int n_planes, int H, int W) {
   if (n_planes < 0 || H <= 0 || W <= 0) return 0;
   return ccl_scratch_bytes(n_planes, H, W);

@@ -114,6 +114,12 @@ int resize_u8(const uint8_t* in, int H, int W, int C, const int32_t* xbounds, co
               const int32_t* ybounds, const int32_t* ykk, int yksize, int out_h, int out_w, uint8_t* tmp, uint8_t* out,
               int out_chw, cudaStream_t stream);
 
+// ---- amg.cu ----------------------------------------------------------------------------------
+// stability score (count(x > thr + off) / count(x > thr - off) per mask) and XYXY boxes of bool masks (amg.py)
+int stability_score(const float* logits, int n, int H, int W, float threshold_hi, float threshold_lo,
+                    float* score_out, int32_t* scratch, cudaStream_t stream);
+int mask_to_box(const uint8_t* masks, int n, int H, int W, long long* boxes_out, int32_t* scratch, cudaStream_t stream);
+
 // ---- unet.cu -----------------------------------------------------------------------------------
 struct UNetCtx;
 int unet_weight_count();
