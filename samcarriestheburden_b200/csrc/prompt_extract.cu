@@ -16,6 +16,8 @@ namespace {
 constexpr int SLOT = 12;  // int32 words per (image, class) accumulator, 48 B (keeps the u64 sums aligned)
 // [0,1] sum_r (u64)  [2,3] sum_c (u64)  [4] n_seed  [5] n_all  [6] min_r  [7] max_r  [8] min_c  [9] max_c
 constexpr int MAX_C = 64;
+constexpr int PE_LOADS = 18;        // class planes fetched per round trip (independent 16-byte loads in flight per thread)
+constexpr int PE_CTAS_PER_SM = 2;   // 256-thread CTAs resident per SM (register budget of the load batch)
 
 __global__ void prompt_init_kernel(int32_t* scratch, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,7 +148,7 @@ B200SAM_DEVINL int bitpos_sum16(uint32_t m) {
 // iteration; the contributions of its 32 lanes are combined with warp reductions (redux.sync / ballot) first, so one
 // lane issues the shared-memory atomics: neighbouring lanes almost always hit the SAME class, and per-lane atomics
 // on one address serialise 32-fold.
-__global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* __restrict__ masks, int C, int H, int W,
+__global__ void __launch_bounds__(256, PE_CTAS_PER_SM) prompt_accum16_kernel(const uint8_t* __restrict__ masks, int C, int H, int W,
                                                              int32_t* __restrict__ scratch, long long total_groups,
                                                              int groups_per_cta) {
   __shared__ unsigned long long s_sum[MAX_C][2];
@@ -175,18 +177,19 @@ __global__ void __launch_bounds__(256, 4) prompt_accum16_kernel(const uint8_t* _
       const int p0 = (valid ? g : gb) * 16;
       const int r = p0 / W, c0 = p0 - r * W;
       const uint8_t* base = ibytes + p0;
-      // pass 1: 8 independent 16-byte loads in flight per thread; bool bytes are 0/1, so the per-pixel cover count is
+      // pass 1: up to PE_LOADS (all 17 classes of the pipeline) independent 16-byte loads in flight per thread, one HBM
+      // round trip per iteration; bool bytes are 0/1, so the per-pixel cover count is
       // a plain packed byte add (anything else is detected through `odd` and recounted below)
       uint4 cov = make_uint4(0, 0, 0, 0), odd = make_uint4(0, 0, 0, 0);
       unsigned long long any = 0ull;
-      for (int cb = 0; cb < C; cb += 8) {
-        uint4 v[8];
+      for (int cb = 0; cb < C; cb += PE_LOADS) {
+        uint4 v[PE_LOADS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < PE_LOADS; ++j)
           v[j] = (cb + j < C && valid) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(cb + j) * HW))
                                        : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < PE_LOADS; ++j) {
           cov.x += v[j].x; cov.y += v[j].y; cov.z += v[j].z; cov.w += v[j].w;
           odd.x |= v[j].x; odd.y |= v[j].y; odd.z |= v[j].z; odd.w |= v[j].w;
           if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) any |= 1ull << (cb + j);
@@ -315,11 +318,13 @@ int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t
     const bool fast = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && (HW % 16 == 0);
     if (fast) {
       const long long total = static_cast<long long>(n_img) * (HW / 16);
-      const int max_ctas = 148 * 4;  // all CTAs resident (4 x 256 threads per SM): a persistent, balanced grid
+      const int max_ctas = 148 * PE_CTAS_PER_SM;  // all CTAs resident: a persistent, balanced grid
       long long gpc = (total + max_ctas - 1) / max_ctas;
       gpc = (gpc + 31) / 32 * 32;  // whole warps
       B200SAM_REQUIRE(gpc < (1ll << 30), "prompt_extract: batch too large");
       const int ctas = static_cast<int>((total + gpc - 1) / gpc);
+      // (finalising inside this kernel by the last CTA to finish was measured: its serial tail over the n entries costs
+      //  more than the separate finalize launch below: 0.122 vs 0.098 ms per 256 images)
       prompt_accum16_kernel<<<ctas, 256, 0, stream>>>(masks, C, H, W, scratch, total, static_cast<int>(gpc));
     } else {
       dim3 grid((HW + 1023) / 1024, n_img);
