@@ -30,7 +30,11 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 ENC_GFLOP = {"vit_h": 5641.8, "vit_l": 2837.0, "vit_b": 937.6}  # algorithmic, per image
-METRIC = "ViT-H embeds/sec @1024^2"
+METRIC = "ViT-H embeds/sec @1024^2"  # BASELINE.json's metric (the default model)
+
+
+def metric_name(model: str) -> str:
+    return METRIC if model == "vit_h" else METRIC.replace("ViT-H", {"vit_l": "ViT-L", "vit_b": "ViT-B"}[model])
 
 
 def _peaks():
@@ -212,7 +216,7 @@ def run_reference(args, out=sys.stdout):
     cores = torch.get_num_threads()
     sample = f"1 image per step through the full {args.model} encoder (fp32, {cores} threads); {k} timed steps"
     print(file=out, flush=True, *[json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": k,
+        "impl": "reference", "metric": metric_name(args.model), "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": k,
         "warmup": 1 + warm_left, "ms_per_step": 1e3 * T / k, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"SAM {args.model} image-embedding generation, synthetic 1024x1024 radiographs "
@@ -325,7 +329,7 @@ def main():
     e2e = world * B * K / (ms_e2e / 1e3)
     peaks = _peaks()
     out = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": metric_name(args.model), "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": f"SAM {args.model} image-embedding generation (generate_img_embeddings), synthetic "
