@@ -487,12 +487,13 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
         upscale_mask_fast_kernel<false, true, false>,  upscale_mask_fast_kernel<false, true, true>,
         upscale_mask_fast_kernel<true, false, false>,  upscale_mask_fast_kernel<true, false, true>,
         upscale_mask_fast_kernel<true, true, false>,   upscale_mask_fast_kernel<true, true, true>};
-    static bool attr_set = false;
-    if (!attr_set) {
+    // once per process (thread-safe magic static; one process drives one device)
+    static const cudaError_t attr_rc = [] {
       for (KernelFn k : kernels)
-        B200SAM_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+        if (cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) return e;
+      return cudaSuccess;
+    }();
+    B200SAM_CHECK_CUDA(attr_rc);
     const KernelFn kernel = kernels[(aligned ? 4 : 0) | (thresh == 0.0f ? 2 : 0) | (in_h != out_h ? 1 : 0)];
     kernel<<<grid, bt, smem, stream>>>(p, mask_out, rpb, col_groups, so);
     if (small_out != nullptr && !fuse_small) {
