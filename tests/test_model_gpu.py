@@ -214,6 +214,33 @@ def test_vit_l_encoder_batch16_matches_oracle():
     torch.cuda.empty_cache()
 
 
+def test_vit_h_encoder_batch8_matches_oracle():
+    """BASELINE.json configs[1], the headline configuration: ViT-H (D 1280, hd 80, depth 32, global blocks 7/15/23/31) at
+    the bench's batch of 8 (so the boustrophedon traversal and the multi-image attention grids are exercised), one image
+    of the batch against the fp32 CPU oracle (a few seconds on the box's host cores).  Tolerance as stated in
+    north_star / SURVEY 8d: rel-L2 <= 2e-2, cosine >= 0.9995 (bf16 operands, fp32 accumulate, 32 blocks)."""
+    from samcarriestheburden_b200.segment_anything import sam_model_registry
+    sd = O.random_state_dict("vit_h", seed=2)
+    sam = sam_model_registry["vit_h"]()
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.to(DEV)
+    imgs = torch.stack([torch.from_numpy(O.synthetic_radiograph(60 + i)).permute(2, 0, 1) for i in range(8)]).to(DEV)
+    emb = sam.encode_image(imgs)
+    torch.cuda.synchronize()
+    assert emb.shape == (8, 256, 64, 64) and bool(torch.isfinite(emb).all())
+    ref = O.image_encoder(sd, O.preprocess(imgs[6].cpu().float())[None], **O.VIT_CONFIGS["vit_h"])
+    got = emb[6:7].float().cpu()
+    rel = float((got - ref).norm() / ref.norm())
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+    print(f"encoder vit_h rel_l2={rel:.3e} cos={cos:.6f}")
+    assert rel <= 2e-2 and cos >= 0.9995, (rel, cos)
+    # the same image alone gives the same embedding (batch / traversal order independence)
+    one = sam.encode_image(imgs[6:7])
+    assert torch.equal(one, emb[6:7])
+    del sam
+    torch.cuda.empty_cache()
+
+
 def test_sam_forward_and_return_logits(vit_b, embedding):
     """Upstream batched API `Sam.forward` (sam.py:53-131) and `predict(return_logits=True)`."""
     sam, sd = vit_b
