@@ -137,10 +137,10 @@ int lin(const float* A, const float* A2, int a2mod, const float* W, const float*
 // out[M,N] fp32 = [hi|lo|hi][M,3K] . W'[N,3K]^T + bias (+GELU) (+residual): tcgen05 GEMM on the split operands
 // (A is stored as [hi|lo] with pitch 2K; the kernel's A loader wraps the third K segment back to hi)
 int tc_lin(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* b, const float* res, float* out, int M, int N,
-           int K, int gelu, cudaStream_t s) {
+           int K, int gelu, cudaStream_t s, int res_row_mod = 0) {
   GemmArgs g;
   g.A = As; g.B = Ws; g.out = out; g.bias = b; g.residual = res;
-  g.M = M; g.N = N; g.K = 3 * K; g.lda = 2 * K; g.ldb = 3 * K; g.ldo = N; g.ldr = N; g.res_row_mod = 0;
+  g.M = M; g.N = N; g.K = 3 * K; g.lda = 2 * K; g.ldb = 3 * K; g.ldo = N; g.ldr = N; g.res_row_mod = res_row_mod;
   g.gelu = gelu; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * K;
   return gemm_bf16_tn(g, s);
 }
@@ -205,12 +205,39 @@ int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_
     }
     off += static_cast<size_t>(it.N) * 3 * it.K;
   }
+  // pe W^T + b tables of the five projections that take keys + pe (fp32 linear, once)
+  d->pek = nullptr;
+  if (cudaMalloc(&d->pek, 5 * 4096 * 128 * sizeof(float)) != cudaSuccess) {
+    set_last_error("decoder_create: cudaMalloc of the positional-encoding tables failed");
+    cudaFree(d->wsplit); cudaFree(d->pe_tok); delete d;
+    return 1;
+  }
+  {
+    const float* const* Wt = d->w.data();
+    struct PeItem { int w_idx, b_idx; const float** dst; };
+    std::vector<PeItem> pis;
+    for (int l = 0; l < 2; ++l) {
+      const int L = W_LAYER0 + l * LAYER_STRIDE;
+      pis.push_back({L + L_T2I + 2, L + L_T2I + 3, &d->pek_t2i_k[l]});
+      pis.push_back({L + L_I2T + 0, L + L_I2T + 1, &d->pek_i2t_q[l]});
+    }
+    pis.push_back({W_FINAL + 2, W_FINAL + 3, &d->pek_fin_k});
+    float* dstp = d->pek;
+    for (const PeItem& it : pis) {
+      *it.dst = dstp;
+      if (int rc = lin(d->pe_tok, nullptr, 0, Wt[it.w_idx], Wt[it.b_idx], nullptr, dstp, 4096, 128, 256, 0, stream)) {
+        cudaFree(d->pek); cudaFree(d->wsplit); cudaFree(d->pe_tok); delete d; return rc;
+      }
+      dstp += 4096 * 128;
+    }
+  }
   *out = d;
   return 0;
 }
 
 void decoder_destroy(Decoder* d) {
   if (d == nullptr) return;
+  if (d->pek) cudaFree(d->pek);
   if (d->pe_tok) cudaFree(d->pe_tok);
   if (d->wsplit) cudaFree(d->wsplit);
   delete d;
@@ -239,14 +266,14 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   TRY(prompt_tokens(a.coords, a.labels, NB, a.Np, W[W_GAUSS], W[W_POINT4], W[W_NOT_A_POINT], W[W_IOU_TOKEN],
                     W[W_MASK_TOKENS], a.img_w, a.img_h, w.tokens, w.ntok, s));
   TRY(nchw_to_tokens(a.emb, w.emb_tok, a.n_images, s));
-  // the producers of the image-side keys also emit the bf16 split operands of the projections that consume them:
-  // sa = split(keys + pe) feeds the k / image-query projections, sb = split(keys) the v projection and the upscaler
+  // the producers of the image-side keys also emit sb = split(keys), the bf16 [hi | lo] operand of EVERY image-side
+  // projection: the ones that take keys + pe (k of the token->image attentions, q of the image->token attention) add
+  // their positional term as the per-token table pek_* = pe W^T + b in the GEMM epilogue (residual row = row % 4096)
   if (a.mask_prev != nullptr) {
     TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, a.image_of, s));
-    TRY(split3_bf16(w.keys, pe, 4096, w.sa, Mi, 256, 0, s));
     TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
   } else {
-    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, pe, w.sa, w.sb, s));
+    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, pe, nullptr, w.sb, s));
   }
   B200SAM_CHECK_CUDA(cudaMemcpyAsync(w.queries, w.tokens, static_cast<size_t>(Mt) * 256 * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
@@ -267,9 +294,9 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(lin(w.queries, w.tokens, 0, TI[0], TI[1], nullptr, w.tq, Mt, 128, 256, 0, s));
     // image-side projections on the tensor cores (3-way bf16 split operands, fp32 accumulate); keys are constant
     // until the end of the layer, so the two split operands also serve the image->token query projection
-    TRY(tc_lin(w.sa, d->ws_t2i_k[l], TI[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
+    TRY(tc_lin(w.sb, d->ws_t2i_k[l], nullptr, d->pek_t2i_k[l], w.kbuf, Mi, 128, 256, 0, s, 4096));
     TRY(tc_lin(w.sb, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
-    TRY(tc_lin(w.sa, d->ws_i2t_q[l], L[L_I2T + 1], nullptr, w.qibuf, Mi, 128, 256, 0, s));
+    TRY(tc_lin(w.sb, d->ws_i2t_q[l], nullptr, d->pek_i2t_q[l], w.qibuf, Mi, 128, 256, 0, s, 4096));
     TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s));
     TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
@@ -283,12 +310,12 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(lin(w.queries, nullptr, 0, IT[4], IT[5], nullptr, w.tv, Mt, 128, 256, 0, s));
     TRY(attn_few_keys(w.qibuf, w.tk, w.tv, nullptr, NB, 4096, T, w.ntok, w.sa, s));  // -> split(attention out)
     TRY(tc_lin(w.sa, d->ws_i2t_o[l], IT[7], w.keys, w.keys, Mi, 256, 128, 0, s));
-    TRY(ln256_keys_split(w.keys, L[L_N4], L[L_N4 + 1], pe, Mi, w.sa, w.sb, s));  // norm4 + next splits
+    TRY(ln256_keys_split(w.keys, L[L_N4], L[L_N4 + 1], pe, Mi, nullptr, w.sb, s));  // norm4 + split(keys)
   }
   {
     const float* const* F = W + W_FINAL;
     TRY(lin(w.queries, w.tokens, 0, F[0], F[1], nullptr, w.tq, Mt, 128, 256, 0, s));
-    TRY(tc_lin(w.sa, d->ws_fin_k, F[3], nullptr, w.kbuf, Mi, 128, 256, 0, s));
+    TRY(tc_lin(w.sb, d->ws_fin_k, nullptr, d->pek_fin_k, w.kbuf, Mi, 128, 256, 0, s, 4096));
     TRY(tc_lin(w.sb, d->ws_fin_v, F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
     TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s));
     TRY(lin(w.ta, nullptr, 0, F[6], F[7], w.queries, w.queries, Mt, 256, 128, 0, s));

@@ -19,6 +19,13 @@ struct Decoder {
   const __nv_bfloat16* ws_fin_v;
   const __nv_bfloat16* ws_up1;
   const __nv_bfloat16* ws_up2;
+  // positional-encoding terms of the projections that consume keys + pe, folded into per-token tables (owned):
+  // (keys + pe) W^T + b = keys W^T + (pe W^T + b); pek_* = pe W^T + b, fp32 [4096, 128], added by the GEMM epilogue as a
+  // residual indexed by row % 4096, so only split(keys) is ever materialised (not split(keys + pe) as well)
+  float* pek;  // 5 tables: t2i k (layer 0, 1), i2t q (layer 0, 1), final k
+  const float* pek_t2i_k[2];
+  const float* pek_i2t_q[2];
+  const float* pek_fin_k;
 };
 
 struct DecodeArgs {

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) ln256_keys_split_kernel(float* __restrict
   xr[0] = make_float4(f[0], f[1], f[2], f[3]);
   xr[1] = make_float4(f[4], f[5], f[6], f[7]);
   store_split8(sb, row, 256, lane * 8, f);
+  if (sa == nullptr) return;  // the positional term is added by the consumers' GEMM epilogues (decoder.h, pek_*)
   const float4* pr = reinterpret_cast<const float4*>(pe + (row & 4095) * 256) + lane * 2;
   const float4 p0 = pr[0], p1 = pr[1];
   f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
@@ -631,6 +632,7 @@ __global__ void keys_init_kernel(const float4* __restrict__ emb_tok, const float
     const size_t row = static_cast<size_t>(b) * 4096 + (i >> 5);
     const int c = static_cast<int>(i & 31) * 8;
     store_split8(sb, row, 256, c, f);
+    if (sa == nullptr) continue;
     const float4 p0 = pe[2 * i], p1 = pe[2 * i + 1];
     f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
     store_split8(sa, row, 256, c, f);
