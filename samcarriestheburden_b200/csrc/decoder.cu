@@ -103,7 +103,8 @@ Workspace carve(uint8_t* base, int n_images, int NB, int T) {
     off += align_up(nfloat * sizeof(float));
     return p;
   };
-  const size_t Mi = static_cast<size_t>(NB) * 4096, Mt = static_cast<size_t>(NB) * T;
+  // (image-side buffers also hold one block per IMAGE in the shared first layer: size them for max(prompts, images))
+  const size_t Mi = static_cast<size_t>(NB > n_images ? NB : n_images) * 4096, Mt = static_cast<size_t>(NB) * T;
   w.emb_tok = take(static_cast<size_t>(n_images) * 4096 * 256);
   w.ntok = reinterpret_cast<int*>(take(static_cast<size_t>(NB)));
   w.keys = take(Mi * 256);
@@ -260,6 +261,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   B200SAM_REQUIRE(w.total <= a.workspace_bytes, "decode: workspace too small (%zu < %zu)", a.workspace_bytes, w.total);
   const float* const* W = d->w.data();
   const int Mi = NB * 4096, Mt = NB * T;
+  const bool share0 = a.mask_prev == nullptr && a.image_of != nullptr && a.n_images < NB;
   const float* pe = d->pe_tok;
 
   // ---- prompt encoder (prompt_encoder.py:128-168) + output tokens (mask_decoder.py:120-122)
@@ -273,7 +275,10 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, a.image_of, s));
     TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
   } else {
-    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, pe, nullptr, w.sb, s));
+    // Without mask prompts the image-side keys emb + no_mask are the same for all prompts of an image until the first
+    // image->token block updates them: the three image-side projections of layer 0 then run once per IMAGE (shared)
+    // and the attention kernels pick the image's block through image_of.
+    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, pe, nullptr, share0 ? nullptr : w.sb, s));
   }
   B200SAM_CHECK_CUDA(cudaMemcpyAsync(w.queries, w.tokens, static_cast<size_t>(Mt) * 256 * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
@@ -294,10 +299,18 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(lin(w.queries, w.tokens, 0, TI[0], TI[1], nullptr, w.tq, Mt, 128, 256, 0, s));
     // image-side projections on the tensor cores (3-way bf16 split operands, fp32 accumulate); keys are constant
     // until the end of the layer, so the two split operands also serve the image->token query projection
-    TRY(tc_lin(w.sb, d->ws_t2i_k[l], nullptr, d->pek_t2i_k[l], w.kbuf, Mi, 128, 256, 0, s, 4096));
-    TRY(tc_lin(w.sb, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
-    TRY(tc_lin(w.sb, d->ws_i2t_q[l], nullptr, d->pek_i2t_q[l], w.qibuf, Mi, 128, 256, 0, s, 4096));
-    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s));
+    const bool shared = share0 && l == 0;
+    const int Mp = shared ? a.n_images * 4096 : Mi;            // rows of the image-side projections
+    const __nv_bfloat16* sbp = w.sb;
+    if (shared) {  // split(emb + no_mask) per image, in the (still unused) sa buffer
+      TRY(split3_bf16(w.emb_tok, W[W_NO_MASK], 1, w.sa, static_cast<size_t>(Mp), 256, 0, s));
+      sbp = w.sa;
+    }
+    const int* blk_of = shared ? a.image_of : nullptr;
+    TRY(tc_lin(sbp, d->ws_t2i_k[l], nullptr, d->pek_t2i_k[l], w.kbuf, Mp, 128, 256, 0, s, 4096));
+    TRY(tc_lin(sbp, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mp, 128, 256, 0, s));
+    TRY(tc_lin(sbp, d->ws_i2t_q[l], nullptr, d->pek_i2t_q[l], w.qibuf, Mp, 128, 256, 0, s, 4096));
+    TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s, blk_of));
     TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
@@ -308,7 +321,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     const float* const* IT = L + L_I2T;  // image tokens are the queries here
     TRY(lin(w.queries, w.tokens, 0, IT[2], IT[3], nullptr, w.tk, Mt, 128, 256, 0, s));
     TRY(lin(w.queries, nullptr, 0, IT[4], IT[5], nullptr, w.tv, Mt, 128, 256, 0, s));
-    TRY(attn_few_keys(w.qibuf, w.tk, w.tv, nullptr, NB, 4096, T, w.ntok, w.sa, s));  // -> split(attention out)
+    TRY(attn_few_keys(w.qibuf, w.tk, w.tv, nullptr, NB, 4096, T, w.ntok, w.sa, s, blk_of));  // -> split(attention out)
     TRY(tc_lin(w.sa, d->ws_i2t_o[l], IT[7], w.keys, w.keys, Mi, 256, 128, 0, s));
     TRY(ln256_keys_split(w.keys, L[L_N4], L[L_N4 + 1], pe, Mi, nullptr, w.sb, s));  // norm4 + split(keys)
   }

@@ -326,7 +326,8 @@ B200SAM_DEVINL float ex2f_approx(float x) {
 template <int QL>
 __global__ void __launch_bounds__(256) attn_fewq_long_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                              const float* __restrict__ v, int Tq, int Tk, int heads,
-                                                             int nsplit, float* __restrict__ part) {
+                                                             int nsplit, float* __restrict__ part,
+                                                             const int* __restrict__ kv_of) {
   constexpr int DH = 16, KS = 32 / QL, NSUB = 8 * KS;  // key subsets per warp / per CTA
   __shared__ __align__(16) float ks[FQL_KEYS][FQL_PAD];
   __shared__ __align__(16) float vs[FQL_KEYS][FQL_PAD];
@@ -336,8 +337,11 @@ __global__ void __launch_bounds__(256) attn_fewq_long_kernel(const float* __rest
   const int C = heads * DH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kbeg = z * FQL_KEYS, nk = min(FQL_KEYS, Tk - kbeg);
-  const float* kb = k + (static_cast<size_t>(b) * Tk + kbeg) * C + h * DH;
-  const float* vb = v + (static_cast<size_t>(b) * Tk + kbeg) * C + h * DH;
+  // kv_of != null: k / v hold one block per IMAGE (prompts of an image share them while the image-side keys are still
+  // the same for all of them: first layer of a pass without mask prompts) and prompt b reads block kv_of[b]
+  const size_t kvb = kv_of != nullptr ? static_cast<size_t>(kv_of[b]) : static_cast<size_t>(b);
+  const float* kb = k + (kvb * Tk + kbeg) * C + h * DH;
+  const float* vb = v + (kvb * Tk + kbeg) * C + h * DH;
   for (int i = tid; i < FQL_KEYS * 4; i += 256) {
     const int r = i >> 2, c4 = i & 3;
     float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
@@ -471,7 +475,8 @@ __global__ void attn_fewq_combine_kernel(const float* __restrict__ part, float* 
 __global__ void __launch_bounds__(256) attn_fewk_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                         const float* __restrict__ v, float* __restrict__ out, int Nq,
                                                         int Tk_pitch, const int* __restrict__ tk_valid,
-                                                        __nv_bfloat16* __restrict__ split_out) {
+                                                        __nv_bfloat16* __restrict__ split_out,
+                                                        const int* __restrict__ q_of) {
   constexpr int DH = 16, HEADS = 8, C = 128, PAD = 20, MAXK = 32;
   __shared__ __align__(16) float ks[MAXK][HEADS][PAD];
   __shared__ __align__(16) float vs[MAXK][HEADS][PAD];
@@ -486,7 +491,9 @@ __global__ void __launch_bounds__(256) attn_fewk_kernel(const float* __restrict_
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const int row = idx >> 3, h = idx & 7;
   if (row >= Nq) return;
-  const float* qp = q + (static_cast<size_t>(b) * Nq + row) * C + h * DH;
+  // q_of != null: the image-side queries are shared by the prompts of an image (see kv_of above)
+  const size_t qb = q_of != nullptr ? static_cast<size_t>(q_of[b]) : static_cast<size_t>(b);
+  const float* qp = q + (qb * Nq + row) * C + h * DH;
   float qr[DH];
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
@@ -631,7 +638,7 @@ __global__ void keys_init_kernel(const float4* __restrict__ emb_tok, const float
     k4[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
     const size_t row = static_cast<size_t>(b) * 4096 + (i >> 5);
     const int c = static_cast<int>(i & 31) * 8;
-    store_split8(sb, row, 256, c, f);
+    if (sb != nullptr) store_split8(sb, row, 256, c, f);
     if (sa == nullptr) continue;
     const float4 p0 = pe[2 * i], p1 = pe[2 * i + 1];
     f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
@@ -909,7 +916,7 @@ int linear_f32(const LinearArgs& p, cudaStream_t stream) {
 }
 
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
-                     int dh, float* part, const int* tk_valid, cudaStream_t stream) {
+                     int dh, float* part, const int* tk_valid, cudaStream_t stream, const int* kv_of) {
   B200SAM_REQUIRE(NB > 0 && Tq > 0 && Tk > 0, "attn_few_queries: empty problem");
   if (part != nullptr && Tk >= 1024 && dh == 16 && Tq <= 32 && tk_valid == nullptr) {
     // token -> image attention: keys split over ceil(Tk / 256) CTAs per (prompt, head)
@@ -917,13 +924,14 @@ int attn_few_queries(const float* q, const float* k, const float* v, float* out,
     B200SAM_REQUIRE(nsplit <= ATTN_FEWQ_SPLITS, "attn_few_queries: at most %d keys supported, got %d",
                     ATTN_FEWQ_SPLITS * FQL_KEYS, Tk);
     dim3 grid(heads, NB, nsplit);
-    if (Tq <= 8) attn_fewq_long_kernel<8><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part);
-    else if (Tq <= 16) attn_fewq_long_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part);
-    else attn_fewq_long_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part);
+    if (Tq <= 8) attn_fewq_long_kernel<8><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part, kv_of);
+    else if (Tq <= 16) attn_fewq_long_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part, kv_of);
+    else attn_fewq_long_kernel<32><<<grid, 256, 0, stream>>>(q, k, v, Tq, Tk, heads, nsplit, part, kv_of);
     attn_fewq_combine_kernel<16><<<dim3(heads, NB), 128, 0, stream>>>(part, out, Tq, heads, nsplit);
     B200SAM_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
+  B200SAM_REQUIRE(kv_of == nullptr, "attn_few_queries: shared k / v blocks are only supported by the token->image kernel");
   const int nsplit = (part != nullptr && Tk >= 1024) ? 8 : 1;
   dim3 grid(heads, NB, nsplit);
   if (dh == 16) attn_fewq_kernel<16><<<grid, 256, 0, stream>>>(q, k, v, out, Tq, Tk, heads, nsplit, part, tk_valid);
@@ -939,10 +947,10 @@ int attn_few_queries(const float* q, const float* k, const float* v, float* out,
 }
 
 int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
-                  const int* tk_valid, __nv_bfloat16* split_out, cudaStream_t stream) {
+                  const int* tk_valid, __nv_bfloat16* split_out, cudaStream_t stream, const int* q_of) {
   B200SAM_REQUIRE(Tk > 0 && Tk <= 32, "attn_few_keys: at most 32 prompt tokens supported, got %d", Tk);
   dim3 grid((Nq * 8 + 255) / 256, NB);
-  attn_fewk_kernel<<<grid, 256, 0, stream>>>(q, k, v, out, Nq, Tk, tk_valid, split_out);
+  attn_fewk_kernel<<<grid, 256, 0, stream>>>(q, k, v, out, Nq, Tk, tk_valid, split_out, q_of);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

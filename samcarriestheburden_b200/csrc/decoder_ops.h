@@ -26,11 +26,11 @@ int linear_f32(const LinearArgs& p, cudaStream_t stream);
 constexpr int ATTN_FEWQ_SPLITS = 16;
 // tk_valid: optional per-batch count of valid keys (<= Tk; Tk stays the row pitch) for ragged prompt batches
 int attn_few_queries(const float* q, const float* k, const float* v, float* out, int NB, int Tq, int Tk, int heads,
-                     int dh, float* part, const int* tk_valid, cudaStream_t stream);
+                     int dh, float* part, const int* tk_valid, cudaStream_t stream, const int* kv_of = nullptr);
 // q [NB,Nq,128], k/v [NB,Tk<=32,128] (8 heads x 16) -> out [NB,Nq,128]
 // split_out != null: write the bf16 [hi | lo] split operand [NB*Nq, 256] instead of the fp32 `out`
 int attn_few_keys(const float* q, const float* k, const float* v, float* out, int NB, int Nq, int Tk,
-                  const int* tk_valid, __nv_bfloat16* split_out, cudaStream_t stream);
+                  const int* tk_valid, __nv_bfloat16* split_out, cudaStream_t stream, const int* q_of = nullptr);
 int dense_pe_tokens(const float* G, float* pe, cudaStream_t stream);
 int prompt_tokens(const float* coords, const int* labels, int NB, int Np, const float* G, const float* point_emb,
                   const float* not_a_point, const float* iou_token, const float* mask_tokens, float img_w, float img_h,
