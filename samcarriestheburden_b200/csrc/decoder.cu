@@ -272,8 +272,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   // projection: the ones that take keys + pe (k of the token->image attentions, q of the image->token attention) add
   // their positional term as the per-token table pek_* = pe W^T + b in the GEMM epilogue (residual row = row % 4096)
   if (a.mask_prev != nullptr) {
-    TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, a.image_of, s));
-    TRY(split3_bf16(w.keys, nullptr, 0, w.sb, Mi, 256, 0, s));
+    TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, a.image_of, w.sb, s));
   } else {
     // Without mask prompts the image-side keys emb + no_mask are the same for all prompts of an image until the first
     // image->token block updates them: the three image-side projections of layer 0 then run once per IMAGE (shared)

@@ -654,7 +654,8 @@ struct MaskDownW {
 __global__ void __launch_bounds__(256) mask_downscale_keys_kernel(const float* __restrict__ mask /*[NB,256,256]*/,
                                                                   MaskDownW w, const float* __restrict__ emb_tok,
                                                                   float* __restrict__ keys,
-                                                                  const int* __restrict__ image_of) {
+                                                                  const int* __restrict__ image_of,
+                                                                  __nv_bfloat16* __restrict__ sb) {
   __shared__ float hid[32][17];
   const int b = blockIdx.y;
   emb_tok += static_cast<size_t>(image_of != nullptr ? image_of[b] : 0) * 4096 * 256;
@@ -727,7 +728,14 @@ __global__ void __launch_bounds__(256) mask_downscale_keys_kernel(const float* _
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) a = fmaf(wr[kk], hid[t][kk], a);
     const size_t o = static_cast<size_t>(tok0 + t) * 256 + tid;
-    keys[static_cast<size_t>(b) * 4096 * 256 + o] = emb_tok[o] + a;
+    const float kv = emb_tok[o] + a;
+    keys[static_cast<size_t>(b) * 4096 * 256 + o] = kv;
+    if (sb != nullptr) {  // [hi | lo] split operand of the image-side projections, written by the producer of the keys
+      const size_t row = static_cast<size_t>(b) * 4096 + tok0 + t;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(kv);
+      sb[row * 512 + tid] = hi;
+      sb[row * 512 + 256 + tid] = __float2bfloat16_rn(kv - __bfloat162float(hi));
+    }
   }
 }
 
@@ -988,9 +996,9 @@ int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, c
 }
 
 int mask_downscale_keys(const float* mask, const float* const* w10, const float* emb_tok, float* keys, int NB,
-                        const int* image_of, cudaStream_t stream) {
+                        const int* image_of, __nv_bfloat16* sb, cudaStream_t stream) {
   MaskDownW w{w10[0], w10[1], w10[2], w10[3], w10[4], w10[5], w10[6], w10[7], w10[8], w10[9]};
-  mask_downscale_keys_kernel<<<dim3(128, NB), 256, 0, stream>>>(mask, w, emb_tok, keys, image_of);
+  mask_downscale_keys_kernel<<<dim3(128, NB), 256, 0, stream>>>(mask, w, emb_tok, keys, image_of, sb);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -45,7 +45,7 @@ int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, c
 int ln256_keys_split(float* keys, const float* gamma, const float* beta, const float* pe, size_t M, __nv_bfloat16* sa,
                      __nv_bfloat16* sb, cudaStream_t stream);
 int mask_downscale_keys(const float* mask, const float* const* w10, const float* emb_tok, float* keys, int NB,
-                        const int* image_of, cudaStream_t stream);
+                        const int* image_of, __nv_bfloat16* sb, cudaStream_t stream);
 // split_out != null: write the bf16 [hi | lo] split operand [ngroups, 128] instead of updating x in place
 int ln64_gelu(float* x, const float* g, const float* b, size_t ngroups, __nv_bfloat16* split_out, cudaStream_t stream);
 int mlp3_tokens(const float* hs, int NB, int T, const float* const* w15, const float* const* b15, float* hyper,
