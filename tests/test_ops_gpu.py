@@ -155,7 +155,8 @@ def test_prompt_extraction_bit_exact(seed):
 def test_prompt_extraction_ragged_shapes():
     from samcarriestheburden_b200.segment_anything.utils.prompt_utils import extract_seeds_boxes
     rng = np.random.default_rng(0)
-    for (C_, H, W) in [(1, 1, 1), (5, 37, 53), (17, 384, 224), (3, 1, 1000), (64, 33, 31)]:
+    # (40, 48, 64) / (64, 32, 32): the 16-pixel fast path with more classes than one load batch and than 32 (two masks)
+    for (C_, H, W) in [(1, 1, 1), (5, 37, 53), (17, 384, 224), (3, 1, 1000), (64, 33, 31), (40, 48, 64), (64, 32, 32)]:
         masks = rng.random((2, C_, H, W)) < 0.3
         seeds, boxes, has_seed, has_box = extract_seeds_boxes(torch.from_numpy(masks).to(DEV))
         for i in range(2):

@@ -44,6 +44,16 @@ def test_apply_image_cuda_native_sizes_bit_exact(shape):
     assert np.array_equal(tr.apply_image(img), want)  # the host path (Pillow itself) agrees as well
 
 
+def test_resize_extreme_ratios():
+    """Many taps per output sample (50x down-scaling: 101 taps) and strong up-scaling, both axes different."""
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, size=(700, 900, 3), dtype=np.uint8)
+    assert np.array_equal(_resize(img, 14, 21, chw=False), O.resize_bilinear_u8(img, 14, 21))
+    small = rng.integers(0, 256, size=(7, 5, 3), dtype=np.uint8)
+    assert np.array_equal(_resize(small, 333, 129, chw=False), O.resize_bilinear_u8(small, 333, 129))
+    assert np.array_equal(_resize(small, 1, 1, chw=True), np.transpose(O.resize_bilinear_u8(small, 1, 1), (2, 0, 1)))
+
+
 def test_resize_identity_and_single_channel_and_errors():
     from samcarriestheburden_b200 import _lib
     from samcarriestheburden_b200.segment_anything.utils.transforms import resize_u8_cuda
