@@ -113,7 +113,7 @@ class ClockSampler:
 
 def build_model(model: str, device):
     import torch
-    from oracle import sam_oracle as O  # synthetic weights only (seeded init shared with the parity tests)
+    from samcarriestheburden_b200 import synthetic as O  # seeded random-init weights (shared with the parity tests)
     from samcarriestheburden_b200.segment_anything import sam_model_registry
     sam = sam_model_registry[model]()
     sam.load_state_dict(O.random_state_dict(model, seed=0), strict=True)
@@ -123,7 +123,7 @@ def build_model(model: str, device):
 def synthetic_batch(batch: int, seed: int):
     import numpy as np
     import torch
-    from oracle import sam_oracle as O
+    from samcarriestheburden_b200 import synthetic as O
     base = torch.from_numpy(O.synthetic_radiograph(seed)).permute(2, 0, 1).contiguous()
     rng = np.random.default_rng(seed)
     imgs = [torch.roll(base, shifts=(int(rng.integers(0, 1024)), int(rng.integers(0, 1024))), dims=(1, 2))
@@ -435,7 +435,7 @@ def refine_throughput(sam, dev, n_images: int = 32, batch: int = 8):
     `value` = SAMSegRefiner.refine_batch over `batch` images per launch sequence (what the pipeline driver calls);
     `per_image_api` = the reference-shaped one-image `refine` call in a loop."""
     import torch
-    from oracle import sam_oracle as O
+    from samcarriestheburden_b200 import synthetic as O
     from samcarriestheburden_b200.segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
     from samcarriestheburden_b200.utils.seg_refinement import SAMSegRefiner
     store = EmbeddingStore()
@@ -484,7 +484,7 @@ def refine_throughput(sam, dev, n_images: int = 32, batch: int = 8):
 def unet_throughput(dev, batch: int = 8, reps: int = 5):
     """the U-Net that produces the masks (17 classes, 384 x 224), random-init weights, batch 8."""
     import torch
-    from oracle import unet_oracle as U
+    from samcarriestheburden_b200 import synthetic as U
     from samcarriestheburden_b200.custom_arcitecture.classic_u_net import UNet
     m = UNet(1, 17)
     m.load_state_dict(U.random_unet_state_dict(0), strict=True)
@@ -509,7 +509,7 @@ def pipeline_throughput(sam, dev, n_images: int = 32, batch: int = 8):
     connected-component selection on the U-Net probability maps -> prompt extraction -> two decoder passes ->
     upscale to native + threshold + 384x224 tap -> refined masks copied back to the host."""
     import torch
-    from oracle import sam_oracle as O
+    from samcarriestheburden_b200 import synthetic as O
     from samcarriestheburden_b200.scripts.pipelines import generate_img_embeddings, refine_segmentations
     imgs = [O.synthetic_radiograph(100 + i) for i in range(n_images)]
     names = [f"p{i}" for i in range(n_images)]

@@ -24,11 +24,8 @@ import torch.nn.functional as F
 SD = Dict[str, torch.Tensor]
 
 # segment_anything/build_sam.py:14-44
-VIT_CONFIGS = {
-    "vit_h": dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31)),
-    "vit_l": dict(embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23)),
-    "vit_b": dict(embed_dim=768, depth=12, num_heads=12, global_attn_indexes=(2, 5, 8, 11)),
-}
+from samcarriestheburden_b200.synthetic import (VIT_CONFIGS, random_state_dict, synthetic_radiograph,  # noqa: E402,F401
+                                            synthetic_unet_masks, synthetic_unet_probs)
 PIXEL_MEAN = (123.675, 116.28, 103.53)  # build_sam.py:99
 PIXEL_STD = (58.395, 57.12, 57.375)     # build_sam.py:100
 
@@ -486,132 +483,6 @@ def refine(sd: SD, features: torch.Tensor, seg: np.ndarray, input_size: Sequence
     return seg, est, native, lows
 
 
-# ----------------------------------------------------------------------------------------------- synthetic inputs
-def random_state_dict(model_type: str = "vit_b", seed: int = 0) -> SD:
-    """Random-init weights with the reference's parameter names/shapes (build_sam.py:55-107), PyTorch
-    default initialisers, plus N(0, 0.02) pos_embed / rel_pos tables (zero at init in the reference,
-    image_encoder.py:68-70,221-222 — randomised so the rel-pos path is exercised)."""
-    cfg = VIT_CONFIGS[model_type]
-    g = torch.Generator().manual_seed(seed)
-    sd: SD = {}
-
-    def lin(name, out_f, in_f, bias=True):
-        bound = 1.0 / math.sqrt(in_f)
-        sd[name + ".weight"] = (torch.rand((out_f, in_f), generator=g) * 2 - 1) * bound
-        if bias:
-            sd[name + ".bias"] = (torch.rand((out_f,), generator=g) * 2 - 1) * bound
-
-    def conv(name, out_c, in_c, k, bias=True, transposed=False):
-        fan_in = (out_c if transposed else in_c) * k * k
-        bound = 1.0 / math.sqrt(fan_in)
-        shape = (in_c, out_c, k, k) if transposed else (out_c, in_c, k, k)
-        sd[name + ".weight"] = (torch.rand(shape, generator=g) * 2 - 1) * bound
-        if bias:
-            sd[name + ".bias"] = (torch.rand((out_c,), generator=g) * 2 - 1) * bound
-
-    def norm(name, n):
-        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn((n,), generator=g)
-        sd[name + ".bias"] = 0.1 * torch.randn((n,), generator=g)
-
-    D, depth, heads = cfg["embed_dim"], cfg["depth"], cfg["num_heads"]
-    hd = D // heads
-    ie = "image_encoder."
-    conv(ie + "patch_embed.proj", D, 3, 16)
-    sd[ie + "pos_embed"] = 0.02 * torch.randn((1, 64, 64, D), generator=g)
-    for i in range(depth):
-        b = f"{ie}blocks.{i}."
-        S = 64 if i in cfg["global_attn_indexes"] else 14
-        norm(b + "norm1", D)
-        lin(b + "attn.qkv", 3 * D, D)
-        lin(b + "attn.proj", D, D)
-        sd[b + "attn.rel_pos_h"] = 0.02 * torch.randn((2 * S - 1, hd), generator=g)
-        sd[b + "attn.rel_pos_w"] = 0.02 * torch.randn((2 * S - 1, hd), generator=g)
-        norm(b + "norm2", D)
-        lin(b + "mlp.lin1", 4 * D, D)
-        lin(b + "mlp.lin2", D, 4 * D)
-    conv(ie + "neck.0", 256, D, 1, bias=False)
-    norm(ie + "neck.1", 256)
-    conv(ie + "neck.2", 256, 256, 3, bias=False)
-    norm(ie + "neck.3", 256)
-
-    pe = "prompt_encoder."
-    sd[pe + "pe_layer.positional_encoding_gaussian_matrix"] = torch.randn((2, 128), generator=g)
-    for i in range(4):
-        sd[f"{pe}point_embeddings.{i}.weight"] = torch.randn((1, 256), generator=g)
-    sd[pe + "not_a_point_embed.weight"] = torch.randn((1, 256), generator=g)
-    sd[pe + "no_mask_embed.weight"] = torch.randn((1, 256), generator=g)
-    conv(pe + "mask_downscaling.0", 4, 1, 2)
-    norm(pe + "mask_downscaling.1", 4)
-    conv(pe + "mask_downscaling.3", 16, 4, 2)
-    norm(pe + "mask_downscaling.4", 16)
-    conv(pe + "mask_downscaling.6", 256, 16, 1)
-
-    d = "mask_decoder."
-    sd[d + "iou_token.weight"] = torch.randn((1, 256), generator=g)
-    sd[d + "mask_tokens.weight"] = torch.randn((4, 256), generator=g)
-    t = d + "transformer."
-
-    def attn(name, internal):
-        for pr in ("q_proj", "k_proj", "v_proj"):
-            lin(f"{name}.{pr}", internal, 256)
-        lin(f"{name}.out_proj", 256, internal)
-
-    for i in range(2):
-        L = f"{t}layers.{i}."
-        attn(L + "self_attn", 256)
-        norm(L + "norm1", 256)
-        attn(L + "cross_attn_token_to_image", 128)
-        norm(L + "norm2", 256)
-        lin(L + "mlp.lin1", 2048, 256)
-        lin(L + "mlp.lin2", 256, 2048)
-        norm(L + "norm3", 256)
-        norm(L + "norm4", 256)
-        attn(L + "cross_attn_image_to_token", 128)
-    attn(t + "final_attn_token_to_image", 128)
-    norm(t + "norm_final_attn", 256)
-    conv(d + "output_upscaling.0", 64, 256, 2, transposed=True)
-    norm(d + "output_upscaling.1", 64)
-    conv(d + "output_upscaling.3", 32, 64, 2, transposed=True)
-    for i in range(4):
-        m = f"{d}output_hypernetworks_mlps.{i}.layers."
-        lin(m + "0", 256, 256); lin(m + "1", 256, 256); lin(m + "2", 32, 256)
-    m = d + "iou_prediction_head.layers."
-    lin(m + "0", 256, 256); lin(m + "1", 256, 256); lin(m + "2", 4, 256)
-    return sd
-
-
-def synthetic_radiograph(seed: int, h: int = 1024, w: int = 1024) -> np.ndarray:
-    """Smooth blobs + noise, grayscale replicated to RGB like generate_img_embeddings.py:39-40. uint8 HWC."""
-    rng = np.random.default_rng(seed)
-    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
-    img = np.zeros((h, w), np.float32)
-    for _ in range(6):
-        cy, cx = rng.uniform(0, h), rng.uniform(0, w)
-        sy, sx = rng.uniform(h / 12, h / 3), rng.uniform(w / 12, w / 3)
-        img += rng.uniform(0.3, 1.0) * np.exp(-(((yy - cy) / sy) ** 2 + ((xx - cx) / sx) ** 2))
-    img = img / max(float(img.max()), 1e-6) * 200.0 + rng.uniform(0, 40, size=(h, w)).astype(np.float32)
-    g = np.clip(img, 0, 255).astype(np.uint8)
-    return np.repeat(g[:, :, None], 3, axis=2)
-
-
-def synthetic_unet_masks(seed: int, C: int = 17, H: int = 384, W: int = 224) -> np.ndarray:
-    """Bool [C,H,W]: one ellipse per class (+ optional distractor blob), some overlaps, 1-2 empty classes."""
-    rng = np.random.default_rng(1000 + seed)
-    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
-    m = np.zeros((C, H, W), bool)
-    empty = set(rng.choice(C, size=int(rng.integers(1, 3)), replace=False).tolist())
-    for c in range(C):
-        if c in empty:
-            continue
-        cy, cx = rng.uniform(0.1 * H, 0.9 * H), rng.uniform(0.15 * W, 0.85 * W)
-        ry, rx = rng.uniform(8, 45), rng.uniform(6, 30)
-        m[c] = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0
-        if rng.random() < 0.4:
-            by, bx = rng.uniform(0, H), rng.uniform(0, W)
-            m[c] |= ((yy - by) / 4.0) ** 2 + ((xx - bx) / 4.0) ** 2 <= 1.0
-    return m
-
-
 # ---------------------------------------------------------------------------------------------------------------
 # Connected-component pre-processing (SURVEY 8f-1; reference utils/segmentation_preprocessing.py:7-52).
 # The labelling itself lives in kornia 0.7.0 (`kornia.contrib.connected_components`, absent from this image): its
@@ -619,28 +490,6 @@ def synthetic_unet_masks(seed: int, C: int = 17, H: int = 384, W: int = 224) -> 
 # mask, so after convergence a component's label is the largest global index it contains.  This restatement labels
 # with scipy (8-connectivity) and assigns exactly those converged labels.  Pinned against the reference's own
 # selection code driven by a torch restatement of the kornia loop (tests/golden/make_golden_ccl.py).
-def synthetic_unet_probs(seed: int, C: int = 17, H: int = 384, W: int = 224) -> np.ndarray:
-    """float32 [C,H,W] probabilities: per class a main ellipse (p in [0.6, 0.95]) + 0-2 distractor blobs of higher or
-    lower confidence, smooth background < 0.5, 1-2 empty classes."""
-    rng = np.random.default_rng(5000 + seed)
-    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
-    out = np.zeros((C, H, W), np.float32)
-    empty = set(rng.choice(C, size=int(rng.integers(1, 3)), replace=False).tolist())
-    for c in range(C):
-        p = (0.05 + 0.3 * rng.random((H, W))).astype(np.float32)
-        if c not in empty:
-            cy, cx = rng.uniform(0.1 * H, 0.9 * H), rng.uniform(0.15 * W, 0.85 * W)
-            ry, rx = rng.uniform(8, 45), rng.uniform(6, 30)
-            core = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0
-            p[core] = (rng.uniform(0.6, 0.95) + 0.04 * rng.standard_normal(int(core.sum()))).astype(np.float32)
-            for _ in range(int(rng.integers(0, 3))):
-                by, bx, br = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(1.5, 9.0)
-                blob = ((yy - by) / br) ** 2 + ((xx - bx) / br) ** 2 <= 1.0
-                p[blob] = (rng.uniform(0.55, 0.99) + 0.02 * rng.standard_normal(int(blob.sum()))).astype(np.float32)
-        out[c] = np.clip(p, 0.0, 1.0)
-    return out
-
-
 def ccl_labels(bin_mask: np.ndarray) -> np.ndarray:
     """bool [C,H,W] -> int64 labels like converged kornia.contrib.connected_components on a (C,1,H,W) batch: the
     largest batch-global pixel index of the 8-connected component (0 = background and, as in the reference, a lone

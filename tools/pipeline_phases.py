@@ -8,7 +8,7 @@ sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
 from bench import build_model  # noqa: E402
-from oracle import sam_oracle as O  # noqa: E402
+from samcarriestheburden_b200 import synthetic as O  # noqa: E402  (synthetic inputs)
 from samcarriestheburden_b200.scripts.pipelines import generate_img_embeddings, refine_segmentations  # noqa: E402
 
 dev = torch.device("cuda", 0)

@@ -9,7 +9,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from bench import build_model  # noqa: E402
-from oracle import sam_oracle as O  # noqa: E402  (synthetic inputs only)
+from samcarriestheburden_b200 import synthetic as O  # noqa: E402  (synthetic inputs)
 from samcarriestheburden_b200.segment_anything.modeling.sam import upscale_masks  # noqa: E402
 from samcarriestheburden_b200.segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead  # noqa: E402
 from samcarriestheburden_b200.segment_anything.utils.prompt_utils import extract_seeds_boxes  # noqa: E402

@@ -9,9 +9,10 @@ sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from oracle import sam_oracle as O  # noqa: E402  (synthetic masks only)
+from samcarriestheburden_b200 import synthetic as O  # noqa: E402  (synthetic inputs)
 from samcarriestheburden_b200.segment_anything.modeling.sam import upscale_masks  # noqa: E402
 from samcarriestheburden_b200.segment_anything.utils.prompt_utils import extract_seeds_boxes  # noqa: E402
+from samcarriestheburden_b200.segment_anything.utils.transforms import ResizeLongestSide  # noqa: E402
 
 
 def timed(fn, reps=8, warm=3):
@@ -39,13 +40,12 @@ def run(peak_gbs=6545.9):
     for (oh, ow) in [(1024, 1024), (1182, 754)]:
         n = 256
         low = torch.randn((n, 1, 256, 256), device="cuda")
-        inp = O.get_preprocess_shape(oh, ow)
+        inp = ResizeLongestSide.get_preprocess_shape(oh, ow, 1024)
         t = timed(lambda: upscale_masks(low, inp, (oh, ow), small_size=(384, 224)))
         by = n * (256 * 256 * 4 + oh * ow + 384 * 224)
         out[f"upscale_threshold_{oh}x{ow}"] = {"masks": n, "ms": t, "bytes": by, "gbs": by / t / 1e6,
                                                "frac_hbm": by / t / 1e6 / peak_gbs}
     # image ingest: native-resolution uint8 radiographs (largest CVAT size) -> encoder input size, Pillow-exact resize
-    from samcarriestheburden_b200.segment_anything.utils.transforms import ResizeLongestSide
     tr = ResizeLongestSide(1024)
     H, W = 2570, 2040
     n = 16
