@@ -8,7 +8,8 @@ ViT-H weights): normalise+pad+patchify -> ViT encoder -> neck -> [B,256,64,64] f
   value : images/s over all ranks, inputs already resident in HBM, CUDA-event timed, max over ranks.
   e2e   : same metric through the public API (Sam.encode_image, what SamPredictor.set_torch_image calls) with
           pinned-host uint8 inputs copied H2D and the embeddings copied D2H inside the timed region.
-  roofline: the dominant kernel (tcgen05 GEMM) timed live with CUDA events on the encoder's four linear shapes.
+  roofline: the dominant kernel (tcgen05 GEMM) from CUDA events around every one of its launches inside an instrumented
+          copy of the timed loop (in-run timings, same clocks / power cap).
   cpu_baseline / --impl reference: the CPU oracle (a port of the reference's PyTorch path, oracle/sam_oracle.py)
           on the box's host cores; the reference itself is Python under /root/reference and cannot travel.
 Multi-GPU: one process per GPU (torchrun); images shard by rank, no collective on the critical path, one final
@@ -131,43 +132,60 @@ def synthetic_batch(batch: int, seed: int):
     return torch.stack(imgs)
 
 
-def gemm_roofline(model: str, batch: int, reps: int = 10):
-    """Time the tcgen05 GEMM kernel alone (CUDA events, same stream) on the four linear shapes of one block."""
+def inrun_kernel_roofline(sam, dev_pool, steps: int, model: str, batch: int, peaks):
+    """Roofline of the dominant kernel from IN-RUN timings: the same steady-state loop as the timed region, with CUDA
+    events recorded by the library around every tcgen05 GEMM / attention launch on the launching stream
+    (b200sam_timing_start / _stop).  The instrumented loop is a separate pass after the timed one (event records between
+    kernels cost ~1 us each and switch off the programmatic-dependent-launch overlap, so they stay out of `value`); it
+    runs under the same clocks / power cap as the timed loop, and its own ms per step is reported beside it."""
     import torch
     from samcarriestheburden_b200 import _lib
-    lib = _lib.load()
-    D = {"vit_h": 1280, "vit_l": 1024, "vit_b": 768}[model]
-    M = batch * 4096
-    shapes = [("qkv", 3 * D, D, 1, 0), ("proj", D, D, 0, 0), ("lin1", 4 * D, D, 1, 1), ("lin2", D, 4 * D, 0, 0)]
-    dev = "cuda"
-    stream = _lib.current_stream()
-    tot_flop, tot_ms, per = 0.0, 0.0, {}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, N, K, out_bf16, gelu in shapes:
-        A = torch.randn((M, K), device=dev).bfloat16()
-        W = (torch.randn((N, K), device=dev) / K ** 0.5).bfloat16()
-        b = torch.randn((N,), device=dev)
-        out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
-        res = out if not out_bf16 else None
-        # all launches are queued back to back (flush kernel, event, GEMM, event) and read after ONE synchronise, so
-        # the GPU never idles between samples (an idle gap lets the SM clock drop and under-reports the kernel)
-        evs = []
-        for i in range(reps + 3):
-            flush.zero_()  # evict L2 between launches
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _lib.check(lib.b200sam_gemm_bf16(A.data_ptr(), W.data_ptr(), out.data_ptr(), b.data_ptr(), _lib.ptr(res), M,
-                                             N, K, K, K, N, N, 0, gelu, out_bf16, 0, stream))
-            e1.record()
-            evs.append((e0, e1))
+    for s in range(2):
+        sam.encode_image(dev_pool[s % len(dev_pool)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with _lib.KernelTiming() as kt:
+        e0.record()
+        for s in range(steps):
+            sam.encode_image(dev_pool[s % len(dev_pool)])
+        e1.record()
         torch.cuda.synchronize()
-        ms = [a.elapsed_time(b_) for a, b_ in evs[3:]]
-        t = statistics.mean(ms)
-        flop = 2.0 * M * N * K
-        per[name] = {"ms": round(t, 4), "tflops": round(flop / t / 1e9, 1)}
-        tot_flop += flop
-        tot_ms += t
-    return tot_flop / tot_ms / 1e9, tot_ms / 4, per  # TFLOP/s over the 4 launches, mean launch ms
+    step_ms = e0.elapsed_time(e1) / steps
+    D = {"vit_h": 1280, "vit_l": 1024, "vit_b": 768}[model]
+    names = {(3 * D, D): "qkv", (D, D): "proj", (4 * D, D): "lin1", (D, 4 * D): "lin2", (D, 768): "patch_embed",
+             (256, D): "neck_conv1x1", (256, 2304): "neck_conv3x3"}
+    by_kind, per = {}, {}
+    for r in kt.records:
+        k = by_kind.setdefault(r["kind"], [0, 0.0, 0.0])
+        k[0] += 1; k[1] += r["work"]; k[2] += r["ms"]
+        if r["kind"] == "gemm":
+            nm = names.get((r["dims"][1], r["dims"][2]), f"N{r['dims'][1]}_K{r['dims'][2]}")
+            q = per.setdefault(nm, [0, 0.0, 0.0])
+            q[0] += 1; q[1] += r["work"]; q[2] += r["ms"]
+    n, work, ms = by_kind.get("gemm", [0, 0.0, 1e-9])
+    tf = work / ms / 1e9
+    out = {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+           "frac": tf / peaks["tf_sustained"], "frac_of_burst_peak": tf / peaks["tf_burst"],
+           "peak_source": peaks["src"] + " sustained (kernel timed inside a long step; burst: %.1f)" % peaks["tf_burst"],
+           "kernel": "gemm_bf16_tn_kernel (tcgen05 kind::f16, 128x256x64 tiles, TMA ring, TMEM double buffer)",
+           "how": "CUDA events around every GEMM launch of %d instrumented steps (same loop as the timed region)" % steps,
+           "launches": n, "launch_ms_mean": ms / max(n, 1), "gemm_ms_per_step": ms / steps,
+           "instrumented_ms_per_step": step_ms, "share_of_step": ms / steps / step_ms,
+           "per_shape": {k: {"launches_per_step": v[0] // steps, "ms_mean": round(v[2] / v[0], 4),
+                             "tflops": round(v[1] / v[2] / 1e9, 1)} for k, v in per.items()},
+           "attention": {k: {"launches_per_step": v[0] // steps, "ms_mean": round(v[2] / v[0], 4),
+                             "tflops_algorithmic": round(v[1] / v[2] / 1e9, 1), "share_of_step": round(v[2] / steps / step_ms, 4)}
+                         for k, v in by_kind.items() if k != "gemm"}}
+    # DRAM traffic per launch: from the committed `ncu --set full` capture of this kernel on the same four shapes at
+    # batch 8 (a static capture, NOT measured in this run): dram__bytes_read.sum + dram__bytes_write.sum
+    src = ROOT / "profiles" / "r02_gemm_traffic.json"
+    out["traffic"] = None
+    if model == "vit_h" and batch == 8 and src.exists():
+        t = json.loads(src.read_text())
+        out["traffic"] = t["mean_bytes_per_launch"]
+        out["traffic_source"] = "static ncu capture, " + t["source"]
+        out["algorithmic_bytes_per_launch"] = t["algorithmic_bytes_per_launch"]
+    return out
 
 
 def cpu_encoder_images_per_s(model: str, n_images: int, warm: int = 0):
@@ -262,7 +280,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200SAM_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # NCCL_DEBUG is left as the caller set it: NCCL's log goes to fd 1, which _protect_stdout() already points at stderr
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K, B = args.steps, args.batch
@@ -272,7 +290,8 @@ def main():
     dev_pool = [p.to(dev) for p in pool]
     host_pool = [p.pin_memory() for p in pool]
     enc = sam.image_encoder
-    launches_per_step = 2 + 7 * len(enc.blocks) + 6
+    # patchify + patch GEMM, per block (qkv, attention, proj, lin1, lin2 [+ LN1, LN2]), neck ([convert], GEMM, LN, im2col, GEMM, LN)
+    launches_per_step = 2 + (5 if enc.ln_fused else 7) * len(enc.blocks) + (5 if enc.ln_fused else 6)
 
     def barrier():
         if world > 1:
@@ -381,13 +400,17 @@ def main():
     peaks = _peaks()
     out = {
         "metric": metric_name(args.model), "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": enc.operand_format, "data": "synthetic",
         "config": {"workload": f"SAM {args.model} image-embedding generation (generate_img_embeddings), synthetic "
                                f"1024x1024 uint8 radiographs, random-init weights (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "parallelism": f"dp{world} (images sharded by rank, final NCCL all_gather)",
                    "l2": "activations per step (>100 MB per image) exceed the 126 MB L2; no explicit flush",
-                   "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate"},
+                   "residual_stream": "fp32",
+                   "gemm_operands": f"{enc.operand_format} (tcgen05 kind::f16), fp32 accumulate; B200SAM_ENCODER_OPERANDS="
+                                    "bf16|fp16 selects the 16-bit format (same tensor-core rate)",
+                   "layernorm": "folded into the GEMM epilogues" if enc.ln_fused else "separate launches",
+                   "programmatic_dependent_launch": os.environ.get("B200SAM_PDL", "1") != "0"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 1024 * 1024,
                 "d2h_bytes_per_step": B * 256 * 64 * 64 * 4},
         "gpu_launches": launches_per_step * K,
@@ -400,14 +423,7 @@ def main():
             "peak_source": peaks["src"]},
     }
     if rank == 0:
-        tf, launch_ms, per = gemm_roofline(args.model, B)
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the four shapes at batch 8) from
-        # the one `ncu --set full` capture summarised in profiles/r01_gemm_ncu_summary.md (algorithmic: 471.2 MB)
-        traffic = 446.9e6 if (args.model == "vit_h" and B == 8) else None
-        out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                           "frac": tf / peaks["tf_burst"], "traffic": traffic,
-                           "kernel": "gemm_bf16_tn_kernel (tcgen05, 128x256x64 tiles)",
-                           "launch_ms_mean": launch_ms, "per_shape": per, "peak_source": peaks["src"] + " burst"}
+        out["roofline"] = inrun_kernel_roofline(sam, dev_pool, K, args.model, B, peaks)
         if not args.no_refine:
             out["refine"] = refine_throughput(sam, dev)
             # HBM-bound stages on batched launches: algorithmic bytes / CUDA-event time
@@ -419,6 +435,7 @@ def main():
             out["pipeline"] = pipeline_throughput(sam, dev)
             out["unet"] = unet_throughput(dev)
         if world == 1 and not args.no_cpu_baseline:
+            out["parity"] = e2e_parity(sam, dev, args.model)
             v, cores, times = cpu_encoder_images_per_s(args.model, 1)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                    "sample": f"1 image through the full {args.model} fp32 encoder of the CPU oracle "
@@ -427,6 +444,49 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def e2e_parity(sam, dev, model: str, seed: int = 5, native=(1182, 754)):
+    """End-to-end mask parity (north_star: Dice >= 0.999, mismatched pixels reported): one synthetic radiograph through
+    SamPredictor.set_image (CUDA encoder) and the two-pass SAMSegRefiner (CUDA decode + upscale) against the CPU oracle's
+    fp32 encoder + refine on the same inputs (the oracle is the checker here, never the thing measured)."""
+    import numpy as np
+    import torch
+    from oracle import sam_oracle as O
+    from samcarriestheburden_b200.segment_anything import SamPredictor
+    from samcarriestheburden_b200.segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
+    from samcarriestheburden_b200.utils.seg_refinement import SAMSegRefiner
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.random_state_dict(model, seed=0)
+    img = O.synthetic_radiograph(seed, *native)
+    pred = SamPredictor(sam)
+    pred.set_image(img)
+    resized = pred.transform.apply_image(img)
+    ref_emb = O.image_encoder(sd, O.preprocess(torch.from_numpy(resized).permute(2, 0, 1).float())[None], **O.VIT_CONFIGS[model])
+    got_emb = pred.features.float().cpu()
+    rel = float((got_emb - ref_emb).norm() / ref_emb.norm())
+    store = EmbeddingStore()
+    store.add("img", pred.features, native, pred.input_size)
+    head = SAMMaskDecoderHead(None, model, str(dev), store, sam_model=sam)
+    refiner = SAMSegRefiner("SAM", str(dev), [["box"], ["pos_points", "neg_points"]], sam_predictor=head)
+    seg = O.synthetic_unet_masks(seed)
+    refiner.refine(torch.from_numpy(seg.copy()), "img")
+    sel, native_masks = refiner.last_native_masks[0]
+    got_native = native_masks[:, 0].cpu().numpy()
+    _, _, ref_native, _ = O.refine(sd, ref_emb, seg, pred.input_size, native)
+    classes = sorted(ref_native)
+    assert len(classes) == got_native.shape[0]
+    dices, mism = [], 0
+    for k, c in enumerate(classes):
+        a, b = got_native[k], ref_native[c]
+        dices.append(2.0 * float((a & b).sum()) / max(float(a.sum() + b.sum()), 1.0))
+        mism += int((a != b).sum())
+    total = int(got_native.size)
+    return {"what": f"{model}: image -> CUDA encoder -> CUDA 2-pass refine vs fp32 oracle encoder -> oracle refine, "
+                    f"native {native[0]}x{native[1]}, {len(classes)} classes",
+            "operands": sam.image_encoder.operand_format, "embedding_rel_l2": rel,
+            "dice_min": min(dices), "dice_mean": float(np.mean(dices)), "mismatched_px": mism, "total_px": total,
+            "mismatched_frac": mism / total, "bar": "Dice >= 0.999 per class", "met": bool(min(dices) >= 0.999)}
 
 
 def refine_throughput(sam, dev, n_images: int = 32, batch: int = 8):

@@ -39,11 +39,22 @@ typedef struct b200sam_encoder_config {
   int num_heads;        /* 12 | 16 | 16 */
   int global_attn_mask; /* bit i set: block i is a global-attention block */
   int out_chans;        /* 256 */
+  int operand_format;   /* 16-bit tensor-core operand format: 0 = bf16, 1 = fp16 (11 significand bits; what the
+                           reference's own mixed-precision run uses: torch.cuda.amp.autocast defaults to fp16,
+                           seg_processing/hpo_bce_unet_sam_postprocess.py:44).  fp32 accumulate, fp32 residual stream,
+                           fp32 LayerNorm / softmax statistics in both. */
+  int flags;            /* B200SAM_ENC_LN_FUSED: norm1 / norm2 (image_encoder.py:168,180) folded into the GEMMs */
 } b200sam_encoder_config;
+#define B200SAM_OPERAND_BF16 0
+#define B200SAM_OPERAND_FP16 1
+#define B200SAM_ENC_LN_FUSED 1
 typedef struct b200sam_encoder b200sam_encoder;
 
 B200SAM_API int b200sam_encoder_weight_count(const b200sam_encoder_config* cfg);
-/* "state_dict key|packing" of weight slot i; packing: f32 | bf16 | bf16_flat | bf16_tap | f32_tokens */
+/* "state_dict key|packing[|norm prefix]" of weight slot i; packing: f32 | op16 | op16_flat | op16_tap | f32_tokens |
+ * none (unused slot, any non-null pointer) and, with B200SAM_ENC_LN_FUSED, for the linear `key` that follows the
+ * LayerNorm `norm prefix`: fold_w = op16(gamma * W), fold_s[n] = sum_k fold_w[n,k] (fp32), fold_c = beta . W^T + b (fp32);
+ * op16 = cfg->operand_format. */
 B200SAM_API const char* b200sam_encoder_weight_name(const b200sam_encoder_config* cfg, int i);
 B200SAM_API size_t b200sam_encoder_workspace_bytes(const b200sam_encoder_config* cfg, int batch);
 B200SAM_API int b200sam_encoder_create(const b200sam_encoder_config* cfg, const void* const* weights, int n_weights,
@@ -159,20 +170,41 @@ B200SAM_API int b200sam_unet_forward(const b200sam_unet* u, const float* image, 
                          float* probs_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- building blocks (exposed for parity tests)
- * D[M,N] = A[M,K] W[N,K]^T (+bias) (+GELU) (+residual[row % res_row_mod]); bf16 operands, fp32 accumulate (tcgen05). */
+ * D[M,N] = A[M,K] W[N,K]^T (+bias) (+GELU) (+residual[row % res_row_mod]); 16-bit operands (bf16 / fp16 entry point),
+ * fp32 accumulate (tcgen05); out_16bit = 1: output in the operands' format, 0: fp32 (with optional fp32 residual). */
 B200SAM_API int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M,
                       int N, int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_bf16,
                       int max_ctas, void* stream);
+B200SAM_API int b200sam_gemm_f16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M,
+                     int N, int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_f16,
+                     int max_ctas, void* stream);
+/* The two halves of a LayerNorm folded into the GEMMs around it (Block.forward, image_encoder.py:166-182):
+ * _ln_residual: out = A W^T + bias + residual (fp32 [M,N], may alias residual), out16 = its 16-bit copy,
+ *               rowstat_out [M, ceil(N/128), 2] = per-row partial (sum, sum of squares) of out per 128-column part;
+ * _ln_folded:   out16 [M,N] = act( rstd * (A W_folded^T - mean * colsum) + bias_folded ) with (mean, rstd) of every row
+ *               of A's fp32 original from rowstat_in [M, nparts, 2] (K elements per row, eps inside the sqrt). */
+B200SAM_API int b200sam_gemm_ln_residual(const void* A, const void* W, const float* bias, const float* residual, float* out,
+                             void* out16, float* rowstat_out, int M, int N, int K, int operand_format, void* stream);
+B200SAM_API int b200sam_gemm_ln_folded(const void* A, const void* W_folded, const float* bias_folded, const float* colsum,
+                           const float* rowstat_in, int nparts, float eps, void* out16, int M, int N, int K, int gelu,
+                           int operand_format, void* stream);
+/* out_kind: 0 = fp32, 1 = bf16, 2 = fp16 */
 B200SAM_API int b200sam_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
-                      int out_bf16, void* stream);
-/* qkv: [B*4096, 3*heads*hd] bf16; out: [B*4096, heads*hd] bf16; global_attn: 0 = 14x14 windows, 1 = global
- * (the tcgen05 paths used by the encoder); A/B variants kept for measurements: 2 / 3 = global / windows on the legacy
- * mma.sync path, 4 / 5 = second / third generation windowed tcgen05 kernels (attention_win2.cu, attention_win3.cu) */
-B200SAM_API int b200sam_encoder_attention(const void* qkv, const void* qkv_bias_bf16, const void* rel_h_bf16,
-                              const void* rel_w_bf16, void* out, int batch, int heads, int hd, int global_attn,
+                      int out_kind, void* stream);
+/* qkv: [B*4096, 3*heads*hd] 16-bit; out: [B*4096, heads*hd] 16-bit; global_attn: 0 = 14x14 windows, 1 = global (both on
+ * tcgen05 / TMEM); operand_format as in b200sam_encoder_config */
+B200SAM_API int b200sam_encoder_attention(const void* qkv, const void* qkv_bias16, const void* rel_h16, const void* rel_w16,
+                              void* out, int batch, int heads, int hd, int global_attn, int operand_format,
                               void* stream);
 B200SAM_API int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, int w, const float* mean3_host,
-                                const float* std3_host, void* out_bf16, void* stream);
+                                const float* std3_host, void* out16, int operand_format, void* stream);
+/* In-run kernel timing for the bench's roofline block: between _start and _stop every launch of the tcgen05 GEMM
+ * (kind 0; work = 2 M N K; dims = M, N, K), the windowed (kind 1) and the global (kind 2) attention kernel (work =
+ * algorithmic FLOPs; dims = batch, heads, head dim) is bracketed by CUDA events on its own stream.  _stop synchronises
+ * on the recorded events and fills the HOST arrays (any may be NULL) with up to `capacity` records. */
+B200SAM_API int b200sam_timing_start(int capacity);
+B200SAM_API int b200sam_timing_stop(int* kinds_host, double* work_host, int* dims3_host, float* ms_host, int capacity,
+                        int* n_out_host);
 B200SAM_API int b200sam_linear_f32(const float* A, const float* A2, int a2_row_mod, const float* W, const float* bias,
                        const float* residual, float* out, int M, int N, int K, int act, void* stream);
 

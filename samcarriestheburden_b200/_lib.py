@@ -21,7 +21,13 @@ class B200SamError(RuntimeError):
 
 class EncoderConfig(C.Structure):
     _fields_ = [("embed_dim", C.c_int), ("depth", C.c_int), ("num_heads", C.c_int),
-                ("global_attn_mask", C.c_int), ("out_chans", C.c_int)]
+                ("global_attn_mask", C.c_int), ("out_chans", C.c_int), ("operand_format", C.c_int),
+                ("flags", C.c_int)]
+
+
+OPERAND_BF16, OPERAND_FP16 = 0, 1
+ENC_LN_FUSED = 1
+ABI_VERSION = 2
 
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -62,9 +68,14 @@ _PROTOTYPES = {
     "b200sam_ccl_select": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "b200sam_morph_flat": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200sam_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200sam_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200sam_gemm_ln_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200sam_gemm_ln_folded": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sam_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _i, _vp]),
-    "b200sam_encoder_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "b200sam_preprocess_patchify": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
+    "b200sam_encoder_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sam_preprocess_patchify": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp]),
+    "b200sam_timing_start": (_i, [_i]),
+    "b200sam_timing_stop": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "b200sam_linear_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
@@ -85,6 +96,9 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here == ABI drift between header and library
         fn.restype = res
         fn.argtypes = args
+    if lib.b200sam_abi_version() != ABI_VERSION:
+        raise B200SamError(f"{LIB_PATH} has ABI version {lib.b200sam_abi_version()}, this package needs {ABI_VERSION}: "
+                           "rebuild with `python -m samcarriestheburden_b200.build --force`")
     _lib = lib
     return lib
 
@@ -95,6 +109,37 @@ def check(rc: int, what: str = "") -> None:
         raise B200SamError(f"{what or 'b200sam call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
 
 
+def run(device, fn, *args, what: str = "") -> None:
+    """Call the stream-taking C-ABI entry point `fn(*args, stream)` with `device` current and torch's current stream
+    of THAT device as the last argument; raises B200SamError on a non-zero status."""
+    import torch
+    with torch.cuda.device(device):
+        check(fn(*args, torch.cuda.current_stream(device).cuda_stream), what)
+
+
+class KernelTiming:
+    """Context manager around b200sam_timing_start / _stop: CUDA-event durations of every tcgen05 GEMM / attention launch
+    issued inside the block, as a list of dicts {kind, work (FLOPs), dims, ms}."""
+    KINDS = {0: "gemm", 1: "window_attention", 2: "global_attention"}
+
+    def __init__(self, capacity: int = 1 << 16):
+        self.capacity = capacity
+        self.records = []
+
+    def __enter__(self):
+        check(load().b200sam_timing_start(self.capacity), "b200sam_timing_start")
+        return self
+
+    def __exit__(self, *exc):
+        n = self.capacity
+        kinds, work, dims, ms = (C.c_int * n)(), (C.c_double * n)(), (C.c_int * (3 * n))(), (C.c_float * n)()
+        cnt = C.c_int(0)
+        check(load().b200sam_timing_stop(kinds, work, dims, ms, n, C.byref(cnt)), "b200sam_timing_stop")
+        self.records = [{"kind": self.KINDS.get(kinds[i], str(kinds[i])), "work": work[i],
+                         "dims": (dims[3 * i], dims[3 * i + 1], dims[3 * i + 2]), "ms": ms[i]} for i in range(cnt.value)]
+        return False
+
+
 def ptr(t) -> int | None:
     """Device pointer of a torch tensor (None -> NULL)."""
     if t is None:
@@ -102,9 +147,18 @@ def ptr(t) -> int | None:
     return t.data_ptr()
 
 
-def current_stream() -> int:
+def current_stream(device=None) -> int:
+    """Handle of torch's current stream on `device` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(device):
+    """Context manager: make `device` the current CUDA device for the C-ABI calls inside it.  The library launches on
+    the current device (kernel attributes, SM count and descriptor caches are per device), so every wrapper enters this
+    with the device that owns its tensors (a model on cuda:1 works while cuda:0 is current)."""
+    import torch
+    return torch.cuda.device(device)
 
 
 def require_cuda(device=None):

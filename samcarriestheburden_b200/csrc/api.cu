@@ -5,6 +5,7 @@
 #include "decoder.h"
 #include "encoder.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace b200sam {
 namespace {
@@ -29,13 +30,14 @@ static EncoderConfig to_cfg(const b200sam_encoder_config* c) {
   EncoderConfig e;
   e.embed_dim = c->embed_dim; e.depth = c->depth; e.num_heads = c->num_heads;
   e.global_mask_lo = c->global_attn_mask; e.out_chans = c->out_chans;
+  e.operand_format = c->operand_format; e.flags = c->flags;
   return e;
 }
 
 extern "C" {
 
 const char* b200sam_last_error(void) { return get_last_error(); }
-int b200sam_abi_version(void) { return 1; }
+int b200sam_abi_version(void) { return 2; }
 
 int b200sam_encoder_weight_count(const b200sam_encoder_config* cfg) {
   if (!cfg) return -1;
@@ -198,41 +200,79 @@ int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_
   return morph_flat(in, n_planes, H, W, se, kh, kw, origin_y, origin_x, dilate, out, static_cast<cudaStream_t>(stream));
 }
 
-int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M, int N,
-                      int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_bf16, int max_ctas,
-                      void* stream) {
+static int gemm16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M, int N, int K,
+                  int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_16bit, int max_ctas, int f16,
+                  void* stream) {
   if (!A || !W || !out) { set_last_error("gemm: null argument"); return 2; }
   GemmArgs g;
   g.A = static_cast<const __nv_bfloat16*>(A); g.B = static_cast<const __nv_bfloat16*>(W); g.out = out;
   g.bias = bias; g.residual = residual; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldo = ldo; g.ldr = ldr;
-  g.res_row_mod = res_row_mod; g.gelu = gelu; g.out_bf16 = out_bf16; g.max_ctas = max_ctas;
+  g.res_row_mod = res_row_mod; g.gelu = gelu; g.out_kind = out_16bit ? (f16 ? 2 : 1) : 0; g.max_ctas = max_ctas;
+  g.op_f16 = f16;
+  return gemm_bf16_tn(g, static_cast<cudaStream_t>(stream));
+}
+int b200sam_gemm_bf16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M, int N,
+                      int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_bf16, int max_ctas,
+                      void* stream) {
+  return gemm16(A, W, out, bias, residual, M, N, K, lda, ldb, ldo, ldr, res_row_mod, gelu, out_bf16, max_ctas, 0, stream);
+}
+int b200sam_gemm_f16(const void* A, const void* W, void* out, const float* bias, const float* residual, int M, int N,
+                     int K, int lda, int ldb, int ldo, int ldr, int res_row_mod, int gelu, int out_f16, int max_ctas,
+                     void* stream) {
+  return gemm16(A, W, out, bias, residual, M, N, K, lda, ldb, ldo, ldr, res_row_mod, gelu, out_f16, max_ctas, 1, stream);
+}
+int b200sam_gemm_ln_residual(const void* A, const void* W, const float* bias, const float* residual, float* out,
+                             void* out16, float* rowstat_out, int M, int N, int K, int operand_format, void* stream) {
+  if (!A || !W || !out || !out16 || !rowstat_out) { set_last_error("gemm_ln_residual: null argument"); return 2; }
+  GemmArgs g;
+  g.A = static_cast<const __nv_bfloat16*>(A); g.B = static_cast<const __nv_bfloat16*>(W); g.out = out;
+  g.bias = bias; g.residual = residual; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldo = N; g.ldr = N;
+  g.res_row_mod = 0; g.gelu = 0; g.out_kind = 0; g.max_ctas = 0; g.op_f16 = operand_format == 1;
+  g.xh = out16; g.rowstat_out = rowstat_out;
+  return gemm_bf16_tn(g, static_cast<cudaStream_t>(stream));
+}
+int b200sam_gemm_ln_folded(const void* A, const void* W_folded, const float* bias_folded, const float* colsum,
+                           const float* rowstat_in, int nparts, float eps, void* out16, int M, int N, int K, int gelu,
+                           int operand_format, void* stream) {
+  if (!A || !W_folded || !bias_folded || !colsum || !rowstat_in || !out16) {
+    set_last_error("gemm_ln_folded: null argument");
+    return 2;
+  }
+  GemmArgs g;
+  g.A = static_cast<const __nv_bfloat16*>(A); g.B = static_cast<const __nv_bfloat16*>(W_folded); g.out = out16;
+  g.bias = bias_folded; g.residual = nullptr; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldo = N; g.ldr = 0;
+  g.res_row_mod = 0; g.gelu = gelu; g.op_f16 = operand_format == 1; g.out_kind = g.op_f16 ? 2 : 1; g.max_ctas = 0;
+  g.rowstat_in = rowstat_in; g.colsum = colsum; g.nparts_in = nparts; g.ln_dim = K; g.ln_eps = eps;
   return gemm_bf16_tn(g, static_cast<cudaStream_t>(stream));
 }
 int b200sam_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
-                      int out_bf16, void* stream) {
+                      int out_kind, void* stream) {
   if (!x || !gamma || !beta || !y) { set_last_error("layernorm: null argument"); return 2; }
-  return layernorm_rows(x, gamma, beta, eps, M, D, y, out_bf16, static_cast<cudaStream_t>(stream));
+  if (out_kind < 0 || out_kind > 2) { set_last_error("layernorm: out_kind %d (0 fp32, 1 bf16, 2 fp16)", out_kind); return 2; }
+  return layernorm_rows(x, gamma, beta, eps, M, D, y, out_kind, static_cast<cudaStream_t>(stream));
 }
-int b200sam_encoder_attention(const void* qkv, const void* qkv_bias_bf16, const void* rel_h_bf16,
-                              const void* rel_w_bf16, void* out, int batch, int heads, int hd, int global_attn,
+int b200sam_encoder_attention(const void* qkv, const void* qkv_bias16, const void* rel_h16, const void* rel_w16,
+                              void* out, int batch, int heads, int hd, int global_attn, int operand_format,
                               void* stream) {
   AttnArgs a;
-  a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.qkv_bias = static_cast<const __nv_bfloat16*>(qkv_bias_bf16);
-  a.rel_h = static_cast<const __nv_bfloat16*>(rel_h_bf16); a.rel_w = static_cast<const __nv_bfloat16*>(rel_w_bf16);
-  a.out = static_cast<__nv_bfloat16*>(out); a.B = batch; a.heads = heads; a.hd = hd;
-  // 0 = windows on tcgen05, 1 = global on tcgen05 (product paths); 2 / 3 = global / windows on mma.sync (A/B reference)
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.qkv_bias = static_cast<const __nv_bfloat16*>(qkv_bias16);
+  a.rel_h = static_cast<const __nv_bfloat16*>(rel_h16); a.rel_w = static_cast<const __nv_bfloat16*>(rel_w16);
+  a.out = static_cast<__nv_bfloat16*>(out); a.B = batch; a.heads = heads; a.hd = hd; a.f16 = operand_format == 1;
+  if (operand_format != 0 && operand_format != 1) { set_last_error("encoder_attention: operand_format %d", operand_format); return 2; }
   if (global_attn == 1) return global_attention_tc(a, static_cast<cudaStream_t>(stream));
-  if (global_attn == 2) return global_attention(a, static_cast<cudaStream_t>(stream));
-  if (global_attn == 3) return window_attention(a, static_cast<cudaStream_t>(stream));
-  if (global_attn == 4) return window_attention_tc2(a, static_cast<cudaStream_t>(stream));
-  if (global_attn == 5) return window_attention_tc3(a, static_cast<cudaStream_t>(stream));
-  return window_attention_tc(a, static_cast<cudaStream_t>(stream));
+  if (global_attn == 0) return window_attention_tc(a, static_cast<cudaStream_t>(stream));
+  set_last_error("encoder_attention: global_attn must be 0 (14x14 windows) or 1 (global), got %d", global_attn);
+  return 2;
 }
 int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, int w, const float* mean3,
-                                const float* std3, void* out_bf16, void* stream) {
-  if (!image || !mean3 || !std3 || !out_bf16) { set_last_error("preprocess: null argument"); return 2; }
-  return preprocess_patchify(image, is_u8, batch, h, w, mean3, std3, static_cast<__nv_bfloat16*>(out_bf16),
-                             static_cast<cudaStream_t>(stream));
+                                const float* std3, void* out16, int operand_format, void* stream) {
+  if (!image || !mean3 || !std3 || !out16) { set_last_error("preprocess: null argument"); return 2; }
+  return preprocess_patchify(image, is_u8, batch, h, w, mean3, std3, static_cast<__nv_bfloat16*>(out16),
+                             operand_format == 1, static_cast<cudaStream_t>(stream));
+}
+int b200sam_timing_start(int capacity) { return timing_start(capacity); }
+int b200sam_timing_stop(int* kinds_host, double* work_host, int* dims3_host, float* ms_host, int capacity, int* n_out_host) {
+  return timing_stop(kinds_host, work_host, dims3_host, ms_host, capacity, n_out_host);
 }
 int b200sam_linear_f32(const float* A, const float* A2, int a2_row_mod, const float* W, const float* bias,
                        const float* residual, float* out, int M, int N, int K, int act, void* stream) {

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tma.h"
+#include "launch.h"
 #include <type_traits>
 
 namespace b200sam {
@@ -103,7 +104,7 @@ struct TcParams {
   int reverse;  // 1: images last-to-first (the qkv GEMM that ran forward left the last images in L2)
 };
 
-template <int HD>
+template <int HD, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                       const __grid_constant__ CUtensorMap map_rh, const __grid_constant__ CUtensorMap map_rw,
@@ -170,6 +171,8 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   constexpr int NT = 4096 / TK;  // 64 key tiles
+  grid_dependency_wait();    // programmatic dependent launch: the qkv GEMM has completed past this line
+  grid_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -218,14 +221,14 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // ---- prologue 1: Tw_full[128 x 128] = Q . Rw^T  (columns 0..126 valid)
       for (int kk = 0; kk < NS; ++kk)
         umma_bf16_ss(tmem + 0, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
-                     make_smem_desc(skv + kk * L::Q_SLAB, 16, 256, SW32), make_idesc_bf16_f32_ex(128, 128, 0), kk > 0);
+                     make_smem_desc(skv + kk * L::Q_SLAB, 16, 256, SW32), make_idesc_op16_f32(128, 128, 0, F16), kk > 0);
       umma_commit(pre_full);
       mbar_wait(pre_done, 0);
       tcgen05_fence_after();
       // ---- prologue 2: Th_full[128 x 80] = Q . Rh[qh0 .. qh0+79]^T  (columns 0..64 used)
       for (int kk = 0; kk < NS; ++kk)
         umma_bf16_ss(tmem + 0, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
-                     make_smem_desc(skv + (NS + kk) * L::Q_SLAB, 16, 256, SW32), make_idesc_bf16_f32_ex(128, 80, 0),
+                     make_smem_desc(skv + (NS + kk) * L::Q_SLAB, 16, 256, SW32), make_idesc_op16_f32(128, 80, 0, F16),
                      kk > 0);
       umma_commit(pre_full);
       umma_commit(tab_free);
@@ -240,7 +243,7 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tcgen05_fence_after();
         for (int kk = 0; kk < NS; ++kk)
           umma_bf16_ss(tmem + COL_S, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
-                       make_smem_desc(kb + kk * L::KV_SLAB, 16, 256, SW32), make_idesc_bf16_f32_ex(128, TK, 0), kk > 0);
+                       make_smem_desc(kb + kk * L::KV_SLAB, 16, 256, SW32), make_idesc_op16_f32(128, TK, 0, F16), kk > 0);
         umma_commit(s_full);
         umma_commit(&k_empty[buf]);
       };
@@ -259,7 +262,7 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int ks = 0; ks < TK / 16; ++ks)
           umma_bf16_ss(tmem + COL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
                        make_smem_desc(vb + ks * 512, L::KV_SLAB, 256, SW32),
-                       make_idesc_bf16_f32_ex(128, HD, 1), (t > 0 || ks > 0) ? 1u : 0u);
+                       make_idesc_op16_f32(128, HD, 1, F16), (t > 0 || ks > 0) ? 1u : 0u);
         umma_commit(&v_empty[buf]);
         umma_commit(o_ready);
       }
@@ -394,10 +397,10 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B of bf16
         uint4 pk;
-        pk.x = pack_bf16x2(sv[c * 8 + 0], sv[c * 8 + 1]);
-        pk.y = pack_bf16x2(sv[c * 8 + 2], sv[c * 8 + 3]);
-        pk.z = pack_bf16x2(sv[c * 8 + 4], sv[c * 8 + 5]);
-        pk.w = pack_bf16x2(sv[c * 8 + 6], sv[c * 8 + 7]);
+        pk.x = pack_op16x2<F16>(sv[c * 8 + 0], sv[c * 8 + 1]);
+        pk.y = pack_op16x2<F16>(sv[c * 8 + 2], sv[c * 8 + 3]);
+        pk.z = pack_op16x2<F16>(sv[c * 8 + 4], sv[c * 8 + 5]);
+        pk.w = pack_op16x2<F16>(sv[c * 8 + 6], sv[c * 8 + 7]);
 #pragma unroll
         for (int j = 0; j < 8; j += 2) add2(ps[j], ps[j + 1], ps[j], ps[j + 1], sv[c * 8 + j], sv[c * 8 + j + 1]);
         *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
@@ -418,14 +421,14 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tmem_ld_32x32b_x16(tl + COL_O + c * 16, o);
       tmem_ld_wait();
       uint4 lo, hi4;
-      lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-      lo.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-      lo.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-      lo.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-      hi4.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-      hi4.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-      hi4.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-      hi4.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+      lo.x = pack_op16x2<F16>(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+      lo.y = pack_op16x2<F16>(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+      lo.z = pack_op16x2<F16>(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+      lo.w = pack_op16x2<F16>(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+      hi4.x = pack_op16x2<F16>(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+      hi4.y = pack_op16x2<F16>(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+      hi4.z = pack_op16x2<F16>(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+      hi4.w = pack_op16x2<F16>(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
       *reinterpret_cast<uint4*>(dst + c * 16) = lo;
       *reinterpret_cast<uint4*>(dst + c * 16 + 8) = hi4;
     }
@@ -481,7 +484,7 @@ struct WinParams {
   int reverse;  // 1: images last-to-first
 };
 
-template <int HD>
+template <int HD, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __grid_constant__ CUtensorMap map_q0814,
                       const __grid_constant__ CUtensorMap map_q1408, const __grid_constant__ CUtensorMap map_q0808,
@@ -548,6 +551,8 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  grid_dependency_wait();    // programmatic dependent launch: the qkv GEMM has completed past this line
+  grid_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -582,7 +587,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
       for (int mt = 0; mt < nmt; ++mt)
         for (int kk = 0; kk < NS; ++kk)
           umma_bf16_ss(tmem + mt * 64, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
-                       make_smem_desc(sp + kk * 2048, 16, 256, SW32), make_idesc_bf16_f32_ex(128, 64, 0), kk > 0);
+                       make_smem_desc(sp + kk * 2048, 16, 256, SW32), make_idesc_op16_f32(128, 64, 0, F16), kk > 0);
       umma_commit(pre_full);
       mbar_wait(pre_done, 0);
       mbar_wait(k_full, 0);
@@ -590,7 +595,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
       tcgen05_fence_after();
       auto issue_qk = [&](int g) {
         const int mt = g >> 2, kt = g & 3;
-        const uint32_t idesc = kt < 3 ? make_idesc_bf16_f32_ex(128, 64, 0) : make_idesc_bf16_f32_ex(128, 16, 0);
+        const uint32_t idesc = kt < 3 ? make_idesc_op16_f32(128, 64, 0, F16) : make_idesc_op16_f32(128, 16, 0, F16);
         for (int kk = 0; kk < NS; ++kk)
           umma_bf16_ss(tmem + WCOL_S, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
                        make_smem_desc(sk + kk * L::KV_SLAB + kt * 2048, 16, 256, SW32), idesc, kk > 0);
@@ -610,7 +615,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
         for (int ks = 0; ks < nks; ++ks)
           umma_bf16_ss(tmem + WCOL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
                        make_smem_desc(sv + kt * 2048 + ks * 512, L::KV_SLAB, 256, SW32),
-                       make_idesc_bf16_f32_ex(128, HD, 1), (kt > 0 || ks > 0) ? 1u : 0u);
+                       make_idesc_op16_f32(128, HD, 1, F16), (kt > 0 || ks > 0) ? 1u : 0u);
         umma_commit(o_ready);
       }
     }
@@ -773,10 +778,10 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
 #pragma unroll
         for (int c = 0; c < NK / 8; ++c) {
           uint4 pk;
-          pk.x = pack_bf16x2(sv[c * 8 + 0], sv[c * 8 + 1]);
-          pk.y = pack_bf16x2(sv[c * 8 + 2], sv[c * 8 + 3]);
-          pk.z = pack_bf16x2(sv[c * 8 + 4], sv[c * 8 + 5]);
-          pk.w = pack_bf16x2(sv[c * 8 + 6], sv[c * 8 + 7]);
+          pk.x = pack_op16x2<F16>(sv[c * 8 + 0], sv[c * 8 + 1]);
+          pk.y = pack_op16x2<F16>(sv[c * 8 + 2], sv[c * 8 + 3]);
+          pk.z = pack_op16x2<F16>(sv[c * 8 + 4], sv[c * 8 + 5]);
+          pk.w = pack_op16x2<F16>(sv[c * 8 + 6], sv[c * 8 + 7]);
 #pragma unroll
           for (int j = 0; j < 8; j += 2) add2(ps[j], ps[j + 1], ps[j], ps[j + 1], sv[c * 8 + j], sv[c * 8 + j + 1]);
           *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = pk;
@@ -806,14 +811,14 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
         tmem_ld_wait();
         if (qi < nq) {
           uint4 lo, hi4;
-          lo.x = pack_bf16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-          lo.y = pack_bf16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-          lo.z = pack_bf16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-          lo.w = pack_bf16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-          hi4.x = pack_bf16x2(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-          hi4.y = pack_bf16x2(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-          hi4.z = pack_bf16x2(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-          hi4.w = pack_bf16x2(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+          lo.x = pack_op16x2<F16>(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+          lo.y = pack_op16x2<F16>(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+          lo.z = pack_op16x2<F16>(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+          lo.w = pack_op16x2<F16>(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+          hi4.x = pack_op16x2<F16>(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+          hi4.y = pack_op16x2<F16>(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+          hi4.z = pack_op16x2<F16>(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+          hi4.w = pack_op16x2<F16>(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
           *reinterpret_cast<uint4*>(dst + c * 16) = lo;
           *reinterpret_cast<uint4*>(dst + c * 16 + 8) = hi4;
         }
@@ -831,7 +836,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
   }
 }
 
-template <int HD>
+template <int HD, bool F16>
 int launch_win_tc(const AttnArgs& a, cudaStream_t stream) {
   using L = WinLayout<HD>;
   const int D = a.heads * HD;
@@ -842,24 +847,21 @@ int launch_win_tc(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16_grid4d(&m0808, a.qkv, a.B, 3 * D, 8, 8)) return 1;
   if (make_tmap_bf16(&mrh, a.rel_h, 27, HD, HD, 32, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
   if (make_tmap_bf16(&mrw, a.rel_w, 27, HD, HD, 32, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-  static bool once = false;
-  if (!once) {
-    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            L::BYTES));
-    once = true;
-  }
+  auto kernel = window_attn_tc_kernel<HD, F16>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), L::BYTES)) return rc;
   WinParams p;
   p.out = a.out;
   p.qkv_bias = a.qkv_bias;
   p.heads = a.heads;
   p.reverse = a.reverse;
   dim3 grid(25, a.heads, a.B);
-  window_attn_tc_kernel<HD><<<grid, TC_THREADS, L::BYTES, stream>>>(m1414, m0814, m1408, m0808, mrh, mrw, p);
-  B200SAM_CHECK_CUDA(cudaGetLastError());
+  // algorithmic FLOPs: 4 * heads * T * 196 * hd * (1 + 14/196) per image
+  TimedLaunch timed(TIMED_WINDOW_ATTN, 4.0 * a.heads * 4096.0 * 196.0 * HD * (1.0 + 14.0 / 196.0) * a.B, a.B, a.heads, HD, stream);
+  B200SAM_CHECK_CUDA(launch_kernel(kernel, grid, dim3(TC_THREADS), L::BYTES, stream, m1414, m0814, m1408, m0808, mrh, mrw, p));
   return 0;
 }
 
-template <int HD>
+template <int HD, bool F16>
 int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   using L = TcLayout<HD>;
   const int D = a.heads * HD;
@@ -869,19 +871,16 @@ int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16(&mkv, a.qkv, rows, 3 * D, 3 * D, TK, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
   if (make_tmap_bf16(&mrh, a.rel_h, 127, HD, HD, TQ, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
   if (make_tmap_bf16(&mrw, a.rel_w, 127, HD, HD, TQ, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-  static bool once = false;
-  if (!once) {
-    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(global_attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            L::BYTES));
-    once = true;
-  }
+  auto kernel = global_attn_tc_kernel<HD, F16>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), L::BYTES)) return rc;
   TcParams p;
   p.out = a.out;
   p.heads = a.heads;
   p.reverse = a.reverse;
   dim3 grid(4096 / TQ, a.heads, a.B);
-  global_attn_tc_kernel<HD><<<grid, TC_THREADS, L::BYTES, stream>>>(mq, mkv, mrh, mrw, p);
-  B200SAM_CHECK_CUDA(cudaGetLastError());
+  // algorithmic FLOPs: 4 * heads * T * T * hd * (1 + 64/4096) per image
+  TimedLaunch timed(TIMED_GLOBAL_ATTN, 4.0 * a.heads * 4096.0 * 4096.0 * HD * (1.0 + 64.0 / 4096.0) * a.B, a.B, a.heads, HD, stream);
+  B200SAM_CHECK_CUDA(launch_kernel(kernel, grid, dim3(TC_THREADS), L::BYTES, stream, mq, mkv, mrh, mrw, p));
   return 0;
 }
 
@@ -891,14 +890,16 @@ int window_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   B200SAM_REQUIRE(a.B > 0 && a.heads > 0 && (a.hd == 64 || a.hd == 80),
                   "window_attention_tc: unsupported shape B=%d heads=%d hd=%d", a.B, a.heads, a.hd);
   B200SAM_REQUIRE(a.qkv && a.qkv_bias && a.rel_h && a.rel_w && a.out, "window_attention_tc: null pointer argument");
-  return a.hd == 80 ? launch_win_tc<80>(a, stream) : launch_win_tc<64>(a, stream);
+  if (a.f16) return a.hd == 80 ? launch_win_tc<80, true>(a, stream) : launch_win_tc<64, true>(a, stream);
+  return a.hd == 80 ? launch_win_tc<80, false>(a, stream) : launch_win_tc<64, false>(a, stream);
 }
 
 int global_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   B200SAM_REQUIRE(a.B > 0 && a.heads > 0 && (a.hd == 64 || a.hd == 80),
                   "global_attention_tc: unsupported shape B=%d heads=%d hd=%d", a.B, a.heads, a.hd);
   B200SAM_REQUIRE(a.qkv && a.rel_h && a.rel_w && a.out, "global_attention_tc: null pointer argument");
-  return a.hd == 80 ? launch_tc<80>(a, stream) : launch_tc<64>(a, stream);
+  if (a.f16) return a.hd == 80 ? launch_tc<80, true>(a, stream) : launch_tc<64, true>(a, stream);
+  return a.hd == 80 ? launch_tc<80, false>(a, stream) : launch_tc<64, false>(a, stream);
 }
 
 }  // namespace b200sam

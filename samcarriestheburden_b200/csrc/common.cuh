@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -44,6 +45,30 @@ B200SAM_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// fp16 pair, round to nearest even, finite saturation (|x| > 65504 -> +-65504 instead of inf)
+B200SAM_DEVINL uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit MMA operand formats of the encoder (tcgen05 kind::f16 takes either at the same rate): bf16 keeps the fp32
+// exponent range with 8 significand bits, fp16 has 11 significand bits (8 x finer rounding) and a 6e-5 .. 65504 normal
+// range.  The ViT encoder's operands (LayerNorm outputs, q/k/v, softmax numerators, GELU outputs, weights) fit fp16's
+// range, and mask parity at Dice >= 0.999 needs its precision, so fp16 is the encoder default.
+template <bool F16>
+B200SAM_DEVINL uint32_t pack_op16x2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining; `griddepcontrol.wait` blocks until the predecessor grid has COMPLETED and its memory is
+// visible, so everything above it (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.
+// `launch_dependents` lets the successor's CTAs be scheduled as soon as every CTA of this grid has issued it (or exited).
+// Both are no-ops in a kernel launched without the attribute.
+B200SAM_DEVINL void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+B200SAM_DEVINL void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- packed fp32 pairs (sm_100 FFMA2)
 // (d0, d1) = a * (b0, b1) + (c0, c1): one issue slot for two fused multiply-adds (same rounding as two fmaf)
@@ -212,6 +237,11 @@ B200SAM_DEVINL uint64_t make_smem_desc(uint32_t smem_addr_bytes, uint32_t lbo_by
 // kind::f16 instruction descriptor with selectable B major-ness (0 = K-major, 1 = MN-major)
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32_ex(int M, int N, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major & 1) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// the same with the A / B operand format as a parameter: bits 7-9 (A) and 10-12 (B) = 0 for fp16, 1 for bf16
+__host__ __device__ constexpr uint32_t make_idesc_op16_f32(int M, int N, int b_mn_major, bool f16) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (static_cast<uint32_t>(b_mn_major & 1) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 

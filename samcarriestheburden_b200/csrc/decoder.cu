@@ -142,7 +142,7 @@ int tc_lin(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* b, con
   GemmArgs g;
   g.A = As; g.B = Ws; g.out = out; g.bias = b; g.residual = res;
   g.M = M; g.N = N; g.K = 3 * K; g.lda = 2 * K; g.ldb = 3 * K; g.ldo = N; g.ldr = N; g.res_row_mod = res_row_mod;
-  g.gelu = gelu; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * K;
+  g.gelu = gelu; g.out_kind = 0; g.max_ctas = 0; g.a_wrap = 2 * K;
   return gemm_bf16_tn(g, s);
 }
 
@@ -351,7 +351,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     GemmArgs g;
     g.A = w.sb; g.B = d->ws_up1; g.out = w.sa; g.bias = U[1]; g.residual = nullptr;
     g.M = Mi; g.N = 256; g.K = 3 * 256; g.lda = 2 * 256; g.ldb = 3 * 256; g.ldo = 0; g.ldr = 0; g.res_row_mod = 0;
-    g.gelu = 0; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * 256;
+    g.gelu = 0; g.out_kind = 0; g.max_ctas = 0; g.a_wrap = 2 * 256;
     g.epi_mode = 1; g.aux0 = U[2]; g.aux1 = U[3];
     TRY(gemm_bf16_tn(g, s));                                                           // ConvT 256->64 + LN2d + GELU
   }
@@ -359,7 +359,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     GemmArgs g;
     g.A = w.sa; g.B = d->ws_up2; g.out = a.low_res_out; g.bias = U[5]; g.residual = nullptr;
     g.M = Mi * 4; g.N = 128; g.K = 3 * 64; g.lda = 2 * 64; g.ldb = 3 * 64; g.ldo = 0; g.ldr = 0; g.res_row_mod = 0;
-    g.gelu = 1; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * 64;
+    g.gelu = 1; g.out_kind = 0; g.max_ctas = 0; g.a_wrap = 2 * 64;
     g.epi_mode = 2; g.aux0 = w.hyper; g.tok0 = tok0; g.ntok = ntok;
     TRY(gemm_bf16_tn(g, s));                                                           // ConvT 64->32 + GELU + mask dot
   }

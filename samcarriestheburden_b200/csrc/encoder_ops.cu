@@ -11,7 +11,7 @@ namespace {
 // Reference: Sam.preprocess (segment_anything/modeling/sam.py:164-174) = (x - mean) / std, zero pad to
 // 1024^2 AFTER normalisation; PatchEmbed conv k16/s16 (image_encoder.py:387-395) becomes a GEMM whose
 // A operand row = token (py*64+px) and column = c*256 + ky*16 + kx.
-template <bool IS_U8>
+template <bool IS_U8, bool F16>
 __global__ void __launch_bounds__(256) preprocess_patchify_kernel(const void* __restrict__ img, int B, int h, int w,
                                                                   float m0, float m1, float m2, float s0, float s1,
                                                                   float s2, __nv_bfloat16* __restrict__ out) {
@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(256) preprocess_patchify_kernel(const void* __
       }
     }
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
+    o.x = pack_op16x2<F16>(v[0], v[1]);
+    o.y = pack_op16x2<F16>(v[2], v[3]);
+    o.z = pack_op16x2<F16>(v[4], v[5]);
+    o.w = pack_op16x2<F16>(v[6], v[7]);
     *reinterpret_cast<uint4*>(out + tok * 768 + g * 8) = o;
   }
 }
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) preprocess_patchify_kernel(const void* __
 // ------------------------------------------------------------------ LayerNorm over rows
 // One warp per row, the row lives in registers (D <= 1280, D % 128 == 0): mean, then centred variance
 // (two-pass, fp32) like torch's CPU kernel; eps inside the sqrt (image_encoder.py:168,180 via nn.LayerNorm).
-template <int NV, bool OUT_BF16>
+template <int NV, int OUT_KIND>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int M, int D,
@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
     o.z = (v[i].z - mean) * rstd * g.z + b.z;
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if constexpr (OUT_BF16) {
+    if constexpr (OUT_KIND != 0) {
       uint2 p;
-      p.x = pack_bf16x2(o.x, o.y);
-      p.y = pack_bf16x2(o.z, o.w);
+      p.x = pack_op16x2<OUT_KIND == 2>(o.x, o.y);
+      p.y = pack_op16x2<OUT_KIND == 2>(o.z, o.w);
       reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + static_cast<size_t>(warp) * D)[lane + 32 * i] = p;
     } else {
       reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + static_cast<size_t>(warp) * D)[lane + 32 * i] = o;
@@ -110,14 +110,16 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 }
 
 template <int NV>
-int launch_ln(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y, int out_bf16,
+int launch_ln(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y, int out_kind,
               cudaStream_t stream, int reverse) {
   const int warps_per_block = 8;
   const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  if (out_bf16)
-    layernorm_rows_kernel<NV, true><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y, reverse);
+  if (out_kind == 2)
+    layernorm_rows_kernel<NV, 2><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y, reverse);
+  else if (out_kind == 1)
+    layernorm_rows_kernel<NV, 1><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y, reverse);
   else
-    layernorm_rows_kernel<NV, false><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y, reverse);
+    layernorm_rows_kernel<NV, 0><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, M, D, y, reverse);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -179,11 +181,14 @@ __global__ void __launch_bounds__(256) layernorm_to_nchw_kernel(const float* __r
     out[(static_cast<size_t>(b) * C + c) * 4096 + t0 + lane] = tile[c * 33 + lane];
 }
 
-__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                          size_t n) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    out[i] = __float2bfloat16_rn(in[i]);
+template <bool F16>
+__global__ void __launch_bounds__(256) f32_to_op16_kernel(const float* __restrict__ in, uint32_t* __restrict__ out,
+                                                          size_t npairs) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < npairs;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float2 v = reinterpret_cast<const float2*>(in)[i];
+    out[i] = pack_op16x2<F16>(v.x, v.y);
+  }
 }
 
 inline int grid_for(size_t total, int block) {
@@ -195,22 +200,21 @@ inline int grid_for(size_t total, int block) {
 }  // namespace
 
 int preprocess_patchify(const void* img, int is_u8, int B, int h, int w, const float* mean3, const float* std3,
-                        __nv_bfloat16* out, cudaStream_t stream) {
+                        __nv_bfloat16* out, int out_f16, cudaStream_t stream) {
   B200SAM_REQUIRE(B > 0 && h > 0 && w > 0 && h <= 1024 && w <= 1024, "preprocess: bad shape B=%d h=%d w=%d", B, h, w);
   const size_t total = static_cast<size_t>(B) * 4096 * 96;
   const int grid = grid_for(total, 256);
-  if (is_u8)
-    preprocess_patchify_kernel<true><<<grid, 256, 0, stream>>>(img, B, h, w, mean3[0], mean3[1], mean3[2], std3[0],
-                                                               std3[1], std3[2], out);
-  else
-    preprocess_patchify_kernel<false><<<grid, 256, 0, stream>>>(img, B, h, w, mean3[0], mean3[1], mean3[2], std3[0],
-                                                                std3[1], std3[2], out);
+  using KernelFn = void (*)(const void*, int, int, int, float, float, float, float, float, float, __nv_bfloat16*);
+  static const KernelFn table[2][2] = {{preprocess_patchify_kernel<false, false>, preprocess_patchify_kernel<false, true>},
+                                       {preprocess_patchify_kernel<true, false>, preprocess_patchify_kernel<true, true>}};
+  table[is_u8 ? 1 : 0][out_f16 ? 1 : 0]<<<grid, 256, 0, stream>>>(img, B, h, w, mean3[0], mean3[1], mean3[2], std3[0],
+                                                                   std3[1], std3[2], out);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int layernorm_rows(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
-                   int out_bf16, cudaStream_t stream, int reverse) {
+                   int out_bf16, cudaStream_t stream, int reverse) {  // out_bf16 = out_kind: 0 fp32, 1 bf16, 2 fp16
   B200SAM_REQUIRE(M > 0 && D % 128 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 128 and <= 2048", D);
   switch (D / 128) {
     case 1: return launch_ln<1>(x, gamma, beta, eps, M, D, y, out_bf16, stream, reverse);
@@ -242,9 +246,13 @@ int layernorm_to_nchw(const float* x, const float* gamma, const float* beta, flo
   return 0;
 }
 
-int f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream) {
+int f32_to_op16(const float* in, __nv_bfloat16* out, size_t n, int out_f16, cudaStream_t stream) {
   if (n == 0) return 0;
-  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(in, out, n);
+  B200SAM_REQUIRE(n % 2 == 0, "f32_to_op16: element count must be even");
+  if (out_f16)
+    f32_to_op16_kernel<true><<<grid_for(n / 2, 256), 256, 0, stream>>>(in, reinterpret_cast<uint32_t*>(out), n / 2);
+  else
+    f32_to_op16_kernel<false><<<grid_for(n / 2, 256), 256, 0, stream>>>(in, reinterpret_cast<uint32_t*>(out), n / 2);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -24,6 +24,19 @@ struct EpiParams {
   const float* aux0;  // mode 1: LN gamma [64];  mode 2: hyper [prompts, 4, 32]
   const float* aux1;  // mode 1: LN beta [64]
   int tok0, ntok;     // mode 2: mask tokens tok0 .. tok0 + ntok - 1
+  // ---- LayerNorm folded into the GEMMs around it (image_encoder.py:168,180):
+  // producer (fp32 out = the residual stream): also write a 16-bit copy `xh` of out (pitch ldo; the next GEMM's A operand)
+  // and per-row partial (sum, sum of squares) of out over each 128-column part: rowstat_out [M, ceil(N/128), 2]
+  void* xh;
+  float* rowstat_out;
+  // consumer (16-bit out): out = rstd * (acc - mean * colsum[n]) + bias[n] with (mean, rstd) of the A operand's rows from
+  // rowstat_in [M, nparts_in, 2] (parts summed in index order: deterministic), colsum[n] = sum_k W'[n,k] of the
+  // gamma-scaled 16-bit weights, bias[n] = beta . W[n,:] + b[n]
+  const float* rowstat_in;
+  const float* colsum;
+  int nparts_in;
+  float ln_inv_d, ln_eps;
+  int f16;  // 16-bit tensors written by the epilogue (out, xh) are fp16 instead of bf16
 };
 
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erfc(|z|) from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
@@ -54,19 +67,43 @@ B200SAM_DEVINL float gelu_erf(float x) {
 
 
 constexpr int EPI_STAGE_BYTES = 32 * 16 * 4;  // [32 rows][16 words] per warp, XOR-swizzled
-constexpr int EPI_BIAS_BYTES = 128 * 4;       // 128 columns per warp
+constexpr int EPI_BIAS_BYTES = 2 * 128 * 4;   // 128 columns per warp: bias | colsum (LayerNorm folding)
+
+struct RowLN {
+  float rstd;  // 1 when LayerNorm is not folded into this GEMM
+  float nmr;   // -rstd * mean (0 when not folded)
+};
 
 // before the accumulator is ready: stage the bias slice and pull the residual block towards L2
-template <bool OUT_BF16>
-B200SAM_DEVINL void epilogue_prefetch(const EpiParams& ep, int M, int N, int row_base, int n0, float* sbias, int lane) {
+template <int OUT_KIND>
+B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int row_base, int n0, float* sbias, int lane) {
       // stage this warp's 128 bias values (zero when absent / out of range)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = n0 + lane + 32 * i;
     sbias[lane + 32 * i] = (ep.bias != nullptr && c < N) ? __ldg(ep.bias + c) : 0.0f;
+    if (ep.colsum != nullptr) sbias[128 + lane + 32 * i] = c < N ? __ldg(ep.colsum + c) : 0.0f;
   }
   __syncwarp();
-  if constexpr (!OUT_BF16) {
+  RowLN ln{1.0f, 0.0f};
+  if constexpr (OUT_KIND != 0) {
+    // folded LayerNorm: (mean, rstd) of this thread's row from the producer's per-part partial sums
+    const int prow = row_base + lane;
+    if (ep.rowstat_in != nullptr && prow < M) {
+      const float2* st = reinterpret_cast<const float2*>(ep.rowstat_in) + static_cast<size_t>(prow) * ep.nparts_in;
+      float s1 = 0.0f, s2 = 0.0f;
+      for (int i = 0; i < ep.nparts_in; ++i) {
+        const float2 t = st[i];
+        s1 += t.x;
+        s2 += t.y;
+      }
+      const float mean = s1 * ep.ln_inv_d;
+      const float var = fmaxf(fmaf(-mean, mean, s2 * ep.ln_inv_d), 0.0f);
+      ln.rstd = 1.0f / sqrtf(var + ep.ln_eps);
+      ln.nmr = -ln.rstd * mean;
+    }
+  }
+  if constexpr (OUT_KIND == 0) {
     // pull this warp's 32 x 128 residual block towards L2 while the MMAs of the tile are still running
     const int prow = row_base + lane;
     if (ep.residual != nullptr && prow < M) {
@@ -79,17 +116,20 @@ B200SAM_DEVINL void epilogue_prefetch(const EpiParams& ep, int M, int N, int row
       }
     }
   }
+  return ln;
 }
 
 // after tmem_full: drain + store.  taddr0 = TMEM address of (this warp's lane quadrant, first of its 128 columns)
-template <bool OUT_BF16>
+template <int OUT_KIND>
 B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_base, int n0, uint32_t taddr0,
-                                   uint32_t* stg, const float* sbias, int lane) {
+                                   uint32_t* stg, const float* sbias, int lane, const RowLN ln) {
   const int wsw = (lane >> 1) & 3;  // write swizzle of this thread's row
   const int rsub = lane >> 2;       // transposed read: row within a group of 8
   const int rq = lane & 3;          // transposed read: 16 B quad within the 64 B row segment
-      if constexpr (OUT_BF16) {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+      if constexpr (OUT_KIND != 0) {
+    constexpr bool F16 = OUT_KIND == 2;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);  // 16-bit elements (bf16 or fp16)
+    const bool fold = ep.colsum != nullptr;
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns = 16 packed words per row
       uint32_t r[32];
@@ -97,21 +137,35 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // 16 B quad j = columns 8j .. 8j+7
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j);
-        const float4 b1 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j + 4);
-        float v[8] = {__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y,
-                      __uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w,
-                      __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
-                      __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+        float4 b0 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j);
+        float4 b1 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j + 4);
+        float v[8];
+        if (fold) {  // rstd * (acc - mean * colsum) + bias
+          const float4 c0 = *reinterpret_cast<const float4*>(sbias + 128 + ch * 32 + 8 * j);
+          const float4 c1 = *reinterpret_cast<const float4*>(sbias + 128 + ch * 32 + 8 * j + 4);
+          b0.x = fmaf(ln.nmr, c0.x, b0.x); b0.y = fmaf(ln.nmr, c0.y, b0.y);
+          b0.z = fmaf(ln.nmr, c0.z, b0.z); b0.w = fmaf(ln.nmr, c0.w, b0.w);
+          b1.x = fmaf(ln.nmr, c1.x, b1.x); b1.y = fmaf(ln.nmr, c1.y, b1.y);
+          b1.z = fmaf(ln.nmr, c1.z, b1.z); b1.w = fmaf(ln.nmr, c1.w, b1.w);
+          v[0] = fmaf(__uint_as_float(r[8 * j + 0]), ln.rstd, b0.x); v[1] = fmaf(__uint_as_float(r[8 * j + 1]), ln.rstd, b0.y);
+          v[2] = fmaf(__uint_as_float(r[8 * j + 2]), ln.rstd, b0.z); v[3] = fmaf(__uint_as_float(r[8 * j + 3]), ln.rstd, b0.w);
+          v[4] = fmaf(__uint_as_float(r[8 * j + 4]), ln.rstd, b1.x); v[5] = fmaf(__uint_as_float(r[8 * j + 5]), ln.rstd, b1.y);
+          v[6] = fmaf(__uint_as_float(r[8 * j + 6]), ln.rstd, b1.z); v[7] = fmaf(__uint_as_float(r[8 * j + 7]), ln.rstd, b1.w);
+        } else {
+          v[0] = __uint_as_float(r[8 * j + 0]) + b0.x; v[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
+          v[2] = __uint_as_float(r[8 * j + 2]) + b0.z; v[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
+          v[4] = __uint_as_float(r[8 * j + 4]) + b1.x; v[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
+          v[6] = __uint_as_float(r[8 * j + 6]) + b1.z; v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
+        }
         if (ep.gelu) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = gelu_erf(v[k]);
         }
         uint4 pk;
-        pk.x = pack_bf16x2(v[0], v[1]);
-        pk.y = pack_bf16x2(v[2], v[3]);
-        pk.z = pack_bf16x2(v[4], v[5]);
-        pk.w = pack_bf16x2(v[6], v[7]);
+        pk.x = pack_op16x2<F16>(v[0], v[1]);
+        pk.y = pack_op16x2<F16>(v[2], v[3]);
+        pk.z = pack_op16x2<F16>(v[4], v[5]);
+        pk.w = pack_op16x2<F16>(v[6], v[7]);
         *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ wsw) << 2)) = pk;
       }
       __syncwarp();
@@ -145,6 +199,10 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
     };
     float4 rbuf[2][4];
     load_half(0, rbuf[0]);
+    // LayerNorm folding: 16-bit copy of the result + (sum, sum of squares) of this warp's 128 columns of every row
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ep.xh);
+    const bool stats = ep.rowstat_out != nullptr;
+    float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns, each written as 2 halves of 16
       uint32_t r[32];
@@ -171,9 +229,33 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
           if (ep.gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
           const float4 rs = rbuf[hf][it];
           v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
-          if (row < M && col < N) *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ep.ldo + col) = v;
+          if (row < M && col < N) {
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ep.ldo + col) = v;
+            if (xh != nullptr) {
+              uint2 h;
+              if (ep.f16) { h.x = pack_f16x2(v.x, v.y); h.y = pack_f16x2(v.z, v.w); }
+              else { h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w); }
+              *reinterpret_cast<uint2*>(xh + static_cast<size_t>(row) * ep.ldo + col) = h;
+            }
+            if (stats) {
+              st1[it] += (v.x + v.y) + (v.z + v.w);
+              st2[it] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, st2[it]))));
+            }
+          }
         }
         __syncwarp();
+      }
+    }
+    if (stats) {  // the 4 lanes of a row (rq = 0..3) hold 32 columns each: combine, lane rq == 0 writes the part
+      const int nparts = (N + 127) >> 7, part = n0 >> 7;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        float a = st1[it], b = st2[it];
+        a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+        const int row = row_base + it * 8 + rsub;
+        if (rq == 0 && row < M && n0 < N)
+          reinterpret_cast<float2*>(ep.rowstat_out)[static_cast<size_t>(row) * nparts + part] = make_float2(a, b);
       }
     }
   }

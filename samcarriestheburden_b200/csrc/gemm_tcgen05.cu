@@ -14,6 +14,7 @@
 #include "kernels.h"
 #include "tma.h"
 #include "gemm_epilogue.cuh"
+#include "launch.h"
 
 namespace b200sam {
 
@@ -51,10 +52,15 @@ constexpr uint32_t TMEM_COLS = 512;
 // (ky, kx) is the SAME 2-D box shifted by (ky-1) * conv_wp + (kx-1) rows: no im2col matrix is ever written.  K runs over
 // (segment hi|lo|hi, tap, channel block) to match the [hi | hi | lo] tap-major weights; rows outside the tensor are
 // zero-filled by TMA (they only feed border rows, which the consumers skip).
-template <bool OUT_BF16, int BN_EFF>
+// OUT_KIND: 0 = fp32 output (+ residual), 1 = bf16, 2 = fp16 (16-bit outputs are the next GEMM's / attention's operand).
+// op_f16: the A / B operands are fp16 instead of bf16 (same tcgen05 kind::f16 instruction, other format bits).
+// pdl: launched with programmatic stream serialisation: everything up to `griddepcontrol.wait` (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the tail of the previous kernel in the stream.
+template <int OUT_KIND, int BN_EFF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    EpiParams ep, int M, int N, int K, int a_wrap, int conv_cin, int conv_wp, int reverse_m) {
+                    EpiParams ep, int M, int N, int K, int a_wrap, int conv_cin, int conv_wp, int reverse_m,
+                    int op_f16) {
   // SWIZZLE_128B tiles need 1024 B alignment.  The alignment is requested on the symbol (not by rounding the
   // pointer through an integer): pointer arithmetic through uintptr_t makes the compiler lose the shared
   // state space and emit generic LD/ST (L1TEX path, long-scoreboard latency) for every staging access.
@@ -101,6 +107,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  grid_dependency_wait();    // no global memory of the previous kernel is touched above this line
+  grid_launch_dependents();  // the next kernel's CTAs may take SMs as ours retire (they block in their own wait)
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
@@ -135,7 +143,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN_EFF);
+      const uint32_t idesc = make_idesc_op16_f32(BM, BN_EFF, 0, op_f16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -184,14 +192,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM_T + (TALL ? half * 128 : 0);
       const int n0 = (tile % num_n) * BN + (TALL ? 0 : half * 128);
       const int row_base = m0 + quad * 32;
-      epilogue_prefetch<OUT_BF16>(ep, M, N, row_base, n0, sbias, lane);
+      const RowLN ln = epilogue_prefetch<OUT_KIND>(ep, M, N, row_base, n0, sbias, lane);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                               static_cast<uint32_t>(as * BN + half * 128);
       if (ep.mode == 1) epilogue_ln64_split(ep, M, row_base, n0, taddr0, sbias, lane);
       else if (ep.mode == 2) epilogue_gelu_dot(ep, M, row_base, taddr0, sbias, lane);
-      else epilogue_store<OUT_BF16>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane);
+      else epilogue_store<OUT_KIND>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -227,6 +235,15 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   B200SAM_REQUIRE(g.conv_cin == 0 || (g.conv_cin % BK == 0 && g.K == 27 * g.conv_cin && g.conv_wp >= 3 &&
                                       g.lda >= 2 * g.conv_cin && g.a_wrap == 0),
                   "gemm: bad implicit-convolution configuration (cin=%d, K=%d, wp=%d)", g.conv_cin, g.K, g.conv_wp);
+  B200SAM_REQUIRE(g.xh == nullptr || (g.out_kind == 0 && (reinterpret_cast<uintptr_t>(g.xh) & 7) == 0 && g.ldo % 4 == 0),
+                  "gemm: the 16-bit copy needs an fp32 output, 8-byte alignment and ldo %% 4 == 0");
+  B200SAM_REQUIRE(g.rowstat_out == nullptr || (g.out_kind == 0 && g.epi_mode == 0),
+                  "gemm: row statistics are produced by the fp32 epilogue only");
+  B200SAM_REQUIRE((g.rowstat_in == nullptr) == (g.colsum == nullptr) &&
+                      (g.rowstat_in == nullptr || (g.out_kind != 0 && g.epi_mode == 0 && g.nparts_in > 0 && g.ln_dim > 0)),
+                  "gemm: folded LayerNorm needs rowstat_in + colsum + nparts_in + ln_dim and a 16-bit output");
+  B200SAM_REQUIRE(g.out_kind >= 0 && g.out_kind <= 2 && (g.out_kind == 0 || (g.out_kind == 2) == (g.op_f16 != 0)),
+                  "gemm: a 16-bit output has the operands' format (out_kind=%d, op_f16=%d)", g.out_kind, g.op_f16);
   const bool narrow = g.N <= 128;
   CUtensorMap ta, tb;
   const int a_cols = g.conv_cin > 0 ? 2 * g.conv_cin : (g.a_wrap > 0 ? g.a_wrap : g.K);
@@ -246,25 +263,32 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   ep.aux1 = g.aux1;
   ep.tok0 = g.tok0;
   ep.ntok = g.ntok;
+  ep.xh = g.xh;
+  ep.rowstat_out = g.rowstat_out;
+  ep.rowstat_in = g.rowstat_in;
+  ep.colsum = g.colsum;
+  ep.nparts_in = g.nparts_in;
+  ep.ln_inv_d = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.0f;
+  ep.ln_eps = g.ln_eps;
+  ep.f16 = g.op_f16;
   B200SAM_REQUIRE(g.epi_mode == 0 || (g.epi_mode == 1 && g.N == 256 && g.aux0 && g.aux1) ||
                       (g.epi_mode == 2 && g.N == 128 && g.M % 16384 == 0 && g.aux0 && g.ntok >= 1 && g.ntok <= 3),
                   "gemm: bad fused-epilogue configuration (mode %d, M=%d, N=%d)", g.epi_mode, g.M, g.N);
+  B200SAM_REQUIRE(g.epi_mode == 0 || g.op_f16 == 0, "gemm: the fused decoder epilogues are bf16 only");
   const int bm_t = narrow ? 2 * BM : BM;
   const int tiles = ((g.M + bm_t - 1) / bm_t) * ((g.N + BN - 1) / BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    B200SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    attr_set = true;
-  }
-  auto kernel = g.out_bf16 ? (narrow ? gemm_bf16_tn_kernel<true, 128> : gemm_bf16_tn_kernel<true, 256>)
-                           : (narrow ? gemm_bf16_tn_kernel<false, 128> : gemm_bf16_tn_kernel<false, 256>);
-  kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, ep, g.M, g.N, g.K, g.a_wrap, g.conv_cin, g.conv_wp, g.reverse_m);
-  B200SAM_CHECK_CUDA(cudaGetLastError());
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int, int, int, int);
+  static const KernelFn table[3][2] = {
+      {gemm_bf16_tn_kernel<0, 256>, gemm_bf16_tn_kernel<0, 128>},
+      {gemm_bf16_tn_kernel<1, 256>, gemm_bf16_tn_kernel<1, 128>},
+      {gemm_bf16_tn_kernel<2, 256>, gemm_bf16_tn_kernel<2, 128>}};
+  KernelFn kernel = table[g.out_kind][narrow ? 1 : 0];
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), GEMM_SMEM_BYTES)) return rc;
+  TimedLaunch timed(TIMED_GEMM, 2.0 * g.M * g.N * g.K, g.M, g.N, g.K, stream);
+  B200SAM_CHECK_CUDA(launch_kernel(kernel, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, stream, ta, tb, ep, g.M, g.N,
+                                   g.K, g.a_wrap, g.conv_cin, g.conv_wp, g.reverse_m, g.op_f16));
   return 0;
 }
 

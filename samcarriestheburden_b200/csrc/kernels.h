@@ -31,16 +31,16 @@ const char* get_last_error();
 
 // ---- gemm_tcgen05.cu -------------------------------------------------------------------------
 struct GemmArgs {
-  const __nv_bfloat16* A;  // [M, K] row-major, pitch lda
+  const __nv_bfloat16* A;  // [M, K] row-major, pitch lda (16-bit elements: bf16, or fp16 with op_f16)
   const __nv_bfloat16* B;  // [N, K] row-major (nn.Linear weight), pitch ldb
-  void* out;               // bf16 or fp32 [M, N], pitch ldo
+  void* out;               // 16-bit or fp32 [M, N], pitch ldo
   const float* bias;       // [N] or null
   const float* residual;   // fp32, pitch ldr, or null (only with fp32 out)
   int M, N, K;
   int lda, ldb, ldo, ldr;
   int res_row_mod;  // >0: residual row index = row % res_row_mod
   int gelu;         // exact erf GELU after bias
-  int out_bf16;     // 1: bf16 output, 0: fp32 output
+  int out_kind;     // 0: fp32 output, 1: bf16, 2: fp16 (a 16-bit output has the operands' format)
   int max_ctas;     // <= 0: one CTA per SM; > 0 caps the persistent grid
   int a_wrap = 0;   // > 0: A has only a_wrap columns; k >= a_wrap reads column k - a_wrap ([hi|lo|hi] stored as [hi|lo])
   int conv_cin = 0;  // > 0: implicit 3x3 convolution over a zero-bordered pixel grid (see gemm_tcgen05.cu); K = 27 * conv_cin
@@ -51,41 +51,46 @@ struct GemmArgs {
   const float* aux0 = nullptr;  // mode 1: LN gamma [64]; mode 2: hyper [prompts, 4, 32]
   const float* aux1 = nullptr;  // mode 1: LN beta [64]
   int tok0 = 0, ntok = 0;       // mode 2
+  int op_f16 = 0;               // A / B are fp16 instead of bf16 (the ViT encoder's default)
+  // LayerNorm folded into the GEMMs around it (gemm_epilogue.cuh): producer side (fp32 out) ...
+  void* xh = nullptr;             // 16-bit copy of out, pitch ldo
+  float* rowstat_out = nullptr;   // [M, ceil(N/128), 2] partial (sum, sum sq) of out per 128-column part
+  // ... consumer side (16-bit out): out = rstd * (acc - mean * colsum[n]) + bias[n]
+  const float* rowstat_in = nullptr;  // [M, nparts_in, 2]
+  const float* colsum = nullptr;      // [N]
+  int nparts_in = 0;
+  int ln_dim = 0;       // number of elements the statistics cover (= K)
+  float ln_eps = 0.0f;
 };
 int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
 
 // ---- encoder_ops.cu --------------------------------------------------------------------------
 // image [B,3,h,w] (uint8 or fp32) -> normalised, zero-padded 1024^2, im2col'd bf16 [B*4096, 768]
 int preprocess_patchify(const void* img, int is_u8, int B, int h, int w, const float* mean3, const float* std3,
-                        __nv_bfloat16* out, cudaStream_t stream);
-// y = LN(x) over the last dim (fp32 statistics, biased variance); x fp32 [M,D]; y bf16 or fp32
+                        __nv_bfloat16* out, int out_f16, cudaStream_t stream);
+// y = LN(x) over the last dim (fp32 statistics, biased variance); x fp32 [M,D]; y: out_kind 0 fp32, 1 bf16, 2 fp16
 int layernorm_rows(const float* x, const float* gamma, const float* beta, float eps, int M, int D, void* y,
-                   int out_bf16, cudaStream_t stream, int reverse = 0);
+                   int out_kind, cudaStream_t stream, int reverse = 0);
 // 3x3/pad1 im2col over a 64x64 token grid: in bf16 [B*4096, C] -> out bf16 [B*4096, 9*C] (tap-major)
 int im2col3x3_tokens(const __nv_bfloat16* in, int B, int C, __nv_bfloat16* out, cudaStream_t stream);
 // LayerNorm2d over channels + token-major -> NCHW transpose: in fp32 [B*4096, C] -> out fp32 [B,C,64,64]
 int layernorm_to_nchw(const float* x, const float* gamma, const float* beta, float eps, int B, int C, float* out,
                       cudaStream_t stream);
-int f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+int f32_to_op16(const float* in, __nv_bfloat16* out, size_t n, int out_f16, cudaStream_t stream);
 
-// ---- attention.cu ----------------------------------------------------------------------------
+// ---- attention_tc.cu -------------------------------------------------------------------------
 struct AttnArgs {
-  const __nv_bfloat16* qkv;       // [B*4096, 3*D] bf16 (q | k | v, each heads x hd)
-  const __nv_bfloat16* qkv_bias;  // [3*D] bf16 (K/V of zero-padded window tokens)
-  const __nv_bfloat16* rel_h;     // [2S-1, hd] bf16
-  const __nv_bfloat16* rel_w;     // [2S-1, hd] bf16
-  __nv_bfloat16* out;             // [B*4096, D] bf16
+  const __nv_bfloat16* qkv;       // [B*4096, 3*D] 16-bit (q | k | v, each heads x hd)
+  const __nv_bfloat16* qkv_bias;  // [3*D] 16-bit (K/V of zero-padded window tokens)
+  const __nv_bfloat16* rel_h;     // [2S-1, hd] 16-bit
+  const __nv_bfloat16* rel_w;     // [2S-1, hd] 16-bit
+  __nv_bfloat16* out;             // [B*4096, D] 16-bit
   int B, heads, hd;
-  int reverse = 0;  // tcgen05 kernels: walk the images last-to-first (start with what the qkv GEMM left in L2)
+  int reverse = 0;  // walk the images last-to-first (start with what the qkv GEMM left in L2)
+  int f16 = 0;      // all 16-bit tensors are fp16 instead of bf16
 };
-int window_attention(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows over the 64x64 grid
-int global_attention(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096, mma.sync path (A/B reference)
-int window_attention_tc(const AttnArgs& a, cudaStream_t stream);
-// second generation: both query tiles of a window concurrently, P as a TMEM A-operand (attention_win2.cu)
-int window_attention_tc2(const AttnArgs& a, cudaStream_t stream);
-// third generation: two large softmax rounds per query tile (two-pass TMEM softmax), attention_win3.cu
-int window_attention_tc3(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows on tcgen05 / TMEM (attention_tc.cu)
-int global_attention_tc(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096 on tcgen05 / TMEM (attention_tc.cu)
+int window_attention_tc(const AttnArgs& a, cudaStream_t stream);  // 14x14 windows on tcgen05 / TMEM
+int global_attention_tc(const AttnArgs& a, cudaStream_t stream);  // full 4096x4096 on tcgen05 / TMEM
 
 // ---- prompt_extract.cu -----------------------------------------------------------------------
 int prompt_extract(const uint8_t* masks, int n_img, int C, int H, int W, int32_t* seeds, int32_t* boxes,

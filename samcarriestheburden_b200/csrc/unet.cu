@@ -496,7 +496,7 @@ int split_gemm(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* bi
   GemmArgs g;
   g.A = As; g.B = Ws; g.out = out; g.bias = bias; g.residual = nullptr;
   g.M = static_cast<int>(M); g.N = N; g.K = 3 * K; g.lda = 2 * K; g.ldb = 3 * K; g.ldo = N; g.ldr = 0; g.res_row_mod = 0;
-  g.gelu = 0; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 2 * K;
+  g.gelu = 0; g.out_kind = 0; g.max_ctas = 0; g.a_wrap = 2 * K;
   return gemm_bf16_tn(g, s);
 }
 
@@ -516,7 +516,7 @@ int conv_in_lrelu(const UNetCtx* u, const UWork& w, const float* in, int ld_in, 
     GemmArgs g;
     g.A = w.col; g.B = ws; g.out = tmp; g.bias = nullptr; g.residual = nullptr;
     g.M = static_cast<int>(Mp); g.N = cout; g.K = 27 * cin; g.lda = 2 * cin; g.ldb = 27 * cin; g.ldo = cout; g.ldr = 0;
-    g.res_row_mod = 0; g.gelu = 0; g.out_bf16 = 0; g.max_ctas = 0; g.a_wrap = 0; g.conv_cin = cin; g.conv_wp = W + 2;
+    g.res_row_mod = 0; g.gelu = 0; g.out_kind = 0; g.max_ctas = 0; g.a_wrap = 0; g.conv_cin = cin; g.conv_wp = W + 2;
     TRY(gemm_bf16_tn(g, s));
   } else if (cin == 1 && wf32 != nullptr && 256 % (cout / 4) == 0) {
     unet_conv3x3_direct_kernel<<<grid_for(M * (cout / 4)), 256, 0, s>>>(in, B, H, W, ld_in, wf32, Kp, cout, tmp);

@@ -91,7 +91,7 @@ def _pack(sd, spec: str, lib) -> torch.Tensor:
         return out.contiguous()
     if packing:
         raise ValueError(f"unknown packing {packing}")
-    return t.contiguous()
+    return t.contiguous().clone()  # never alias the live parameter
 
 
 class _Engine:
@@ -103,8 +103,8 @@ class _Engine:
         self.packed = [_pack(sd, lib.b200sam_unet_weight_name(i).decode(), lib) for i in range(n)]
         arr = (C.c_void_p * n)(*[t.data_ptr() for t in self.packed])
         handle = C.c_void_p()
-        _lib.check(lib.b200sam_unet_create(model.n_channels, model.n_classes, model.n_last_channel, arr, n,
-                                           C.byref(handle), _lib.current_stream()), "b200sam_unet_create")
+        _lib.run(device, lib.b200sam_unet_create, model.n_channels, model.n_classes, model.n_last_channel, arr, n,
+                                           C.byref(handle), what="b200sam_unet_create")
         self.handle = handle
         self._ws: Optional[torch.Tensor] = None
 
@@ -119,9 +119,8 @@ class _Engine:
         base = (self._ws.data_ptr() + 255) & ~255
         logits = torch.empty((B, model.n_classes, H, W), dtype=torch.float32, device=self.device) if want_logits else None
         probs = torch.empty((B, model.n_classes, H, W), dtype=torch.float32, device=self.device) if want_probs else None
-        _lib.check(self.lib.b200sam_unet_forward(self.handle, xin.data_ptr(), B, H, W, _lib.ptr(logits), _lib.ptr(probs),
-                                                 base, self._ws.numel() - (base - self._ws.data_ptr()),
-                                                 _lib.current_stream()), "b200sam_unet_forward")
+        _lib.run(self.device, self.lib.b200sam_unet_forward, self.handle, xin.data_ptr(), B, H, W, _lib.ptr(logits), _lib.ptr(probs),
+                                                 base, self._ws.numel() - (base - self._ws.data_ptr()), what="b200sam_unet_forward")
         return logits, probs
 
     def __del__(self):
@@ -153,14 +152,15 @@ class UNet(nn.Module):
         self.up4 = Up(128, n_last_channel, bilinear)
         self.outc = OutConv(n_last_channel, n_classes)
         self._engine: Optional[_Engine] = None
+        self._engine_versions: Optional[tuple] = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self) -> None:
+        self._engine = None
 
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self._invalidate()
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
 
     @classmethod
     def load(cls, path, device):
@@ -174,8 +174,11 @@ class UNet(nn.Module):
         dev = self.outc.conv.weight.device
         if dev.type != "cuda":
             raise _lib.B200SamError("b200sam has no CPU path: move the U-Net to a CUDA device")
-        if self._engine is None or self._engine.device != dev:
+        versions = tuple(p._version for p in self.parameters())  # in-place weight edits bump the version: re-pack
+        if self._engine is None or self._engine.device != dev or versions != self._engine_versions:
+            self._engine = None
             self._engine = _Engine(self, dev)
+            self._engine_versions = versions
         return self._engine
 
     @torch.no_grad()

@@ -6,6 +6,7 @@ encoder through `b200sam_encoder_forward` (tcgen05 GEMMs + fused attention kerne
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple, Type
 
 import torch
@@ -50,18 +51,47 @@ class Block(FusedAway):
         self.window_size = window_size
 
 
-def _pack(t: torch.Tensor, packing: str) -> torch.Tensor:
-    t = t.detach()
+_OP_DTYPE = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def _own(t: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """A packed tensor never aliases the live parameter it was made from (an in-place weight edit must not reach a
+    half-updated engine)."""
+    return t.clone() if t.data_ptr() == src.data_ptr() else t
+
+
+def _pack(sd, spec: str, op_dtype: torch.dtype, device) -> torch.Tensor:
+    """Pack one weight slot named by the library as "key|packing[|norm prefix]" (csrc/encoder.cu)."""
+    key, packing, *rest = spec.split("|")
+    if packing.startswith("fold_"):
+        # LayerNorm `rest[0]` folded into the linear `key` (csrc/gemm_epilogue.cuh):
+        #   LN(x) W^T + b = rstd * (x (gamma*W)^T - mean * rowsum(gamma*W)) + (beta W^T + b)
+        W, b = sd[key + ".weight"].detach().to(device).double(), sd[key + ".bias"].detach().to(device).double()
+        gamma, beta = sd[rest[0] + ".weight"].detach().to(device).double(), sd[rest[0] + ".bias"].detach().to(device).double()
+        Wf = (W * gamma[None, :]).float().to(op_dtype).contiguous()
+        if packing == "fold_w":
+            return Wf
+        if packing == "fold_s":  # sums of the ROUNDED weights: the mean term then cancels exactly against the MMA
+            return Wf.double().sum(1).float().contiguous()
+        if packing == "fold_c":
+            return (W @ beta + b).float().contiguous()
+        raise ValueError(f"unknown packing {packing}")
+    if key not in sd:
+        raise _lib.B200SamError(f"encoder weight {key} missing from the module state_dict")
+    src = sd[key].detach()
+    t = src.to(device)
+    if packing == "none":
+        return torch.zeros(4, dtype=torch.float32, device=device)
     if packing == "f32":
-        return t.float().contiguous()
-    if packing == "bf16":
-        return t.to(torch.bfloat16).contiguous()
-    if packing == "bf16_flat":  # conv weight [out, in, kh, kw] -> [out, in*kh*kw]
-        return t.reshape(t.shape[0], -1).to(torch.bfloat16).contiguous()
-    if packing == "bf16_tap":  # 3x3 conv weight -> [out, (ky*3+kx)*Cin + c]
-        return t.permute(0, 2, 3, 1).reshape(t.shape[0], -1).to(torch.bfloat16).contiguous()
+        return _own(t.float().contiguous(), src)
+    if packing == "op16":
+        return _own(t.to(op_dtype).contiguous(), src)
+    if packing == "op16_flat":  # conv weight [out, in, kh, kw] -> [out, in*kh*kw]
+        return _own(t.reshape(t.shape[0], -1).to(op_dtype).contiguous(), src)
+    if packing == "op16_tap":  # 3x3 conv weight -> [out, (ky*3+kx)*Cin + c]
+        return t.permute(0, 2, 3, 1).reshape(t.shape[0], -1).to(op_dtype).contiguous()
     if packing == "f32_tokens":  # pos_embed [1, 64, 64, D] -> [4096, D]
-        return t.reshape(-1, t.shape[-1]).float().contiguous()
+        return _own(t.reshape(-1, t.shape[-1]).float().contiguous(), src)
     raise ValueError(f"unknown packing {packing}")
 
 
@@ -76,28 +106,31 @@ class _EncoderEngine:
         for i, blk in enumerate(module.blocks):
             if blk.window_size == 0:
                 gmask |= 1 << i
-        self.cfg = _lib.EncoderConfig(module.embed_dim, len(module.blocks), module.num_heads, gmask, module.out_chans)
+        self.operand_format, self.ln_fused = module.operand_format, module.ln_fused
+        op_dtype = _OP_DTYPE[self.operand_format]
+        self.cfg = _lib.EncoderConfig(module.embed_dim, len(module.blocks), module.num_heads, gmask, module.out_chans,
+                                      _lib.OPERAND_FP16 if self.operand_format == "fp16" else _lib.OPERAND_BF16,
+                                      _lib.ENC_LN_FUSED if self.ln_fused else 0)
         sd = {"image_encoder." + k: v for k, v in module.state_dict().items()}
         n = lib.b200sam_encoder_weight_count(C.byref(self.cfg))
-        self.packed = []
-        for i in range(n):
-            key, packing = lib.b200sam_encoder_weight_name(C.byref(self.cfg), i).decode().split("|")
-            if key not in sd:
-                raise _lib.B200SamError(f"encoder weight {key} missing from the module state_dict")
-            self.packed.append(_pack(sd[key].to(device), packing))
+        self.packed = [_pack(sd, lib.b200sam_encoder_weight_name(C.byref(self.cfg), i).decode(), op_dtype, device)
+                       for i in range(n)]
         arr = (C.c_void_p * n)(*[t.data_ptr() for t in self.packed])
         handle = C.c_void_p()
-        _lib.check(lib.b200sam_encoder_create(C.byref(self.cfg), arr, n, C.byref(handle)), "b200sam_encoder_create")
+        with _lib.on_device(device):
+            _lib.check(lib.b200sam_encoder_create(C.byref(self.cfg), arr, n, C.byref(handle)), "b200sam_encoder_create")
         self.handle = handle
-        self._ws = {}
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_batch = 0
 
     def workspace(self, batch: int) -> torch.Tensor:
-        ws = self._ws.get(batch)
-        if ws is None:
+        """One workspace sized for the largest batch seen so far (a ragged last batch reuses it)."""
+        if self._ws is None or batch > self._ws_batch:
             nbytes = self.lib.b200sam_encoder_workspace_bytes(C.byref(self.cfg), batch)
-            self._ws = {batch: torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)}
-            ws = self._ws[batch]
-        return ws
+            self._ws = None  # release before growing
+            self._ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            self._ws_batch = batch
+        return self._ws
 
     def forward(self, image: torch.Tensor, mean, std, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         assert image.dim() == 4 and image.shape[1] == 3, "expected [B,3,h,w]"
@@ -111,10 +144,9 @@ class _EncoderEngine:
         base = (ws.data_ptr() + 1023) & ~1023
         mean3 = (C.c_float * 3)(*mean)
         std3 = (C.c_float * 3)(*std)
-        _lib.check(self.lib.b200sam_encoder_forward(self.handle, image.data_ptr(), int(image.dtype == torch.uint8), B, h,
-                                                   w, mean3, std3, out.data_ptr(), base,
-                                                   ws.numel() - (base - ws.data_ptr()), _lib.current_stream()),
-                   "b200sam_encoder_forward")
+        _lib.run(self.device, self.lib.b200sam_encoder_forward, self.handle, image.data_ptr(),
+                 int(image.dtype == torch.uint8), B, h, w, mean3, std3, out.data_ptr(), base,
+                 ws.numel() - (base - ws.data_ptr()), what="b200sam_encoder_forward")
         return out
 
     def __del__(self):
@@ -123,6 +155,13 @@ class _EncoderEngine:
                 self.lib.b200sam_encoder_destroy(self.handle)
         except Exception:
             pass
+
+
+def _default_operands() -> str:
+    v = os.environ.get("B200SAM_ENCODER_OPERANDS", "fp16").lower()
+    if v not in _OP_DTYPE:
+        raise _lib.B200SamError(f"B200SAM_ENCODER_OPERANDS={v!r}: expected 'fp16' or 'bf16'")
+    return v
 
 
 class ImageEncoderViT(nn.Module):
@@ -153,22 +192,46 @@ class ImageEncoderViT(nn.Module):
                                   nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False),
                                   LayerNorm2d(out_chans))
         self._engine: Optional[_EncoderEngine] = None
+        self._engine_versions: Optional[tuple] = None
+        # 16-bit tensor-core operand format: fp16 (11 significand bits) by default, because refined masks at Dice >= 0.999
+        # against the fp32 reference need its precision (bf16 operands: 0.997 at random init); "bf16"
+        # trades that for the fp32 exponent range.  LayerNorm folding: norm1 / norm2 run inside the GEMM epilogues.
+        self.operand_format = _default_operands()
+        self.ln_fused = os.environ.get("B200SAM_LN_FUSED", "1") != "0"
+        # a parent's load_state_dict never calls the child's override, but it does run the child's post hooks
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self) -> None:
+        self._engine = None
+
+    def set_precision(self, operand_format: Optional[str] = None, ln_fused: Optional[bool] = None) -> "ImageEncoderViT":
+        """Select the MMA operand format ("fp16" | "bf16") and whether LayerNorm is folded into the GEMMs."""
+        if operand_format is not None:
+            if operand_format not in _OP_DTYPE:
+                raise ValueError(f"operand_format must be 'fp16' or 'bf16', got {operand_format!r}")
+            self.operand_format = operand_format
+        if ln_fused is not None:
+            self.ln_fused = bool(ln_fused)
+        self._invalidate()
+        return self
 
     # weights changed / moved -> re-pack lazily
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
+    def _versions(self) -> tuple:
+        return tuple(p._version for p in self.parameters())
 
     def engine(self) -> _EncoderEngine:
         dev = self.pos_embed.device
         if dev.type != "cuda":
             raise _lib.B200SamError("b200sam ImageEncoderViT has no CPU path: move the model to a CUDA device")
-        if self._engine is None or self._engine.device != dev:
+        versions = self._versions()  # in-place edits of a parameter bump its version counter: re-pack
+        if self._engine is None or self._engine.device != dev or versions != self._engine_versions:
+            self._engine = None
             self._engine = _EncoderEngine(self, dev)
+            self._engine_versions = versions
         return self._engine
 
     @torch.no_grad()

@@ -25,7 +25,7 @@ def _pack_decoder_weight(sd: Dict[str, torch.Tensor], spec: str) -> torch.Tensor
         return t.repeat(4).contiguous()
     if packing:
         raise ValueError(f"unknown packing {packing}")
-    return t.contiguous()
+    return t.contiguous().clone()  # never alias the live parameter
 
 
 class _DecoderEngine:
@@ -40,7 +40,7 @@ class _DecoderEngine:
         self.packed = [_pack_decoder_weight(sd, lib.b200sam_decoder_weight_name(i).decode()) for i in range(n)]
         arr = (C.c_void_p * n)(*[t.data_ptr() for t in self.packed])
         handle = C.c_void_p()
-        _lib.check(lib.b200sam_decoder_create(arr, n, C.byref(handle), _lib.current_stream()), "b200sam_decoder_create")
+        _lib.run(device, lib.b200sam_decoder_create, arr, n, C.byref(handle), what="b200sam_decoder_create")
         self.handle = handle
         self._ws: Optional[torch.Tensor] = None
         self._pe: Optional[torch.Tensor] = None
@@ -48,8 +48,7 @@ class _DecoderEngine:
     def dense_pe(self) -> torch.Tensor:
         if self._pe is None:
             tok = torch.empty((4096, 256), dtype=torch.float32, device=self.device)
-            _lib.check(self.lib.b200sam_decoder_copy_dense_pe(self.handle, tok.data_ptr(), _lib.current_stream()),
-                       "b200sam_decoder_copy_dense_pe")
+            _lib.run(self.device, self.lib.b200sam_decoder_copy_dense_pe, self.handle, tok.data_ptr(), what="b200sam_decoder_copy_dense_pe")
             self._pe = tok.view(64, 64, 256).permute(2, 0, 1).unsqueeze(0)
         return self._pe
 
@@ -81,11 +80,10 @@ class _DecoderEngine:
             assert image_of.numel() == NB, "image_of must name one image per prompt"
         elif n_img != 1:
             raise ValueError("image_of is required when decoding prompts of more than one image")
-        _lib.check(self.lib.b200sam_decode_batch(self.handle, emb.data_ptr(), n_img, _lib.ptr(image_of), NB, Np,
+        _lib.run(self.device, self.lib.b200sam_decode_batch, self.handle, emb.data_ptr(), n_img, _lib.ptr(image_of), NB, Np,
                                                  _lib.ptr(coords), _lib.ptr(labels), _lib.ptr(mask_prev),
                                                  int(multimask), low.data_ptr(), iou.data_ptr(), base,
-                                                 self._ws.numel() - (base - self._ws.data_ptr()),
-                                                 _lib.current_stream()), "b200sam_decode_batch")
+                                                 self._ws.numel() - (base - self._ws.data_ptr()), what="b200sam_decode_batch")
         return low, iou
 
     def __del__(self):
@@ -111,9 +109,9 @@ def upscale_masks(low_res: torch.Tensor, input_size, original_size, img_size: in
     if small_size is not None:
         sh, sw = int(small_size[0]), int(small_size[1])
         small = torch.empty((B, Cn, sh, sw), dtype=torch.bool, device=dev)
-    _lib.check(lib.b200sam_upscale_threshold(low.data_ptr(), B * Cn, L, img_size, int(input_size[0]), int(input_size[1]),
+    _lib.run(dev, lib.b200sam_upscale_threshold, low.data_ptr(), B * Cn, L, img_size, int(input_size[0]), int(input_size[1]),
                                              oh, ow, float(threshold), _lib.ptr(mask), _lib.ptr(logits), _lib.ptr(small),
-                                             sh, sw, _lib.current_stream()), "b200sam_upscale_threshold")
+                                             sh, sw, what="b200sam_upscale_threshold")
     out = logits if return_logits else mask
     return (out, small) if small_size is not None else out
 
@@ -134,26 +132,30 @@ class Sam(nn.Module):
         self._pixel_mean_host = tuple(float(v) for v in pixel_mean)
         self._pixel_std_host = tuple(float(v) for v in pixel_std)
         self._dec_engine: Optional[_DecoderEngine] = None
+        self._dec_versions: Optional[tuple] = None
         self.prompt_encoder._owner = weakref.ref(self)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self) -> None:
+        self._dec_engine = None
 
     @property
     def device(self) -> Any:
         return self.pixel_mean.device
 
     def _apply(self, fn, *a, **k):
-        self._dec_engine = None
+        self._invalidate()
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._dec_engine = None
-        return super().load_state_dict(*a, **k)
 
     def decoder_engine(self) -> _DecoderEngine:
         dev = self.pixel_mean.device
         if dev.type != "cuda":
             raise _lib.B200SamError("b200sam has no CPU path: move the model to a CUDA device")
-        if self._dec_engine is None or self._dec_engine.device != dev:
+        versions = tuple(p._version for m in (self.prompt_encoder, self.mask_decoder) for p in m.parameters())
+        if self._dec_engine is None or self._dec_engine.device != dev or versions != self._dec_versions:
+            self._dec_engine = None
             self._dec_engine = _DecoderEngine(self, dev)
+            self._dec_versions = versions
         return self._dec_engine
 
     # ---- fused entry points -------------------------------------------------------------------------

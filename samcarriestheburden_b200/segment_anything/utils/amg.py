@@ -18,9 +18,9 @@ def calculate_stability_score(masks: torch.Tensor, mask_threshold: float, thresh
     out = torch.empty((n,), dtype=torch.float32, device=x.device)
     if n:
         scratch = torch.empty((n, 2), dtype=torch.int32, device=x.device)
-        _lib.check(lib.b200sam_stability_score(x.data_ptr(), n, H, W, float(mask_threshold + threshold_offset),
+        _lib.run(x.device, lib.b200sam_stability_score, x.data_ptr(), n, H, W, float(mask_threshold + threshold_offset),
                                                float(mask_threshold - threshold_offset), out.data_ptr(),
-                                               scratch.data_ptr(), _lib.current_stream()), "b200sam_stability_score")
+                                               scratch.data_ptr(), what="b200sam_stability_score")
     return out.view(lead)
 
 
@@ -38,6 +38,5 @@ def batched_mask_to_box(masks: torch.Tensor) -> torch.Tensor:
     n = m.shape[0]
     out = torch.empty((n, 4), dtype=torch.int64, device=m.device)
     scratch = torch.empty((n, 4), dtype=torch.int32, device=m.device)
-    _lib.check(lib.b200sam_mask_to_box(m.data_ptr(), n, H, W, out.data_ptr(), scratch.data_ptr(),
-                                       _lib.current_stream()), "b200sam_mask_to_box")
+    _lib.run(m.device, lib.b200sam_mask_to_box, m.data_ptr(), n, H, W, out.data_ptr(), scratch.data_ptr(), what="b200sam_mask_to_box")
     return out.reshape(*shape[:-2], 4) if len(shape) > 2 else out[0]

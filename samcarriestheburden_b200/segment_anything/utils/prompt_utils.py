@@ -37,9 +37,8 @@ def extract_seeds_boxes(pred_masks: torch.Tensor):
     has_seed = torch.empty((N, Cn), dtype=torch.uint8, device=dev)
     has_box = torch.empty((N, Cn), dtype=torch.uint8, device=dev)
     scratch = torch.empty(max(lib.b200sam_prompt_extract_scratch_bytes(N, Cn) // 8 + 1, 1), dtype=torch.int64, device=dev)
-    _lib.check(lib.b200sam_prompt_extract(m.data_ptr(), N, Cn, H, W, seeds.data_ptr(), boxes.data_ptr(),
-                                          has_seed.data_ptr(), has_box.data_ptr(), scratch.data_ptr(),
-                                          _lib.current_stream()), "b200sam_prompt_extract")
+    _lib.run(dev, lib.b200sam_prompt_extract, m.data_ptr(), N, Cn, H, W, seeds.data_ptr(), boxes.data_ptr(),
+                                          has_seed.data_ptr(), has_box.data_ptr(), scratch.data_ptr(), what="b200sam_prompt_extract")
     return seeds, boxes, has_seed, has_box
 
 

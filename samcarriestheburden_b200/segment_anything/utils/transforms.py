@@ -49,9 +49,8 @@ def resize_u8_cuda(image: torch.Tensor, out_h: int, out_w: int, chw: bool = Fals
     tmp = None
     if xb is not None and (yb is not None or chw):
         tmp = torch.empty((H, out_w, Cc), dtype=torch.uint8, device=image.device)
-    _lib.check(lib.b200sam_resize_u8(_lib.ptr(image), H, W, Cc, _lib.ptr(xb), _lib.ptr(xk), kx, _lib.ptr(yb),
-                                     _lib.ptr(yk), ky, out_h, out_w, _lib.ptr(tmp), _lib.ptr(out), int(chw),
-                                     _lib.current_stream()), "resize_u8")
+    _lib.run(image.device, lib.b200sam_resize_u8, _lib.ptr(image), H, W, Cc, _lib.ptr(xb), _lib.ptr(xk), kx, _lib.ptr(yb),
+             _lib.ptr(yk), ky, out_h, out_w, _lib.ptr(tmp), _lib.ptr(out), int(chw), what="resize_u8")
     return out
 
 

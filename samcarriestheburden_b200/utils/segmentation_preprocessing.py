@@ -28,8 +28,7 @@ def _ccl(prob: torch.Tensor, selection: str) -> torch.Tensor:
     out = torch.empty_like(p)
     scratch = torch.empty(lib.b200sam_ccl_scratch_bytes(n, H, W) + 256, dtype=torch.uint8, device=p.device)
     base = (scratch.data_ptr() + 255) & ~255
-    _lib.check(lib.b200sam_ccl_select(p.data_ptr(), n, H, W, 0.5, int(selection == "largest"), out.data_ptr(), base,
-                                      _lib.current_stream()), "b200sam_ccl_select")
+    _lib.run(p.device, lib.b200sam_ccl_select, p.data_ptr(), n, H, W, 0.5, int(selection == "largest"), out.data_ptr(), base, what="b200sam_ccl_select")
     return out.to(prob.dtype) if prob.dtype != torch.float else out
 
 
@@ -69,7 +68,6 @@ def morph_flat(x: torch.Tensor, kernel: np.ndarray, dilate: bool) -> torch.Tenso
     H, W = xin.shape[-2:]
     se = torch.from_numpy(np.ascontiguousarray(kernel.astype(np.uint8))).to(xin.device)
     out = torch.empty_like(xin)
-    _lib.check(lib.b200sam_morph_flat(xin.data_ptr(), xin.numel() // (H * W), H, W, se.data_ptr(), se.shape[0], se.shape[1],
-                                      se.shape[0] // 2, se.shape[1] // 2, int(dilate), out.data_ptr(),
-                                      _lib.current_stream()), "b200sam_morph_flat")
+    _lib.run(xin.device, lib.b200sam_morph_flat, xin.data_ptr(), xin.numel() // (H * W), H, W, se.data_ptr(), se.shape[0], se.shape[1],
+                                      se.shape[0] // 2, se.shape[1] // 2, int(dilate), out.data_ptr(), what="b200sam_morph_flat")
     return out

@@ -38,15 +38,108 @@ def embedding(vit_b):
     return img, ref, pred
 
 
+# Embedding gates = ~1.5-2 x the measured error of each operand format against the fp32 oracle (ViT-B/L/H all measure
+# 5.1e-3 .. 5.5e-3 with bf16 operands and 6e-4 .. 7e-4 with fp16 operands).
+REL_GATE = {"fp16": 1.5e-3, "bf16": 9e-3}
+COS_GATE = {"fp16": 0.999998, "bf16": 0.99995}
+
+
+def _rel_cos(got, ref):
+    rel = float((got - ref).norm() / ref.norm())
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten().double(), ref.flatten().double(), dim=0))
+    return rel, cos
+
+
 def test_encoder_embedding_tolerance(embedding):
-    """bf16 operands / fp32 accumulate: rel-L2 <= 2e-2, cosine >= 0.9995."""
+    """16-bit operands / fp32 accumulate against the fp32 oracle, default format (fp16) and LayerNorm folding."""
     _, ref, pred = embedding
+    enc = pred.model.image_encoder
+    assert enc.operand_format == "fp16" and enc.ln_fused
     got = pred.get_image_embedding().float().cpu()
     assert got.shape == (1, 256, 64, 64)
-    rel = float((got - ref).norm() / ref.norm())
-    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
-    print(f"encoder vit_b rel_l2={rel:.3e} cos={cos:.6f}")
-    assert rel <= 2e-2 and cos >= 0.9995, (rel, cos)
+    rel, cos = _rel_cos(got, ref)
+    print(f"encoder vit_b fp16 rel_l2={rel:.3e} cos={cos:.7f}")
+    assert rel <= REL_GATE["fp16"] and cos >= COS_GATE["fp16"], (rel, cos)
+
+
+@pytest.mark.parametrize("fmt,fused", [("fp16", False), ("bf16", True), ("bf16", False)])
+def test_encoder_operand_formats_and_unfused_layernorm(vit_b, embedding, fmt, fused):
+    """The other three (operand format, LayerNorm folding) combinations of the encoder against the same oracle embedding."""
+    from samcarriestheburden_b200.segment_anything import SamPredictor
+    sam, _ = vit_b
+    img, ref, _ = embedding
+    enc = sam.image_encoder
+    try:
+        enc.set_precision(fmt, fused)
+        pred = SamPredictor(sam)
+        pred.set_image(img)
+        got = pred.get_image_embedding().float().cpu()
+    finally:
+        enc.set_precision("fp16", True)
+    rel, cos = _rel_cos(got, ref)
+    print(f"encoder vit_b {fmt} ln_fused={fused} rel_l2={rel:.3e} cos={cos:.7f}")
+    assert rel <= REL_GATE[fmt] and cos >= COS_GATE[fmt], (fmt, fused, rel, cos)
+
+
+def _e2e_refine(sam, sd, model, seed, native):
+    """image -> CUDA encoder -> CUDA two-pass refine, against the oracle's fp32 encoder -> oracle refine (the reference
+    path: predictor.py:34-90 features into utils/seg_refinement.py:99-116)."""
+    from samcarriestheburden_b200.segment_anything import SamPredictor
+    from samcarriestheburden_b200.segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
+    from samcarriestheburden_b200.utils.seg_refinement import SAMSegRefiner
+    img = O.synthetic_radiograph(seed, *native)
+    pred = SamPredictor(sam)
+    pred.set_image(img)
+    resized = pred.transform.apply_image(img)
+    ref_emb = O.image_encoder(sd, O.preprocess(torch.from_numpy(resized).permute(2, 0, 1).float())[None], **O.VIT_CONFIGS[model])
+    rel, _ = _rel_cos(pred.features.float().cpu(), ref_emb)
+    store = EmbeddingStore()
+    store.add("img", pred.features, native, pred.input_size)
+    head = SAMMaskDecoderHead(None, model, DEV, store, sam_model=sam)
+    refiner = SAMSegRefiner("SAM", DEV, [["box"], ["pos_points", "neg_points"]], sam_predictor=head)
+    seg = O.synthetic_unet_masks(seed)
+    got_seg, got_dice = refiner.refine(torch.from_numpy(seg.copy()), "img")
+    ref_seg, ref_dice, ref_native, _ = O.refine(sd, ref_emb, seg, pred.input_size, native)
+    # native-resolution masks of every refined class (second pass) through the reference-shaped predict_mask API
+    from samcarriestheburden_b200.segment_anything.utils.prompt_utils import PromptExtractor
+    ds, mism, total = [], 0, 0
+    for p in PromptExtractor(torch.from_numpy(seg).to(DEV)).extract():
+        _, _, low1 = head.predict_mask("img", p, ["box"])
+        m2, _, _ = head.predict_mask("img", p, ["pos_points", "neg_points"], low1)
+        got = m2[0, 0].cpu().numpy()
+        ds.append(dice(got, ref_native[p.class_idx]))
+        mism += int((got != ref_native[p.class_idx]).sum())
+        total += got.size
+    got_small = got_seg.cpu().numpy()
+    ds_small = [dice(got_small[c], ref_seg[c]) for c in range(seg.shape[0])]
+    return dict(rel=rel, min_dice=min(ds), mean_dice=float(np.mean(ds)), mismatched=mism, total=total,
+                min_dice_small=min(ds_small), est_dice_err=float(np.nanmax(np.abs(got_dice.numpy() - ref_dice))))
+
+
+@pytest.mark.parametrize("native", [(754, 589), (1024, 1024)])
+def test_e2e_mask_parity_vit_b(vit_b, native):
+    """north_star's end-to-end bar: CUDA encoder -> CUDA refine masks vs the fp32 reference path at Dice >= 0.999 per
+    class, mismatched-pixel count reported, embedding rel-L2 beside it (VERDICT r1 missing #1)."""
+    sam, sd = vit_b
+    r = _e2e_refine(sam, sd, "vit_b", 3, native)
+    print(f"e2e vit_b fp16 {native}: emb rel-L2 {r['rel']:.2e}  native masks min Dice {r['min_dice']:.5f} mean {r['mean_dice']:.5f}  "
+          f"mismatched {r['mismatched']} / {r['total']} px  384x224 min Dice {r['min_dice_small']:.5f}")
+    assert r["min_dice"] >= 0.999 and r["min_dice_small"] >= 0.998, r
+    assert r["est_dice_err"] < 2e-3
+
+
+def test_e2e_mask_parity_bf16_operands_reported(vit_b):
+    """The same end-to-end comparison with bf16 operands: NOT at the 0.999 bar at random init (logits hug the threshold,
+    SURVEY section 7) -- which is why fp16 is the default.  Gated as a regression bound only; the number is printed."""
+    sam, sd = vit_b
+    try:
+        sam.image_encoder.set_precision("bf16")
+        r = _e2e_refine(sam, sd, "vit_b", 3, (754, 589))
+    finally:
+        sam.image_encoder.set_precision("fp16")
+    print(f"e2e vit_b bf16: emb rel-L2 {r['rel']:.2e}  native masks min Dice {r['min_dice']:.5f}  "
+          f"mismatched {r['mismatched']} / {r['total']} px")
+    assert r["min_dice"] >= 0.994, r
 
 
 def test_encoder_batch_matches_single(vit_b):
@@ -204,12 +297,13 @@ def test_vit_l_encoder_batch16_matches_oracle():
     emb = sam.encode_image(imgs)
     torch.cuda.synchronize()
     assert emb.shape == (16, 256, 64, 64)
-    ref = O.image_encoder(sd, O.preprocess(imgs[5].cpu().float())[None], **O.VIT_CONFIGS["vit_l"])
-    got = emb[5:6].float().cpu()
-    rel = float((got - ref).norm() / ref.norm())
-    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
-    print(f"encoder vit_l rel_l2={rel:.3e} cos={cos:.6f}")
-    assert rel <= 2e-2 and cos >= 0.9995, (rel, cos)
+    for i in (5, 15):
+        ref = O.image_encoder(sd, O.preprocess(imgs[i].cpu().float())[None], **O.VIT_CONFIGS["vit_l"])
+        rel, cos = _rel_cos(emb[i:i + 1].float().cpu(), ref)
+        print(f"encoder vit_l image {i} rel_l2={rel:.3e} cos={cos:.7f}")
+        assert rel <= REL_GATE["fp16"] and cos >= COS_GATE["fp16"], (i, rel, cos)
+    for i in range(0, 16, 4):  # every batch position class: the same image alone gives the same embedding
+        assert torch.equal(sam.encode_image(imgs[i:i + 1]), emb[i:i + 1]), i
     del sam
     torch.cuda.empty_cache()
 
@@ -217,8 +311,8 @@ def test_vit_l_encoder_batch16_matches_oracle():
 def test_vit_h_encoder_batch8_matches_oracle():
     """BASELINE.json configs[1], the headline configuration: ViT-H (D 1280, hd 80, depth 32, global blocks 7/15/23/31) at
     the bench's batch of 8 (so the boustrophedon traversal and the multi-image attention grids are exercised), one image
-    of the batch against the fp32 CPU oracle (a few seconds on the box's host cores).  Tolerance as stated in
-    north_star / SURVEY 8d: rel-L2 <= 2e-2, cosine >= 0.9995 (bf16 operands, fp32 accumulate, 32 blocks)."""
+    two images of the batch against the fp32 CPU oracle (a few seconds each on the box's host cores), every image of the
+    batch against its own single-image run (bit-identical), then the end-to-end mask parity on the headline model."""
     from samcarriestheburden_b200.segment_anything import sam_model_registry
     sd = O.random_state_dict("vit_h", seed=2)
     sam = sam_model_registry["vit_h"]()
@@ -228,17 +322,71 @@ def test_vit_h_encoder_batch8_matches_oracle():
     emb = sam.encode_image(imgs)
     torch.cuda.synchronize()
     assert emb.shape == (8, 256, 64, 64) and bool(torch.isfinite(emb).all())
-    ref = O.image_encoder(sd, O.preprocess(imgs[6].cpu().float())[None], **O.VIT_CONFIGS["vit_h"])
-    got = emb[6:7].float().cpu()
-    rel = float((got - ref).norm() / ref.norm())
-    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
-    print(f"encoder vit_h rel_l2={rel:.3e} cos={cos:.6f}")
-    assert rel <= 2e-2 and cos >= 0.9995, (rel, cos)
-    # the same image alone gives the same embedding (batch / traversal order independence)
-    one = sam.encode_image(imgs[6:7])
-    assert torch.equal(one, emb[6:7])
+    for i in (0, 6):
+        ref = O.image_encoder(sd, O.preprocess(imgs[i].cpu().float())[None], **O.VIT_CONFIGS["vit_h"])
+        rel, cos = _rel_cos(emb[i:i + 1].float().cpu(), ref)
+        print(f"encoder vit_h image {i} rel_l2={rel:.3e} cos={cos:.7f}")
+        assert rel <= REL_GATE["fp16"] and cos >= COS_GATE["fp16"], (i, rel, cos)
+    # every image alone gives the same embedding (batch / traversal order independence)
+    for i in range(8):
+        assert torch.equal(sam.encode_image(imgs[i:i + 1]), emb[i:i + 1]), i
+    r = _e2e_refine(sam, sd, "vit_h", 5, (1182, 754))
+    print(f"e2e vit_h fp16 (1182, 754): emb rel-L2 {r['rel']:.2e}  native masks min Dice {r['min_dice']:.5f} mean "
+          f"{r['mean_dice']:.5f}  mismatched {r['mismatched']} / {r['total']} px  384x224 min Dice {r['min_dice_small']:.5f}")
+    assert r["min_dice"] >= 0.999, r
     del sam
     torch.cuda.empty_cache()
+
+
+def test_engine_follows_weight_reloads_and_inplace_edits(vit_b):
+    """`sam.load_state_dict(...)` on the PARENT module and in-place parameter edits after the first forward
+    must re-pack the cached engines (packed tensors never alias live parameters)."""
+    from samcarriestheburden_b200.segment_anything import sam_model_registry
+    _, sd = vit_b
+    img = torch.from_numpy(O.synthetic_radiograph(2)).permute(2, 0, 1)[None].to(DEV)
+    sam = sam_model_registry["vit_b"]()
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.to(DEV)
+    e0 = sam.encode_image(img).clone()
+    sd2 = O.random_state_dict("vit_b", seed=9)
+    sam.load_state_dict(sd2, strict=True)          # parent-level reload after the first forward
+    e1 = sam.encode_image(img).clone()
+    fresh = sam_model_registry["vit_b"]()
+    fresh.load_state_dict(sd2, strict=True)
+    fresh = fresh.to(DEV)
+    assert torch.equal(e1, fresh.encode_image(img)) and not torch.equal(e0, e1)
+    with torch.no_grad():                           # in-place edit of one weight
+        sam.image_encoder.blocks[3].mlp.lin2.bias.add_(0.5)
+        fresh.image_encoder.blocks[3].mlp.lin2.bias.add_(0.5)
+    e2 = sam.encode_image(img)
+    assert not torch.equal(e1, e2)
+    fresh2 = sam_model_registry["vit_b"]()
+    fresh2.load_state_dict(fresh.state_dict(), strict=True)
+    assert torch.equal(e2, fresh2.to(DEV).encode_image(img))
+    # decoder engine: dense PE follows a reload of the prompt encoder's gaussian matrix
+    pe_before = sam.prompt_encoder.get_dense_pe().clone()
+    sam.load_state_dict(sd, strict=True)
+    assert not torch.equal(pe_before, sam.prompt_encoder.get_dense_pe())
+    del sam, fresh, fresh2
+    torch.cuda.empty_cache()
+
+
+def test_model_on_second_device_while_first_is_current():
+    """the C ABI launches on the CURRENT device; every wrapper must enter the device that owns its tensors."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from samcarriestheburden_b200.segment_anything import sam_model_registry
+    sd = O.random_state_dict("vit_b", seed=0)
+    img = torch.from_numpy(O.synthetic_radiograph(2)).permute(2, 0, 1)[None]
+    sam0 = sam_model_registry["vit_b"]()
+    sam0.load_state_dict(sd, strict=True)
+    e0 = sam0.to("cuda:0").encode_image(img.to("cuda:0"))
+    sam1 = sam_model_registry["vit_b"]()
+    sam1.load_state_dict(sd, strict=True)
+    torch.cuda.set_device(0)
+    e1 = sam1.to("cuda:1").encode_image(img.to("cuda:1"))
+    torch.cuda.synchronize(1)
+    assert torch.equal(e0.cpu(), e1.cpu())
 
 
 def test_sam_forward_and_return_logits(vit_b, embedding):
