@@ -119,10 +119,12 @@ B200SAM_API int b200sam_upscale_threshold(const float* low_res, int n, int low, 
  * Replaces remove_all_but_one_connected_component (utils/segmentation_preprocessing.py:7-52, called from
  * SegEnhance.enhance, utils/seg_refinement.py:64-72) for n_planes = images x classes probability planes at once:
  * out = prob * (winning 8-connected component of prob > threshold); by_area = 1: 'largest', 0: 'highest_probability'.
- * Labels follow kornia.contrib.connected_components after convergence (component label = its largest pixel index). */
+ * Labels follow kornia.contrib.connected_components after convergence (component label = its largest pixel index), so
+ * the component labelled 0 - a lone pixel at index 0 of the FIRST plane of a reference call - is background there and
+ * here; planes_per_call = planes of one reference call (C when n_planes = images x C; <= 0: all planes are one call). */
 B200SAM_API size_t b200sam_ccl_scratch_bytes(int n_planes, int H, int W);
-B200SAM_API int b200sam_ccl_select(const float* prob, int n_planes, int H, int W, float threshold, int by_area,
-                       float* out, void* scratch, void* stream);
+B200SAM_API int b200sam_ccl_select(const float* prob, int n_planes, int planes_per_call, int H, int W, float threshold,
+                       int by_area, float* out, void* scratch, void* stream);
 /* Flat grey-scale dilation (dilate = 1) / erosion (0) with a 0/1 structuring element se [kh,kw] (device) anchored at
  * (origin_y, origin_x); replaces kornia.morphology.dilation / erosion as used by SegEnhance (seg_refinement.py:44-62). */
 B200SAM_API int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw,
@@ -198,6 +200,12 @@ B200SAM_API int b200sam_encoder_attention(const void* qkv, const void* qkv_bias1
                               void* stream);
 B200SAM_API int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, int w, const float* mean3_host,
                                 const float* std3_host, void* out16, int operand_format, void* stream);
+/* The encoder's plain linears run on the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles over the two SMs of a TPC)
+ * unless B200SAM_GEMM_PAIR=0; b200sam_set_gemm_pair overrides the environment at run time (-1: environment, 0: single-CTA
+ * kernel, 1: pair kernel) for A/B measurements and parity tests.  _max_clusters = co-resident CTA pairs on the current
+ * device (SMs whose TPC partner is fused off cannot host one). */
+B200SAM_API int b200sam_set_gemm_pair(int mode);
+B200SAM_API int b200sam_gemm_pair_max_clusters(void);
 /* In-run kernel timing for the bench's roofline block: between _start and _stop every launch of the tcgen05 GEMM
  * (kind 0; work = 2 M N K; dims = M, N, K), the windowed (kind 1) and the global (kind 2) attention kernel (work =
  * algorithmic FLOPs; dims = batch, heads, head dim) is bracketed by CUDA events on its own stream.  _stop synchronises

@@ -65,7 +65,7 @@ _PROTOTYPES = {
     "b200sam_stability_score": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
     "b200sam_mask_to_box": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "b200sam_ccl_scratch_bytes": (_sz, [_i, _i, _i]),
-    "b200sam_ccl_select": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "b200sam_ccl_select": (_i, [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "b200sam_morph_flat": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200sam_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sam_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -74,6 +74,8 @@ _PROTOTYPES = {
     "b200sam_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _i, _vp]),
     "b200sam_encoder_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sam_preprocess_patchify": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp]),
+    "b200sam_set_gemm_pair": (_i, [_i]),
+    "b200sam_gemm_pair_max_clusters": (_i, []),
     "b200sam_timing_start": (_i, [_i]),
     "b200sam_timing_stop": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "b200sam_linear_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

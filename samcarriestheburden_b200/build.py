@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libb200sam.so"
 OBJ = HERE / "build"
-SOURCES = ["api.cu", "tma.cu", "gemm_tcgen05.cu", "attention_tc.cu", "encoder_ops.cu", "encoder.cu", "decoder_ops.cu", "decoder.cu",
+SOURCES = ["api.cu", "tma.cu", "gemm_tcgen05.cu", "gemm_pair.cu", "attention_tc.cu", "encoder_ops.cu", "encoder.cu", "decoder_ops.cu", "decoder.cu",
            "prompt_extract.cu", "upscale.cu", "ccl.cu", "unet.cu", "resize.cu", "amg.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

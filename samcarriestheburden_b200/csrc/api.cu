@@ -191,9 +191,9 @@ size_t b200sam_ccl_scratch_bytes(int n_planes, int H, int W) {
   if (n_planes < 0 || H <= 0 || W <= 0) return 0;
   return ccl_scratch_bytes(n_planes, H, W);
 }
-int b200sam_ccl_select(const float* prob, int n_planes, int H, int W, float threshold, int by_area, float* out,
+int b200sam_ccl_select(const float* prob, int n_planes, int planes_per_call, int H, int W, float threshold, int by_area, float* out,
                        void* scratch, void* stream) {
-  return ccl_select(prob, n_planes, H, W, threshold, by_area, out, scratch, static_cast<cudaStream_t>(stream));
+  return ccl_select(prob, n_planes, planes_per_call, H, W, threshold, by_area, out, scratch, static_cast<cudaStream_t>(stream));
 }
 int b200sam_morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw, int origin_y,
                        int origin_x, int dilate, float* out, void* stream) {
@@ -270,6 +270,8 @@ int b200sam_preprocess_patchify(const void* image, int is_u8, int batch, int h, 
   return preprocess_patchify(image, is_u8, batch, h, w, mean3, std3, static_cast<__nv_bfloat16*>(out16),
                              operand_format == 1, static_cast<cudaStream_t>(stream));
 }
+int b200sam_set_gemm_pair(int mode) { gemm_pair_set_mode(mode); return 0; }
+int b200sam_gemm_pair_max_clusters(void) { return gemm_pair_max_clusters(); }
 int b200sam_timing_start(int capacity) { return timing_start(capacity); }
 int b200sam_timing_stop(int* kinds_host, double* work_host, int* dims3_host, float* ms_host, int capacity, int* n_out_host) {
   return timing_stop(kinds_host, work_host, dims3_host, ms_host, capacity, n_out_host);

@@ -101,10 +101,12 @@ __global__ void __launch_bounds__(256) ccl_stats_kernel(const float* __restrict_
 
 // one CTA per plane: winner = arg-max over the roots (ties: smallest root index, like torch.argmax over the sorted
 // unique labels).  The reference's labels are batch-global pixel indices, so the component labelled 0 (a lone
-// top-left pixel of the very first plane) is indistinguishable from the background there and is skipped here too.
+// top-left pixel of the first plane of a reference call) is indistinguishable from the background there and is skipped
+// here too.  planes_per_call = the number of planes ONE reference call labels together (C for a batch of images that the
+// reference would pass one by one; n_planes when the whole array is one call).
 __global__ void __launch_bounds__(256) ccl_select_kernel(const int* __restrict__ parent, const int* __restrict__ area,
                                                          const double* __restrict__ psum, int HW, int by_area,
-                                                         int* __restrict__ winner) {
+                                                         int planes_per_call, int* __restrict__ winner) {
   __shared__ float s_score[256];
   __shared__ int s_idx[256];
   const int plane = blockIdx.x;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) ccl_select_kernel(const int* __restrict__
   int bidx = -1;
   for (int p = threadIdx.x; p < HW; p += 256) {
     if (par[p] != p) continue;
-    if (plane == 0 && p == 0) continue;
+    if (p == 0 && plane % planes_per_call == 0) continue;
     const int a = area[static_cast<size_t>(plane) * HW + p];
     // reference: fp32 sum of the probabilities / area (fp32 division); the sum is accumulated in fp64 here
     const float score = by_area ? static_cast<float>(a)
@@ -185,7 +187,7 @@ size_t ccl_scratch_bytes(int n_planes, int H, int W) {
          al256(static_cast<size_t>(n_planes) * sizeof(int)) + 256;
 }
 
-int ccl_select(const float* prob, int n_planes, int H, int W, float threshold, int by_area, float* out, void* scratch,
+int ccl_select(const float* prob, int n_planes, int planes_per_call, int H, int W, float threshold, int by_area, float* out, void* scratch,
                cudaStream_t stream) {
   B200SAM_REQUIRE(n_planes >= 0 && H > 0 && W > 0, "ccl_select: bad shape n=%d H=%d W=%d", n_planes, H, W);
   B200SAM_REQUIRE(static_cast<long long>(H) * W < (1ll << 30), "ccl_select: plane too large");
@@ -208,7 +210,8 @@ int ccl_select(const float* prob, int n_planes, int H, int W, float threshold, i
   ccl_init_kernel<<<grid, 256, 0, stream>>>(prob, threshold, total, parent, area, psum, HW);
   ccl_merge_kernel<<<grid, 256, 0, stream>>>(parent, H, W, n_planes);
   ccl_stats_kernel<<<grid, 256, 0, stream>>>(prob, parent, area, psum, HW, n_planes);
-  ccl_select_kernel<<<n_planes, 256, 0, stream>>>(parent, area, psum, HW, by_area, winner);
+  ccl_select_kernel<<<n_planes, 256, 0, stream>>>(parent, area, psum, HW, by_area,
+                                                  planes_per_call > 0 ? planes_per_call : (n_planes > 0 ? n_planes : 1), winner);
   ccl_apply_kernel<<<grid, 256, 0, stream>>>(prob, parent, winner, HW, total, out);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;

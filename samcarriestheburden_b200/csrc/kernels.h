@@ -51,6 +51,7 @@ struct GemmArgs {
   const float* aux0 = nullptr;  // mode 1: LN gamma [64]; mode 2: hyper [prompts, 4, 32]
   const float* aux1 = nullptr;  // mode 1: LN beta [64]
   int tok0 = 0, ntok = 0;       // mode 2
+  int use_pair = 0;             // CTA-pair kernel: 0 = follow gemm_pair_enabled(), 1 = force, -1 = never
   int op_f16 = 0;               // A / B are fp16 instead of bf16 (the ViT encoder's default)
   // LayerNorm folded into the GEMMs around it (gemm_epilogue.cuh): producer side (fp32 out) ...
   void* xh = nullptr;             // 16-bit copy of out, pitch ldo
@@ -63,6 +64,13 @@ struct GemmArgs {
   float ln_eps = 0.0f;
 };
 int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
+// CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles) variant for the encoder's plain linears (gemm_pair.cu);
+// gemm_bf16_tn dispatches to it when enabled (B200SAM_GEMM_PAIR != 0 or gemm_pair_set_mode) and eligible
+bool gemm_pair_enabled();
+void gemm_pair_set_mode(int mode);  // -1: environment decides, 0: off, 1: on
+bool gemm_pair_eligible(const GemmArgs& g);
+int gemm_pair_max_clusters();
+int gemm_f16_tn_pair(const GemmArgs& g, cudaStream_t stream);
 
 // ---- encoder_ops.cu --------------------------------------------------------------------------
 // image [B,3,h,w] (uint8 or fp32) -> normalised, zero-padded 1024^2, im2col'd bf16 [B*4096, 768]
@@ -105,7 +113,9 @@ int upscale_threshold(const float* low_res, int n, int low, int img_size, int in
 // ---- ccl.cu ----------------------------------------------------------------------------------
 // prob [n_planes, H, W] fp32 -> out = prob * (winning 8-connected component of prob > threshold), per plane
 size_t ccl_scratch_bytes(int n_planes, int H, int W);
-int ccl_select(const float* prob, int n_planes, int H, int W, float threshold, int by_area, float* out, void* scratch,
+// planes_per_call: planes the reference labels in ONE call (its label 0 = pixel 0 of the call's first plane is background);
+// <= 0: all n_planes are one call
+int ccl_select(const float* prob, int n_planes, int planes_per_call, int H, int W, float threshold, int by_area, float* out, void* scratch,
                cudaStream_t stream);
 // flat (0/1 structuring element) grey-scale dilation / erosion, out-of-image taps ignored
 int morph_flat(const float* in, int n_planes, int H, int W, const uint8_t* se, int kh, int kw, int origin_y,

@@ -28,7 +28,10 @@ def _ccl(prob: torch.Tensor, selection: str) -> torch.Tensor:
     out = torch.empty_like(p)
     scratch = torch.empty(lib.b200sam_ccl_scratch_bytes(n, H, W) + 256, dtype=torch.uint8, device=p.device)
     base = (scratch.data_ptr() + 255) & ~255
-    _lib.run(p.device, lib.b200sam_ccl_select, p.data_ptr(), n, H, W, 0.5, int(selection == "largest"), out.data_ptr(), base, what="b200sam_ccl_select")
+    # a (N, C, H, W) batch = N reference calls of C planes each (the reference's label 0 is per call)
+    per_call = p.shape[-3] if p.dim() >= 3 else n
+    _lib.run(p.device, lib.b200sam_ccl_select, p.data_ptr(), n, per_call, H, W, 0.5, int(selection == "largest"),
+             out.data_ptr(), base, what="b200sam_ccl_select")
     return out.to(prob.dtype) if prob.dtype != torch.float else out
 
 

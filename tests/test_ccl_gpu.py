@@ -29,14 +29,15 @@ def test_ccl_batch_edge_cases_and_shapes():
         prob[prob < 0.35] = 0.0
         if N > 1:
             prob[1, 0] = 0.0           # empty plane
-            prob[0, 0, 0, 0] = 0.99    # lone pixel at batch-global index 0 (background in the reference)
-            if W > 1:
-                prob[0, 0, 0, 1] = 0.0
-            if H > 1:
-                prob[0, 0, 1, :2] = 0.0
+            for n in (0, N - 1):       # lone pixel at index 0 of an image's first class: label 0 == background in the
+                prob[n, 0, 0, 0] = 0.99  # reference, for EVERY image (the reference labels one image per call)
+                if W > 1:
+                    prob[n, 0, 0, 1] = 0.0
+                if H > 1:
+                    prob[n, 0, 1, :2] = 0.0
         for sel in ("largest", "highest_probability"):
             got = remove_all_but_one_connected_component_batch(torch.from_numpy(prob).to(DEV), sel).cpu().numpy()
-            ref = O.remove_all_but_one_connected_component(prob.reshape(N * C, H, W), sel).reshape(N, C, H, W)
+            ref = np.stack([O.remove_all_but_one_connected_component(prob[n], sel) for n in range(N)])
             assert np.array_equal(got, ref), (N, C, H, W, sel)
     # a long serpentine component (geodesic length >> max(H, W)): one component after convergence
     H, W = 33, 33

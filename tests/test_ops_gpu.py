@@ -82,9 +82,43 @@ def test_gemm_epilogues():
     assert bool(torch.isfinite(big.float()).all()) and float(big.float().abs().max()) == 65504.0
 
 
+@pytest.fixture(params=["single", "pair"])
+def gemm_kernel(request):
+    """Run a test on both GEMM kernels: the single-CTA one and the CTA-pair one (tcgen05 cta_group::2)."""
+    lib = _lib.load()
+    lib.b200sam_set_gemm_pair(1 if request.param == "pair" else 0)
+    yield request.param
+    lib.b200sam_set_gemm_pair(-1)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (4096, 3840, 1280), (8192, 1280, 5120), (1000, 264, 72), (131, 384, 192),
+                                   (300, 136, 64), (32768, 1280, 1280)])
+def test_gemm_pair_kernel_is_bit_identical_to_single(M, N, K):
+    """The CTA-pair kernel accumulates every output element over the same K sequence as the single-CTA kernel and shares
+    its epilogue: the results must be bit-identical (16-bit + GELU, fp32 + residual, ragged M / N tails)."""
+    lib = _lib.load()
+    assert lib.b200sam_gemm_pair_max_clusters() >= 32
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn((M, K), generator=g).to(DEV).half()
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(DEV).half()
+    b = torch.randn((N,), generator=g).to(DEV)
+    res = torch.randn((M, N), generator=g).to(DEV)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            lib.b200sam_set_gemm_pair(mode)
+            outs[mode] = (_gemm(A, W, b, gelu=True), _gemm(A, W, b, residual=res, out_bf16=False))
+    finally:
+        lib.b200sam_set_gemm_pair(-1)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    ref = A.float() @ W.float().T + b
+    assert torch.allclose(outs[1][1], ref + res, atol=2e-3, rtol=2e-3)
+
+
 @pytest.mark.parametrize("fmt", ["bf16", "fp16"])
 @pytest.mark.parametrize("M,D,N", [(8192, 1280, 3840), (4096, 768, 3072), (1000, 1024, 1024)])
-def test_gemm_layernorm_folding(fmt, M, D, N):
+def test_gemm_layernorm_folding(fmt, M, D, N, gemm_kernel):
     """The two halves of a LayerNorm folded into the GEMMs around it (Block.forward, image_encoder.py:166-182):
     producer x = A W^T + b + residual with the 16-bit copy of x and per-row partial sums, consumer
     y = act(LN(x) W2^T + b2) computed as rstd * (x16 (gamma * W2)^T - mean * colsum) + (beta W2^T + b2)."""
