@@ -154,6 +154,17 @@ B200SAM_API int b200sam_resize_u8(const uint8_t* image, int H, int W, int C, con
                       int xksize, const int32_t* ybounds, const int32_t* ykk, int yksize, int out_h, int out_w,
                       uint8_t* tmp, uint8_t* out, int out_chw, void* stream);
 
+/* U-Net ingest: replaces cv2.resize(grey uint8, (W, H), interpolation=cv2.INTER_LINEAR) + `.float() / 255` +
+ * `(img - IMG_MEAN) / IMG_STD` of scripts/save_refined_segmentations.py:62-67 (OpenCV's 11-bit fixed-point uint8 path,
+ * bit-exact with cv2).  b200sam_cvresize_coeffs_host is a pure HOST function: idx2_host [out_size,2] = the two taps,
+ * w2_host [out_size,2] = their weights; clamp_weights = 1 for the x axis, 0 for the y axis (OpenCV clamps the horizontal
+ * taps with weight (1,0) but only the ROW indices vertically).  image: [n,H,W] uint8; out_u8 [n,out_h,out_w] and / or
+ * out_norm [n,out_h,out_w] float32 = ((u8 / 255) - mean) / std; either may be NULL. */
+B200SAM_API int b200sam_cvresize_coeffs_host(int in_size, int out_size, int clamp_weights, int32_t* idx2_host, int32_t* w2_host);
+B200SAM_API int b200sam_cvresize_linear_u8(const uint8_t* image, int n, int H, int W, const int32_t* xidx, const int32_t* xw,
+                               const int32_t* yidx, const int32_t* yw, int out_h, int out_w, uint8_t* out_u8,
+                               float* out_norm, float mean, float std, void* stream);
+
 /* ---------------------------------------------------------------- U-Net inference
  * Replaces UNet.forward (custom_arcitecture/classic_u_net.py:81-119, bilinear = False) as called from
  * scripts/save_refined_segmentations.py:67-69 (+ the torch.sigmoid that follows).  Weight table like the SAM handles:
@@ -182,7 +193,7 @@ B200SAM_API int b200sam_gemm_f16(const void* A, const void* W, void* out, const 
                      int max_ctas, void* stream);
 /* The two halves of a LayerNorm folded into the GEMMs around it (Block.forward, image_encoder.py:166-182):
  * _ln_residual: out = A W^T + bias + residual (fp32 [M,N], may alias residual), out16 = its 16-bit copy,
- *               rowstat_out [M, ceil(N/128), 2] = per-row partial (sum, sum of squares) of out per 128-column part;
+ *               rowstat_out [M, N/64, 2] = per-row partial (sum, sum of squares) of out per 64-column part (N % 128 == 0);
  * _ln_folded:   out16 [M,N] = act( rstd * (A W_folded^T - mean * colsum) + bias_folded ) with (mean, rstd) of every row
  *               of A's fp32 original from rowstat_in [M, nparts, 2] (K elements per row, eps inside the sqrt). */
 B200SAM_API int b200sam_gemm_ln_residual(const void* A, const void* W, const float* bias, const float* residual, float* out,

@@ -438,6 +438,45 @@ def scale_coords(coords: torch.Tensor, original_size: Sequence[int], target_size
     return coords.float() * (t / o).flip(-1)
 
 
+# ----------------------------------------------------------------------------------------------- U-Net ingest resize
+# scripts/save_refined_segmentations.py:63 `cv2.resize(img, (W, H), interpolation=cv2.INTER_LINEAR)` on the uint8 grey
+# radiograph.  OpenCV (environment.yml: opencv 4.9) is an un-vendored dependency; its published uint8 linear path
+# (modules/imgproc/src/resize.cpp: resizeGeneric_ with HResizeLinear / VResizeLinear<uchar, int, short, FixedPtCast>)
+# is restated here: 11-bit fixed-point coefficients `saturate_cast<short>(w * 2048)` from the fp32 fractional position
+# ((d + 0.5) * scale - 0.5 in double, rounded to float), horizontal taps clamped with the weight forced to (1, 0) at the
+# borders, vertical ROWS clamped but the weights kept (two truncating products of the same row at the borders),
+# horizontal pass in exact int32, vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+# Pinned bit-exactly against cv2 itself by tests/golden/make_golden_cv2resize.py -> tests/golden/cv2resize_golden.npz.
+def cv2_linear_coeffs(ssize: int, dsize: int, clamp_weights: bool):
+    """-> (i0 [dsize], i1 [dsize], w [dsize, 2] int32) of one axis."""
+    d = np.arange(dsize, dtype=np.float64)
+    f = ((d + 0.5) * (ssize / dsize) - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp_weights:
+        lo, hi = s < 0, s >= ssize - 1
+        f = np.where(lo | hi, np.float32(0), f).astype(np.float32)
+        s = np.where(lo, 0, np.where(hi, ssize - 1, s))
+    w1 = np.clip(np.rint(f * np.float32(2048)), -32768, 32767).astype(np.int32)
+    w0 = np.clip(np.rint((np.float32(1.0) - f) * np.float32(2048)), -32768, 32767).astype(np.int32)
+    i0 = np.clip(s, 0, ssize - 1)
+    i1 = np.clip(s + 1, 0, ssize - 1)
+    return i0, i1, np.stack([w0, w1], axis=1)
+
+
+def cv2_resize_linear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """uint8 [H, W] -> uint8 [out_h, out_w], bit-exact with cv2.resize(..., interpolation=cv2.INTER_LINEAR)."""
+    assert img.dtype == np.uint8 and img.ndim == 2
+    H, W = img.shape
+    x0, x1, xw = cv2_linear_coeffs(W, out_w, True)
+    y0, y1, yw = cv2_linear_coeffs(H, out_h, False)
+    im = img.astype(np.int64)
+    rows = im[:, x0] * xw[:, 0][None, :] + im[:, x1] * xw[:, 1][None, :]
+    b0, b1 = yw[:, 0].astype(np.int64)[:, None], yw[:, 1].astype(np.int64)[:, None]
+    out = (((b0 * (rows[y0] >> 4)) >> 16) + ((b1 * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 # ----------------------------------------------------------------------------------------------- refinement loop
 @torch.no_grad()
 def predict_mask(sd: SD, features: torch.Tensor, prompt: OraclePrompt, prompt2use: Sequence[str],

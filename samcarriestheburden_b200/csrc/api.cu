@@ -178,6 +178,16 @@ int b200sam_resize_u8(const uint8_t* image, int H, int W, int C, const int32_t* 
                    static_cast<cudaStream_t>(stream));
 }
 
+int b200sam_cvresize_coeffs_host(int in_size, int out_size, int clamp_weights, int32_t* idx2_host, int32_t* w2_host) {
+  return cvresize_coeffs_host(in_size, out_size, clamp_weights, idx2_host, w2_host);
+}
+int b200sam_cvresize_linear_u8(const uint8_t* image, int n, int H, int W, const int32_t* xidx, const int32_t* xw,
+                               const int32_t* yidx, const int32_t* yw, int out_h, int out_w, uint8_t* out_u8,
+                               float* out_norm, float mean, float std, void* stream) {
+  return cvresize_linear_u8(image, n, H, W, xidx, xw, yidx, yw, out_h, out_w, out_u8, out_norm, mean, std,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int b200sam_stability_score(const float* logits, int n, int H, int W, float threshold_hi, float threshold_lo,
                             float* score_out, int32_t* scratch, void* stream) {
   return stability_score(logits, n, H, W, threshold_hi, threshold_lo, score_out, scratch,

@@ -72,7 +72,7 @@ struct Workspace {
   __nv_bfloat16* qkv;   // [M, 3D]                                (neck: fp32 [M,256] conv1x1 output)
   __nv_bfloat16* att;   // [M, D] attention output                (neck: 16-bit [M,256] LN output)
   __nv_bfloat16* h;     // [M, 4D] MLP hidden; also patch im2col [M,768] and neck im2col [M,2304]
-  float* stat;          // [M, D/128, 2] per-row partial (sum, sum of squares) of x (LayerNorm folding)
+  float* stat;          // [M, D/64, 2] per-row partial (sum, sum of squares) of x (LayerNorm folding)
   size_t total;
 };
 
@@ -86,7 +86,7 @@ Workspace carve(uint8_t* base, const EncoderConfig& c, int B) {
   w.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D * 2));
   w.att = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
   w.h = reinterpret_cast<__nv_bfloat16*>(take(M * 4 * D * 2));
-  w.stat = reinterpret_cast<float*>(take(M * (D / 128) * 2 * 4));
+  w.stat = reinterpret_cast<float*>(take(M * (D / 64) * 2 * 4));
   w.total = off;
   return w;
 }
@@ -145,7 +145,7 @@ int encoder_forward(const Encoder* e, const void* img, int is_u8, int B, int h, 
   const int f16 = c.operand_format == 1;
   const int k16 = f16 ? 2 : 1;  // out_kind of the 16-bit tensors
   const bool fused = ln_fused(c);
-  const int nparts = D / 128;
+  const int nparts = D / 64;  // row statistics come in 64-column parts (gemm_epilogue.cuh)
   const void* const* W = e->w.data();
   auto F = [&](int i) { return reinterpret_cast<const float*>(W[i]); };
   auto H = [&](int i) { return reinterpret_cast<const __nv_bfloat16*>(W[i]); };

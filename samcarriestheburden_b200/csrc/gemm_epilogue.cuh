@@ -26,7 +26,7 @@ struct EpiParams {
   int tok0, ntok;     // mode 2: mask tokens tok0 .. tok0 + ntok - 1
   // ---- LayerNorm folded into the GEMMs around it (image_encoder.py:168,180):
   // producer (fp32 out = the residual stream): also write a 16-bit copy `xh` of out (pitch ldo; the next GEMM's A operand)
-  // and per-row partial (sum, sum of squares) of out over each 128-column part: rowstat_out [M, ceil(N/128), 2]
+  // and per-row partial (sum, sum of squares) of out over each 64-column part: rowstat_out [M, N/64, 2] (N % 128 == 0)
   void* xh;
   float* rowstat_out;
   // consumer (16-bit out): out = rstd * (acc - mean * colsum[n]) + bias[n] with (mean, rstd) of the A operand's rows from
@@ -64,38 +64,75 @@ B200SAM_DEVINL float gelu_erf(float x) {
   const float w = (0.5f * x) * e;
   return x >= 0.0f ? x - w : w;
 }
+// the same for two values with the FMA-pipe part in packed fp32 pairs (FFMA2 / FMUL2: one issue slot per two elements;
+// identical roundings per element): ~11.5 instead of ~17 issue slots per element in the lin1 epilogue
+B200SAM_DEVINL void mul2_s(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b));
+}
+B200SAM_DEVINL void mul2_v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+B200SAM_DEVINL void gelu_erf2(float& x0, float& x1) {
+  float z0, z1, d0, d1, p0, p1, q0, q1, e0, e1, w0, w1;
+  mul2_s(z0, z1, fabsf(x0), fabsf(x1), 0.70710678118654752f);
+  fma2_s(d0, d1, 0.3275911f, z0, z1, 1.0f, 1.0f);
+  const float t0 = rcp_approx(d0), t1 = rcp_approx(d1);
+  fma2_s(p0, p1, 1.061405429f, t0, t1, -1.453152027f, -1.453152027f);
+  fma2_v(p0, p1, p0, p1, t0, t1, 1.421413741f, 1.421413741f);
+  fma2_v(p0, p1, p0, p1, t0, t1, -0.284496736f, -0.284496736f);
+  fma2_v(p0, p1, p0, p1, t0, t1, 0.254829592f, 0.254829592f);
+  mul2_v(q0, q1, x0, x1, x0, x1);
+  mul2_s(q0, q1, q0, q1, -0.72134752044448170f);
+  mul2_v(p0, p1, p0, p1, t0, t1);
+  mul2_v(e0, e1, p0, p1, ex2_approx(q0), ex2_approx(q1));
+  mul2_s(w0, w1, x0, x1, 0.5f);
+  mul2_v(w0, w1, w0, w1, e0, e1);
+  x0 = x0 >= 0.0f ? x0 - w0 : w0;
+  x1 = x1 >= 0.0f ? x1 - w1 : w1;
+}
 
 
 constexpr int EPI_STAGE_BYTES = 32 * 16 * 4;  // [32 rows][16 words] per warp, XOR-swizzled
-constexpr int EPI_BIAS_BYTES = 2 * 128 * 4;   // 128 columns per warp: bias | colsum (LayerNorm folding)
+constexpr int EPI_BIAS_BYTES = 2 * 128 * 4;   // up to 128 columns per warp: bias | colsum (LayerNorm folding)
+constexpr int EPI_STAT_COLS = 64;             // row statistics are emitted per 64-column part (both GEMM kernels)
 
 struct RowLN {
   float rstd;  // 1 when LayerNorm is not folded into this GEMM
   float nmr;   // -rstd * mean (0 when not folded)
 };
 
-// before the accumulator is ready: stage the bias slice and pull the residual block towards L2
-template <int OUT_KIND>
+// before the accumulator is ready: stage the bias slice and pull the residual block towards L2.
+// COLS = columns drained by one warp: 128 (single-CTA kernel, 8 epilogue warps) or 64 (pair kernel, 16 epilogue warps)
+template <int OUT_KIND, int COLS = 128>
 B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int row_base, int n0, float* sbias, int lane) {
-      // stage this warp's 128 bias values (zero when absent / out of range)
+      // stage this warp's bias values (zero when absent / out of range)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < COLS / 32; ++i) {
     const int c = n0 + lane + 32 * i;
     sbias[lane + 32 * i] = (ep.bias != nullptr && c < N) ? __ldg(ep.bias + c) : 0.0f;
-    if (ep.colsum != nullptr) sbias[128 + lane + 32 * i] = c < N ? __ldg(ep.colsum + c) : 0.0f;
+    if (ep.colsum != nullptr) sbias[COLS + lane + 32 * i] = c < N ? __ldg(ep.colsum + c) : 0.0f;
   }
   __syncwarp();
   RowLN ln{1.0f, 0.0f};
   if constexpr (OUT_KIND != 0) {
-    // folded LayerNorm: (mean, rstd) of this thread's row from the producer's per-part partial sums
+    // folded LayerNorm: (mean, rstd) of this thread's row from the producer's per-part partial sums (summed in index
+    // order: deterministic, independent of the batch and of the traversal order)
     const int prow = row_base + lane;
     if (ep.rowstat_in != nullptr && prow < M) {
-      const float2* st = reinterpret_cast<const float2*>(ep.rowstat_in) + static_cast<size_t>(prow) * ep.nparts_in;
+      const float4* st = reinterpret_cast<const float4*>(ep.rowstat_in) + static_cast<size_t>(prow) * (ep.nparts_in >> 1);
       float s1 = 0.0f, s2 = 0.0f;
-      for (int i = 0; i < ep.nparts_in; ++i) {
-        const float2 t = st[i];
-        s1 += t.x;
-        s2 += t.y;
+      for (int i = 0; i < (ep.nparts_in >> 1); ++i) {  // nparts_in is even (N % 128 == 0): two parts per 16-byte load
+        const float4 t = st[i];
+        s1 += t.x; s2 += t.y;
+        s1 += t.z; s2 += t.w;
       }
       const float mean = s1 * ep.ln_inv_d;
       const float var = fmaxf(fmaf(-mean, mean, s2 * ep.ln_inv_d), 0.0f);
@@ -104,12 +141,12 @@ B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int ro
     }
   }
   if constexpr (OUT_KIND == 0) {
-    // pull this warp's 32 x 128 residual block towards L2 while the MMAs of the tile are still running
+    // pull this warp's 32 x COLS residual block towards L2 while the MMAs of the tile are still running
     const int prow = row_base + lane;
     if (ep.residual != nullptr && prow < M) {
       const int rr = ep.res_row_mod > 0 ? (prow % ep.res_row_mod) : prow;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < COLS / 32; ++i) {
         const int c = n0 + 32 * i;
         if (c < N)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + static_cast<size_t>(rr) * ep.ldr + c));
@@ -119,10 +156,13 @@ B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int ro
   return ln;
 }
 
-// after tmem_full: drain + store.  taddr0 = TMEM address of (this warp's lane quadrant, first of its 128 columns)
-template <int OUT_KIND>
+// after tmem_full: drain + store.  taddr0 = TMEM address of (this warp's lane quadrant, first of its COLS columns).
+// PIPE: the TMEM load of chunk ch + 1 is in flight while chunk ch is converted, staged and stored (two epilogue warps per
+// scheduler need it; with four the other warps hide the latency and the registers are better spent elsewhere).
+template <int OUT_KIND, int COLS = 128, bool PIPE = true>
 B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_base, int n0, uint32_t taddr0,
                                    uint32_t* stg, const float* sbias, int lane, const RowLN ln) {
+  constexpr int NCH = COLS / 32;    // chunks of 32 columns
   const int wsw = (lane >> 1) & 3;  // write swizzle of this thread's row
   const int rsub = lane >> 2;       // transposed read: row within a group of 8
   const int rq = lane & 3;          // transposed read: 16 B quad within the 64 B row segment
@@ -130,32 +170,32 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
     constexpr bool F16 = OUT_KIND == 2;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);  // 16-bit elements (bf16 or fp16)
     const bool fold = ep.colsum != nullptr;
-    // software pipeline over the 4 chunks of 32 columns: the TMEM load of chunk ch + 1 is in flight while chunk ch is
-    // converted, staged and stored (a serial load -> wait -> compute -> store chain per chunk left the two epilogue warps
-    // of a scheduler waiting on latencies ~60 % of the time: 25 instructions per element, 123 clocks per element)
-    uint32_t rr[2][32];
-    tmem_ld_32x32b_x32(taddr0, rr[0]);
+    uint32_t rr[PIPE ? 2 : 1][32];
+    if constexpr (PIPE) tmem_ld_32x32b_x32(taddr0, rr[0]);
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns = 16 packed words per row
-      uint32_t (&r)[32] = rr[ch & 1];
+    for (int ch = 0; ch < NCH; ++ch) {  // chunks of 32 columns = 16 packed words per row
+      uint32_t (&r)[32] = rr[PIPE ? (ch & 1) : 0];
+      if constexpr (!PIPE) tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
       tmem_ld_wait();
-      if (ch < 3) tmem_ld_32x32b_x32(taddr0 + (ch + 1) * 32, rr[(ch + 1) & 1]);
+      if constexpr (PIPE) {
+        if (ch + 1 < NCH) tmem_ld_32x32b_x32(taddr0 + (ch + 1) * 32, rr[(ch + 1) & 1]);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // 16 B quad j = columns 8j .. 8j+7
         float4 b0 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j);
         float4 b1 = *reinterpret_cast<const float4*>(sbias + ch * 32 + 8 * j + 4);
         float v[8];
-        if (fold) {  // rstd * (acc - mean * colsum) + bias
-          const float4 c0 = *reinterpret_cast<const float4*>(sbias + 128 + ch * 32 + 8 * j);
-          const float4 c1 = *reinterpret_cast<const float4*>(sbias + 128 + ch * 32 + 8 * j + 4);
-          b0.x = fmaf(ln.nmr, c0.x, b0.x); b0.y = fmaf(ln.nmr, c0.y, b0.y);
-          b0.z = fmaf(ln.nmr, c0.z, b0.z); b0.w = fmaf(ln.nmr, c0.w, b0.w);
-          b1.x = fmaf(ln.nmr, c1.x, b1.x); b1.y = fmaf(ln.nmr, c1.y, b1.y);
-          b1.z = fmaf(ln.nmr, c1.z, b1.z); b1.w = fmaf(ln.nmr, c1.w, b1.w);
-          v[0] = fmaf(__uint_as_float(r[8 * j + 0]), ln.rstd, b0.x); v[1] = fmaf(__uint_as_float(r[8 * j + 1]), ln.rstd, b0.y);
-          v[2] = fmaf(__uint_as_float(r[8 * j + 2]), ln.rstd, b0.z); v[3] = fmaf(__uint_as_float(r[8 * j + 3]), ln.rstd, b0.w);
-          v[4] = fmaf(__uint_as_float(r[8 * j + 4]), ln.rstd, b1.x); v[5] = fmaf(__uint_as_float(r[8 * j + 5]), ln.rstd, b1.y);
-          v[6] = fmaf(__uint_as_float(r[8 * j + 6]), ln.rstd, b1.z); v[7] = fmaf(__uint_as_float(r[8 * j + 7]), ln.rstd, b1.w);
+        if (fold) {  // rstd * (acc - mean * colsum) + bias, in packed fp32 pairs
+          const float4 c0 = *reinterpret_cast<const float4*>(sbias + COLS + ch * 32 + 8 * j);
+          const float4 c1 = *reinterpret_cast<const float4*>(sbias + COLS + ch * 32 + 8 * j + 4);
+          fma2_s(b0.x, b0.y, ln.nmr, c0.x, c0.y, b0.x, b0.y);
+          fma2_s(b0.z, b0.w, ln.nmr, c0.z, c0.w, b0.z, b0.w);
+          fma2_s(b1.x, b1.y, ln.nmr, c1.x, c1.y, b1.x, b1.y);
+          fma2_s(b1.z, b1.w, ln.nmr, c1.z, c1.w, b1.z, b1.w);
+          fma2_s(v[0], v[1], ln.rstd, __uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]), b0.x, b0.y);
+          fma2_s(v[2], v[3], ln.rstd, __uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]), b0.z, b0.w);
+          fma2_s(v[4], v[5], ln.rstd, __uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]), b1.x, b1.y);
+          fma2_s(v[6], v[7], ln.rstd, __uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]), b1.z, b1.w);
         } else {
           v[0] = __uint_as_float(r[8 * j + 0]) + b0.x; v[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
           v[2] = __uint_as_float(r[8 * j + 2]) + b0.z; v[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
@@ -164,7 +204,7 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
         }
         if (ep.gelu) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = gelu_erf(v[k]);
+          for (int k = 0; k < 8; k += 2) gelu_erf2(v[k], v[k + 1]);
         }
         uint4 pk;
         pk.x = pack_op16x2<F16>(v[0], v[1]);
@@ -204,19 +244,19 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
     };
     float4 rbuf[2][4];
     load_half(0, rbuf[0]);
-    // LayerNorm folding: 16-bit copy of the result + (sum, sum of squares) of this warp's 128 columns of every row
+    // LayerNorm folding: 16-bit copy of the result + (sum, sum of squares) of every 64-column part of every row
     __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ep.xh);
     const bool stats = ep.rowstat_out != nullptr;
     float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 32 columns, each written as 2 halves of 16
+    for (int ch = 0; ch < NCH; ++ch) {  // chunks of 32 columns, each written as 2 halves of 16
       uint32_t r[32];
       tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
       load_half(2 * ch + 1, rbuf[1]);
       tmem_ld_wait();
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        if (hf == 1 && ch < 3) load_half(2 * ch + 2, rbuf[0]);
+        if (hf == 1 && ch + 1 < NCH) load_half(2 * ch + 2, rbuf[0]);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ wsw) << 2)) =
@@ -250,17 +290,21 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
         }
         __syncwarp();
       }
-    }
-    if (stats) {  // the 4 lanes of a row (rq = 0..3) hold 32 columns each: combine, lane rq == 0 writes the part
-      const int nparts = (N + 127) >> 7, part = n0 >> 7;
+      if (stats && (ch & 1) == 1) {
+        // a 64-column part is complete: the 4 lanes of a row (rq = 0..3) hold 16 columns each: combine, lane rq == 0
+        // writes (the summation order is fixed, so the statistics do not depend on which kernel / grid produced them)
+        const int nparts = (N + EPI_STAT_COLS - 1) / EPI_STAT_COLS, part = (n0 + (ch - 1) * 32) / EPI_STAT_COLS;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        float a = st1[it], b = st2[it];
-        a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
-        const int row = row_base + it * 8 + rsub;
-        if (rq == 0 && row < M && n0 < N)
-          reinterpret_cast<float2*>(ep.rowstat_out)[static_cast<size_t>(row) * nparts + part] = make_float2(a, b);
+        for (int it = 0; it < 4; ++it) {
+          float a = st1[it], b = st2[it];
+          a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+          const int row = row_base + it * 8 + rsub;
+          if (rq == 0 && row < M && n0 + (ch - 1) * 32 < N)
+            reinterpret_cast<float2*>(ep.rowstat_out)[static_cast<size_t>(row) * nparts + part] = make_float2(a, b);
+          st1[it] = 0.0f;
+          st2[it] = 0.0f;
+        }
       }
     }
   }

@@ -34,16 +34,21 @@ namespace {
 constexpr int BM2 = 256;  // rows per cluster tile (128 per CTA)
 constexpr int BN2 = 256;
 constexpr int BK2 = 64;
-constexpr int STAGES2 = 6;
+constexpr int STAGES2 = 5;
 constexpr int UMMA_K2 = 16;
-constexpr int NUM_EPI_WARPS2 = 8;
+// 16 epilogue warps (4 per scheduler), each draining 32 rows x 64 columns: with 8 warps (2 per scheduler) the K = 1280
+// epilogues (25 instructions per element with GELU) were latency bound and longer than the tile's MMAs (ncu: tensor pipe
+// 65 % on lin1, issue slots 43 % busy)
+constexpr int NUM_EPI_WARPS2 = 16;
+constexpr int EPI_COLS2 = 64;
 constexpr int EPI_WARP02 = 4;
-constexpr int THREADS2 = (EPI_WARP02 + NUM_EPI_WARPS2) * 32;  // 384
+constexpr int THREADS2 = (EPI_WARP02 + NUM_EPI_WARPS2) * 32;  // 640
 constexpr int A_BYTES2 = 128 * BK2 * 2;                       // 16 KiB: this CTA's 128 rows of A
 constexpr int B_BYTES2 = 128 * BK2 * 2;                       // 16 KiB: this CTA's half of the B tile
 constexpr int STAGE_BYTES2 = A_BYTES2 + B_BYTES2;
 constexpr int SMEM_TILES2 = STAGES2 * STAGE_BYTES2;
-constexpr int SMEM_EPI2 = NUM_EPI_WARPS2 * (EPI_STAGE_BYTES + EPI_BIAS_BYTES);
+constexpr int EPI_BIAS_BYTES2 = 2 * EPI_COLS2 * 4;             // bias | colsum of this warp's 64 columns
+constexpr int SMEM_EPI2 = NUM_EPI_WARPS2 * (EPI_STAGE_BYTES + EPI_BIAS_BYTES2);
 constexpr int SMEM_BYTES2 = SMEM_TILES2 + SMEM_EPI2 + 256;
 constexpr uint32_t TMEM_COLS2 = 512;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader CTA
@@ -205,23 +210,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else if (warp >= EPI_WARP02) {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
     const int e = warp - EPI_WARP02;
-    const int quad = warp & 3;
-    const int half = e >> 2;
-    uint32_t* stg = reinterpret_cast<uint32_t*>(smem_epi + e * (EPI_STAGE_BYTES + EPI_BIAS_BYTES));
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int cpart = e >> 2;    // which 64-column quarter of the 256-wide tile
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smem_epi + e * (EPI_STAGE_BYTES + EPI_BIAS_BYTES2));
     float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stg) + EPI_STAGE_BYTES);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mb = tile / num_n;
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM2 + static_cast<int>(rank) * 128;
-      const int n0 = (tile % num_n) * BN2 + half * 128;
+      const int n0 = (tile % num_n) * BN2 + cpart * EPI_COLS2;
       const int row_base = m0 + quad * 32;
-      const RowLN ln = epilogue_prefetch<OUT_KIND>(ep, M, N, row_base, n0, sbias, lane);
+      const RowLN ln = epilogue_prefetch<OUT_KIND, EPI_COLS2>(ep, M, N, row_base, n0, sbias, lane);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                              static_cast<uint32_t>(as * BN2 + half * 128);
-      epilogue_store<OUT_KIND>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln);
+                              static_cast<uint32_t>(as * BN2 + cpart * EPI_COLS2);
+      epilogue_store<OUT_KIND, EPI_COLS2, false>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[as], 0);

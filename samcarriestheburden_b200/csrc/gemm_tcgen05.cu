@@ -237,10 +237,11 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
                   "gemm: bad implicit-convolution configuration (cin=%d, K=%d, wp=%d)", g.conv_cin, g.K, g.conv_wp);
   B200SAM_REQUIRE(g.xh == nullptr || (g.out_kind == 0 && (reinterpret_cast<uintptr_t>(g.xh) & 7) == 0 && g.ldo % 4 == 0),
                   "gemm: the 16-bit copy needs an fp32 output, 8-byte alignment and ldo %% 4 == 0");
-  B200SAM_REQUIRE(g.rowstat_out == nullptr || (g.out_kind == 0 && g.epi_mode == 0),
-                  "gemm: row statistics are produced by the fp32 epilogue only");
+  B200SAM_REQUIRE(g.rowstat_out == nullptr || (g.out_kind == 0 && g.epi_mode == 0 && g.N % 128 == 0),
+                  "gemm: row statistics are produced by the fp32 epilogue only and need N %% 128 == 0 (N=%d)", g.N);
   B200SAM_REQUIRE((g.rowstat_in == nullptr) == (g.colsum == nullptr) &&
-                      (g.rowstat_in == nullptr || (g.out_kind != 0 && g.epi_mode == 0 && g.nparts_in > 0 && g.ln_dim > 0)),
+                      (g.rowstat_in == nullptr || (g.out_kind != 0 && g.epi_mode == 0 && g.nparts_in > 0 &&
+                                                   g.nparts_in % 2 == 0 && g.ln_dim > 0)),
                   "gemm: folded LayerNorm needs rowstat_in + colsum + nparts_in + ln_dim and a 16-bit output");
   B200SAM_REQUIRE(g.out_kind >= 0 && g.out_kind <= 2 && (g.out_kind == 0 || (g.out_kind == 2) == (g.op_f16 != 0)),
                   "gemm: a 16-bit output has the operands' format (out_kind=%d, op_f16=%d)", g.out_kind, g.op_f16);

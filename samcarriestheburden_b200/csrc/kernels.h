@@ -55,7 +55,7 @@ struct GemmArgs {
   int op_f16 = 0;               // A / B are fp16 instead of bf16 (the ViT encoder's default)
   // LayerNorm folded into the GEMMs around it (gemm_epilogue.cuh): producer side (fp32 out) ...
   void* xh = nullptr;             // 16-bit copy of out, pitch ldo
-  float* rowstat_out = nullptr;   // [M, ceil(N/128), 2] partial (sum, sum sq) of out per 128-column part
+  float* rowstat_out = nullptr;   // [M, N/64, 2] partial (sum, sum sq) of out per 64-column part (N % 128 == 0)
   // ... consumer side (16-bit out): out = rstd * (acc - mean * colsum[n]) + bias[n]
   const float* rowstat_in = nullptr;  // [M, nparts_in, 2]
   const float* colsum = nullptr;      // [N]
@@ -128,6 +128,13 @@ int resize_coeffs_host(int in_size, int out_size, int32_t* bounds, int32_t* kk);
 int resize_u8(const uint8_t* in, int H, int W, int C, const int32_t* xbounds, const int32_t* xkk, int xksize,
               const int32_t* ybounds, const int32_t* ykk, int yksize, int out_h, int out_w, uint8_t* tmp, uint8_t* out,
               int out_chw, cudaStream_t stream);
+
+// OpenCV-exact uint8 INTER_LINEAR resize (+ optional /255 and (x - mean) / std) for the U-Net ingest; tables: idx [out, 2]
+// (the two taps), w [out, 2] (11-bit weights); clamp_weights = 1 for the x axis, 0 for the y axis
+int cvresize_coeffs_host(int in_size, int out_size, int clamp_weights, int32_t* idx2, int32_t* w2);
+int cvresize_linear_u8(const uint8_t* in, int n, int H, int W, const int32_t* xi, const int32_t* xw, const int32_t* yi,
+                       const int32_t* yw, int out_h, int out_w, uint8_t* out_u8, float* out_norm, float mean, float sd,
+                       cudaStream_t stream);
 
 // ---- amg.cu ----------------------------------------------------------------------------------
 // stability score (count(x > thr + off) / count(x > thr - off) per mask) and XYXY boxes of bool masks (amg.py)

@@ -151,4 +151,84 @@ int resize_u8(const uint8_t* in, int H, int W, int C, const int32_t* xbounds, co
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// U-Net ingest: cv2.resize(uint8 grey, (W, H), INTER_LINEAR) of scripts/save_refined_segmentations.py:63
+// followed by `.float() / 255` (:64) and `(img - IMG_MEAN) / IMG_STD` (:67).  OpenCV is an un-vendored dependency of the
+// reference (environment.yml: opencv 4.9); its published uint8 linear path (modules/imgproc/src/resize.cpp, resizeGeneric_
+// with HResizeLinear / VResizeLinear<uchar, int, short, FixedPtCast<int, uchar, 22>>) is restated:
+//   per axis: f = (float)((d + 0.5) * (double)(in / out) - 0.5), s = floor(f), f -= s; 11-bit weights
+//   saturate_cast<short>((1 - f) * 2048), saturate_cast<short>(f * 2048) (round half to even);
+//   x axis: s < 0 -> (s, f) = (0, 0); s >= in - 1 -> (in - 1, 0); y axis: the two ROWS are clamped to the image but the
+//   weights are kept; horizontal pass exact in int32; vertical pass
+//   uchar((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2).
+// Tables are built on the host (cvresize_coeffs_host, IEEE double / float in OpenCV's order); the passes are integer, so
+// the uint8 result is bit-exact (tests/golden/cv2resize_golden.npz was written by cv2 itself).
+namespace {
+
+__global__ void __launch_bounds__(256) cvresize_linear_kernel(const uint8_t* __restrict__ in, int H, int W,
+                                                              const int32_t* __restrict__ xi, const int32_t* __restrict__ xw,
+                                                              const int32_t* __restrict__ yi, const int32_t* __restrict__ yw,
+                                                              int out_h, int out_w, uint8_t* __restrict__ out_u8,
+                                                              float* __restrict__ out_norm, float mean, float sd) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;
+  if (x >= out_w) return;
+  const uint8_t* img = in + static_cast<size_t>(n) * H * W;
+  const int x0 = __ldg(xi + 2 * x), x1 = __ldg(xi + 2 * x + 1), a0 = __ldg(xw + 2 * x), a1 = __ldg(xw + 2 * x + 1);
+  const int y0 = __ldg(yi + 2 * y), y1 = __ldg(yi + 2 * y + 1), b0 = __ldg(yw + 2 * y), b1 = __ldg(yw + 2 * y + 1);
+  const uint8_t* r0 = img + static_cast<size_t>(y0) * W;
+  const uint8_t* r1 = img + static_cast<size_t>(y1) * W;
+  const int s0 = static_cast<int>(r0[x0]) * a0 + static_cast<int>(r0[x1]) * a1;
+  const int s1 = static_cast<int>(r1[x0]) * a0 + static_cast<int>(r1[x1]) * a1;
+  int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+  v = v < 0 ? 0 : (v > 255 ? 255 : v);
+  const size_t o = (static_cast<size_t>(n) * out_h + y) * out_w + x;
+  if (out_u8 != nullptr) out_u8[o] = static_cast<uint8_t>(v);
+  if (out_norm != nullptr)  // fp32: u8 / 255, then (v - mean) / std, each op rounded like torch's elementwise kernels
+    out_norm[o] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), mean), sd);
+}
+
+}  // namespace
+
+int cvresize_coeffs_host(int in_size, int out_size, int clamp_weights, int32_t* idx2, int32_t* w2) {
+  B200SAM_REQUIRE(in_size > 0 && out_size > 0 && idx2 != nullptr && w2 != nullptr, "cvresize_coeffs: bad arguments");
+  const double scale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  for (int d = 0; d < out_size; ++d) {
+    volatile double pos = (d + 0.5) * scale;  // volatile: no fused multiply-add contraction across the two operations
+    float f = static_cast<float>(pos - 0.5);
+    int s = static_cast<int>(std::floor(f));
+    f -= static_cast<float>(s);
+    if (clamp_weights) {
+      if (s < 0) { s = 0; f = 0.0f; }
+      if (s >= in_size - 1) { s = in_size - 1; f = 0.0f; }
+    }
+    auto sat16 = [](float v) {
+      const long r = std::lrint(v);  // round half to even (default rounding mode), like cvRound
+      return static_cast<int32_t>(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+    };
+    w2[2 * d] = sat16((1.0f - f) * 2048.0f);
+    w2[2 * d + 1] = sat16(f * 2048.0f);
+    const int i0 = s < 0 ? 0 : (s > in_size - 1 ? in_size - 1 : s);
+    const int i1 = s + 1 < 0 ? 0 : (s + 1 > in_size - 1 ? in_size - 1 : s + 1);
+    idx2[2 * d] = i0;
+    idx2[2 * d + 1] = i1;
+  }
+  return 0;
+}
+
+int cvresize_linear_u8(const uint8_t* in, int n, int H, int W, const int32_t* xi, const int32_t* xw, const int32_t* yi,
+                       const int32_t* yw, int out_h, int out_w, uint8_t* out_u8, float* out_norm, float mean, float sd,
+                       cudaStream_t stream) {
+  B200SAM_REQUIRE(in != nullptr && n > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && xi && xw && yi && yw,
+                  "cvresize: bad arguments (n=%d H=%d W=%d out=%dx%d)", n, H, W, out_h, out_w);
+  B200SAM_REQUIRE(out_u8 != nullptr || out_norm != nullptr, "cvresize: no output requested");
+  B200SAM_REQUIRE(out_h <= 65535 && n <= 65535, "cvresize: at most 65535 output rows / images");
+  B200SAM_REQUIRE(out_norm == nullptr || sd != 0.0f, "cvresize: std must be non-zero");
+  dim3 grid((out_w + 255) / 256, out_h, n);
+  cvresize_linear_kernel<<<grid, 256, 0, stream>>>(in, H, W, xi, xw, yi, yw, out_h, out_w, out_u8, out_norm, mean, sd);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace b200sam

@@ -69,19 +69,20 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
 @torch.no_grad()
 def predict_unet_probabilities(unet, images: Sequence[np.ndarray], size=(384, 224), batch: int = 8,
                                mean: float = 0.3505533917353781, std: float = 0.22763733675869177) -> List[torch.Tensor]:
-    """The U-Net stage of save_refined_segmentations.py:61-69 for the local shard: grey uint8 images -> bilinear
-    resize to (H, W) (cv2.INTER_LINEAR == half-pixel bilinear without antialiasing) -> / 255 -> normalise -> U-Net ->
-    sigmoid.  Returns one [C, H, W] probability map per input image (on the model's device)."""
+    """The U-Net stage of save_refined_segmentations.py:61-69 for the local shard: grey uint8 images ->
+    cv2.resize(INTER_LINEAR) to (H, W) (OpenCV's fixed-point uint8 path, restated bit-exactly on the GPU: the result is
+    ROUNDED to uint8 before / 255, like the reference) -> / 255 -> normalise -> U-Net -> sigmoid.
+    Returns one [C, H, W] probability map per input image (on the model's device)."""
+    from ..segment_anything.utils.transforms import cv_resize_linear_cuda
     dev = unet.outc.conv.weight.device
     H, W = size
     out: List[torch.Tensor] = []
     for j in range(0, len(images), batch):
         xs = []
         for img in images[j:j + batch]:
-            g = torch.from_numpy(np.ascontiguousarray(img if img.ndim == 2 else img[..., 0])).to(dev).float()[None, None]
-            if tuple(g.shape[-2:]) != (H, W):
-                g = torch.nn.functional.interpolate(g, size=(H, W), mode="bilinear", align_corners=False)
-            xs.append((g / 255.0 - mean) / std)
+            g = torch.from_numpy(np.ascontiguousarray(img if img.ndim == 2 else img[..., 0])).to(dev, non_blocking=True)
+            # cv2.resize returns the input unchanged when the size already matches; the kernel's identity tables do too
+            xs.append(cv_resize_linear_cuda(g, H, W, normalize=(mean, std))[None, None])
         probs = unet.predict_proba(torch.cat(xs))
         out.extend(probs[k] for k in range(probs.shape[0]))
     return out

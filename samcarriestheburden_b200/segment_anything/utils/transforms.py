@@ -54,6 +54,48 @@ def resize_u8_cuda(image: torch.Tensor, out_h: int, out_w: int, chw: bool = Fals
     return out
 
 
+_CV_TABLES = {}
+
+
+def _cv_tables(in_size: int, out_size: int, clamp: bool, device: torch.device):
+    """OpenCV INTER_LINEAR tap / weight tables of one axis (library host function), cached on the device."""
+    from ... import _lib
+    key = (in_size, out_size, clamp, str(device))
+    hit = _CV_TABLES.get(key)
+    if hit is None:
+        lib = _lib.load()
+        idx = np.zeros((out_size, 2), np.int32)
+        w = np.zeros((out_size, 2), np.int32)
+        _lib.check(lib.b200sam_cvresize_coeffs_host(in_size, out_size, int(clamp), idx.ctypes.data_as(C.c_void_p),
+                                                    w.ctypes.data_as(C.c_void_p)), "cvresize_coeffs_host")
+        hit = (torch.from_numpy(idx).to(device), torch.from_numpy(w).to(device))
+        _CV_TABLES[key] = hit
+    return hit
+
+
+def cv_resize_linear_cuda(image: torch.Tensor, out_h: int, out_w: int, normalize=None):
+    """image: [H, W] or [N, H, W] uint8 CUDA tensor -> `cv2.resize(img, (out_w, out_h), interpolation=cv2.INTER_LINEAR)`
+    of every image, bit-exact (the U-Net ingest of scripts/save_refined_segmentations.py:63).  normalize = (mean, std):
+    return float32 ((u8 / 255) - mean) / std instead (save_refined_segmentations.py:64-67 fused)."""
+    from ... import _lib
+    assert image.is_cuda and image.dtype == torch.uint8 and image.dim() in (2, 3), "expected a [N,] H, W uint8 CUDA tensor"
+    squeeze = image.dim() == 2
+    img = image.contiguous().view(-1, image.shape[-2], image.shape[-1])
+    n, H, W = img.shape
+    lib = _lib.load()
+    xi, xw = _cv_tables(W, out_w, True, img.device)
+    yi, yw = _cv_tables(H, out_h, False, img.device)
+    if normalize is None:
+        out = torch.empty((n, out_h, out_w), dtype=torch.uint8, device=img.device)
+        o8, of, mean, std = out.data_ptr(), None, 0.0, 1.0
+    else:
+        out = torch.empty((n, out_h, out_w), dtype=torch.float32, device=img.device)
+        o8, of, mean, std = None, out.data_ptr(), float(normalize[0]), float(normalize[1])
+    _lib.run(img.device, lib.b200sam_cvresize_linear_u8, img.data_ptr(), n, H, W, xi.data_ptr(), xw.data_ptr(),
+             yi.data_ptr(), yw.data_ptr(), out_h, out_w, o8, of, mean, std, what="b200sam_cvresize_linear_u8")
+    return out[0] if squeeze else out
+
+
 class ResizeLongestSide:
     def __init__(self, target_length: int) -> None:
         self.target_length = target_length

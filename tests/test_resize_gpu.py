@@ -11,6 +11,7 @@ from oracle import sam_oracle as O
 pytestmark = pytest.mark.gpu
 GOLD = np.load(Path(__file__).parent / "golden" / "resize_golden.npz")
 N_CASES = sum(1 for k in GOLD.files if k.startswith("in"))
+DEV = "cuda"
 
 
 def _resize(img: np.ndarray, oh: int, ow: int, chw: bool) -> np.ndarray:
@@ -88,3 +89,26 @@ def test_set_image_uses_gpu_resize_and_matches_host_resize():
     host = torch.from_numpy(O.apply_image(img, 1024)).permute(2, 0, 1).contiguous()[None].cuda()
     pred.set_torch_image(host, (591, 377))
     assert torch.equal(a, pred.get_image_embedding())
+
+
+def test_cv2_linear_resize_matches_cv2_golden_and_oracle():
+    """U-Net ingest (scripts/save_refined_segmentations.py:63-67): the GPU restatement of cv2.resize(INTER_LINEAR) on uint8 is
+    bit-exact against goldens written by cv2 itself, and the fused normalisation equals the reference's fp32 operations."""
+    from test_cv2resize_oracle import golden_cases, make_image
+    from samcarriestheburden_b200.segment_anything.utils.transforms import cv_resize_linear_cuda
+    g, seeds = golden_cases()
+    mean, std = 0.3505533917353781, 0.22763733675869177
+    for seed in seeds:
+        H, W = (int(v) for v in g[f"shape_{seed}"])
+        img = make_image(seed, H, W)
+        got = cv_resize_linear_cuda(torch.from_numpy(img).to(DEV), 384, 224)
+        assert got.dtype == torch.uint8 and np.array_equal(got.cpu().numpy(), g[f"out_{seed}"]), (seed, H, W)
+        norm = cv_resize_linear_cuda(torch.from_numpy(img).to(DEV), 384, 224, normalize=(mean, std)).cpu()
+        ref = (torch.from_numpy(g[f"out_{seed}"]).float() / 255 - mean) / std      # the reference's :64 and :67
+        assert torch.equal(norm, ref), (seed, float((norm - ref).abs().max()))
+    # batched same-size images and other target sizes against the oracle
+    rng = np.random.default_rng(3)
+    batch = rng.integers(0, 256, (3, 301, 517), dtype=np.uint8)
+    got = cv_resize_linear_cuda(torch.from_numpy(batch).to(DEV), 97, 131).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], O.cv2_resize_linear_u8(batch[i], 97, 131))

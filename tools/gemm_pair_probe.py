@@ -19,7 +19,7 @@ st = _lib.current_stream()
 g = torch.Generator(device="cpu").manual_seed(0)
 x = torch.randn((M, D), generator=g).to(dev)
 x16 = torch.empty((M, D), dtype=torch.float16, device=dev)
-stat = torch.empty((M, D // 128, 2), device=dev)
+stat = torch.empty((M, D // 64, 2), device=dev)
 h16 = torch.randn((M, 4 * D), generator=g).to(dev).half()
 
 
@@ -42,12 +42,12 @@ def proj():
 
 def qkv_():
     _lib.check(lib.b200sam_gemm_ln_folded(x16.data_ptr(), Wq.data_ptr(), bq.data_ptr(), sq.data_ptr(), stat.data_ptr(),
-                                          D // 128, 1e-6, qkv.data_ptr(), M, 3 * D, D, 0, 1, st))
+                                          D // 64, 1e-6, qkv.data_ptr(), M, 3 * D, D, 0, 1, st))
 
 
 def lin1():
     _lib.check(lib.b200sam_gemm_ln_folded(x16.data_ptr(), W1.data_ptr(), b1.data_ptr(), s1.data_ptr(), stat.data_ptr(),
-                                          D // 128, 1e-6, hid.data_ptr(), M, 4 * D, D, 1, 1, st))
+                                          D // 64, 1e-6, hid.data_ptr(), M, 4 * D, D, 1, 1, st))
 
 
 def lin2():
