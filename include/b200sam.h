@@ -165,6 +165,17 @@ B200SAM_API int b200sam_cvresize_linear_u8(const uint8_t* image, int n, int H, i
                                const int32_t* yidx, const int32_t* yw, int out_h, int out_w, uint8_t* out_u8,
                                float* out_norm, float mean, float std, void* stream);
 
+/* MedSAM ingest (the reference's default sam_type): replaces cv2.resize(img, (1024, 1024), interpolation=cv2.INTER_CUBIC)
+ * + min-max normalisation of scripts/generate_img_embeddings.py:49-62 (OpenCV's own uint8 cubic path, i.e. without Intel
+ * IPP; the result feeds b200sam_encoder_forward as float32 with mean 0 / std 1, bypassing Sam.preprocess like the
+ * reference).  gray: [H,W] uint8 (its RGB replication has three identical channels); tables from the HOST function
+ * (idx4 [size,4] clamped taps, w4 [size,4]); resized_u8 [size,size] and minmax [2] are outputs / scratch;
+ * out3: [3,size,size] float32 in [0,1]. */
+B200SAM_API int b200sam_cvresize_cubic_coeffs_host(int in_size, int out_size, int32_t* idx4_host, int32_t* w4_host);
+B200SAM_API int b200sam_medsam_preprocess(const uint8_t* gray, int H, int W, const int32_t* xidx, const int32_t* xw,
+                              const int32_t* yidx, const int32_t* yw, int size, uint8_t* resized_u8, int32_t* minmax,
+                              float* out3, void* stream);
+
 /* ---------------------------------------------------------------- U-Net inference
  * Replaces UNet.forward (custom_arcitecture/classic_u_net.py:81-119, bilinear = False) as called from
  * scripts/save_refined_segmentations.py:67-69 (+ the torch.sigmoid that follows).  Weight table like the SAM handles:

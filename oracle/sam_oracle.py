@@ -477,6 +477,54 @@ def cv2_resize_linear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
+# ----------------------------------------------------------------------------------------------- MedSAM ingest
+# scripts/generate_img_embeddings.py:49-64 (the reference's DEFAULT sam_type = 'medsam', :16): cv2.resize(RGB uint8,
+# (1024, 1024), INTER_CUBIC) -> min-max normalise to [0, 1] in float64 -> float32 [1, 3, 1024, 1024] -> image_encoder
+# (Sam.preprocess is bypassed: no mean / std, no padding).  OpenCV's published uint8 cubic path (resize.cpp:
+# interpolateCubic with A = -0.75 in fp32, 11-bit weights saturate_cast<short>(c * 2048), HResizeCubic in int32 with the
+# tap indices clamped to the image, VResizeCubic's vector body for uchar: fp32 ((S3 b3 + S2 b2) + S1 b1) + S0 b0 with
+# b = w / 2^22, round half to even, saturate) is restated; pinned bit-exactly against cv2 with Intel IPP switched off
+# (conda's opencv 4.9 of environment.yml has no IPP; pip wheels route cubic through IPP, which differs by 1 LSB in ~4 %
+# of the pixels) by tests/golden/make_golden_cv2resize.py.
+def cv2_cubic_coeffs(ssize: int, dsize: int):
+    d = np.arange(dsize, dtype=np.float64)
+    f = ((d + 0.5) * (ssize / dsize) - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    x = (f - s.astype(np.float32)).astype(np.float32)
+    A, one = np.float32(-0.75), np.float32(1)
+    c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    c2 = ((A + np.float32(2)) * (one - x) - (A + np.float32(3))) * (one - x) * (one - x) + one
+    c3 = one - c0 - c1 - c2
+    w = np.clip(np.rint(np.stack([c0, c1, c2, c3], 1).astype(np.float32) * np.float32(2048)), -32768, 32767).astype(np.int32)
+    idx = np.clip(s[:, None] - 1 + np.arange(4)[None, :], 0, ssize - 1)
+    return idx, w
+
+
+def cv2_resize_cubic_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """uint8 [H, W] -> uint8 [out_h, out_w], bit-exact with cv2.resize(..., INTER_CUBIC) of an IPP-less OpenCV."""
+    assert img.dtype == np.uint8 and img.ndim == 2
+    xi, xw = cv2_cubic_coeffs(img.shape[1], out_w)
+    yi, yw = cv2_cubic_coeffs(img.shape[0], out_h)
+    im = img.astype(np.int64)
+    rows = sum(im[:, xi[:, k]] * xw[:, k].astype(np.int64)[None, :] for k in range(4))
+    scale = np.float32(1.0) / np.float32(2048.0 * 2048.0)
+    S = [rows[yi[:, k]].astype(np.float32) for k in range(4)]
+    b = [(yw[:, k].astype(np.float32) * scale).astype(np.float32)[:, None] for k in range(4)]
+    acc = (S[3] * b[3]).astype(np.float32)
+    for k in (2, 1, 0):
+        acc = ((S[k] * b[k]).astype(np.float32) + acc).astype(np.float32)
+    return np.clip(np.rint(acc), 0, 255).astype(np.uint8)
+
+
+def medsam_preprocess(gray: np.ndarray, size: int = 1024) -> torch.Tensor:
+    """scripts/generate_img_embeddings.py:39-40,49-62: grey uint8 [H, W] -> float32 [1, 3, size, size] in [0, 1]."""
+    r = cv2_resize_cubic_u8(gray, size, size)
+    lo, hi = r.min(), r.max()
+    norm = (r - lo) / np.clip(hi - lo, a_min=1e-8, a_max=None)  # uint8 difference / float64, like the reference
+    return torch.tensor(np.repeat(norm[:, :, None], 3, axis=2)).float().permute(2, 0, 1).unsqueeze(0)
+
+
 # ----------------------------------------------------------------------------------------------- refinement loop
 @torch.no_grad()
 def predict_mask(sd: SD, features: torch.Tensor, prompt: OraclePrompt, prompt2use: Sequence[str],

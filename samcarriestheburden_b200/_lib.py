@@ -64,6 +64,8 @@ _PROTOTYPES = {
     "b200sam_resize_u8": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "b200sam_cvresize_coeffs_host": (_i, [_i, _i, _i, _vp, _vp]),
     "b200sam_cvresize_linear_u8": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _f, _f, _vp]),
+    "b200sam_cvresize_cubic_coeffs_host": (_i, [_i, _i, _vp, _vp]),
+    "b200sam_medsam_preprocess": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "b200sam_stability_score": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
     "b200sam_mask_to_box": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "b200sam_ccl_scratch_bytes": (_sz, [_i, _i, _i]),

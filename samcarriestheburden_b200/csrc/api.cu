@@ -188,6 +188,14 @@ int b200sam_cvresize_linear_u8(const uint8_t* image, int n, int H, int W, const 
                             static_cast<cudaStream_t>(stream));
 }
 
+int b200sam_cvresize_cubic_coeffs_host(int in_size, int out_size, int32_t* idx4_host, int32_t* w4_host) {
+  return cvresize_cubic_coeffs_host(in_size, out_size, idx4_host, w4_host);
+}
+int b200sam_medsam_preprocess(const uint8_t* gray, int H, int W, const int32_t* xidx, const int32_t* xw, const int32_t* yidx,
+                              const int32_t* yw, int size, uint8_t* resized_u8, int32_t* minmax, float* out3, void* stream) {
+  return medsam_preprocess(gray, H, W, xidx, xw, yidx, yw, size, resized_u8, minmax, out3, static_cast<cudaStream_t>(stream));
+}
+
 int b200sam_stability_score(const float* logits, int n, int H, int W, float threshold_hi, float threshold_lo,
                             float* score_out, int32_t* scratch, void* stream) {
   return stability_score(logits, n, H, W, threshold_hi, threshold_lo, score_out, scratch,

@@ -136,6 +136,12 @@ int cvresize_linear_u8(const uint8_t* in, int n, int H, int W, const int32_t* xi
                        const int32_t* yw, int out_h, int out_w, uint8_t* out_u8, float* out_norm, float mean, float sd,
                        cudaStream_t stream);
 
+// MedSAM ingest: OpenCV-exact uint8 INTER_CUBIC resize of a grey image to size x size, min-max normalisation in float64,
+// three identical fp32 channels [3, size, size]; tables: idx [size, 4] clamped taps, w [size, 4] 11-bit weights
+int cvresize_cubic_coeffs_host(int in_size, int out_size, int32_t* idx4, int32_t* w4);
+int medsam_preprocess(const uint8_t* gray, int H, int W, const int32_t* xi, const int32_t* xw, const int32_t* yi,
+                      const int32_t* yw, int size, uint8_t* tmp_u8, int32_t* minmax, float* out3, cudaStream_t stream);
+
 // ---- amg.cu ----------------------------------------------------------------------------------
 // stability score (count(x > thr + off) / count(x > thr - off) per mask) and XYXY boxes of bool masks (amg.py)
 int stability_score(const float* logits, int n, int H, int W, float threshold_hi, float threshold_lo,

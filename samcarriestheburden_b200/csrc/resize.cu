@@ -231,4 +231,109 @@ int cvresize_linear_u8(const uint8_t* in, int n, int H, int W, const int32_t* xi
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// MedSAM ingest (scripts/generate_img_embeddings.py:49-62, the reference's default sam_type): cv2.resize(RGB uint8,
+// (1024, 1024), INTER_CUBIC) -> (x - min) / clip(max - min, 1e-8) in float64 -> float32 [3, S, S].  OpenCV's published
+// (IPP-less) uint8 cubic path: interpolateCubic (A = -0.75, fp32), 11-bit weights, HResizeCubic in int32 with clamped
+// tap indices, VResizeCubic's vector body for uchar in fp32: ((S3 b3 + S2 b2) + S1 b1) + S0 b0, b = w / 2^22, round half
+// to even, saturate.  The grey image is resized once; its three identical channels are written by the normalise pass.
+namespace {
+
+__global__ void __launch_bounds__(256) cvresize_cubic_kernel(const uint8_t* __restrict__ in, int H, int W,
+                                                             const int32_t* __restrict__ xi, const int32_t* __restrict__ xw,
+                                                             const int32_t* __restrict__ yi, const int32_t* __restrict__ yw,
+                                                             int out_h, int out_w, uint8_t* __restrict__ out,
+                                                             int32_t* __restrict__ minmax) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  int v = 0;
+  if (x < out_w) {
+    int xs[4], ws[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { xs[k] = __ldg(xi + 4 * x + k); ws[k] = __ldg(xw + 4 * x + k); }
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {  // S3 first, like the nested multiply-adds of OpenCV's vector body
+      const uint8_t* r = in + static_cast<size_t>(__ldg(yi + 4 * y + k)) * W;
+      const int s = static_cast<int>(r[xs[0]]) * ws[0] + static_cast<int>(r[xs[1]]) * ws[1] +
+                    static_cast<int>(r[xs[2]]) * ws[2] + static_cast<int>(r[xs[3]]) * ws[3];
+      const float b = __fmul_rn(static_cast<float>(__ldg(yw + 4 * y + k)), 1.0f / (2048.0f * 2048.0f));
+      const float t = __fmul_rn(static_cast<float>(s), b);
+      acc = k == 3 ? t : __fadd_rn(t, acc);
+    }
+    v = __float2int_rn(acc);
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    out[static_cast<size_t>(y) * out_w + x] = static_cast<uint8_t>(v);
+  }
+  if (minmax != nullptr) {
+    int lo = x < out_w ? v : 255, hi = x < out_w ? v : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
+  }
+}
+
+__global__ void minmax_init_kernel(int32_t* minmax) { minmax[0] = 255; minmax[1] = 0; }
+
+// out[c, y, x] = float((double)(u8 - min) / max((double)(max - min), 1e-8)), c = 0..2
+__global__ void __launch_bounds__(256) minmax_normalize3_kernel(const uint8_t* __restrict__ in, size_t n,
+                                                                const int32_t* __restrict__ minmax,
+                                                                float* __restrict__ out) {
+  const int lo = minmax[0], hi = minmax[1];
+  const double den = fmax(static_cast<double>(hi - lo), 1e-8);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = __double2float_rn(static_cast<double>(static_cast<int>(in[i]) - lo) / den);
+    out[i] = v;
+    out[n + i] = v;
+    out[2 * n + i] = v;
+  }
+}
+
+}  // namespace
+
+int cvresize_cubic_coeffs_host(int in_size, int out_size, int32_t* idx4, int32_t* w4) {
+  B200SAM_REQUIRE(in_size > 0 && out_size > 0 && idx4 != nullptr && w4 != nullptr, "cvresize_cubic_coeffs: bad arguments");
+  const double scale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  for (int d = 0; d < out_size; ++d) {
+    volatile double pos = (d + 0.5) * scale;
+    const float f0 = static_cast<float>(pos - 0.5);
+    const int s = static_cast<int>(std::floor(f0));
+    // interpolateCubic, every operation rounded to fp32 (volatile: no contraction, no excess precision)
+    volatile float x = f0 - static_cast<float>(s);
+    const float A = -0.75f;
+    volatile float x1 = x + 1.0f, u = 1.0f - x;
+    volatile float t;
+    volatile float c[4];
+    t = A * x1; t = t - 5.0f * A; t = t * x1; t = t + 8.0f * A; t = t * x1; c[0] = t - 4.0f * A;
+    t = (A + 2.0f) * x; t = t - (A + 3.0f); t = t * x; t = t * x; c[1] = t + 1.0f;
+    t = (A + 2.0f) * u; t = t - (A + 3.0f); t = t * u; t = t * u; c[2] = t + 1.0f;
+    t = 1.0f - c[0]; t = t - c[1]; c[3] = t - c[2];
+    for (int k = 0; k < 4; ++k) {
+      volatile float scaled = c[k] * 2048.0f;
+      const long r = std::lrint(scaled);
+      w4[4 * d + k] = static_cast<int32_t>(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+      const int i = s - 1 + k;
+      idx4[4 * d + k] = i < 0 ? 0 : (i > in_size - 1 ? in_size - 1 : i);
+    }
+  }
+  return 0;
+}
+
+int medsam_preprocess(const uint8_t* gray, int H, int W, const int32_t* xi, const int32_t* xw, const int32_t* yi,
+                      const int32_t* yw, int size, uint8_t* tmp_u8, int32_t* minmax, float* out3, cudaStream_t stream) {
+  B200SAM_REQUIRE(gray && xi && xw && yi && yw && tmp_u8 && minmax && out3 && H > 0 && W > 0 && size > 0 && size <= 65535,
+                  "medsam_preprocess: bad arguments (H=%d W=%d size=%d)", H, W, size);
+  minmax_init_kernel<<<1, 1, 0, stream>>>(minmax);
+  dim3 grid((size + 255) / 256, size);
+  cvresize_cubic_kernel<<<grid, 256, 0, stream>>>(gray, H, W, xi, xw, yi, yw, size, size, tmp_u8, minmax);
+  const size_t n = static_cast<size_t>(size) * size;
+  minmax_normalize3_kernel<<<148 * 8, 256, 0, stream>>>(tmp_u8, n, minmax, out3);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace b200sam

@@ -25,11 +25,17 @@ from ..utils.seg_refinement import SAMSegRefiner, SegEnhance
 
 @torch.no_grad()
 def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[str], batch: int = 8,
-                            store: EmbeddingStore | None = None, gather: bool = False):
+                            store: EmbeddingStore | None = None, gather: bool = False, sam_type: str = "sam"):
     """images: HWC uint8 RGB arrays (gray replicated to 3 channels like the reference :39-40).  Each rank encodes
     its shard in batches (same-shape images are batched together) and registers the results in `store`.
+    sam_type = 'sam': SamPredictor.set_image semantics (:45-48); 'medsam' (the reference's default, :16): cubic resize to
+    1024 x 1024 + min-max normalisation, the encoder is called directly without Sam.preprocess (:49-64).
     Returns (store, gathered [N,256,64,64] tensor or None)."""
     assert len(images) == len(names)
+    if sam_type not in ("sam", "medsam"):
+        raise NotImplementedError(f"Unknown SAM type: {sam_type}")
+    if sam_type == "medsam":
+        return _generate_medsam_embeddings(sam, images, names, batch, store, gather)
     dev = sam.device
     store = store if store is not None else EmbeddingStore(img_encoder_img_size=sam.image_encoder.img_size)
     pred = SamPredictor(sam)
@@ -62,6 +68,31 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
             flush(key)
     for key in list(pending):
         flush(key)
+    gathered = sharding.gather_sharded(local, len(images)) if gather else None
+    return store, gathered
+
+
+def _generate_medsam_embeddings(sam, images, names, batch, store, gather):
+    """scripts/generate_img_embeddings.py:49-64: per image cv2 INTER_CUBIC resize (bit-exact GPU restatement) + min-max
+    normalise, then `image_encoder(img_tensor)` on batches of the resulting float tensors; original_size = the native
+    size, input_size = (1024, 1024)."""
+    from ..segment_anything.utils.transforms import medsam_preprocess_cuda
+    dev = sam.device
+    size = sam.image_encoder.img_size
+    store = store if store is not None else EmbeddingStore(img_encoder_img_size=size)
+    mine = sharding.shard_indices(len(images))
+    local = torch.empty((len(mine), 256, 64, 64), dtype=torch.float32, device=dev)
+    for j in range(0, len(mine), batch):
+        chunk = mine[j:j + batch]
+        xs = []
+        for i in chunk:
+            img = images[i]
+            g = torch.from_numpy(np.ascontiguousarray(img if img.ndim == 2 else img[..., 0])).to(dev, non_blocking=True)
+            xs.append(medsam_preprocess_cuda(g, size))
+        emb = sam.image_encoder(torch.cat(xs))
+        for k, i in enumerate(chunk):
+            local[j + k] = emb[k]
+            store.add(names[i], local[j + k:j + k + 1], tuple(images[i].shape[:2]), (size, size))
     gathered = sharding.gather_sharded(local, len(images)) if gather else None
     return store, gathered
 

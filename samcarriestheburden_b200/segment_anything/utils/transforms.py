@@ -96,6 +96,38 @@ def cv_resize_linear_cuda(image: torch.Tensor, out_h: int, out_w: int, normalize
     return out[0] if squeeze else out
 
 
+def _cv_cubic_tables(in_size: int, out_size: int, device: torch.device):
+    from ... import _lib
+    key = ("cubic", in_size, out_size, str(device))
+    hit = _CV_TABLES.get(key)
+    if hit is None:
+        idx = np.zeros((out_size, 4), np.int32)
+        w = np.zeros((out_size, 4), np.int32)
+        _lib.check(_lib.load().b200sam_cvresize_cubic_coeffs_host(in_size, out_size, idx.ctypes.data_as(C.c_void_p),
+                                                                   w.ctypes.data_as(C.c_void_p)), "cvresize_cubic_coeffs_host")
+        hit = (torch.from_numpy(idx).to(device), torch.from_numpy(w).to(device))
+        _CV_TABLES[key] = hit
+    return hit
+
+
+def medsam_preprocess_cuda(gray: torch.Tensor, size: int = 1024, return_resized: bool = False):
+    """The MedSAM branch of scripts/generate_img_embeddings.py:39-40,49-62 on the GPU: grey uint8 [H, W] CUDA tensor (the
+    reference replicates it to RGB) -> cv2 INTER_CUBIC resize to size x size -> min-max normalise -> float32
+    [1, 3, size, size] in [0, 1], the tensor the reference feeds straight into `image_encoder` (no Sam.preprocess)."""
+    from ... import _lib
+    assert gray.is_cuda and gray.dtype == torch.uint8 and gray.dim() == 2, "expected a [H, W] uint8 CUDA tensor"
+    g = gray.contiguous()
+    H, W = g.shape
+    xi, xw = _cv_cubic_tables(W, size, g.device)
+    yi, yw = _cv_cubic_tables(H, size, g.device)
+    resized = torch.empty((size, size), dtype=torch.uint8, device=g.device)
+    minmax = torch.empty((2,), dtype=torch.int32, device=g.device)
+    out = torch.empty((1, 3, size, size), dtype=torch.float32, device=g.device)
+    _lib.run(g.device, _lib.load().b200sam_medsam_preprocess, g.data_ptr(), H, W, xi.data_ptr(), xw.data_ptr(), yi.data_ptr(),
+             yw.data_ptr(), size, resized.data_ptr(), minmax.data_ptr(), out.data_ptr(), what="b200sam_medsam_preprocess")
+    return (out, resized) if return_resized else out
+
+
 class ResizeLongestSide:
     def __init__(self, target_length: int) -> None:
         self.target_length = target_length

@@ -60,3 +60,39 @@ def test_library_host_tables_match_oracle():
             i0, i1, ww = O.cv2_linear_coeffs(ssize, dsize, bool(clamp))
             assert np.array_equal(idx[:, 0], i0) and np.array_equal(idx[:, 1], i1), (ssize, dsize, clamp)
             assert np.array_equal(w, ww), (ssize, dsize, clamp)
+
+
+@pytest.mark.parametrize("seed", [20, 21, 22])
+def test_oracle_cubic_matches_cv2_golden(seed):
+    """MedSAM ingest (scripts/generate_img_embeddings.py:49-53): the oracle's INTER_CUBIC restatement against goldens written
+    by cv2 with Intel IPP switched off (OpenCV's own code path), bit-exact."""
+    g, _ = golden_cases()
+    H, W = (int(v) for v in g[f"cubic_shape_{seed}"])
+    got = O.cv2_resize_cubic_u8(make_image(seed, H, W), 1024, 1024)
+    assert np.array_equal(got[::8], g[f"cubic_rows_{seed}"])
+    assert [int(got.min()), int(got.max())] == [int(v) for v in g[f"cubic_minmax_{seed}"]]
+
+
+def test_library_cubic_tables_match_oracle():
+    import ctypes as C
+    from samcarriestheburden_b200 import _lib
+    lib = _lib.load()
+    for (ssize, dsize) in [(754, 1024), (1182, 1024), (2040, 1024), (200, 1024), (1024, 1024), (3, 1024), (2920, 1024)]:
+        idx = np.zeros((dsize, 4), np.int32)
+        w = np.zeros((dsize, 4), np.int32)
+        assert lib.b200sam_cvresize_cubic_coeffs_host(ssize, dsize, idx.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p)) == 0
+        oi, ow = O.cv2_cubic_coeffs(ssize, dsize)
+        assert np.array_equal(idx, oi) and np.array_equal(w, ow), (ssize, dsize)
+
+
+def test_medsam_preprocess_oracle_against_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    if hasattr(cv2, "ipp"):
+        cv2.ipp.setUseIPP(False)
+    gray = make_image(31, 411, 263)
+    rgb = cv2.cvtColor(gray, cv2.COLOR_GRAY2RGB)
+    r = cv2.resize(rgb, (1024, 1024), interpolation=cv2.INTER_CUBIC)
+    ref = (r - r.min()) / np.clip(r.max() - r.min(), a_min=1e-8, a_max=None)      # generate_img_embeddings.py:55-56
+    import torch
+    ref_t = torch.tensor(ref).float().permute(2, 0, 1).unsqueeze(0)               # :60
+    assert torch.equal(O.medsam_preprocess(gray), ref_t)

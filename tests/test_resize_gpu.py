@@ -112,3 +112,33 @@ def test_cv2_linear_resize_matches_cv2_golden_and_oracle():
     got = cv_resize_linear_cuda(torch.from_numpy(batch).to(DEV), 97, 131).cpu().numpy()
     for i in range(3):
         assert np.array_equal(got[i], O.cv2_resize_linear_u8(batch[i], 97, 131))
+
+
+def test_medsam_ingest_matches_oracle_and_embeds():
+    """MedSAM branch (scripts/generate_img_embeddings.py:49-64): cubic resize + min-max normalisation bit-exact against the
+    oracle (pinned to cv2 goldens), and the embeddings of the `medsam` driver against the oracle encoder on that input."""
+    from test_cv2resize_oracle import golden_cases, make_image
+    from samcarriestheburden_b200.scripts.pipelines import generate_img_embeddings
+    from samcarriestheburden_b200.segment_anything import sam_model_registry
+    from samcarriestheburden_b200.segment_anything.utils.transforms import medsam_preprocess_cuda
+    g, _ = golden_cases()
+    for seed in (20, 22):
+        H, W = (int(v) for v in g[f"cubic_shape_{seed}"])
+        gray = make_image(seed, H, W)
+        out, resized = medsam_preprocess_cuda(torch.from_numpy(gray).to(DEV), 1024, return_resized=True)
+        assert np.array_equal(resized.cpu().numpy()[::8], g[f"cubic_rows_{seed}"])
+        assert torch.equal(out.cpu(), O.medsam_preprocess(gray))
+    flat = np.full((50, 70), 9, np.uint8)  # max == min: the reference divides by clip(0, 1e-8) -> all zeros
+    assert float(medsam_preprocess_cuda(torch.from_numpy(flat).to(DEV)).abs().max()) == 0.0
+    sd = O.random_state_dict("vit_b", seed=0)
+    sam = sam_model_registry["vit_b"]()
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.to(DEV)
+    imgs = [np.repeat(make_image(40 + i, 300 + 50 * i, 200)[:, :, None], 3, axis=2) for i in range(3)]
+    store, emb = generate_img_embeddings(sam, imgs, ["a", "b", "c"], batch=2, gather=True, sam_type="medsam")
+    assert emb.shape == (3, 256, 64, 64)
+    assert tuple(store["b"].attrs["original_size"]) == (350, 200) and tuple(store["b"].attrs["input_size"]) == (1024, 1024)
+    ref = O.image_encoder(sd, O.medsam_preprocess(imgs[1][..., 0]), **O.VIT_CONFIGS["vit_b"])
+    rel = float((emb[1:2].cpu() - ref).norm() / ref.norm())
+    print(f"medsam embedding rel-L2 {rel:.2e}")
+    assert rel < 1.5e-3
