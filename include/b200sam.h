@@ -106,6 +106,22 @@ B200SAM_API int b200sam_decode_batch(const b200sam_decoder* dec, const float* em
                          const int32_t* labels, const float* mask_prev, int multimask, float* low_res_out,
                          float* iou_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two halves on their own, for callers of the reference's standalone module API:
+ * b200sam_prompt_encode = PromptEncoder.forward (modeling/prompt_encoder.py:128-168): sparse_out [n_prompts,n_points,256]
+ * (points, pad point and box corners already assembled by the caller as coords / labels like for b200sam_decode) and
+ * dense_tok_out [n_prompts,4096,256] = the dense embedding TOKEN-MAJOR (NCHW view: .view(n,64,64,256).permute(0,3,1,2));
+ * tokens_tmp [n_prompts,5+n_points,256] and ntok_tmp [n_prompts] are scratch.
+ * b200sam_decode_embedded = MaskDecoder.forward (modeling/mask_decoder.py:71-110) on caller-supplied sparse
+ * [n_prompts,n_sparse,256] and token-major dense [n_prompts,4096,256] embeddings; the image positional encoding is the
+ * model's own dense PE (b200sam_decoder_copy_dense_pe). */
+B200SAM_API int b200sam_prompt_encode(const b200sam_decoder* dec, const float* coords, const int32_t* labels, int n_prompts,
+                          int n_points, const float* mask_prev, float* tokens_tmp, int32_t* ntok_tmp, float* sparse_out,
+                          float* dense_tok_out, void* stream);
+B200SAM_API int b200sam_decode_embedded(const b200sam_decoder* dec, const float* embeddings, int n_images,
+                            const int32_t* image_of, int n_prompts, int n_sparse, const float* sparse,
+                            const float* dense_tok, int multimask, float* low_res_out, float* iou_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- mask post-processing
  * Replaces postprocess_masks + threshold (segment_anything/sam_mask_decoder_head.py:99-135,
  * modeling/sam.py:133-162) and the nearest-exact resample of utils/seg_refinement.py:111.

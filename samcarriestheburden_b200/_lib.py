@@ -51,6 +51,8 @@ _PROTOTYPES = {
     "b200sam_decode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200sam_decoder_workspace_bytes_batch": (_sz, [_i, _i, _i]),
     "b200sam_decode_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200sam_prompt_encode": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200sam_decode_embedded": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200sam_upscale_threshold": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "b200sam_unet_weight_count": (_i, []),
     "b200sam_unet_weight_name": (C.c_char_p, [_i]),

@@ -132,6 +132,26 @@ int b200sam_decode_batch(const b200sam_decoder* dec, const float* embeddings, in
   return decoder_forward(dec->impl, a, static_cast<cudaStream_t>(stream));
 }
 
+int b200sam_prompt_encode(const b200sam_decoder* dec, const float* coords, const int32_t* labels, int n_prompts,
+                          int n_points, const float* mask_prev, float* tokens_tmp, int32_t* ntok_tmp, float* sparse_out,
+                          float* dense_tok_out, void* stream) {
+  if (!dec) { set_last_error("prompt_encode: null decoder"); return 2; }
+  return prompt_encode(dec->impl, coords, labels, n_prompts, n_points, mask_prev, tokens_tmp, ntok_tmp, sparse_out,
+                       dense_tok_out, static_cast<cudaStream_t>(stream));
+}
+int b200sam_decode_embedded(const b200sam_decoder* dec, const float* embeddings, int n_images, const int32_t* image_of,
+                            int n_prompts, int n_sparse, const float* sparse, const float* dense_tok, int multimask,
+                            float* low_res_out, float* iou_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dec) { set_last_error("decode_embedded: null decoder"); return 2; }
+  if (!dense_tok || (n_sparse > 0 && !sparse)) { set_last_error("decode_embedded: null embeddings"); return 2; }
+  DecodeArgs a;
+  a.emb = embeddings; a.n_images = n_images; a.image_of = image_of; a.NB = n_prompts; a.Np = n_sparse;
+  a.coords = nullptr; a.labels = nullptr; a.mask_prev = nullptr; a.sparse_tokens = sparse; a.dense_tok = dense_tok;
+  a.img_w = 1024.0f; a.img_h = 1024.0f; a.multimask = multimask; a.low_res_out = low_res_out; a.iou_out = iou_out;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return decoder_forward(dec->impl, a, static_cast<cudaStream_t>(stream));
+}
+
 int b200sam_upscale_threshold(const float* low_res, int n, int low, int img_size, int in_h, int in_w, int out_h,
                               int out_w, float threshold, uint8_t* mask_out, float* logits_out, uint8_t* small_out,
                               int small_h, int small_w, void* stream) {

@@ -246,6 +246,27 @@ void decoder_destroy(Decoder* d) {
 
 const float* decoder_dense_pe(const Decoder* d) { return d->pe_tok; }
 
+int prompt_encode(const Decoder* d, const float* coords, const int* labels, int NB, int Np, const float* mask_prev,
+                  float* tokens_tmp, int* ntok_tmp, float* sparse_out, float* dense_tok_out, cudaStream_t s) {
+  B200SAM_REQUIRE(NB > 0 && Np >= 0 && Np <= 27, "prompt_encode: bad shape NB=%d Np=%d", NB, Np);
+  B200SAM_REQUIRE(dense_tok_out != nullptr && (Np == 0 || (coords && labels && tokens_tmp && ntok_tmp && sparse_out)),
+                  "prompt_encode: null pointer argument");
+  const float* const* W = d->w.data();
+  if (Np > 0) {
+    const int T = 5 + Np;
+    TRY(prompt_tokens(coords, labels, NB, Np, W[W_GAUSS], W[W_POINT4], W[W_NOT_A_POINT], W[W_IOU_TOKEN], W[W_MASK_TOKENS],
+                      1024.0f, 1024.0f, tokens_tmp, ntok_tmp, s));
+    B200SAM_CHECK_CUDA(cudaMemcpy2DAsync(sparse_out, static_cast<size_t>(Np) * 256 * sizeof(float), tokens_tmp + 5 * 256,
+                                         static_cast<size_t>(T) * 256 * sizeof(float),
+                                         static_cast<size_t>(Np) * 256 * sizeof(float), NB, cudaMemcpyDeviceToDevice, s));
+  }
+  if (mask_prev != nullptr)
+    TRY(mask_downscale_keys(mask_prev, W + W_MASKDOWN, nullptr, dense_tok_out, NB, nullptr, nullptr, s));
+  else
+    TRY(broadcast_row256(W[W_NO_MASK], dense_tok_out, static_cast<size_t>(NB) * 4096, s));
+  return 0;
+}
+
 int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   B200SAM_REQUIRE(a.NB > 0 && a.Np >= 0 && a.n_images > 0, "decode: bad prompt batch NB=%d Np=%d images=%d", a.NB, a.Np,
                   a.n_images);
@@ -253,7 +274,8 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   B200SAM_REQUIRE(a.NB <= 65535 && a.NB <= (1 << 30) / 16384, "decode: at most 65535 prompts per call, got %d", a.NB);
   const int NB = a.NB, T = 5 + a.Np;
   B200SAM_REQUIRE(T <= 32, "decode: at most 27 sparse prompt tokens per prompt supported, got %d", a.Np);
-  B200SAM_REQUIRE(a.Np == 0 || (a.coords != nullptr && a.labels != nullptr), "decode: coords/labels missing");
+  B200SAM_REQUIRE(a.Np == 0 || a.sparse_tokens != nullptr || (a.coords != nullptr && a.labels != nullptr),
+                  "decode: coords/labels missing");
   B200SAM_REQUIRE(a.emb != nullptr && a.low_res_out != nullptr && a.iou_out != nullptr, "decode: null in/out pointer");
   B200SAM_REQUIRE(a.workspace != nullptr && (reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0,
                   "decode: workspace must be non-null and 256-byte aligned");
@@ -261,17 +283,22 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   B200SAM_REQUIRE(w.total <= a.workspace_bytes, "decode: workspace too small (%zu < %zu)", a.workspace_bytes, w.total);
   const float* const* W = d->w.data();
   const int Mi = NB * 4096, Mt = NB * T;
-  const bool share0 = a.mask_prev == nullptr && a.image_of != nullptr && a.n_images < NB;
+  const bool share0 = a.mask_prev == nullptr && a.dense_tok == nullptr && a.image_of != nullptr && a.n_images < NB;
   const float* pe = d->pe_tok;
 
   // ---- prompt encoder (prompt_encoder.py:128-168) + output tokens (mask_decoder.py:120-122)
-  TRY(prompt_tokens(a.coords, a.labels, NB, a.Np, W[W_GAUSS], W[W_POINT4], W[W_NOT_A_POINT], W[W_IOU_TOKEN],
-                    W[W_MASK_TOKENS], a.img_w, a.img_h, w.tokens, w.ntok, s));
+  if (a.sparse_tokens != nullptr)
+    TRY(tokens_from_sparse(a.sparse_tokens, NB, a.Np, W[W_IOU_TOKEN], W[W_MASK_TOKENS], w.tokens, w.ntok, s));
+  else
+    TRY(prompt_tokens(a.coords, a.labels, NB, a.Np, W[W_GAUSS], W[W_POINT4], W[W_NOT_A_POINT], W[W_IOU_TOKEN],
+                      W[W_MASK_TOKENS], a.img_w, a.img_h, w.tokens, w.ntok, s));
   TRY(nchw_to_tokens(a.emb, w.emb_tok, a.n_images, s));
   // the producers of the image-side keys also emit sb = split(keys), the bf16 [hi | lo] operand of EVERY image-side
   // projection: the ones that take keys + pe (k of the token->image attentions, q of the image->token attention) add
   // their positional term as the per-token table pek_* = pe W^T + b in the GEMM epilogue (residual row = row % 4096)
-  if (a.mask_prev != nullptr) {
+  if (a.dense_tok != nullptr) {
+    TRY(keys_init(w.emb_tok, W[W_NO_MASK], w.keys, NB, a.image_of, pe, nullptr, w.sb, s, a.dense_tok));
+  } else if (a.mask_prev != nullptr) {
     TRY(mask_downscale_keys(a.mask_prev, W + W_MASKDOWN, w.emb_tok, w.keys, NB, a.image_of, w.sb, s));
   } else {
     // Without mask prompts the image-side keys emb + no_mask are the same for all prompts of an image until the first

@@ -37,6 +37,9 @@ struct DecodeArgs {
   const float* coords;     // [NB, Np, 2] (x, y) in the encoder input frame
   const int* labels;       // [NB, Np]: -1 pad, 0 neg, 1 pos, 2/3 box corners, -2 absent slot (trailing; ragged batches)
   const float* mask_prev;  // [NB, 256, 256] logits of a previous pass, or null
+  // standalone MaskDecoder.forward (mask_decoder.py:71-110): caller-supplied embeddings instead of prompts
+  const float* sparse_tokens = nullptr;  // [NB, Np, 256] sparse prompt embeddings (coords / labels unused)
+  const float* dense_tok = nullptr;      // [NB, 4096, 256] token-major dense prompt embeddings (mask_prev unused)
   float img_w, img_h;      // prompt_encoder.input_image_size (W, H) = (1024, 1024)
   int multimask;           // 0: mask token 0 only, 1: tokens 1..3
   float* low_res_out;      // [NB, 1|3, 256, 256]
@@ -52,5 +55,9 @@ int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_
 void decoder_destroy(Decoder* d);
 const float* decoder_dense_pe(const Decoder* d);
 int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t stream);
+// PromptEncoder.forward alone (prompt_encoder.py:128-168): sparse_out [NB, Np, 256], dense_tok_out [NB, 4096, 256]
+// (token-major); tokens_tmp [NB, 5 + Np, 256] and ntok_tmp [NB] are scratch
+int prompt_encode(const Decoder* d, const float* coords, const int* labels, int NB, int Np, const float* mask_prev,
+                  float* tokens_tmp, int* ntok_tmp, float* sparse_out, float* dense_tok_out, cudaStream_t stream);
 
 }  // namespace b200sam

@@ -621,10 +621,12 @@ __global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __res
 // keys[b, tok, c] = emb_tok[tok, c] + no_mask_embed[c]  (prompt_encoder.py:164-166 + mask_decoder.py:126)
 // grid (x, NB): prompt b reads the token-major embedding of its image (image_of[b], or image 0)
 // and emits the split operands of the first layer: sa = split(keys + pe), sb = split(keys)
+// dense_tok != null: per-prompt dense prompt embedding [NB, 4096, 256] (token-major) instead of the no_mask vector
+// (standalone MaskDecoder.forward with caller-supplied dense embeddings)
 __global__ void keys_init_kernel(const float4* __restrict__ emb_tok, const float4* __restrict__ no_mask,
                                  float4* __restrict__ keys, const int* __restrict__ image_of,
                                  const float4* __restrict__ pe, __nv_bfloat16* __restrict__ sa,
-                                 __nv_bfloat16* __restrict__ sb) {
+                                 __nv_bfloat16* __restrict__ sb, const float4* __restrict__ dense_tok) {
   const size_t n8 = 4096 * 32;  // groups of 8 channels
   const int b = blockIdx.y;
   const float4* e4 = emb_tok + (image_of != nullptr ? image_of[b] : 0) * (n8 * 2);
@@ -632,7 +634,9 @@ __global__ void keys_init_kernel(const float4* __restrict__ emb_tok, const float
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 e0 = e4[2 * i], e1 = e4[2 * i + 1];
-    const float4 d0 = no_mask[(2 * i) & 63], d1 = no_mask[(2 * i + 1) & 63];
+    const float4* dt = dense_tok != nullptr ? dense_tok + static_cast<size_t>(b) * (n8 * 2) : nullptr;
+    const float4 d0 = dt != nullptr ? dt[2 * i] : no_mask[(2 * i) & 63];
+    const float4 d1 = dt != nullptr ? dt[2 * i + 1] : no_mask[(2 * i + 1) & 63];
     float f[8] = {e0.x + d0.x, e0.y + d0.y, e0.z + d0.z, e0.w + d0.w, e1.x + d1.x, e1.y + d1.y, e1.z + d1.z, e1.w + d1.w};
     k4[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
     k4[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -658,7 +662,7 @@ __global__ void __launch_bounds__(256) mask_downscale_keys_kernel(const float* _
                                                                   __nv_bfloat16* __restrict__ sb) {
   __shared__ float hid[32][17];
   const int b = blockIdx.y;
-  emb_tok += static_cast<size_t>(image_of != nullptr ? image_of[b] : 0) * 4096 * 256;
+  if (emb_tok != nullptr) emb_tok += static_cast<size_t>(image_of != nullptr ? image_of[b] : 0) * 4096 * 256;
   const int tok0 = blockIdx.x * 32;
   const int tid = threadIdx.x;
   if (tid < 32) {
@@ -728,7 +732,7 @@ __global__ void __launch_bounds__(256) mask_downscale_keys_kernel(const float* _
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) a = fmaf(wr[kk], hid[t][kk], a);
     const size_t o = static_cast<size_t>(tok0 + t) * 256 + tid;
-    const float kv = emb_tok[o] + a;
+    const float kv = (emb_tok != nullptr ? emb_tok[o] : 0.0f) + a;  // emb_tok == null: the dense embedding alone
     keys[static_cast<size_t>(b) * 4096 * 256 + o] = kv;
     if (sb != nullptr) {  // [hi | lo] split operand of the image-side projections, written by the producer of the keys
       const size_t row = static_cast<size_t>(b) * 4096 + tok0 + t;
@@ -986,11 +990,46 @@ int nchw_to_tokens(const float* in, float* out, int n_images, cudaStream_t strea
 }
 
 int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of, const float* pe,
-              __nv_bfloat16* sa, __nv_bfloat16* sb, cudaStream_t stream) {
+              __nv_bfloat16* sa, __nv_bfloat16* sb, cudaStream_t stream, const float* dense_tok) {
   keys_init_kernel<<<dim3(64, NB), 256, 0, stream>>>(reinterpret_cast<const float4*>(emb_tok),
                                                      reinterpret_cast<const float4*>(no_mask),
                                                      reinterpret_cast<float4*>(keys), image_of,
-                                                     reinterpret_cast<const float4*>(pe), sa, sb);
+                                                     reinterpret_cast<const float4*>(pe), sa, sb,
+                                                     reinterpret_cast<const float4*>(dense_tok));
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+// tokens[b] = [iou_token; 4 mask tokens; sparse[b, 0..Ns)] (mask_decoder.py:120-122 with caller-supplied sparse embeddings)
+__global__ void tokens_from_sparse_kernel(const float* __restrict__ sparse, int Ns, const float* __restrict__ iou_token,
+                                          const float* __restrict__ mask_tokens, float* __restrict__ tokens,
+                                          int* __restrict__ ntok) {
+  const int b = blockIdx.y, t = blockIdx.x, j = threadIdx.x;  // 256 threads
+  const int T = 5 + Ns;
+  float* dst = tokens + (static_cast<size_t>(b) * T + t) * 256;
+  if (t == 0) { dst[j] = iou_token[j]; if (j == 0) ntok[b] = T; }
+  else if (t < 5) dst[j] = mask_tokens[(t - 1) * 256 + j];
+  else dst[j] = sparse[(static_cast<size_t>(b) * Ns + (t - 5)) * 256 + j];
+}
+// out[row, :] = v[0..256) for every row (the no-mask dense embedding, prompt_encoder.py:164-166)
+__global__ void broadcast_row256_kernel(const float4* __restrict__ v, float4* __restrict__ out, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = v[i & 63];
+}
+}  // namespace
+
+int tokens_from_sparse(const float* sparse, int NB, int Ns, const float* iou_token, const float* mask_tokens, float* tokens,
+                       int* ntok, cudaStream_t stream) {
+  tokens_from_sparse_kernel<<<dim3(5 + Ns, NB), 256, 0, stream>>>(sparse, Ns, iou_token, mask_tokens, tokens, ntok);
+  B200SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int broadcast_row256(const float* v, float* out, size_t rows, cudaStream_t stream) {
+  broadcast_row256_kernel<<<148 * 4, 256, 0, stream>>>(reinterpret_cast<const float4*>(v), reinterpret_cast<float4*>(out),
+                                                     rows * 64);
   B200SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -40,7 +40,11 @@ int nchw_to_tokens(const float* in, float* out, int n_images, cudaStream_t strea
 // image_of: optional [NB] index of the image (row block of emb_tok) each prompt belongs to; null = image 0
 // also emits the first layer's split operands sa = split(keys + pe), sb = split(keys) ([NB*4096, 512] bf16 each)
 int keys_init(const float* emb_tok, const float* no_mask, float* keys, int NB, const int* image_of, const float* pe,
-              __nv_bfloat16* sa, __nv_bfloat16* sb, cudaStream_t stream);
+              __nv_bfloat16* sa, __nv_bfloat16* sb, cudaStream_t stream, const float* dense_tok = nullptr);
+// tokens [NB, 5 + Ns, 256] = [iou_token; 4 mask tokens; sparse[b]] for caller-supplied sparse embeddings [NB, Ns, 256]
+int tokens_from_sparse(const float* sparse, int NB, int Ns, const float* iou_token, const float* mask_tokens, float* tokens,
+                       int* ntok, cudaStream_t stream);
+int broadcast_row256(const float* v, float* out, size_t rows, cudaStream_t stream);
 // in-place LayerNorm (eps 1e-5) of the [M, 256] image-side keys fused with sa = split(keys + pe[row % 4096]), sb = split(keys)
 int ln256_keys_split(float* keys, const float* gamma, const float* beta, const float* pe, size_t M, __nv_bfloat16* sa,
                      __nv_bfloat16* sb, cudaStream_t stream);

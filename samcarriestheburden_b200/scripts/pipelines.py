@@ -25,17 +25,20 @@ from ..utils.seg_refinement import SAMSegRefiner, SegEnhance
 
 @torch.no_grad()
 def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[str], batch: int = 8,
-                            store: EmbeddingStore | None = None, gather: bool = False, sam_type: str = "sam"):
+                            store: EmbeddingStore | None = None, gather: bool = False, sam_type: str = "sam",
+                            writer=None):
     """images: HWC uint8 RGB arrays (gray replicated to 3 channels like the reference :39-40).  Each rank encodes
     its shard in batches (same-shape images are batched together) and registers the results in `store`.
     sam_type = 'sam': SamPredictor.set_image semantics (:45-48); 'medsam' (the reference's default, :16): cubic resize to
     1024 x 1024 + min-max normalisation, the encoder is called directly without Sam.preprocess (:49-64).
-    Returns (store, gathered [N,256,64,64] tensor or None)."""
+    `writer`: an `storage.AsyncResultWriter(kind='embedding')`; every embedding is handed to it as soon as its batch is
+    encoded (pinned D2H copy on the writer's stream + background write in the reference's layout, :67-70), off the
+    critical path.  Returns (store, gathered [N,256,64,64] tensor or None)."""
     assert len(images) == len(names)
     if sam_type not in ("sam", "medsam"):
         raise NotImplementedError(f"Unknown SAM type: {sam_type}")
     if sam_type == "medsam":
-        return _generate_medsam_embeddings(sam, images, names, batch, store, gather)
+        return _generate_medsam_embeddings(sam, images, names, batch, store, gather, writer)
     dev = sam.device
     store = store if store is not None else EmbeddingStore(img_encoder_img_size=sam.image_encoder.img_size)
     pred = SamPredictor(sam)
@@ -54,6 +57,8 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
         for j, (slot, _, orig) in enumerate(items):
             local[slot] = emb[j]
             store.add(names[mine[slot]], local[slot:slot + 1], orig, key)
+            if writer is not None:
+                writer.put_embedding(names[mine[slot]], local[slot:slot + 1], orig, key)
 
     for slot, i in enumerate(mine):
         img = images[i]
@@ -72,7 +77,7 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
     return store, gathered
 
 
-def _generate_medsam_embeddings(sam, images, names, batch, store, gather):
+def _generate_medsam_embeddings(sam, images, names, batch, store, gather, writer=None):
     """scripts/generate_img_embeddings.py:49-64: per image cv2 INTER_CUBIC resize (bit-exact GPU restatement) + min-max
     normalise, then `image_encoder(img_tensor)` on batches of the resulting float tensors; original_size = the native
     size, input_size = (1024, 1024)."""
@@ -93,6 +98,8 @@ def _generate_medsam_embeddings(sam, images, names, batch, store, gather):
         for k, i in enumerate(chunk):
             local[j + k] = emb[k]
             store.add(names[i], local[j + k:j + k + 1], tuple(images[i].shape[:2]), (size, size))
+            if writer is not None:
+                writer.put_embedding(names[i], local[j + k:j + k + 1], tuple(images[i].shape[:2]), (size, size))
     gathered = sharding.gather_sharded(local, len(images)) if gather else None
     return store, gathered
 
@@ -122,10 +129,12 @@ def predict_unet_probabilities(unet, images: Sequence[np.ndarray], size=(384, 22
 @torch.no_grad()
 def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor], names: Sequence[str],
                          prompts2use=(("box",), ("pos_points", "neg_points")), gather: bool = False,
-                         batch: int = 8, ccl_selection: str | None = None):
+                         batch: int = 8, ccl_selection: str | None = None, writer=None):
     """segs[i]: [C,H,W] bool (or probabilities) U-Net masks of image names[i]; every rank refines the images of its
     shard whose embeddings it holds.  `ccl_selection` ('highest_probability' | 'largest') runs the SegEnhance
     connected-component pre-processing (save_refined_segmentations.py:25-33,76) on the probability maps first.
+    `writer`: a `storage.AsyncResultWriter(kind='mask')` that persists every image's refined masks + estimated Dice
+    (save_refined_segmentations.py:75-80) off the critical path.
     Returns (list of (index, seg bool [C,H,W], est_dice [C]) for the local shard, gathered [N,C,H,W] uint8 tensor
     or None)."""
     dev = sam.device
@@ -139,6 +148,9 @@ def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor
         x, nm = torch.stack([segs[i].to(dev) for i in chunk]), [names[i] for i in chunk]
         seg_b, est_b = stage.enhance_batch(x, nm) if stage is not None else refiner.refine_batch(x, nm)
         results.extend((i, seg_b[k], est_b[k]) for k, i in enumerate(chunk))
+        if writer is not None:
+            for k, i in enumerate(chunk):
+                writer.put_masks(names[i], seg_b[k], est_b[k])
     gathered = None
     if gather and len(segs):
         local = torch.stack([r[1] for r in results]).to(torch.uint8) if results else \

@@ -1,8 +1,9 @@
 """Mask decoder parameter container (reference: segment_anything/modeling/mask_decoder.py)."""
 from __future__ import annotations
 
-from typing import Type
+from typing import Tuple, Type
 
+import torch
 import torch.nn as nn
 
 from .common import FusedAway, LayerNorm2d
@@ -40,6 +41,20 @@ class MaskDecoder(nn.Module):
             [MLP(transformer_dim, transformer_dim, transformer_dim // 8, 3) for _ in range(self.num_mask_tokens)])
         self.iou_prediction_head = MLP(transformer_dim, iou_head_hidden_dim, self.num_mask_tokens, iou_head_depth)
 
-    def forward(self, *args, **kwargs):  # pragma: no cover - guard rail
-        raise NotImplementedError("MaskDecoder.forward is fused with the prompt encoder in b200sam: call "
-                                  "Sam.decode_prompts / SamPredictor.predict(_torch) / SAMMaskDecoderHead.predict_mask")
+        self._owner = None  # set by Sam: the CUDA decoder engine lives there
+
+    @torch.no_grad()
+    def forward(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor, sparse_prompt_embeddings: torch.Tensor,
+                dense_prompt_embeddings: torch.Tensor, multimask_output: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Standalone mask prediction from prompt EMBEDDINGS (reference mask_decoder.py:71-110) -> (masks B x (1|3) x 256
+        x 256, iou B x (1|3)).  `image_pe` must be the model's own dense positional encoding
+        (`prompt_encoder.get_dense_pe()`, what every caller in the reference passes): its projections are folded into
+        per-token tables when the engine is built."""
+        if self._owner is None or self._owner() is None:
+            raise RuntimeError("MaskDecoder needs the owning Sam model on a CUDA device")
+        eng = self._owner().decoder_engine()
+        own_pe = eng.dense_pe()
+        if image_pe.data_ptr() != own_pe.data_ptr() and not torch.equal(image_pe.to(own_pe.device).expand_as(own_pe), own_pe):
+            raise NotImplementedError("b200sam's MaskDecoder only supports image_pe == prompt_encoder.get_dense_pe()")
+        return eng.decode_embedded(image_embeddings.to(eng.device), sparse_prompt_embeddings.to(eng.device),
+                                   dense_prompt_embeddings.to(eng.device), bool(multimask_output))

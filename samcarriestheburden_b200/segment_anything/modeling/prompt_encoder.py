@@ -48,6 +48,30 @@ class PromptEncoder(nn.Module):
             raise RuntimeError("PromptEncoder.get_dense_pe needs the owning Sam model on a CUDA device")
         return self._owner().decoder_engine().dense_pe()
 
-    def forward(self, points, boxes, masks):  # pragma: no cover - guard rail
-        raise NotImplementedError("PromptEncoder.forward is fused with the mask decoder in b200sam: call "
-                                  "Sam.decode_prompts / SamPredictor.predict(_torch) / SAMMaskDecoderHead.predict_mask")
+    def _engine(self):
+        if self._owner is None or self._owner() is None:
+            raise RuntimeError("PromptEncoder needs the owning Sam model on a CUDA device")
+        return self._owner().decoder_engine()
+
+    @torch.no_grad()
+    def forward(self, points: Optional[Tuple[torch.Tensor, torch.Tensor]], boxes: Optional[torch.Tensor],
+                masks: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Standalone prompt embedding (reference prompt_encoder.py:128-168): points = (coords B x N x 2, labels B x N),
+        boxes B x 4, masks B x 1 x 256 x 256 -> (sparse B x n x 256, dense B x 256 x 64 x 64).  The pipeline itself uses
+        the fused Sam.decode_prompts; this entry point runs the same CUDA kernels for callers of the module API."""
+        from .sam import assemble_prompt_points
+        eng = self._engine()
+        if points is not None:
+            bs = points[0].shape[0]
+        elif boxes is not None:
+            bs = boxes.shape[0]
+        elif masks is not None:
+            bs = masks.shape[0]
+        else:
+            bs = 1
+        c, l = assemble_prompt_points(points[0] if points is not None else None,
+                                      points[1] if points is not None else None, boxes)
+        c = c.to(eng.device) if c is not None else None
+        l = l.to(eng.device) if l is not None else None
+        m = masks.to(eng.device) if masks is not None else None
+        return eng.prompt_encode(c, l, m, bs)

@@ -86,12 +86,82 @@ class _DecoderEngine:
                                                  self._ws.numel() - (base - self._ws.data_ptr()), what="b200sam_decode_batch")
         return low, iou
 
+    def _workspace(self, n_img: int, NB: int, Np: int):
+        need = self.lib.b200sam_decoder_workspace_bytes_batch(n_img, NB, Np)
+        if self._ws is None or self._ws.numel() < need + 256:
+            self._ws = None  # release before growing
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        base = (self._ws.data_ptr() + 255) & ~255
+        return base, self._ws.numel() - (base - self._ws.data_ptr())
+
+    def prompt_encode(self, coords: Optional[torch.Tensor], labels: Optional[torch.Tensor], mask_prev: Optional[torch.Tensor],
+                      batch: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """PromptEncoder.forward alone: -> (sparse [B,Np,256], dense [B,256,64,64] as an NCHW view of token-major data)."""
+        NB = batch
+        Np = coords.shape[1] if coords is not None else 0
+        sparse = torch.empty((NB, Np, 256), dtype=torch.float32, device=self.device)
+        dense_tok = torch.empty((NB, 4096, 256), dtype=torch.float32, device=self.device)
+        tmp = torch.empty((NB, 5 + Np, 256), dtype=torch.float32, device=self.device) if Np else None
+        ntok = torch.empty((NB,), dtype=torch.int32, device=self.device) if Np else None
+        if coords is not None:
+            coords = coords.float().contiguous()
+            labels = labels.to(torch.int32).contiguous()
+        if mask_prev is not None:
+            mask_prev = mask_prev.reshape(NB, 256, 256).float().contiguous()
+        _lib.run(self.device, self.lib.b200sam_prompt_encode, self.handle, _lib.ptr(coords), _lib.ptr(labels), NB, Np,
+                 _lib.ptr(mask_prev), _lib.ptr(tmp), _lib.ptr(ntok), _lib.ptr(sparse), dense_tok.data_ptr(),
+                 what="b200sam_prompt_encode")
+        return sparse, dense_tok.view(NB, 64, 64, 256).permute(0, 3, 1, 2)
+
+    def decode_embedded(self, embedding: torch.Tensor, sparse: torch.Tensor, dense: torch.Tensor,
+                        multimask: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """MaskDecoder.predict_masks + slicing on caller-supplied sparse [B,N,256] / dense [B,256,64,64] embeddings."""
+        emb = embedding.reshape(-1, 256, 64, 64).float().contiguous()
+        n_img, NB, Ns = emb.shape[0], sparse.shape[0], sparse.shape[1]
+        if n_img not in (1, NB):
+            raise ValueError("image_embeddings must hold one image or one image per prompt (mask_decoder.py:125)")
+        image_of = torch.arange(NB, dtype=torch.int32, device=self.device) if n_img > 1 else None
+        sp = sparse.float().contiguous()
+        dt = dense.float().expand(NB, 256, 64, 64).permute(0, 2, 3, 1).reshape(NB, 4096, 256).contiguous()
+        nm = 3 if multimask else 1
+        low = torch.empty((NB, nm, 256, 256), dtype=torch.float32, device=self.device)
+        iou = torch.empty((NB, nm), dtype=torch.float32, device=self.device)
+        base, size = self._workspace(n_img, NB, Ns)
+        _lib.run(self.device, self.lib.b200sam_decode_embedded, self.handle, emb.data_ptr(), n_img, _lib.ptr(image_of), NB,
+                 Ns, _lib.ptr(sp) if Ns else None, dt.data_ptr(), int(multimask), low.data_ptr(), iou.data_ptr(), base,
+                 size, what="b200sam_decode_embedded")
+        return low, iou
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):
                 self.lib.b200sam_decoder_destroy(self.handle)
         except Exception:
             pass
+
+
+def assemble_prompt_points(point_coords: Optional[torch.Tensor], point_labels: Optional[torch.Tensor],
+                           boxes: Optional[torch.Tensor]):
+    """[points | pad point iff no box | box corners] + labels (-1 pad, 0/1 points, 2/3 corners), as the prompt encoder
+    consumes them (prompt_encoder.py:73-100,155).  Built on the inputs' own device."""
+    coords, labels = [], []
+    if point_coords is not None:
+        pc = point_coords.float()
+        pl = point_labels.to(device=pc.device, dtype=torch.int32)
+        coords.append(pc)
+        labels.append(pl)
+        if boxes is None:  # pad point, label -1 (prompt_encoder.py:81-85)
+            coords.append(torch.zeros((pc.shape[0], 1, 2), device=pc.device))
+            labels.append(-torch.ones((pc.shape[0], 1), dtype=torch.int32, device=pc.device))
+    if boxes is not None:
+        b = boxes.float().reshape(-1, 2, 2)
+        if coords:
+            b = b.to(coords[0].device)
+        coords.append(b)
+        labels.append(torch.tensor([[2, 3]], dtype=torch.int32, device=b.device).expand(b.shape[0], 2))
+    if not coords:
+        return None, None
+    return torch.cat(coords, dim=1), torch.cat(labels, dim=1)
 
 
 def upscale_masks(low_res: torch.Tensor, input_size, original_size, img_size: int = 1024, threshold: float = 0.0,
@@ -134,6 +204,7 @@ class Sam(nn.Module):
         self._dec_engine: Optional[_DecoderEngine] = None
         self._dec_versions: Optional[tuple] = None
         self.prompt_encoder._owner = weakref.ref(self)
+        self.mask_decoder._owner = weakref.ref(self)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     def _invalidate(self) -> None:
@@ -175,33 +246,28 @@ class Sam(nn.Module):
         dev = self.device
         # assemble [points | pad point | box corners] + labels on the inputs' own device (CPU tensors stay on the
         # host and cross in ONE copy each), then hand raw pointers to the C ABI
-        coords, labels = [], []
-        if point_coords is not None:
-            pc = point_coords.float()
-            pl = point_labels.to(device=pc.device, dtype=torch.int32)
-            coords.append(pc)
-            labels.append(pl)
-            if boxes is None:  # pad point, label -1 (prompt_encoder.py:81-85)
-                coords.append(torch.zeros((pc.shape[0], 1, 2), device=pc.device))
-                labels.append(-torch.ones((pc.shape[0], 1), dtype=torch.int32, device=pc.device))
-        if boxes is not None:
-            b = boxes.float().reshape(-1, 2, 2)
-            if coords:
-                b = b.to(coords[0].device)
-            coords.append(b)
-            labels.append(torch.tensor([[2, 3]], dtype=torch.int32, device=b.device).expand(b.shape[0], 2))
-        c = torch.cat(coords, dim=1).to(dev, non_blocking=True) if coords else None
-        l = torch.cat(labels, dim=1).to(dev, non_blocking=True) if labels else None
+        c, l = assemble_prompt_points(point_coords, point_labels, boxes)
+        c = c.to(dev, non_blocking=True) if c is not None else None
+        l = l.to(dev, non_blocking=True) if l is not None else None
         m = mask_input.to(dev) if mask_input is not None else None
         return self.decoder_engine().decode(features, c, l, m, multimask_output)
 
     # ---- reference API ------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, batched_input: List[Dict[str, Any]], multimask_output: bool) -> List[Dict[str, torch.Tensor]]:
-        """Batched end-to-end prediction (reference sam.py:53-131)."""
+        """Batched end-to-end prediction (reference sam.py:53-131).  Images of the same (already transformed) shape are
+        encoded together in ONE encoder launch sequence (the reference stacks all of them, :97-98); prompts are decoded per
+        record like the reference's loop (:101-124)."""
+        groups: Dict[Tuple[int, ...], List[int]] = {}
+        for i, rec in enumerate(batched_input):
+            groups.setdefault(tuple(rec["image"].shape), []).append(i)
+        embeddings: List[Optional[torch.Tensor]] = [None] * len(batched_input)
+        for idx in groups.values():
+            emb = self.encode_image(torch.stack([batched_input[i]["image"] for i in idx]))
+            for k, i in enumerate(idx):
+                embeddings[i] = emb[k:k + 1]
         outputs = []
-        for rec in batched_input:
-            emb = self.encode_image(rec["image"][None])
+        for rec, emb in zip(batched_input, embeddings):
             low, iou = self.decode_prompts(emb, rec.get("point_coords"), rec.get("point_labels"), rec.get("boxes"),
                                            rec.get("mask_inputs"), multimask_output)
             masks = upscale_masks(low, rec["image"].shape[-2:], rec["original_size"], self.image_encoder.img_size,

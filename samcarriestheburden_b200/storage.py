@@ -1,0 +1,206 @@
+"""Persistence of embeddings and refined masks OFF the critical path (the writer half).
+
+The reference writes every result synchronously from the hot loop: `predictor.features.cpu().numpy()` followed by an
+h5py `create_dataset(..., compression='gzip', compression_opts=9)` (scripts/generate_img_embeddings.py:46,67-70) and
+`refined_sam_masks.cpu().numpy()` + gzip-9 dataset + `estimated_dice` attribute
+(scripts/save_refined_segmentations.py:75-80) - the gzip-9 compression is the wall-clock sink of both scripts.
+
+Here `put()` only enqueues: the device tensor is copied into a pinned host buffer on a dedicated copy stream (ordered
+after the producing stream by an event) and a background thread waits for that copy and writes the record.  Layouts:
+
+* `.h5` / `.hdf5` path and `h5py` importable -> exactly the reference's layout
+    embeddings: file attrs `checkpoint`, `img_encoder_img_size`; group `img_embedding/<stem>` with dataset `features`
+                (1 x 256 x 64 x 64 float32, gzip-9) and attrs `original_size`, `input_size`;
+    masks:      dataset `segmentation_mask/<stem>` (C x H x W bool, gzip-9) with attr `estimated_dice`; file attrs as given.
+* otherwise (h5py is not part of this image) -> a directory with `attrs.json` and one `<stem>.npz` per record holding
+  the same fields (`features`, `original_size`, `input_size` / `segmentation_mask`, `estimated_dice`); `open_embeddings`
+  reads either layout back into an `EmbeddingStore`.
+"""
+from __future__ import annotations
+
+import json
+import queue
+import threading
+from pathlib import Path
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+
+def _have_h5py() -> bool:
+    try:
+        import h5py  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+class _Backend:
+    def write(self, kind: str, name: str, arrays: Dict[str, np.ndarray]) -> None:
+        raise NotImplementedError
+
+    def close(self) -> None:
+        pass
+
+
+class _H5Backend(_Backend):
+    def __init__(self, path: Path, file_attrs: dict, gzip: int):
+        import h5py
+        self.f = h5py.File(path, "x")  # like the reference: refuse to overwrite
+        for k, v in file_attrs.items():
+            self.f.attrs[k] = v
+        self.kw = dict(compression="gzip", compression_opts=gzip) if gzip else {}
+
+    def write(self, kind, name, arrays):
+        if kind == "embedding":
+            g = self.f.create_group(f"img_embedding/{name}")
+            g.attrs["original_size"] = arrays["original_size"]
+            g.attrs["input_size"] = arrays["input_size"]
+            g.create_dataset("features", data=arrays["features"], **self.kw)
+        else:
+            d = self.f.create_dataset("segmentation_mask/" + name, data=arrays["segmentation_mask"], **self.kw)
+            d.attrs["estimated_dice"] = arrays["estimated_dice"]
+
+    def close(self):
+        self.f.close()
+
+
+class _NpzDirBackend(_Backend):
+    def __init__(self, path: Path, file_attrs: dict, compress: bool):
+        path.mkdir(parents=True, exist_ok=False)  # refuse to overwrite, like h5py's 'x' mode
+        self.path, self.compress = path, compress
+        (path / "attrs.json").write_text(json.dumps({k: (v if isinstance(v, (str, int, float)) else str(v))
+                                                     for k, v in file_attrs.items()}))
+
+    def write(self, kind, name, arrays):
+        (np.savez_compressed if self.compress else np.savez)(self.path / f"{name}.npz", **arrays)
+
+
+class AsyncResultWriter:
+    """Background writer for embeddings (`kind='embedding'`) or refined masks (`kind='mask'`).
+
+    put() cost on the producing stream: one event record; the D2H copy runs on the writer's own stream into a pinned
+    buffer from a small pool (back-pressure: put() blocks only when `depth` records are still being written)."""
+
+    def __init__(self, path, kind: str, file_attrs: Optional[dict] = None, gzip: int = 9, depth: int = 16,
+                 device: Optional[torch.device] = None):
+        assert kind in ("embedding", "mask")
+        self.kind = kind
+        path = Path(path)
+        if path.suffix in (".h5", ".hdf5") and _have_h5py():
+            self.backend: _Backend = _H5Backend(path, file_attrs or {}, gzip)
+        else:
+            self.backend = _NpzDirBackend(path.with_suffix("") if path.suffix in (".h5", ".hdf5") else path,
+                                          file_attrs or {}, compress=False)
+        self.device = device
+        self._stream: Optional[torch.cuda.Stream] = None
+        self._q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._pool: Dict[tuple, list] = {}
+        self._pool_lock = threading.Lock()
+        self._error: Optional[BaseException] = None
+        self.records = 0
+        self._t = threading.Thread(target=self._run, name="b200sam-writer", daemon=True)
+        self._t.start()
+
+    # ------------------------------------------------------------------ producer side
+    def _host_buffer(self, t: torch.Tensor) -> torch.Tensor:
+        key = (tuple(t.shape), t.dtype)
+        with self._pool_lock:
+            free = self._pool.get(key)
+            if free:
+                return free.pop()
+        return torch.empty(t.shape, dtype=t.dtype).pin_memory() if torch.cuda.is_available() else torch.empty(t.shape, dtype=t.dtype)
+
+    def _to_host_async(self, t: torch.Tensor):
+        if not t.is_cuda:
+            return t, None
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=t.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(t.device))
+        host = self._host_buffer(t)
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ready)
+            host.copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._stream)
+        t.record_stream(self._stream)
+        return host, done
+
+    def put_embedding(self, name: str, features: torch.Tensor, original_size, input_size) -> None:
+        """features: [1,256,64,64] float32 (what `predictor.features` holds, generate_img_embeddings.py:46)."""
+        assert self.kind == "embedding"
+        self._put(name, {"features": features.reshape(1, *features.shape[-3:])},
+                  {"original_size": np.asarray(original_size), "input_size": np.asarray(input_size)})
+
+    def put_masks(self, name: str, seg: torch.Tensor, est_dice: torch.Tensor) -> None:
+        """seg: [C,H,W] bool, est_dice: [C] float (save_refined_segmentations.py:75-80)."""
+        assert self.kind == "mask"
+        self._put(name, {"segmentation_mask": seg.bool(), "estimated_dice": est_dice.float()}, {})
+
+    def _put(self, name: str, tensors: Dict[str, torch.Tensor], extra: Dict[str, np.ndarray]) -> None:
+        if self._error is not None:
+            raise RuntimeError("b200sam writer thread failed") from self._error
+        staged = {k: self._to_host_async(v.contiguous()) for k, v in tensors.items()}
+        self._q.put((name, staged, extra))
+
+    # ------------------------------------------------------------------ consumer side
+    def _run(self) -> None:
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            name, staged, extra = item
+            try:
+                arrays = dict(extra)
+                for k, (host, done) in staged.items():
+                    if done is not None:
+                        done.synchronize()
+                    arrays[k] = host.numpy()
+                self.backend.write(self.kind, name, arrays)
+                self.records += 1
+                with self._pool_lock:
+                    for host, done in staged.values():
+                        if done is not None:
+                            self._pool.setdefault((tuple(host.shape), host.dtype), []).append(host)
+            except BaseException as e:  # surfaced on the next put() / close()
+                self._error = e
+
+    def close(self) -> int:
+        """Drain the queue, close the file; returns the number of records written."""
+        self._q.put(None)
+        self._t.join()
+        self.backend.close()
+        if self._error is not None:
+            raise RuntimeError("b200sam writer thread failed") from self._error
+        return self.records
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def open_embeddings(path, device=None):
+    """Read embeddings written by AsyncResultWriter (npz directory) or by the reference (h5, needs h5py) into an
+    `EmbeddingStore` (features stay on `device` when given, else on the host until first use)."""
+    from .segment_anything.sam_mask_decoder_head import EmbeddingStore
+    path = Path(path)
+    if path.is_dir():
+        attrs = json.loads((path / "attrs.json").read_text())
+        store = EmbeddingStore(str(attrs.get("checkpoint", "")), int(attrs.get("img_encoder_img_size", 1024)))
+        for f in sorted(path.glob("*.npz")):
+            with np.load(f) as z:
+                feats = torch.from_numpy(z["features"])
+                store.add(f.stem, feats.to(device) if device is not None else feats, z["original_size"], z["input_size"])
+        return store
+    import h5py
+    with h5py.File(path, "r") as h:
+        store = EmbeddingStore(str(h.attrs["checkpoint"]), int(h.attrs["img_encoder_img_size"]))
+        for name, g in h["img_embedding"].items():
+            feats = torch.from_numpy(g["features"][:])
+            store.add(name, feats.to(device) if device is not None else feats, g.attrs["original_size"], g.attrs["input_size"])
+    return store

@@ -58,6 +58,21 @@ def structuring_element(name: str, radius: int) -> np.ndarray:
         return (yy ** 2 + xx ** 2 <= radius ** 2).astype(np.uint8)
     if name == "diamond":
         return (np.abs(yy) + np.abs(xx) <= radius).astype(np.uint8)
+    if name == "star":
+        # skimage.morphology.star(a): the (2a+1)-square overlaid with its 45-degree rotation, on a (2a+1+2*(a//2))^2 grid.
+        # skimage builds the rotated square as the convex hull of its four vertex pixels; that hull is restated as the
+        # diamond |dy| + |dx| <= c through the vertex centres (skimage is absent here, so this footprint is unpinned; it only
+        # feeds SegEnhance.last_preprocessed_seg, which the pipeline never consumes).
+        if radius == 1:
+            return np.ones((3, 3), np.uint8)
+        m, n = 2 * radius + 1, radius // 2
+        size = m + 2 * n
+        c = (size - 1) // 2
+        r2 = np.arange(size) - c
+        y2, x2 = np.meshgrid(r2, r2, indexing="ij")
+        fp = (np.abs(y2) + np.abs(x2) <= c)
+        fp[n:m + n, n:m + n] = True
+        return fp.astype(np.uint8)
     raise NotImplementedError(f"structuring element {name!r} is not supported")
 
 

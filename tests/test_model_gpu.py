@@ -411,3 +411,29 @@ def test_sam_forward_and_return_logits(vit_b, embedding):
         fresh.get_image_embedding()
     with pytest.raises(AssertionError):
         fresh.set_image(img, image_format="XYZ")
+
+
+def test_standalone_prompt_encoder_and_mask_decoder_forward(vit_b, embedding):
+    """The reference's module-level API (prompt_encoder.py:128-168, mask_decoder.py:71-110), tensors in / tensors out,
+    against the oracle: points + box, points only (pad point), mask input; then MaskDecoder.forward on those embeddings."""
+    sam, sd = vit_b
+    _, ref_emb, _ = embedding
+    pe, md = sam.prompt_encoder, sam.mask_decoder
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand((3, 2, 2), generator=g) * 1000
+    labs = torch.tensor([[1, 0], [1, 1], [0, 1]])
+    boxes = torch.tensor([[10.0, 20.0, 300.0, 400.0], [50.0, 60.0, 900.0, 1000.0], [0.0, 0.0, 512.0, 512.0]])
+    masks = torch.randn((3, 1, 256, 256), generator=g)
+    for points, bx, mk in [((pts, labs), boxes, None), ((pts, labs), None, masks), (None, boxes, None), (None, None, masks)]:
+        sp, de = pe(tuple(t.to(DEV) for t in points) if points else None, bx.to(DEV) if bx is not None else None,
+                    mk.to(DEV) if mk is not None else None)
+        sp_o, de_o = O.prompt_encoder(sd, points, bx, mk)
+        assert sp.shape == sp_o.shape and de.shape[1:] == (256, 64, 64)
+        assert (sp.cpu() - sp_o).abs().max() < 2e-5 if sp_o.numel() else True
+        assert (de.cpu() - de_o.expand_as(de)).abs().max() < 2e-5
+        low, iou = md(ref_emb.to(DEV), pe.get_dense_pe(), sp, de, multimask_output=(bx is None))
+        low_o, iou_o = O.mask_decoder(sd, ref_emb, O.dense_pe(sd), sp_o, de_o, bx is None)
+        assert low.shape == low_o.shape and iou.shape == iou_o.shape
+        assert (low.cpu() - low_o).abs().max() < 1e-3 and (iou.cpu() - iou_o).abs().max() < 1e-3
+    with pytest.raises(NotImplementedError):
+        md(ref_emb.to(DEV), torch.zeros((1, 256, 64, 64), device=DEV), sp, de, multimask_output=False)
