@@ -30,8 +30,8 @@ import torch
 
 def _have_h5py() -> bool:
     try:
-        import h5py  # noqa: F401
-        return True
+        import h5py
+        return hasattr(h5py, "File") and getattr(h5py, "__version__", None) is not None  # not a test stand-in module
     except Exception:
         return False
 

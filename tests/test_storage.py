@@ -41,6 +41,8 @@ def test_mask_writer_layout(tmp_path):
 
 def test_h5_layout_matches_reference_when_h5py_exists(tmp_path):
     h5py = pytest.importorskip("h5py")
+    if getattr(h5py, "__version__", None) is None:
+        pytest.skip("a stand-in h5py module is installed in sys.modules by the oracle-vs-reference tests")
     f = torch.randn((1, 256, 64, 64))
     with AsyncResultWriter(tmp_path / "e.h5", "embedding", {"checkpoint": "c.pth", "img_encoder_img_size": 1024}) as w:
         w.put_embedding("a", f, (10, 20), (1024, 512))
