@@ -422,8 +422,16 @@ def main():
             "frac_of_sustained": value / world * ENC_GFLOP[args.model] / 1e3 / peaks["tf_sustained"],
             "peak_source": peaks["src"]},
     }
+    if not args.no_refine:
+        # BASELINE.json configs[1] + [4] as stated: the 500-image set sharded by image over the N GPUs (strong scaling),
+        # embeddings AND refined masks gathered on every rank at the end (all ranks take part)
+        out["set500"] = pipeline_set500(sam, dev, world, rank)
     if rank == 0:
         out["roofline"] = inrun_kernel_roofline(sam, dev_pool, K, args.model, B, peaks)
+        out["latency_b1"] = set_image_latency(sam)
+        if not args.no_refine:
+            if args.model != "vit_l":
+                out["vit_l_batch16"] = secondary_encoder("vit_l", 16, dev, peaks)
         if not args.no_refine:
             out["refine"] = refine_throughput(sam, dev)
             # HBM-bound stages on batched launches: algorithmic bytes / CUDA-event time
@@ -436,14 +444,111 @@ def main():
             out["unet"] = unet_throughput(dev)
         if world == 1 and not args.no_cpu_baseline:
             out["parity"] = e2e_parity(sam, dev, args.model)
-            v, cores, times = cpu_encoder_images_per_s(args.model, 1)
+            v, cores, times = cpu_encoder_images_per_s(args.model, 3)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                                   "sample": f"1 image through the full {args.model} fp32 encoder of the CPU oracle "
-                                             f"({times[0]:.1f} s)"}
+                                   "sample": f"3 images, one at a time like the reference's loop, through the full "
+                                             f"{args.model} fp32 encoder of the CPU oracle ({sum(times):.1f} s)"}
         print(json.dumps(out), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def set_image_latency(sam, reps: int = 20):
+    """The reference API's own shape: SamPredictor.set_image on ONE 1024 x 1024 image (scripts/generate_img_embeddings.py:45,
+    B = 1, host uint8 in, embedding resident on the device), synchronised per call."""
+    import torch
+    from samcarriestheburden_b200 import synthetic as O
+    from samcarriestheburden_b200.segment_anything import SamPredictor
+    pred = SamPredictor(sam)
+    img = O.synthetic_radiograph(7)
+    for _ in range(3):
+        pred.set_image(img)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        pred.set_image(img)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return {"metric": "SamPredictor.set_image latency, one 1024x1024 image (B = 1), host in, synchronised",
+            "ms_median": 1e3 * statistics.median(ts), "ms_min": 1e3 * min(ts), "images_per_s": 1.0 / statistics.median(ts)}
+
+
+def secondary_encoder(model: str, batch: int, dev, peaks, steps: int = 5):
+    """BASELINE.json configs[3]: another encoder (ViT-L: D 1024, hd 64, depth 24, global blocks 5/11/17/23) at batch 16."""
+    import torch
+    m = build_model(model, dev)
+    x = synthetic_batch(batch, 77).to(dev)
+    for _ in range(3):
+        m.encode_image(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        m.encode_image(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    v = batch / (ms / 1e3)
+    del m
+    torch.cuda.empty_cache()
+    return {"metric": metric_name(model), "value": v, "unit": "images/s", "batch": batch, "ms_per_step": ms,
+            "frac_of_burst": v * ENC_GFLOP[model] / 1e3 / peaks["tf_burst"],
+            "frac_of_sustained": v * ENC_GFLOP[model] / 1e3 / peaks["tf_sustained"]}
+
+
+def pipeline_set500(sam, dev, world: int, rank: int, n_images: int = 500, batch: int = 8):
+    """Strong scaling over the image set of BASELINE.json configs[1] / [4]: 500 synthetic radiographs, image i on rank
+    i % N; per rank: H2D + encoder in batches (embeddings stay in HBM), then CCL + prompt extraction + two decoder passes +
+    upscale / threshold per batch; at the end ONE gather of all embeddings (500 x 4 MiB = 2.1 GB) and ONE gather of all
+    refined masks (500 x 17 x 384 x 224) onto every rank over NCCL.  Wall clock between barriers, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from samcarriestheburden_b200 import sharding
+    from samcarriestheburden_b200 import synthetic as O
+    from samcarriestheburden_b200.scripts.pipelines import generate_img_embeddings, refine_segmentations
+    mine = set(sharding.shard_indices(n_images))
+    bases = [O.synthetic_radiograph(200 + k) for k in range(4)]
+    rng = np.random.default_rng(5)
+    shifts = rng.integers(0, 1024, size=(n_images, 2))
+    imgs = [np.roll(bases[i % 4], (int(shifts[i, 0]), int(shifts[i, 1])), axis=(0, 1)) if i in mine else None
+            for i in range(n_images)]
+    pbase = [torch.from_numpy(O.synthetic_unet_probs(k)).pin_memory() for k in range(8)]
+    probs = [pbase[i % 8] if i in mine else None for i in range(n_images)]
+    names = [f"s{i}" for i in range(n_images)]
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def run():
+        sync()
+        t0 = time.perf_counter()
+        store, emb_all = generate_img_embeddings(sam, imgs, names, batch=batch, gather=True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        results, seg_all = refine_segmentations(sam, store, probs, names, batch=batch, gather=True,
+                                                ccl_selection="highest_probability")
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        n_masks = torch.tensor([sum(int((~torch.isnan(r[2])).sum()) for r in results)], device=dev)
+        times = torch.tensor([t2 - t0, t1 - t0, t2 - t1], device=dev)
+        if world > 1:
+            dist.all_reduce(n_masks)
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        assert tuple(emb_all.shape) == (n_images, 256, 64, 64) and seg_all.shape[0] == n_images
+        return int(n_masks.item()), [float(t) for t in times], emb_all.numel() * 4, seg_all.numel()
+
+    run()  # warm-up: lazy engines, allocator, NCCL communicators
+    n_masks, (t_all, t_emb, t_ref), emb_bytes, seg_bytes = run()
+    return {"metric": "500-image set: embeddings + refined masks, sharded by image, final NCCL gather of both on every rank",
+            "scaling": "strong", "images": n_images, "masks": n_masks, "n_gpus": world,
+            "images_per_s": n_images / t_all, "masks_per_s": n_masks / t_all, "seconds": t_all,
+            "embed_phase": {"seconds": t_emb, "embeds_per_s": n_images / t_emb, "gathered_bytes": emb_bytes},
+            "refine_phase": {"seconds": t_ref, "masks_per_s": n_masks / t_ref, "gathered_bytes": seg_bytes}}
 
 
 def e2e_parity(sam, dev, model: str, seed: int = 5, native=(1182, 754)):
@@ -575,24 +680,48 @@ def pipeline_throughput(sam, dev, n_images: int = 32, batch: int = 8):
     names = [f"p{i}" for i in range(n_images)]
     probs = [torch.from_numpy(O.synthetic_unet_probs(i % 8)).pin_memory() for i in range(n_images)]
 
-    def run():
-        store, _ = generate_img_embeddings(sam, imgs, names, batch=batch)
-        results, _ = refine_segmentations(sam, store, probs, names, batch=batch, ccl_selection="highest_probability")
+    import shutil
+    from samcarriestheburden_b200.storage import AsyncResultWriter
+
+    def run(out_dir=None):
+        we = wm = None
+        if out_dir is not None:  # persistence off the critical path: pinned D2H on a side stream + background writer thread
+            we = AsyncResultWriter(Path(out_dir) / "emb", "embedding", {"checkpoint": "random-init", "img_encoder_img_size": 1024})
+            wm = AsyncResultWriter(Path(out_dir) / "masks", "mask", {"refine_params": "{}"})
+        store, _ = generate_img_embeddings(sam, imgs, names, batch=batch, writer=we)
+        results, _ = refine_segmentations(sam, store, probs, names, batch=batch, ccl_selection="highest_probability",
+                                          writer=wm)
         host = [r[1].cpu() for r in results]
-        return sum(int((~torch.isnan(r[2])).sum()) for r in results), host
+        return sum(int((~torch.isnan(r[2])).sum()) for r in results), host, (we, wm)
+
+    def timed_runs(with_writer):
+        dts, drain = [], []
+        for _ in range(3):  # wall clock with host work inside: median of three runs, all samples reported
+            tmp = tempfile.mkdtemp(prefix="b200sam_bench_") if with_writer else None
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_masks, _, writers = run(tmp)
+            torch.cuda.synchronize()
+            dts.append(time.perf_counter() - t0)
+            if with_writer:  # the background threads finish the last records after the pipeline returned
+                t1 = time.perf_counter()
+                n_rec = sum(w.close() for w in writers)
+                drain.append(time.perf_counter() - t1)
+                assert n_rec == 2 * n_images
+                shutil.rmtree(tmp, ignore_errors=True)
+        return n_masks, dts, drain
 
     run()  # warm-up (lazy handles, allocator)
-    dts = []
-    for _ in range(3):  # wall clock with host work inside: median of three runs, all samples reported
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_masks, _ = run()
-        torch.cuda.synchronize()
-        dts.append(time.perf_counter() - t0)
-    dt = statistics.median(dts)
+    n_masks, dts, _ = timed_runs(False)
+    _, dts_w, drain = timed_runs(True)
+    dt, dt_w = statistics.median(dts), statistics.median(dts_w)
     return {"metric": "end-to-end pseudo-label refinement (embed + CCL + prompts + decode + upscale), host in / host out",
             "images": n_images, "masks": n_masks, "images_per_s": n_images / dt, "masks_per_s": n_masks / dt,
-            "ms_per_image": 1e3 * dt / n_images, "ms_per_image_samples": [round(1e3 * d / n_images, 2) for d in dts]}
+            "ms_per_image": 1e3 * dt / n_images, "ms_per_image_samples": [round(1e3 * d / n_images, 2) for d in dts],
+            "with_async_writer": {"images_per_s": n_images / dt_w, "ms_per_image": 1e3 * dt_w / n_images,
+                                  "ms_per_image_samples": [round(1e3 * d / n_images, 2) for d in dts_w],
+                                  "drain_after_return_s": round(statistics.median(drain), 3),
+                                  "layout": "npz directory (h5py absent); embeddings 4 MiB + masks 1.4 MiB per image"}}
 
 
 if __name__ == "__main__":
