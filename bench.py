@@ -721,7 +721,7 @@ def pipeline_throughput(sam, dev, n_images: int = 32, batch: int = 8):
             "with_async_writer": {"images_per_s": n_images / dt_w, "ms_per_image": 1e3 * dt_w / n_images,
                                   "ms_per_image_samples": [round(1e3 * d / n_images, 2) for d in dts_w],
                                   "drain_after_return_s": round(statistics.median(drain), 3),
-                                  "layout": "npz directory (h5py absent); embeddings 4 MiB + masks 1.4 MiB per image"}}
+                                  "layout": "npy directory (h5py absent); embeddings 4 MiB + masks 1.4 MiB per image"}}
 
 
 if __name__ == "__main__":

@@ -111,8 +111,28 @@ struct RowLN {
 
 // before the accumulator is ready: stage the bias slice and pull the residual block towards L2.
 // COLS = columns drained by one warp: 128 (single-CTA kernel, 8 epilogue warps) or 64 (pair kernel, 16 epilogue warps)
+// residual block of one 16-column half (4 x float4 per thread: rows it * 8 + (lane >> 2), columns 4 * (lane & 3) ..)
+B200SAM_DEVINL void epilogue_load_residual_half(const EpiParams& ep, int M, int N, int row_base, int n0, int h, int lane,
+                                                float4 (&buf)[4]) {
+  const int rsub = lane >> 2, rq = lane & 3;
+  const int col = n0 + h * 16 + 4 * rq;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = row_base + it * 8 + rsub;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.residual != nullptr && row < M && col < N) {
+      const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
+      v = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rr) * ep.ldr + col);
+    }
+    buf[it] = v;
+  }
+}
+
+// rbuf (fp32 output only): the residual values of the first 32-column chunk, loaded BEFORE the accumulator is waited for
+// (they do not depend on the MMAs; ncu showed the epilogue warps of proj / lin2 stalled on these loads after the wait)
 template <int OUT_KIND, int COLS = 128>
-B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int row_base, int n0, float* sbias, int lane) {
+B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int row_base, int n0, float* sbias, int lane,
+                                       float4 (&rbuf)[2][4]) {
       // stage this warp's bias values (zero when absent / out of range)
 #pragma unroll
   for (int i = 0; i < COLS / 32; ++i) {
@@ -127,12 +147,17 @@ B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int ro
     // order: deterministic, independent of the batch and of the traversal order)
     const int prow = row_base + lane;
     if (ep.rowstat_in != nullptr && prow < M) {
+      // all loads first, then the sums (in index order: deterministic): a load -> add loop costs one L2 round trip per
+      // iteration (ncu: the epilogue warps of the folded GEMMs sat on this chain, ~6k clocks per tile)
       const float4* st = reinterpret_cast<const float4*>(ep.rowstat_in) + static_cast<size_t>(prow) * (ep.nparts_in >> 1);
+      const int n4 = ep.nparts_in >> 1;  // nparts_in is even (N % 128 == 0): two parts per 16-byte load
+      float4 t[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t[i] = i < n4 ? st[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       float s1 = 0.0f, s2 = 0.0f;
-      for (int i = 0; i < (ep.nparts_in >> 1); ++i) {  // nparts_in is even (N % 128 == 0): two parts per 16-byte load
-        const float4 t = st[i];
-        s1 += t.x; s2 += t.y;
-        s1 += t.z; s2 += t.w;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < n4) { s1 += t[i].x; s2 += t[i].y; s1 += t[i].z; s2 += t[i].w; }
       }
       const float mean = s1 * ep.ln_inv_d;
       const float var = fmaxf(fmaf(-mean, mean, s2 * ep.ln_inv_d), 0.0f);
@@ -141,12 +166,14 @@ B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int ro
     }
   }
   if constexpr (OUT_KIND == 0) {
-    // pull this warp's 32 x COLS residual block towards L2 while the MMAs of the tile are still running
+    epilogue_load_residual_half(ep, M, N, row_base, n0, 0, lane, rbuf[0]);
+    epilogue_load_residual_half(ep, M, N, row_base, n0, 1, lane, rbuf[1]);
+    // pull the rest of this warp's 32 x COLS residual block towards L2 while the MMAs of the tile are still running
     const int prow = row_base + lane;
     if (ep.residual != nullptr && prow < M) {
       const int rr = ep.res_row_mod > 0 ? (prow % ep.res_row_mod) : prow;
 #pragma unroll
-      for (int i = 0; i < COLS / 32; ++i) {
+      for (int i = 1; i < COLS / 32; ++i) {
         const int c = n0 + 32 * i;
         if (c < N)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + static_cast<size_t>(rr) * ep.ldr + c));
@@ -161,7 +188,7 @@ B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int ro
 // scheduler need it; with four the other warps hide the latency and the registers are better spent elsewhere).
 template <int OUT_KIND, int COLS = 128, bool PIPE = true>
 B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_base, int n0, uint32_t taddr0,
-                                   uint32_t* stg, const float* sbias, int lane, const RowLN ln) {
+                                   uint32_t* stg, const float* sbias, int lane, const RowLN ln, float4 (&rbuf)[2][4]) {
   constexpr int NCH = COLS / 32;    // chunks of 32 columns
   const int wsw = (lane >> 1) & 3;  // write swizzle of this thread's row
   const int rsub = lane >> 2;       // transposed read: row within a group of 8
@@ -226,24 +253,9 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
     }
   } else {
     float* out = reinterpret_cast<float*>(ep.out);
-    const bool has_res = ep.residual != nullptr;
-    // residual block of one 16-column half (4 x float4 per thread), issued one half ahead of its use.  `out`
-    // may alias `residual` (in-place residual stream), so the compiler cannot hoist these loads itself.
-    auto load_half = [&](int h, float4 (&buf)[4]) {
-      const int col = n0 + h * 16 + 4 * rq;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int row = row_base + it * 8 + rsub;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_res && row < M && col < N) {
-          const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
-          v = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rr) * ep.ldr + col);
-        }
-        buf[it] = v;
-      }
-    };
-    float4 rbuf[2][4];
-    load_half(0, rbuf[0]);
+    // residual: rbuf holds the two 16-column halves of chunk 0 (loaded before the accumulator wait); each slot is
+    // refilled with the same half of the NEXT chunk right after it has been consumed, i.e. one whole chunk ahead of its use.
+    // `out` may alias `residual` (in-place residual stream): every element is read and written by the same thread.
     // LayerNorm folding: 16-bit copy of the result + (sum, sum of squares) of every 64-column part of every row
     __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ep.xh);
     const bool stats = ep.rowstat_out != nullptr;
@@ -252,11 +264,9 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
     for (int ch = 0; ch < NCH; ++ch) {  // chunks of 32 columns, each written as 2 halves of 16
       uint32_t r[32];
       tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
-      load_half(2 * ch + 1, rbuf[1]);
       tmem_ld_wait();
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        if (hf == 1 && ch + 1 < NCH) load_half(2 * ch + 2, rbuf[0]);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ wsw) << 2)) =
@@ -288,6 +298,7 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
             }
           }
         }
+        if (ch + 1 < NCH) epilogue_load_residual_half(ep, M, N, row_base, n0, 2 * (ch + 1) + hf, lane, rbuf[hf]);
         __syncwarp();
       }
       if (stats && (ch & 1) == 1) {

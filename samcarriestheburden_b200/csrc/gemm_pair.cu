@@ -98,12 +98,15 @@ B200SAM_DEVINL void umma_commit_pair(uint64_t* bar) {
       "h"(static_cast<uint16_t>(3))
       : "memory");
 }
-// arrive on the barrier at the same offset in CTA `cta` of the cluster
+// arrive on the barrier at the same offset in CTA `cta` of the cluster.  No cluster-scope release: the arrival only
+// publishes "this warp's tcgen05.ld of the accumulator have completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+// precede it); a .release.cluster arrive makes lane 0 wait for all of the warp's outstanding global stores (MEMBAR + ERRBAR,
+// 6 % of the stall samples of the first version)
 B200SAM_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }
@@ -221,12 +224,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM2 + static_cast<int>(rank) * 128;
       const int n0 = (tile % num_n) * BN2 + cpart * EPI_COLS2;
       const int row_base = m0 + quad * 32;
-      const RowLN ln = epilogue_prefetch<OUT_KIND, EPI_COLS2>(ep, M, N, row_base, n0, sbias, lane);
+      float4 rbuf[2][4];
+      const RowLN ln = epilogue_prefetch<OUT_KIND, EPI_COLS2>(ep, M, N, row_base, n0, sbias, lane, rbuf);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                               static_cast<uint32_t>(as * BN2 + cpart * EPI_COLS2);
-      epilogue_store<OUT_KIND, EPI_COLS2, false>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln);
+      epilogue_store<OUT_KIND, EPI_COLS2, false>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln, rbuf);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[as], 0);

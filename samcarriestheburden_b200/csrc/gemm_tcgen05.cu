@@ -192,14 +192,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM_T + (TALL ? half * 128 : 0);
       const int n0 = (tile % num_n) * BN + (TALL ? 0 : half * 128);
       const int row_base = m0 + quad * 32;
-      const RowLN ln = epilogue_prefetch<OUT_KIND>(ep, M, N, row_base, n0, sbias, lane);
+      float4 rbuf[2][4];
+      const RowLN ln = epilogue_prefetch<OUT_KIND>(ep, M, N, row_base, n0, sbias, lane, rbuf);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                               static_cast<uint32_t>(as * BN + half * 128);
       if (ep.mode == 1) epilogue_ln64_split(ep, M, row_base, n0, taddr0, sbias, lane);
       else if (ep.mode == 2) epilogue_gelu_dot(ep, M, row_base, taddr0, sbias, lane);
-      else epilogue_store<OUT_KIND>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln);
+      else epilogue_store<OUT_KIND>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln, rbuf);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);

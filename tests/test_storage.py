@@ -1,4 +1,4 @@
-"""CPU: the asynchronous result writer (storage.py) in its npz-directory layout (h5py is not part of this image) and the
+"""CPU: the asynchronous result writer (storage.py) in its npy-directory layout (h5py is not part of this image) and the
 reader that turns it back into an EmbeddingStore; the h5 layout is exercised only where h5py is importable."""
 import json
 
@@ -34,9 +34,9 @@ def test_mask_writer_layout(tmp_path):
     dice[3] = float("nan")
     with AsyncResultWriter(tmp_path / "masks", "mask", {"labels": "{}", "refine_params": "{}"}) as w:
         w.put_masks("0001_0523", seg, dice)
-    z = np.load(tmp_path / "masks" / "0001_0523.npz")
-    assert z["segmentation_mask"].dtype == np.bool_ and np.array_equal(z["segmentation_mask"], seg.numpy())
-    assert np.array_equal(z["estimated_dice"], dice.numpy(), equal_nan=True)
+    m = np.load(tmp_path / "masks" / "0001_0523.segmentation_mask.npy")
+    assert m.dtype == np.bool_ and np.array_equal(m, seg.numpy())
+    assert np.array_equal(np.load(tmp_path / "masks" / "0001_0523.estimated_dice.npy"), dice.numpy(), equal_nan=True)
 
 
 def test_h5_layout_matches_reference_when_h5py_exists(tmp_path):
