@@ -406,7 +406,8 @@ def main():
                                f"1024x1024 uint8 radiographs, random-init weights (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "parallelism": f"dp{world} (images sharded by rank, final NCCL all_gather)",
                    "l2": "activations per step (>100 MB per image) exceed the 126 MB L2; no explicit flush",
-                   "residual_stream": "fp32",
+                   "residual_stream": "f24 (fp16 plane = GEMM operand + int8 mantissa extension, 19 significant bits)"
+                                      if enc.engine().residual_f24 else "fp32",
                    "gemm_operands": f"{enc.operand_format} (tcgen05 kind::f16), fp32 accumulate; B200SAM_ENCODER_OPERANDS="
                                     "bf16|fp16 selects the 16-bit format (same tensor-core rate)",
                    "layernorm": "folded into the GEMM epilogues" if enc.ln_fused else "separate launches",
@@ -639,10 +640,22 @@ def refine_throughput(sam, dev, n_images: int = 32, batch: int = 8):
 
     n1, ms1 = timed(per_image)
     nb, msb = timed(batched)
+    peaks = _peaks()
+    # roofline of the decode stage: per refined mask 7.55 GFLOP (box pass 3.62 + point pass 3.89 + mask
+    # downscale 0.036, reference-executed) against 786,432 compulsory bytes (3 x 256 x 256 fp32 low-res maps) + the
+    # upscale's 1,396,736 B at 1024^2: compute bound algorithmically -> t_roofline = FLOPs / bf16 burst peak
+    us_per_mask = 1e3 * msb / nb
+    t_compute = 7.55e9 / (peaks["tf_burst"] * 1e12) * 1e6
+    t_bytes = (786432 + 1396736) / (peaks["hbm"] * 1e9) * 1e6
+    roof = {"bound": "tensor (algorithmic); un-fused dataflow makes it HBM / launch bound in practice",
+            "gflop_per_mask": 7.55, "compulsory_bytes_per_mask": 786432 + 1396736,
+            "t_roofline_us_per_mask": max(t_compute, t_bytes), "t_compute_us": t_compute, "t_bytes_us": t_bytes,
+            "achieved_us_per_mask": us_per_mask, "frac": max(t_compute, t_bytes) / us_per_mask,
+            "peak_source": peaks["src"] + " burst"}
     return {"metric": "refined masks/s (decode stage, 1024^2 native, 2 passes, prompts of %d images per launch "
                       "sequence)" % batch,
             "value": nb / (msb / 1e3), "unit": "masks/s", "images": n_images, "masks": nb,
-            "ms_per_image": msb / n_images,
+            "ms_per_image": msb / n_images, "roofline": roof,
             "per_image_api": {"value": n1 / (ms1 / 1e3), "unit": "masks/s", "ms_per_image": ms1 / min(n_images, 8)}}
 
 

@@ -33,8 +33,19 @@ def rounder(fmt):
 class Cfg:
     """which tensors are rounded, and to what"""
 
-    def __init__(self, act="fp32", wgt="fp32", p="fp32", fold=False):
+    def __init__(self, act="fp32", wgt="fp32", p="fp32", fold=False, res="fp32"):
         self.a, self.w, self.p, self.fold = rounder(act), rounder(wgt), rounder(p), fold
+        self.r = f24_round if res == "f24" else (lambda t: t)
+
+
+def f24_round(x):
+    """Residual stream stored as fp16 hi + 8-bit extension of the mantissa (csrc/gemm_epilogue.cuh, `f24`): x ~ hi + q * ulp(hi) / 256,
+    q = round-to-nearest of the remainder in 1/256 ulp, clamped to [-128, 127]."""
+    h = x.half().float()
+    e = torch.floor(torch.log2(h.abs().clamp_min(2.0 ** -14)))   # exponent of hi (subnormals share 2^-14)
+    step = torch.exp2(e - 10 - 8)                                   # ulp(hi) / 256
+    q = torch.clamp(torch.round((x - h) / step), -128, 127)
+    return h + q * step
 
 
 def ln_linear(x, g, b, W, bias, c):
@@ -73,9 +84,9 @@ def block(sd, p, x, heads, window, c):
     out = out.view(Bn, heads, S, S, hd).permute(0, 2, 3, 1, 4).reshape(Bn, S, S, D)
     if window > 0:
         out = out.view(B, Hp // window, Wp // window, window, window, D).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, D)[:, :H, :W_]
-    x = x + F.linear(c.a(out), c.w(sd[p + "attn.proj.weight"]), sd[p + "attn.proj.bias"])
+    x = c.r(x + F.linear(c.a(out), c.w(sd[p + "attn.proj.weight"]), sd[p + "attn.proj.bias"]))
     h = F.gelu(ln_linear(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"], sd[p + "mlp.lin1.weight"], sd[p + "mlp.lin1.bias"], c))
-    return x + F.linear(c.a(h), c.w(sd[p + "mlp.lin2.weight"]), sd[p + "mlp.lin2.bias"])
+    return c.r(x + F.linear(c.a(h), c.w(sd[p + "mlp.lin2.weight"]), sd[p + "mlp.lin2.bias"]))
 
 
 @torch.no_grad()
@@ -84,7 +95,7 @@ def encoder(sd, cfg, x0, c):
     D = cfg["embed_dim"]
     patches = F.unfold(x0, 16, stride=16).transpose(1, 2)  # [B, 4096, 768]
     t = F.linear(c.a(patches), c.w(sd[p + "patch_embed.proj.weight"].reshape(D, -1)), sd[p + "patch_embed.proj.bias"])
-    t = t.view(-1, 64, 64, D) + sd[p + "pos_embed"]
+    t = c.r(t.view(-1, 64, 64, D) + sd[p + "pos_embed"])
     for i in range(cfg["depth"]):
         win = 0 if i in cfg["global_attn_indexes"] else 14
         t = block(sd, f"{p}blocks.{i}.", t, cfg["num_heads"], win, c)
@@ -114,6 +125,8 @@ def run(model="vit_b", variants=None, seeds=(3,), native=(1182, 754)):
         "bf16w": Cfg("fp32", "bf16", "fp32"), "bf16a": Cfg("bf16", "fp32", "bf16"),
         "fp16a_bf16w": Cfg("fp16", "bf16", "fp16"),
         "fp16fold": Cfg("fp16", "fp16", "fp16", fold=True), "bf16fold": Cfg("bf16", "bf16", "bf16", fold=True),
+        "fp16fold_f24": Cfg("fp16", "fp16", "fp16", fold=True, res="f24"),
+        "f24only": Cfg("fp32", "fp32", "fp32", fold=False, res="f24"),
     }
     for seed in seeds:
         img = torch.from_numpy(O.synthetic_radiograph(seed)).permute(2, 0, 1).float()
