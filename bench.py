@@ -406,8 +406,7 @@ def main():
                                f"1024x1024 uint8 radiographs, random-init weights (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "parallelism": f"dp{world} (images sharded by rank, final NCCL all_gather)",
                    "l2": "activations per step (>100 MB per image) exceed the 126 MB L2; no explicit flush",
-                   "residual_stream": "f24 (fp16 plane = GEMM operand + int8 mantissa extension, 19 significant bits)"
-                                      if enc.engine().residual_f24 else "fp32",
+                   "residual_stream": "fp32",
                    "gemm_operands": f"{enc.operand_format} (tcgen05 kind::f16), fp32 accumulate; B200SAM_ENCODER_OPERANDS="
                                     "bf16|fp16 selects the 16-bit format (same tensor-core rate)",
                    "layernorm": "folded into the GEMM epilogues" if enc.ln_fused else "separate launches",

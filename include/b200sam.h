@@ -43,14 +43,11 @@ typedef struct b200sam_encoder_config {
                            reference's own mixed-precision run uses: torch.cuda.amp.autocast defaults to fp16,
                            seg_processing/hpo_bce_unet_sam_postprocess.py:44).  fp32 accumulate, fp32 residual stream,
                            fp32 LayerNorm / softmax statistics in both. */
-  int flags;            /* B200SAM_ENC_LN_FUSED: norm1 / norm2 (image_encoder.py:168,180) folded into the GEMMs;
-                           B200SAM_ENC_RES_F24: the residual stream is stored as an fp16 plane (= the next GEMM's operand) +
-                           an int8 plane extending its mantissa (19 significant bits) instead of fp32 */
+  int flags;            /* B200SAM_ENC_LN_FUSED: norm1 / norm2 (image_encoder.py:168,180) folded into the GEMMs */
 } b200sam_encoder_config;
 #define B200SAM_OPERAND_BF16 0
 #define B200SAM_OPERAND_FP16 1
 #define B200SAM_ENC_LN_FUSED 1
-#define B200SAM_ENC_RES_F24 2
 typedef struct b200sam_encoder b200sam_encoder;
 
 B200SAM_API int b200sam_encoder_weight_count(const b200sam_encoder_config* cfg);
@@ -228,10 +225,6 @@ B200SAM_API int b200sam_gemm_f16(const void* A, const void* W, void* out, const 
  *               of A's fp32 original from rowstat_in [M, nparts, 2] (K elements per row, eps inside the sqrt). */
 B200SAM_API int b200sam_gemm_ln_residual(const void* A, const void* W, const float* bias, const float* residual, float* out,
                              void* out16, float* rowstat_out, int M, int N, int K, int operand_format, void* stream);
-/* _ln_residual with the residual stream in the f24 format, in place: x = hi (fp16 [M,N]) + lo (int8 [M,N]) * ulp(hi) / 256;
- * (x_hi, x_lo) <- f24(A W^T + bias + x); the statistics are those of the unrounded fp32 result. */
-B200SAM_API int b200sam_gemm_ln_residual_f24(const void* A, const void* W, const float* bias, void* x_hi, int8_t* x_lo,
-                                 float* rowstat_out, int M, int N, int K, void* stream);
 B200SAM_API int b200sam_gemm_ln_folded(const void* A, const void* W_folded, const float* bias_folded, const float* colsum,
                            const float* rowstat_in, int nparts, float eps, void* out16, int M, int N, int K, int gelu,
                            int operand_format, void* stream);

@@ -27,7 +27,6 @@ class EncoderConfig(C.Structure):
 
 OPERAND_BF16, OPERAND_FP16 = 0, 1
 ENC_LN_FUSED = 1
-ENC_RES_F24 = 2
 ABI_VERSION = 2
 
 
@@ -77,7 +76,6 @@ _PROTOTYPES = {
     "b200sam_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sam_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sam_gemm_ln_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "b200sam_gemm_ln_residual_f24": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200sam_gemm_ln_folded": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sam_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _i, _vp]),
     "b200sam_encoder_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -269,16 +269,6 @@ int b200sam_gemm_ln_residual(const void* A, const void* W, const float* bias, co
   g.xh = out16; g.rowstat_out = rowstat_out;
   return gemm_bf16_tn(g, static_cast<cudaStream_t>(stream));
 }
-int b200sam_gemm_ln_residual_f24(const void* A, const void* W, const float* bias, void* x_hi, int8_t* x_lo,
-                                 float* rowstat_out, int M, int N, int K, void* stream) {
-  if (!A || !W || !x_hi || !x_lo || !rowstat_out) { set_last_error("gemm_ln_residual_f24: null argument"); return 2; }
-  GemmArgs g;
-  g.A = static_cast<const __nv_bfloat16*>(A); g.B = static_cast<const __nv_bfloat16*>(W); g.out = nullptr;
-  g.bias = bias; g.residual = static_cast<const float*>(x_hi); g.res_lo = x_lo; g.M = M; g.N = N; g.K = K; g.lda = K;
-  g.ldb = K; g.ldo = N; g.ldr = N; g.res_row_mod = 0; g.gelu = 0; g.out_kind = 0; g.max_ctas = 0; g.op_f16 = 1;
-  g.xh = x_hi; g.out_lo = x_lo; g.rowstat_out = rowstat_out;
-  return gemm_bf16_tn(g, static_cast<cudaStream_t>(stream));
-}
 int b200sam_gemm_ln_folded(const void* A, const void* W_folded, const float* bias_folded, const float* colsum,
                            const float* rowstat_in, int nparts, float eps, void* out16, int M, int N, int K, int gelu,
                            int operand_format, void* stream) {

@@ -118,9 +118,7 @@ int encoder_create(const EncoderConfig& c, const void* const* weights, int n, En
   B200SAM_REQUIRE(c.out_chans == 256, "encoder_create: out_chans must be 256, got %d", c.out_chans);
   B200SAM_REQUIRE(c.operand_format == 0 || c.operand_format == 1,
                   "encoder_create: operand_format %d unknown (0 = bf16, 1 = fp16)", c.operand_format);
-  B200SAM_REQUIRE((c.flags & ~(ENC_FLAG_LN_FUSED | ENC_FLAG_RES_F24)) == 0, "encoder_create: unknown flags 0x%x", c.flags);
-  B200SAM_REQUIRE(!(c.flags & ENC_FLAG_RES_F24) || ((c.flags & ENC_FLAG_LN_FUSED) && c.operand_format == 1),
-                  "encoder_create: the f24 residual stream needs fp16 operands and folded LayerNorm");
+  B200SAM_REQUIRE((c.flags & ~ENC_FLAG_LN_FUSED) == 0, "encoder_create: unknown flags 0x%x", c.flags);
   B200SAM_REQUIRE(n == encoder_weight_count(c), "encoder_create: expected %d weight pointers, got %d",
                   encoder_weight_count(c), n);
   for (int i = 0; i < n; ++i)
@@ -147,9 +145,6 @@ int encoder_forward(const Encoder* e, const void* img, int is_u8, int B, int h, 
   const int f16 = c.operand_format == 1;
   const int k16 = f16 ? 2 : 1;  // out_kind of the 16-bit tensors
   const bool fused = ln_fused(c);
-  const bool f24 = (c.flags & ENC_FLAG_RES_F24) != 0;
-  // f24 residual stream: hi plane = ws.xn (fp16, also the A operand of qkv / lin1 / neck), lo plane = int8 in ws.x's memory
-  int8_t* x_lo = reinterpret_cast<int8_t*>(ws.x);
   const int nparts = D / 64;  // row statistics come in 64-column parts (gemm_epilogue.cuh)
   const void* const* W = e->w.data();
   auto F = [&](int i) { return reinterpret_cast<const float*>(W[i]); };
@@ -165,15 +160,10 @@ int encoder_forward(const Encoder* e, const void* img, int is_u8, int B, int h, 
   };
   // residual-stream producer: x = A W^T + b + residual (fp32, in place); with LayerNorm folding also the 16-bit copy of x
   // and its per-row partial sums for the next linear
-  // (res == nullptr: the residual is the stream itself, in place; otherwise a broadcast fp32 table such as pos_embed)
   auto gemm_residual = [&](const __nv_bfloat16* A, int wi, int bi, const float* res, int res_mod, int K, int dir) {
-    GemmArgs g = base(A, wi, f24 ? nullptr : ws.x, F(bi), D, K, dir);
-    g.ldr = D; g.res_row_mod = res_mod;
-    if (res != nullptr) g.residual = res;
-    else if (f24) { g.residual = reinterpret_cast<const float*>(ws.xn); g.res_lo = x_lo; }
-    else g.residual = ws.x;
+    GemmArgs g = base(A, wi, ws.x, F(bi), D, K, dir);
+    g.residual = res; g.ldr = D; g.res_row_mod = res_mod;
     if (fused) { g.xh = ws.xn; g.rowstat_out = ws.stat; }
-    if (f24) g.out_lo = x_lo;
     return gemm_bf16_tn(g, s);
   };
   // 16-bit consumer of LN(x): plain (A = LN output) or folded (A = 16-bit x, statistics applied in the epilogue)
@@ -217,11 +207,16 @@ int encoder_forward(const Encoder* e, const void* img, int is_u8, int B, int h, 
     at.reverse = kBoustrophedon ? !qkv_dir : 0;
     if ((c.global_mask_lo >> b) & 1) TRY(global_attention_tc(at, s));
     else TRY(window_attention_tc(at, s));
-    TRY(gemm_residual(ws.att, o + B_PROJW, o + B_PROJB, nullptr, 0, D, proj_dir));
+    TRY(gemm_residual(ws.att, o + B_PROJW, o + B_PROJB, ws.x, 0, D, proj_dir));
     if (!fused)
       TRY(layernorm_rows(ws.x, F(o + B_N2W), F(o + B_N2B), 1e-6f, M, D, ws.xn, k16, s, kBoustrophedon ? 1 : 0));
     TRY(gemm_after_ln(o + B_L1W, o + B_L1B, o + B_L1S, ws.h, 4 * D, 1, l1_dir));
-    TRY(gemm_residual(ws.h, o + B_L2W, o + B_L2B, nullptr, 0, 4 * D, l2_dir));
+    {
+      GemmArgs g = base(ws.h, o + B_L2W, ws.x, F(o + B_L2B), D, 4 * D, l2_dir);
+      g.residual = ws.x; g.ldr = D;
+      if (fused) { g.xh = ws.xn; g.rowstat_out = ws.stat; }
+      TRY(gemm_bf16_tn(g, s));
+    }
     x_dir = l2_dir;
   }
 

@@ -14,10 +14,7 @@ struct EncoderConfig {
   int operand_format;  // 16-bit MMA operand format: 0 = bf16, 1 = fp16 (default of the Python layer)
   int flags;           // ENC_FLAG_*
 };
-enum : int {
-  ENC_FLAG_LN_FUSED = 1,  // norm1 / norm2 folded into the GEMMs around them (no LayerNorm launches)
-  ENC_FLAG_RES_F24 = 2,   // residual stream stored as fp16 hi plane (= the GEMM operand) + int8 lo plane instead of fp32
-};
+enum : int { ENC_FLAG_LN_FUSED = 1 };  // norm1 / norm2 folded into the GEMMs around them (no LayerNorm launches)
 
 struct Encoder {
   EncoderConfig cfg;

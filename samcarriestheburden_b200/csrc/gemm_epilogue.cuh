@@ -37,33 +37,7 @@ struct EpiParams {
   int nparts_in;
   float ln_inv_d, ln_eps;
   int f16;  // 16-bit tensors written by the epilogue (out, xh) are fp16 instead of bf16
-  // ---- "f24" residual stream: x = hi + lo * ulp(hi) / 256 with hi an fp16 plane (which IS the next GEMM's A operand, so
-  // no separate 16-bit copy is written) and lo an int8 plane: 3 bytes per element read + 3 written instead of 4 + 4 + 2,
-  // 19 significant bits (error 2^-20 relative per update, 3e-6 on the embeddings after 12 blocks).
-  const int8_t* res_lo;  // non-null: `residual` points to the fp16 hi plane (pitch ldr elements), res_lo to its lo plane
-  int8_t* out_lo;        // non-null: the result is written as f24: hi -> xh, lo -> out_lo (pitch ldo); `out` may be null
 };
-
-// f24 encode / decode of one value given its fp16 hi bits
-B200SAM_DEVINL int f24_lo(float v, uint32_t hbits) {
-  const float hf = __half2float(__ushort_as_half(static_cast<unsigned short>(hbits & 0xffffu)));
-  uint32_t e5 = (hbits >> 10) & 31u;
-  e5 = e5 == 0u ? 1u : e5;                                        // zero / subnormal hi: ulp = 2^-24
-  const float inv_step = __uint_as_float((160u - e5) << 23);      // 256 / ulp(hi) = 2^(33 - e5)
-  int q = __float2int_rn((v - hf) * inv_step);                    // v - hf is exact in fp32
-  return q < -128 ? -128 : (q > 127 ? 127 : q);
-}
-B200SAM_DEVINL float f24_value(uint32_t hbits, int q) {
-  const float hf = __half2float(__ushort_as_half(static_cast<unsigned short>(hbits & 0xffffu)));
-  uint32_t e5 = (hbits >> 10) & 31u;
-  e5 = e5 == 0u ? 1u : e5;
-  return fmaf(static_cast<float>(q), __uint_as_float((94u + e5) << 23), hf);   // ulp(hi) / 256 = 2^(e5 - 33)
-}
-B200SAM_DEVINL int sbyte(uint32_t w, int k) {
-  int r;
-  asm("bfe.s32 %0, %1, %2, 8;" : "=r"(r) : "r"(w), "r"(8 * k));
-  return r;
-}
 
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erfc(|z|) from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
 // far below the bf16 output rounding); evaluated as erfc so negative x has no 1 + erf cancellation.
@@ -137,43 +111,28 @@ struct RowLN {
 
 // before the accumulator is ready: stage the bias slice and pull the residual block towards L2.
 // COLS = columns drained by one warp: 128 (single-CTA kernel, 8 epilogue warps) or 64 (pair kernel, 16 epilogue warps)
-// residual block of one 16-column half (4 values per thread and row: rows it * 8 + (lane >> 2), columns 4 * (lane & 3) ..)
-// as RAW bits (decoded where they are used, so the loads stay in flight): fp32 residual -> the float4; f24 residual ->
-// x, y = four fp16 hi values, z = four int8 lo values
+// residual block of one 16-column half (4 x float4 per thread: rows it * 8 + (lane >> 2), columns 4 * (lane & 3) ..)
 B200SAM_DEVINL void epilogue_load_residual_half(const EpiParams& ep, int M, int N, int row_base, int n0, int h, int lane,
-                                                uint4 (&buf)[4]) {
+                                                float4 (&buf)[4]) {
   const int rsub = lane >> 2, rq = lane & 3;
   const int col = n0 + h * 16 + 4 * rq;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int row = row_base + it * 8 + rsub;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ep.residual != nullptr && row < M && col < N) {
       const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
-      const size_t off = static_cast<size_t>(rr) * ep.ldr + col;
-      if (ep.res_lo != nullptr) {
-        const uint2 hi = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(ep.residual) + off);
-        v.x = hi.x; v.y = hi.y;
-        v.z = *reinterpret_cast<const uint32_t*>(ep.res_lo + off);
-      } else {
-        v = *reinterpret_cast<const uint4*>(ep.residual + off);
-      }
+      v = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rr) * ep.ldr + col);
     }
     buf[it] = v;
   }
-}
-B200SAM_DEVINL float4 epilogue_decode_residual(const EpiParams& ep, const uint4 raw) {
-  if (ep.res_lo == nullptr)
-    return make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w));
-  return make_float4(f24_value(raw.x, sbyte(raw.z, 0)), f24_value(raw.x >> 16, sbyte(raw.z, 1)),
-                     f24_value(raw.y, sbyte(raw.z, 2)), f24_value(raw.y >> 16, sbyte(raw.z, 3)));
 }
 
 // rbuf (fp32 output only): the residual values of the first 32-column chunk, loaded BEFORE the accumulator is waited for
 // (they do not depend on the MMAs; ncu showed the epilogue warps of proj / lin2 stalled on these loads after the wait)
 template <int OUT_KIND, int COLS = 128>
 B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int row_base, int n0, float* sbias, int lane,
-                                       uint4 (&rbuf)[2][4]) {
+                                       float4 (&rbuf)[2][4]) {
       // stage this warp's bias values (zero when absent / out of range)
 #pragma unroll
   for (int i = 0; i < COLS / 32; ++i) {
@@ -216,13 +175,8 @@ B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int ro
 #pragma unroll
       for (int i = 1; i < COLS / 32; ++i) {
         const int c = n0 + 32 * i;
-        if (c < N && ep.res_lo == nullptr)
+        if (c < N)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + static_cast<size_t>(rr) * ep.ldr + c));
-        if (c < N && ep.res_lo != nullptr) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(ep.residual) +
-                                                        static_cast<size_t>(rr) * ep.ldr + c));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.res_lo + static_cast<size_t>(rr) * ep.ldr + c));
-        }
       }
     }
   }
@@ -234,7 +188,7 @@ B200SAM_DEVINL RowLN epilogue_prefetch(const EpiParams& ep, int M, int N, int ro
 // scheduler need it; with four the other warps hide the latency and the registers are better spent elsewhere).
 template <int OUT_KIND, int COLS = 128, bool PIPE = true>
 B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_base, int n0, uint32_t taddr0,
-                                   uint32_t* stg, const float* sbias, int lane, const RowLN ln, uint4 (&rbuf)[2][4]) {
+                                   uint32_t* stg, const float* sbias, int lane, const RowLN ln, float4 (&rbuf)[2][4]) {
   constexpr int NCH = COLS / 32;    // chunks of 32 columns
   const int wsw = (lane >> 1) & 3;  // write swizzle of this thread's row
   const int rsub = lane >> 2;       // transposed read: row within a group of 8
@@ -328,22 +282,15 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
           float4 v = make_float4(__uint_as_float(u.x) + b.x, __uint_as_float(u.y) + b.y,
                                  __uint_as_float(u.z) + b.z, __uint_as_float(u.w) + b.w);
           if (ep.gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-          const float4 rs = epilogue_decode_residual(ep, rbuf[hf][it]);
+          const float4 rs = rbuf[hf][it];
           v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
           if (row < M && col < N) {
-            if (out != nullptr) *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ep.ldo + col) = v;
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ep.ldo + col) = v;
             if (xh != nullptr) {
               uint2 h;
               if (ep.f16) { h.x = pack_f16x2(v.x, v.y); h.y = pack_f16x2(v.z, v.w); }
               else { h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w); }
               *reinterpret_cast<uint2*>(xh + static_cast<size_t>(row) * ep.ldo + col) = h;
-              if (ep.out_lo != nullptr) {  // f24: the int8 extension of the four fp16 values just written
-                const uint32_t lo = (static_cast<uint32_t>(f24_lo(v.x, h.x)) & 255u) |
-                                    ((static_cast<uint32_t>(f24_lo(v.y, h.x >> 16)) & 255u) << 8) |
-                                    ((static_cast<uint32_t>(f24_lo(v.z, h.y)) & 255u) << 16) |
-                                    ((static_cast<uint32_t>(f24_lo(v.w, h.y >> 16)) & 255u) << 24);
-                *reinterpret_cast<uint32_t*>(ep.out_lo + static_cast<size_t>(row) * ep.ldo + col) = lo;
-              }
             }
             if (stats) {
               st1[it] += (v.x + v.y) + (v.z + v.w);

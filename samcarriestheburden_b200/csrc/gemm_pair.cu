@@ -224,7 +224,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM2 + static_cast<int>(rank) * 128;
       const int n0 = (tile % num_n) * BN2 + cpart * EPI_COLS2;
       const int row_base = m0 + quad * 32;
-      uint4 rbuf[2][4];
+      float4 rbuf[2][4];
       const RowLN ln = epilogue_prefetch<OUT_KIND, EPI_COLS2>(ep, M, N, row_base, n0, sbias, lane, rbuf);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
@@ -307,7 +307,7 @@ int gemm_f16_tn_pair(const GemmArgs& g, cudaStream_t stream) {
   ep.tok0 = 0; ep.ntok = 0;
   ep.xh = g.xh; ep.rowstat_out = g.rowstat_out; ep.rowstat_in = g.rowstat_in; ep.colsum = g.colsum;
   ep.nparts_in = g.nparts_in; ep.ln_inv_d = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.0f;
-  ep.ln_eps = g.ln_eps; ep.f16 = g.op_f16; ep.res_lo = g.res_lo; ep.out_lo = g.out_lo;
+  ep.ln_eps = g.ln_eps; ep.f16 = g.op_f16;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int);
   static const KernelFn table[3] = {gemm_pair_kernel<0>, gemm_pair_kernel<1>, gemm_pair_kernel<2>};
   KernelFn kernel = table[g.out_kind];

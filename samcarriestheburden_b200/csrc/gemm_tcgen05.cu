@@ -192,7 +192,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM_T + (TALL ? half * 128 : 0);
       const int n0 = (tile % num_n) * BN + (TALL ? 0 : half * 128);
       const int row_base = m0 + quad * 32;
-      uint4 rbuf[2][4];
+      float4 rbuf[2][4];
       const RowLN ln = epilogue_prefetch<OUT_KIND>(ep, M, N, row_base, n0, sbias, lane, rbuf);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
@@ -226,17 +226,9 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
                   "gemm: K/lda/ldb must be multiples of 8 (16 B TMA alignment), got K=%d lda=%d ldb=%d", g.K, g.lda,
                   g.ldb);
   B200SAM_REQUIRE(g.N % 8 == 0 && (g.ldo % 8 == 0 || g.epi_mode != 0), "gemm: N and ldo must be multiples of 8 (N=%d ldo=%d)", g.N, g.ldo);
-  B200SAM_REQUIRE(g.residual == nullptr || (g.ldr % 4 == 0 && (g.res_lo != nullptr || (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0)),
+  B200SAM_REQUIRE(g.residual == nullptr || (g.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0),
                   "gemm: residual must be 16-byte aligned with ldr %% 4 == 0");
-  B200SAM_REQUIRE(g.out != nullptr || g.out_lo != nullptr, "gemm: no output");
   B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0, "gemm: out must be 16-byte aligned");
-  B200SAM_REQUIRE(g.out_lo == nullptr || (g.xh != nullptr && g.op_f16 && g.out_kind == 0 && g.epi_mode == 0 &&
-                                          (reinterpret_cast<uintptr_t>(g.out_lo) & 3) == 0 && g.ldo % 4 == 0),
-                  "gemm: an f24 result needs the fp16 hi plane (xh), fp16 operands and 4-byte aligned lo plane");
-  B200SAM_REQUIRE(g.res_lo == nullptr || (g.residual != nullptr && g.out_kind == 0 && g.epi_mode == 0 && g.res_row_mod == 0 &&
-                                          (reinterpret_cast<uintptr_t>(g.res_lo) & 3) == 0 &&
-                                          (reinterpret_cast<uintptr_t>(g.residual) & 7) == 0),
-                  "gemm: an f24 residual needs hi (8-byte aligned) and lo (4-byte aligned) planes");
   B200SAM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0,
                   "gemm: A and B must be 16-byte aligned");
   B200SAM_REQUIRE(g.a_wrap == 0 || (g.a_wrap % BK == 0 && g.a_wrap > 0 && g.K <= 2 * g.a_wrap),
@@ -282,8 +274,6 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   ep.ln_inv_d = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.0f;
   ep.ln_eps = g.ln_eps;
   ep.f16 = g.op_f16;
-  ep.res_lo = g.res_lo;
-  ep.out_lo = g.out_lo;
   B200SAM_REQUIRE(g.epi_mode == 0 || (g.epi_mode == 1 && g.N == 256 && g.aux0 && g.aux1) ||
                       (g.epi_mode == 2 && g.N == 128 && g.M % 16384 == 0 && g.aux0 && g.ntok >= 1 && g.ntok <= 3),
                   "gemm: bad fused-epilogue configuration (mode %d, M=%d, N=%d)", g.epi_mode, g.M, g.N);

@@ -56,9 +56,6 @@ struct GemmArgs {
   // LayerNorm folded into the GEMMs around it (gemm_epilogue.cuh): producer side (fp32 out) ...
   void* xh = nullptr;             // 16-bit copy of out, pitch ldo
   float* rowstat_out = nullptr;   // [M, N/64, 2] partial (sum, sum sq) of out per 64-column part (N % 128 == 0)
-  // "f24" residual stream (gemm_epilogue.cuh): x = fp16 hi plane + int8 lo plane (hi is the 16-bit copy `xh`)
-  const int8_t* res_lo = nullptr;  // non-null: `residual` is the fp16 hi plane (pitch ldr), res_lo its lo plane
-  int8_t* out_lo = nullptr;        // non-null: the result goes to (xh, out_lo) as f24; `out` may then be null
   // ... consumer side (16-bit out): out = rstd * (acc - mean * colsum[n]) + bias[n]
   const float* rowstat_in = nullptr;  // [M, nparts_in, 2]
   const float* colsum = nullptr;      // [N]

@@ -113,11 +113,10 @@ class _EncoderEngine:
             if blk.window_size == 0:
                 gmask |= 1 << i
         self.operand_format, self.ln_fused = module.operand_format, module.ln_fused
-        self.residual_f24 = module.residual_format == "f24" and self.ln_fused and self.operand_format == "fp16"
         op_dtype = _OP_DTYPE[self.operand_format]
         self.cfg = _lib.EncoderConfig(module.embed_dim, len(module.blocks), module.num_heads, gmask, module.out_chans,
                                       _lib.OPERAND_FP16 if self.operand_format == "fp16" else _lib.OPERAND_BF16,
-                                      (_lib.ENC_LN_FUSED if self.ln_fused else 0) | (_lib.ENC_RES_F24 if self.residual_f24 else 0))
+                                      _lib.ENC_LN_FUSED if self.ln_fused else 0)
         sd = {"image_encoder." + k: v for k, v in module.state_dict().items()}
         n = lib.b200sam_encoder_weight_count(C.byref(self.cfg))
         cache: dict = {}
@@ -206,25 +205,14 @@ class ImageEncoderViT(nn.Module):
         # trades that for the fp32 exponent range.  LayerNorm folding: norm1 / norm2 run inside the GEMM epilogues.
         self.operand_format = _default_operands()
         self.ln_fused = os.environ.get("B200SAM_LN_FUSED", "1") != "0"
-        # residual stream storage: "f24" = fp16 plane (which is the GEMM operand) + int8 mantissa extension (3 B / element
-        # read and written instead of 4 + 4 + 2; needs fp16 operands and folded LayerNorm), "fp32" = plain fp32
-        self.residual_format = os.environ.get("B200SAM_RESIDUAL", "f24").lower()
-        if self.residual_format not in ("f24", "fp32"):
-            raise _lib.B200SamError(f"B200SAM_RESIDUAL={self.residual_format!r}: expected 'f24' or 'fp32'")
         # a parent's load_state_dict never calls the child's override, but it does run the child's post hooks
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     def _invalidate(self) -> None:
         self._engine = None
 
-    def set_precision(self, operand_format: Optional[str] = None, ln_fused: Optional[bool] = None,
-                      residual_format: Optional[str] = None) -> "ImageEncoderViT":
-        """Select the MMA operand format ("fp16" | "bf16"), whether LayerNorm is folded into the GEMMs and the storage of
-        the residual stream ("f24" | "fp32"; f24 silently falls back to fp32 without fp16 operands + folded LayerNorm)."""
-        if residual_format is not None:
-            if residual_format not in ("f24", "fp32"):
-                raise ValueError(f"residual_format must be 'f24' or 'fp32', got {residual_format!r}")
-            self.residual_format = residual_format
+    def set_precision(self, operand_format: Optional[str] = None, ln_fused: Optional[bool] = None) -> "ImageEncoderViT":
+        """Select the MMA operand format ("fp16" | "bf16") and whether LayerNorm is folded into the GEMMs."""
         if operand_format is not None:
             if operand_format not in _OP_DTYPE:
                 raise ValueError(f"operand_format must be 'fp16' or 'bf16', got {operand_format!r}")
