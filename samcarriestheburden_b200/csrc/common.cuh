@@ -134,12 +134,6 @@ B200SAM_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// pull a 2-D tile towards L2 (no shared-memory destination, no completion tracking)
-B200SAM_DEVINL void tma_prefetch_l2_2d(const CUtensorMap* m, int x, int y) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(x), "r"(y)
-               : "memory");
-}
 B200SAM_DEVINL void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

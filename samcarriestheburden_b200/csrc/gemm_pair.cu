@@ -113,9 +113,8 @@ B200SAM_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
 
 template <int OUT_KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_res, EpiParams ep, int M, int N, int K, int reverse_m, int op_f16,
-                 int prefetch_res) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpiParams ep, int M,
+                 int N, int K, int reverse_m, int op_f16) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_epi = smem + SMEM_TILES2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES2 + SMEM_EPI2);
@@ -138,7 +137,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (prefetch_res) tma_prefetch_desc(&tma_res);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES2; ++i) {
@@ -171,15 +169,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int mb = tile / num_n;
         const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM2 + static_cast<int>(rank) * 128;
         const int n0 = (tile % num_n) * BN2 + static_cast<int>(rank) * 128;
-        if (prefetch_res) {
-          // the fp32 residual block this CTA's epilogue will read one mainloop from now (128 rows x 256 columns): pulled
-          // into L2 by the TMA engine here, so the epilogue's loads hit L2 instead of waiting on HBM (ncu: half of the
-          // epilogue warps' samples of the proj GEMM were long-scoreboard stalls on these loads)
-          const int nt = (tile % num_n) * BN2;
-#pragma unroll
-          for (int c = 0; c < BN2 / 64; ++c)
-            if (nt + c * 64 < N) tma_prefetch_l2_2d(&tma_res, nt + c * 64, m0);
-        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES2;
@@ -319,11 +308,7 @@ int gemm_f16_tn_pair(const GemmArgs& g, cudaStream_t stream) {
   ep.xh = g.xh; ep.rowstat_out = g.rowstat_out; ep.rowstat_in = g.rowstat_in; ep.colsum = g.colsum;
   ep.nparts_in = g.nparts_in; ep.ln_inv_d = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.0f;
   ep.ln_eps = g.ln_eps; ep.f16 = g.op_f16;
-  // L2 prefetch of the residual tiles (plain fp32 residual stream only, not the broadcast pos_embed table)
-  CUtensorMap tr = ta;
-  const int prefetch_res = g.residual != nullptr && g.res_row_mod == 0 && g.out_kind == 0 && g.N % 4 == 0;
-  if (prefetch_res && make_tmap_f32(&tr, g.residual, g.M, g.N, g.ldr, 128, 64)) return 1;
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int, int);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int);
   static const KernelFn table[3] = {gemm_pair_kernel<0>, gemm_pair_kernel<1>, gemm_pair_kernel<2>};
   KernelFn kernel = table[g.out_kind];
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), SMEM_BYTES2)) return rc;
@@ -331,8 +316,8 @@ int gemm_f16_tn_pair(const GemmArgs& g, cudaStream_t stream) {
   int clusters = max_active_clusters(reinterpret_cast<const void*>(kernel));
   if (tiles < clusters) clusters = tiles;
   TimedLaunch timed(TIMED_GEMM, 2.0 * g.M * g.N * g.K, g.M, g.N, g.K, stream);
-  B200SAM_CHECK_CUDA(launch_kernel(kernel, dim3(2 * clusters), dim3(THREADS2), SMEM_BYTES2, stream, ta, tb, tr, ep, g.M,
-                                   g.N, g.K, g.reverse_m, g.op_f16, prefetch_res));
+  B200SAM_CHECK_CUDA(launch_kernel(kernel, dim3(2 * clusters), dim3(THREADS2), SMEM_BYTES2, stream, ta, tb, ep, g.M, g.N,
+                                   g.K, g.reverse_m, g.op_f16));
   return 0;
 }
 

@@ -189,34 +189,6 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
   return 0;
 }
 
-int make_tmap_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                  uint32_t box_cols) {
-  const TmapKey key = make_key(ptr, cols, rows, 0, 0, ld, box_cols, box_rows, 0, 0x40u, 2);  // 0x40: fp32 marker
-  TmapCache& cache = tmap_cache();
-  if (auto it = cache.find(key); it != cache.end()) { *map = it->second; return 0; }
-  PFN_encodeTiled enc = get_encode_fn();
-  if (enc == nullptr) {
-    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    return 1;
-  }
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 4};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled(f32) failed with CUresult %d (ptr=%p rows=%llu cols=%llu ld=%llu box=%ux%u)",
-                   (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows,
-                   box_cols);
-    return 1;
-  }
-  if (cache.size() > 8192) cache.clear();
-  cache.emplace(key, *map);
-  return 0;
-}
-
 int make_tmap_bf16_grid4d(CUtensorMap* map, const void* ptr, uint64_t batch, uint64_t cols, uint32_t box_x,
                           uint32_t box_y) {
   const TmapKey key = make_key(ptr, cols, batch, 0, 0, 0, box_x, box_y, 0, 0, 4);

@@ -13,8 +13,5 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 // out-of-grid tokens are zero-filled.
 int make_tmap_bf16_grid4d(CUtensorMap* map, const void* ptr, uint64_t batch, uint64_t cols, uint32_t box_x,
                           uint32_t box_y);
-// 2-D fp32 tensor map (no swizzle) over a row-major [rows, cols] matrix, used for L2 prefetches of residual tiles
-int make_tmap_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                  uint32_t box_cols);
 int num_sms();
 }  // namespace b200sam
