@@ -429,10 +429,11 @@ def main():
     if rank == 0:
         out["roofline"] = inrun_kernel_roofline(sam, dev_pool, K, args.model, B, peaks)
         out["latency_b1"] = set_image_latency(sam)
-        if not args.no_refine:
+        # single-GPU legs (the drivers they call shard by rank): only in the N = 1 run; at N > 1 `set500` is the pipeline leg
+        if not args.no_refine and world == 1:
             if args.model != "vit_l":
                 out["vit_l_batch16"] = secondary_encoder("vit_l", 16, dev, peaks)
-        if not args.no_refine:
+        if not args.no_refine and world == 1:
             out["refine"] = refine_throughput(sam, dev)
             # HBM-bound stages on batched launches: algorithmic bytes / CUDA-event time
             sys.path.insert(0, str(ROOT / "tools"))
