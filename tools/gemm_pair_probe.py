@@ -60,7 +60,18 @@ def plain(N, K, A, W, out):
                                                    0, 0, 0, 1, 0, st))
 
 
-cases = [("proj+res+stats", proj, 2.0 * M * D * D), ("qkv folded", qkv_, 2.0 * M * 3 * D * D),
+x32 = torch.empty((M, D), device=dev)
+
+
+def gen(N, K, A, W, out, res, out16):
+    return lambda: _lib.check(lib.b200sam_gemm_f16(A.data_ptr(), W.data_ptr(), out.data_ptr(), None, _lib.ptr(res), M, N, K,
+                                                   K, K, N, N, 0, 0, out16, 0, st))
+
+
+cases = [("proj+res+stats", proj, 2.0 * M * D * D),
+         ("proj fp32+res", gen(D, D, att, Wp, x, x, 0), 2.0 * M * D * D),
+         ("proj fp32 plain", gen(D, D, att, Wp, x32, None, 0), 2.0 * M * D * D),
+         ("proj fp16 plain", gen(D, D, att, Wp, x16, None, 1), 2.0 * M * D * D), ("qkv folded", qkv_, 2.0 * M * 3 * D * D),
          ("lin1 folded+gelu", lin1, 2.0 * M * 4 * D * D), ("lin2+res+stats", lin2, 2.0 * M * D * 4 * D),
          ("qkv plain", plain(3 * D, D, x16, Wq, qkv), 2.0 * M * 3 * D * D),
          ("lin2 plain16", plain(D, 4 * D, h16, W2, x16), 2.0 * M * D * 4 * D)]
