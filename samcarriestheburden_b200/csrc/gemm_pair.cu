@@ -111,7 +111,8 @@ B200SAM_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
       : "memory");
 }
 
-template <int OUT_KIND>
+// DIRECT (fp32 output only): the epilogue writes rows straight from the TMEM layout (epilogue_store_f32_direct)
+template <int OUT_KIND, bool DIRECT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpiParams ep, int M,
                  int N, int K, int reverse_m, int op_f16) {
@@ -279,9 +280,22 @@ int max_active_clusters(const void* func) {
 }  // namespace
 
 namespace {
-std::atomic<int> g_pair_mode{-1};  // -1: B200SAM_GEMM_PAIR decides, 0 / 1: set by b200sam_set_gemm_pair
+std::atomic<int> g_pair_mode{-1};    // -1: B200SAM_GEMM_PAIR decides, 0 / 1: set by b200sam_set_gemm_pair
+std::atomic<int> g_pair_direct{-1};  // fp32 epilogue without the smem transpose: -1 = B200SAM_GEMM_DIRECT decides
 }
-void gemm_pair_set_mode(int mode) { g_pair_mode.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
+void gemm_pair_set_mode(int mode) {  // -1 env, 0 single-CTA, 1 pair (staged fp32 epilogue), 2 pair + direct fp32 epilogue
+  g_pair_mode.store(mode < 0 ? -1 : (mode ? 1 : 0));
+  g_pair_direct.store(mode < 0 ? -1 : (mode == 2 ? 1 : 0));
+}
+static bool gemm_pair_direct() {
+  const int m = g_pair_direct.load(std::memory_order_relaxed);
+  if (m >= 0) return m == 1;
+  static const bool on = [] {
+    const char* e = std::getenv("B200SAM_GEMM_DIRECT");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
 bool gemm_pair_enabled() {
   const int m = g_pair_mode.load(std::memory_order_relaxed);
   if (m >= 0) return m == 1;
@@ -309,8 +323,10 @@ int gemm_f16_tn_pair(const GemmArgs& g, cudaStream_t stream) {
   ep.nparts_in = g.nparts_in; ep.ln_inv_d = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.0f;
   ep.ln_eps = g.ln_eps; ep.f16 = g.op_f16;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int);
-  static const KernelFn table[3] = {gemm_pair_kernel<0>, gemm_pair_kernel<1>, gemm_pair_kernel<2>};
-  KernelFn kernel = table[g.out_kind];
+  static const KernelFn table[4] = {gemm_pair_kernel<0>, gemm_pair_kernel<1>, gemm_pair_kernel<2>, gemm_pair_kernel<0, true>};
+  // the direct fp32 epilogue handles bias + residual (+ 16-bit copy + row statistics); GELU on an fp32 output stays staged
+  const bool direct = g.out_kind == 0 && !g.gelu && gemm_pair_direct() && g.ldo % 4 == 0 && (g.xh == nullptr || g.ldo % 8 == 0);
+  KernelFn kernel = table[direct ? 3 : g.out_kind];
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), SMEM_BYTES2)) return rc;
   const int tiles = ((g.M + BM2 - 1) / BM2) * ((g.N + BN2 - 1) / BN2);
   int clusters = max_active_clusters(reinterpret_cast<const void*>(kernel));
