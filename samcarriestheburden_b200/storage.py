@@ -15,9 +15,12 @@ after the producing stream by an event) and a background thread waits for that c
 * otherwise (h5py is not part of this image) -> a directory with `attrs.json` and, per record, raw `.npy` files
   `<stem>.<field>.npy` with the same fields (`features`, `original_size`, `input_size` / `segmentation_mask`,
   `estimated_dice`).  Plain `.npy` on purpose: the bytes go to the kernel in one `write` that releases the GIL, whereas
-  `np.savez` (zip + CRC in Python) made the writer thread compete with the launch loop for the interpreter (measured:
-  pipeline 116 -> 78 images/s with npz, unchanged with npy).  `open_embeddings` reads either layout back into an
-  `EmbeddingStore`.
+  `np.savez` (zip + CRC in Python) keeps the interpreter busy on the writer thread.  Records are independent files, so
+  this backend is written by `threads` workers.  `open_embeddings` reads either layout back into an `EmbeddingStore`.
+
+Staging buffers are pinned once per size class (power-of-two bytes) and shared by every writer of the process: native-size
+masks have a different shape per image, and pinning a fresh 4-13 MiB buffer per record (about a millisecond per MiB)
+was what the first version of this writer spent its time on (bench.py `pipeline.with_async_writer`).
 """
 from __future__ import annotations
 
@@ -81,9 +84,14 @@ class _NpyDirBackend(_Backend):
             np.save(self.path / f"{name}.{field}.npy", arr, allow_pickle=False)
 
 
-# pinned staging buffers are shared by all writers of the process (pinning a 4 MiB buffer costs about a millisecond)
-_PINNED_POOL: Dict[tuple, list] = {}
+# pinned staging buffers (uint8, power-of-two size classes) shared by all writers of the process
+_PINNED_POOL: Dict[int, list] = {}
 _PINNED_LOCK = threading.Lock()
+_MIN_CLASS = 1 << 12
+
+
+def _size_class(nbytes: int) -> int:
+    return max(_MIN_CLASS, 1 << max(0, int(nbytes) - 1).bit_length())
 
 
 class AsyncResultWriter:
@@ -93,12 +101,13 @@ class AsyncResultWriter:
     buffer from a small pool (back-pressure: put() blocks only when `depth` records are still being written)."""
 
     def __init__(self, path, kind: str, file_attrs: Optional[dict] = None, gzip: int = 9, depth: int = 64,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, threads: int = 2):
         assert kind in ("embedding", "mask")
         self.kind = kind
         path = Path(path)
         if path.suffix in (".h5", ".hdf5") and _have_h5py():
             self.backend: _Backend = _H5Backend(path, file_attrs or {}, gzip)
+            threads = 1  # one HDF5 file, one writer
         else:
             self.backend = _NpyDirBackend(path.with_suffix("") if path.suffix in (".h5", ".hdf5") else path, file_attrs or {})
         self.device = device
@@ -107,17 +116,20 @@ class AsyncResultWriter:
         self._pool, self._pool_lock = _PINNED_POOL, _PINNED_LOCK
         self._error: Optional[BaseException] = None
         self.records = 0
-        self._t = threading.Thread(target=self._run, name="b200sam-writer", daemon=True)
-        self._t.start()
+        self._rec_lock = threading.Lock()
+        self._threads = [threading.Thread(target=self._run, name=f"b200sam-writer-{i}", daemon=True)
+                         for i in range(max(1, int(threads)))]
+        for t in self._threads:
+            t.start()
 
     # ------------------------------------------------------------------ producer side
-    def _host_buffer(self, t: torch.Tensor) -> torch.Tensor:
-        key = (tuple(t.shape), t.dtype)
+    def _host_buffer(self, nbytes: int) -> torch.Tensor:
+        cls = _size_class(nbytes)
         with self._pool_lock:
-            free = self._pool.get(key)
+            free = self._pool.get(cls)
             if free:
                 return free.pop()
-        return torch.empty(t.shape, dtype=t.dtype).pin_memory() if torch.cuda.is_available() else torch.empty(t.shape, dtype=t.dtype)
+        return torch.empty(cls, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
 
     def _to_host_async(self, t: torch.Tensor):
         if not t.is_cuda:
@@ -126,14 +138,16 @@ class AsyncResultWriter:
             self._stream = torch.cuda.Stream(device=t.device)
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(t.device))
-        host = self._host_buffer(t)
+        nbytes = t.numel() * t.element_size()
+        raw = self._host_buffer(nbytes)
+        host = raw[:nbytes].view(t.dtype).reshape(t.shape)
         with torch.cuda.stream(self._stream):
             self._stream.wait_event(ready)
             host.copy_(t, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self._stream)
         t.record_stream(self._stream)
-        return host, done
+        return host, (done, raw)
 
     def put_embedding(self, name: str, features: torch.Tensor, original_size, input_size) -> None:
         """features: [1,256,64,64] float32 (what `predictor.features` holds, generate_img_embeddings.py:46)."""
@@ -161,23 +175,26 @@ class AsyncResultWriter:
             name, staged, extra = item
             try:
                 arrays = dict(extra)
-                for k, (host, done) in staged.items():
-                    if done is not None:
-                        done.synchronize()
+                for k, (host, pending) in staged.items():
+                    if pending is not None:
+                        pending[0].synchronize()
                     arrays[k] = host.numpy()
                 self.backend.write(self.kind, name, arrays)
-                self.records += 1
+                with self._rec_lock:
+                    self.records += 1
                 with self._pool_lock:
-                    for host, done in staged.values():
-                        if done is not None:
-                            self._pool.setdefault((tuple(host.shape), host.dtype), []).append(host)
+                    for _, pending in staged.values():
+                        if pending is not None:
+                            self._pool.setdefault(pending[1].numel(), []).append(pending[1])
             except BaseException as e:  # surfaced on the next put() / close()
                 self._error = e
 
     def close(self) -> int:
         """Drain the queue, close the file; returns the number of records written."""
-        self._q.put(None)
-        self._t.join()
+        for _ in self._threads:
+            self._q.put(None)
+        for t in self._threads:
+            t.join()
         self.backend.close()
         if self._error is not None:
             raise RuntimeError("b200sam writer thread failed") from self._error
