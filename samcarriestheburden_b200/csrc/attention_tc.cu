@@ -35,6 +35,7 @@ constexpr uint32_t TC_TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0;
 constexpr uint32_t COL_O = 64;
 constexpr uint32_t COL_TW = 160;
+constexpr uint32_t COL_P = 224;   // P as the A operand of the PV MMA: 64 keys x 16 bit = 32 columns
 constexpr float LAZY_RESCALE = 8.0f;
 
 template <int HD>
@@ -113,7 +114,7 @@ struct TcParams {
   int reverse;  // 1: images last-to-first (the qkv GEMM that ran forward left the last images in L2)
 };
 
-template <int HD, bool F16>
+template <int HD, bool F16, bool PT>  // PT: P goes to the PV MMA through TMEM (A operand in TMEM) instead of shared memory
 __global__ void __launch_bounds__(TC_THREADS, 2)
 global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                       const __grid_constant__ CUtensorMap map_rh, const __grid_constant__ CUtensorMap map_rw,
@@ -268,10 +269,15 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tcgen05_fence_after();
         // O += P V: A = P (K-major, SWIZZLE_128B, 32 B per K-step), B = V slabs consumed MN-major
         // (N = head dim: 16-dim slabs KV_SLAB apart = LBO; K = keys: 8-key groups 256 B apart = SBO)
-        for (int ks = 0; ks < TK / 16; ++ks)
-          umma_bf16_ss(tmem + COL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
-                       make_smem_desc(vb + ks * 512, L::KV_SLAB, 256, SW32),
-                       make_idesc_op16_f32(128, HD, 1, F16), (t > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < TK / 16; ++ks) {
+          if constexpr (PT)
+            umma_bf16_ts(tmem + COL_O, tmem + COL_P + ks * 8, make_smem_desc(vb + ks * 512, L::KV_SLAB, 256, SW32),
+                         make_idesc_op16_f32(128, HD, 1, F16), (t > 0 || ks > 0) ? 1u : 0u);
+          else
+            umma_bf16_ss(tmem + COL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
+                         make_smem_desc(vb + ks * 512, L::KV_SLAB, 256, SW32),
+                         make_idesc_op16_f32(128, HD, 1, F16), (t > 0 || ks > 0) ? 1u : 0u);
+        }
         umma_commit(&v_empty[buf]);
         umma_commit(o_ready);
       }
@@ -379,7 +385,7 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
       for (int j = 0; j < 8; ++j) pm[j] = sv[j];
 #pragma unroll
-      for (int j = 8; j < 64; ++j) pm[j & 7] = fmaxf(pm[j & 7], sv[j]);
+      for (int j = 8; j < 64; j += 2) pm[(j >> 1) & 7] = max3(pm[(j >> 1) & 7], sv[j], sv[j + 1]);
       const float mx = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
       const float mt = mx;
       // lazy rescale: keep the old reference maximum unless the new one exceeds it by more than 2^8
@@ -417,19 +423,33 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       l_run *= corr;
       m_run = m_new;
       float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if constexpr (PT) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B of bf16
-        uint4 pk;
-        pk.x = pack_op16x2<F16>(sv[c * 8 + 0], sv[c * 8 + 1]);
-        pk.y = pack_op16x2<F16>(sv[c * 8 + 2], sv[c * 8 + 3]);
-        pk.z = pack_op16x2<F16>(sv[c * 8 + 4], sv[c * 8 + 5]);
-        pk.w = pack_op16x2<F16>(sv[c * 8 + 6], sv[c * 8 + 7]);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) add2(ps[j], ps[j + 1], ps[j], ps[j + 1], sv[c * 8 + j], sv[c * 8 + j + 1]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
+          for (int j = 0; j < 32; j += 2) {
+            pk[j >> 1] = pack_op16x2<F16>(sv[hf * 32 + j], sv[hf * 32 + j + 1]);
+            add2(ps[j & 6], ps[(j & 6) + 1], ps[j & 6], ps[(j & 6) + 1], sv[hf * 32 + j], sv[hf * 32 + j + 1]);
+          }
+          tmem_st_32x32b_x16(tl + COL_P + hf * 16, pk);
+        }
+        tmem_st_wait();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B of bf16
+          uint4 pk;
+          pk.x = pack_op16x2<F16>(sv[c * 8 + 0], sv[c * 8 + 1]);
+          pk.y = pack_op16x2<F16>(sv[c * 8 + 2], sv[c * 8 + 3]);
+          pk.z = pack_op16x2<F16>(sv[c * 8 + 4], sv[c * 8 + 5]);
+          pk.w = pack_op16x2<F16>(sv[c * 8 + 6], sv[c * 8 + 7]);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) add2(ps[j], ps[j + 1], ps[j], ps[j + 1], sv[c * 8 + j], sv[c * 8 + j + 1]);
+          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = pk;
+        }
+        fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the MMA's async-proxy reads
       }
       l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
-      fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the MMA's async-proxy reads
       tcgen05_fence_before();
       mbar_arrive(p_full);
     }
@@ -460,382 +480,6 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem, TC_TMEM_COLS);
-  }
-}
-
-// ================================================================================================
-// Global attention, two threads per query row (the default).  Same CTA shape, shared-memory layout, TMEM columns and MMA
-// schedule as the kernel above; the softmax is done by EIGHT warps: warps 2-5 take key-tile columns 0..31 (local key
-// rows 0..3 of the 8 x 8 block), warps 6-9 columns 32..63, so the SM holds 16 softmax warps with 32 live scores each
-// instead of 8 with 64 - the kernel above keeps no pipe above 50 % because two warps per scheduler cannot hide the
-// MUFU / TMEM / barrier latencies of the chain.  The two threads of a row agree on the tile's row maximum through a
-// double-buffered shared-memory slot and one named barrier per tile; everything else (lazy rescale, FMA-pipe exp2 for a
-// quarter of the pairs, P in the SWIZZLE_128B tile) is as above.  The prologue gathers are done by warps 2-5 only.
-constexpr int G2_THREADS = 320;
-constexpr int G2_SM_WARPS = 8;
-constexpr int G2_SM_THREADS = G2_SM_WARPS * 32;
-
-template <int HD, bool F16>
-__global__ void __launch_bounds__(G2_THREADS, 2)
-global_attn_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                        const __grid_constant__ CUtensorMap map_rh, const __grid_constant__ CUtensorMap map_rw,
-                        TcParams prm) {
-  using L = TcLayout<HD>;
-  constexpr int NS = L::NS;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* tab_full = bars + 1;
-  uint64_t* pre_full = bars + 2;
-  uint64_t* pre_done = bars + 3;
-  uint64_t* tab_free = bars + 4;
-  uint64_t* k_full = bars + 5;    // [2]
-  uint64_t* k_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_full = bars + 10;
-  uint64_t* o_done = bars + 11;
-  uint64_t* s_read = bars + 12;
-  uint64_t* o_ready = bars + 13;
-  uint64_t* v_full = bars + 14;   // [2]
-  uint64_t* v_empty = bars + 16;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  float* th_t = reinterpret_cast<float*>(smem + L::OFF_TH);
-  float* xch = reinterpret_cast<float*>(smem + L::OFF_BAR + 256);  // [2 tile parities][2 halves][128 rows]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y;
-  const int b = prm.reverse ? static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z) : static_cast<int>(blockIdx.z);
-  const int D = prm.heads * HD;
-  const int q0 = qt * TQ;
-  const int qh0 = q0 >> 6;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_kv);
-    tma_prefetch_desc(&map_rh);
-    tma_prefetch_desc(&map_rw);
-    mbar_init(q_full, 1);
-    mbar_init(tab_full, 1);
-    mbar_init(pre_full, 1);
-    mbar_init(pre_done, TQ);
-    mbar_init(tab_free, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, G2_SM_WARPS);
-    mbar_init(o_done, 1);
-    mbar_init(s_read, G2_SM_WARPS);
-    mbar_init(o_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, TC_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  constexpr int NT = 4096 / TK;  // 64 key tiles
-  grid_dependency_wait();    // programmatic dependent launch: the qkv GEMM has completed past this line
-  grid_launch_dependents();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, NS * L::Q_SLAB);
-      for (int kk = 0; kk < NS; ++kk)
-        tma_load_2d(smem + L::OFF_Q + kk * L::Q_SLAB, &map_q, q_full, head * HD + kk * 16, b * 4096 + q0);
-      mbar_arrive_expect_tx(tab_full, 2 * NS * L::Q_SLAB);
-      for (int kk = 0; kk < NS; ++kk) {
-        tma_load_2d(smem + L::OFF_KV + kk * L::Q_SLAB, &map_rw, tab_full, kk * 16, 0);
-        tma_load_2d(smem + L::OFF_KV + (NS + kk) * L::Q_SLAB, &map_rh, tab_full, kk * 16, qh0);
-      }
-      mbar_wait(tab_free, 0);  // both prologue MMAs have consumed the tables
-      auto load_k = [&](int t) {
-        const int buf = t & 1;
-        if (t >= 2) mbar_wait(&k_empty[buf], ((t >> 1) - 1) & 1);
-        uint8_t* kb = smem + L::OFF_K + buf * L::KV_TILE;
-        mbar_arrive_expect_tx(&k_full[buf], L::KV_TILE);
-        for (int kk = 0; kk < NS; ++kk)
-          tma_load_4d(kb + kk * L::KV_SLAB, &map_kv, &k_full[buf], D + head * HD + kk * 16, (t & 7) * 8, (t >> 3) * 8, b);
-      };
-      auto load_v = [&](int t) {
-        const int buf = t & 1;
-        if (t >= 2) mbar_wait(&v_empty[buf], ((t >> 1) - 1) & 1);
-        uint8_t* vb = smem + L::OFF_V + buf * L::KV_TILE;
-        mbar_arrive_expect_tx(&v_full[buf], L::KV_TILE);
-        for (int kk = 0; kk < NS; ++kk)
-          tma_load_4d(vb + kk * L::KV_SLAB, &map_kv, &v_full[buf], 2 * D + head * HD + kk * 16, (t & 7) * 8, (t >> 3) * 8, b);
-      };
-      load_k(0);
-      for (int t = 0; t < NT; ++t) {
-        if (t + 1 < NT) load_k(t + 1);
-        load_v(t);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t sq = smem_u32(smem + L::OFF_Q);
-      const uint32_t skv = smem_u32(smem + L::OFF_KV);
-      const uint32_t sp = smem_u32(smem + L::OFF_P);
-      constexpr uint32_t SW32 = 6, SW128 = 2;
-      mbar_wait(q_full, 0);
-      mbar_wait(tab_full, 0);
-      tcgen05_fence_after();
-      for (int kk = 0; kk < NS; ++kk)
-        umma_bf16_ss(tmem + 0, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
-                     make_smem_desc(skv + kk * L::Q_SLAB, 16, 256, SW32), make_idesc_op16_f32(128, 128, 0, F16), kk > 0);
-      umma_commit(pre_full);
-      mbar_wait(pre_done, 0);
-      tcgen05_fence_after();
-      for (int kk = 0; kk < NS; ++kk)
-        umma_bf16_ss(tmem + 0, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
-                     make_smem_desc(skv + (NS + kk) * L::Q_SLAB, 16, 256, SW32), make_idesc_op16_f32(128, 80, 0, F16),
-                     kk > 0);
-      umma_commit(pre_full);
-      umma_commit(tab_free);
-      mbar_wait(pre_done, 1);
-      tcgen05_fence_after();
-      auto issue_qk = [&](int t) {
-        const int buf = t & 1;
-        const uint32_t kb = skv + buf * L::KV_TILE;
-        mbar_wait(&k_full[buf], (t >> 1) & 1);
-        tcgen05_fence_after();
-        for (int kk = 0; kk < NS; ++kk)
-          umma_bf16_ss(tmem + COL_S, make_smem_desc(sq + kk * L::Q_SLAB, 16, 256, SW32),
-                       make_smem_desc(kb + kk * L::KV_SLAB, 16, 256, SW32), make_idesc_op16_f32(128, TK, 0, F16), kk > 0);
-        umma_commit(s_full);
-        umma_commit(&k_empty[buf]);
-      };
-      issue_qk(0);
-      for (int t = 0; t < NT; ++t) {
-        const int buf = t & 1;
-        const uint32_t vb = skv + 2 * L::KV_TILE + buf * L::KV_TILE;
-        mbar_wait(s_read, t & 1);
-        tcgen05_fence_after();
-        if (t + 1 < NT) issue_qk(t + 1);
-        mbar_wait(&v_full[buf], (t >> 1) & 1);
-        mbar_wait(p_full, t & 1);
-        tcgen05_fence_after();
-        for (int ks = 0; ks < TK / 16; ++ks)
-          umma_bf16_ss(tmem + COL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
-                       make_smem_desc(vb + ks * 512, L::KV_SLAB, 256, SW32),
-                       make_idesc_op16_f32(128, HD, 1, F16), (t > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&v_empty[buf]);
-        umma_commit(o_ready);
-      }
-      umma_commit(o_done);
-    }
-  } else {
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;  // warp-uniform: which 32 columns of every key tile
-    const int r = quad * 32 + lane;    // query row inside the tile
-    const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16);
-    const int qw = r & 63;
-    if (half == 0) {
-      // ---- prologue 1: gather the row's 64 w-bias terms Tw[kw] = Tw_full[qw - kw + 63] into TMEM (x log2 e)
-      {
-        float* scratch = th_t;  // [64][128], column r is private to this thread
-        uint32_t v[64];
-        mbar_wait(pre_full, 0);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            uint32_t a[32];
-            tmem_ld_32x32b_x32(tl + hf * 64 + c2 * 32, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) scratch[(c2 * 32 + j) * TQ + r] = __uint_as_float(a[j]) * LOG2E;
-          }
-#pragma unroll
-          for (int kw = 0; kw < 64; ++kw) {
-            const int idx = qw + 63 - kw;
-            if ((idx >> 6) == hf) v[kw] = __float_as_uint(scratch[(idx & 63) * TQ + r]);
-          }
-        }
-        uint32_t w0[32], w1[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { w0[j] = v[j]; w1[j] = v[32 + j]; }
-        tmem_st_32x32b_x32(tl + COL_TW, w0);
-        tmem_st_32x32b_x32(tl + COL_TW + 32, w1);
-        tmem_st_wait();
-        tcgen05_fence_before();
-        mbar_arrive(pre_done);
-      }
-      // ---- prologue 2: h-bias Th[kh] = Th_full[63 - kh + hi], hi = 1 for the second grid row of the tile
-      {
-        mbar_wait(pre_full, 1);
-        tcgen05_fence_after();
-        const int hi = r >> 6;  // warp-uniform
-#pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t a[32];
-          tmem_ld_32x32b_x32(tl + c2 * 32, a);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int kh = 63 + hi - (c2 * 32 + j);
-            if (kh >= 0 && kh < 64) th_t[kh * TQ + r] = __uint_as_float(a[j]) * LOG2E;
-          }
-        }
-        {
-          uint32_t a[16];
-          tmem_ld_32x32b_x16(tl + 64, a);
-          tmem_ld_wait();
-          if (hi) th_t[0 * TQ + r] = __uint_as_float(a[0]) * LOG2E;  // column 64 <-> kh = 0 when hi = 1
-        }
-        tcgen05_fence_before();
-        mbar_arrive(pre_done);
-      }
-    }
-    // the other half starts here: the bias terms (TMEM and shared memory) written by warps 2-5 must be visible to it
-    tcgen05_fence_before();
-    named_barrier_sync(1, G2_SM_THREADS);
-    tcgen05_fence_after();
-
-    const float scale_l2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
-    float m_run = -INFINITY, l_run = 0.0f;
-    uint8_t* prow = smem + L::OFF_P + r * 128;
-    const uint32_t t_s = tl + COL_S + half * 32;
-    constexpr int HC = HD / 2;  // O columns rescaled / stored by this thread
-    const uint32_t t_o = tl + COL_O + half * HC;
-    for (int t = 0; t < NT; ++t) {
-      // key tile t = the 8 x 8 block at grid rows (t / 8) * 8, columns (t % 8) * 8; this thread's 32 score columns are the
-      // keys at local rows half * 4 .. half * 4 + 3, all 8 local columns
-      float th4[4], tw8[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) th4[i] = th_t[((t >> 3) * 8 + half * 4 + i) * TQ + r];
-      mbar_wait(s_full, t & 1);
-      tcgen05_fence_after();
-      float sv[32];
-      {
-        uint32_t a[32], w[8];
-        tmem_ld_32x32b_x32(t_s, a);
-        tmem_ld_32x32b_x8(tl + COL_TW + (t & 7) * 8, w);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_read);  // S(t) is in registers: the MMA warp may start QK(t+1)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tw8[i] = __uint_as_float(w[i]);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float b0, b1;
-          add2(b0, b1, th4[j >> 3], th4[j >> 3], tw8[j & 7], tw8[(j & 7) + 1]);
-          fma2(sv[j], sv[j + 1], __uint_as_float(a[j]), __uint_as_float(a[j + 1]), scale_l2, b0, b1);
-        }
-      }
-      float pm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) pm[(j >> 1) & 3] = max3(pm[(j >> 1) & 3], sv[j], sv[j + 1]);
-      float mt = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
-      float* slot = xch + (t & 1) * 2 * TQ;
-      slot[half * TQ + r] = mt;
-      named_barrier_sync(1, G2_SM_THREADS);
-      mt = fmaxf(mt, slot[(half ^ 1) * TQ + r]);
-      // lazy rescale: keep the old reference maximum unless the new one exceeds it by more than 2^8
-      const float m_new = (mt > m_run + LAZY_RESCALE) ? mt : m_run;
-      const float corr = ex2_approx(m_run - m_new);  // 1 when unchanged, 0 on the first tile
-      const float noff = -m_new, noff_h = noff - 0.5f;
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float x0, x1;
-        if ((j / 2) % GLOBAL_POLY_EVERY == GLOBAL_POLY_EVERY - 1) {  // every 4th pair on the FMA pipe (see ex2_poly2)
-          add2(x0, x1, sv[j], sv[j + 1], noff_h, noff_h);
-          ex2_poly2(sv[j], sv[j + 1], x0, x1);
-        } else {
-          add2(x0, x1, sv[j], sv[j + 1], noff, noff);
-          sv[j] = ex2_approx(x0);
-          sv[j + 1] = ex2_approx(x1);
-        }
-      }
-      if (t > 0) {
-        mbar_wait(o_ready, (t - 1) & 1);  // PV(t-1) retired: P and O are free again
-        tcgen05_fence_after();
-        if (__any_sync(0xffffffffu, m_new != m_run)) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(t_o, o);
-          if constexpr (HC > 32) {
-            uint32_t o8[8];
-            tmem_ld_32x32b_x8(t_o + 32, o8);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] = __float_as_uint(__uint_as_float(o8[j]) * corr);
-            tmem_st_32x32b_x8(t_o + 32, o8);
-          } else {
-            tmem_ld_wait();
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
-          tmem_st_32x32b_x32(t_o, o);
-          tmem_st_wait();
-        }
-      }
-      l_run *= corr;
-      m_run = m_new;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {  // 4 pieces of 8 keys = 16 B
-        uint4 pk;
-        pk.x = pack_op16x2<F16>(sv[c * 8 + 0], sv[c * 8 + 1]);
-        pk.y = pack_op16x2<F16>(sv[c * 8 + 2], sv[c * 8 + 3]);
-        pk.z = pack_op16x2<F16>(sv[c * 8 + 4], sv[c * 8 + 5]);
-        pk.w = pack_op16x2<F16>(sv[c * 8 + 6], sv[c * 8 + 7]);
-        add2(ps[0], ps[1], ps[0], ps[1], sv[c * 8 + 0], sv[c * 8 + 1]);
-        add2(ps[2], ps[3], ps[2], ps[3], sv[c * 8 + 2], sv[c * 8 + 3]);
-        add2(ps[0], ps[1], ps[0], ps[1], sv[c * 8 + 4], sv[c * 8 + 5]);
-        add2(ps[2], ps[3], ps[2], ps[3], sv[c * 8 + 6], sv[c * 8 + 7]);
-        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (r & 7)) << 4)) = pk;
-      }
-      l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
-      fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the MMA's async-proxy reads
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // ---- epilogue: the two halves of a row add their sums; O / l -> 16 bit -> out[b, q0 + r, head*HD + half*HC ...]
-    float* slot = xch;  // (tile parity 0 was last written for t = 62; every thread passed the barrier of t = 63 since)
-    slot[half * TQ + r] = l_run;
-    named_barrier_sync(1, G2_SM_THREADS);
-    const float inv = 1.0f / (l_run + slot[(half ^ 1) * TQ + r]);
-    mbar_wait(o_done, 0);
-    tcgen05_fence_after();
-    __nv_bfloat16* dst = prm.out + (static_cast<size_t>(b) * 4096 + q0 + r) * D + head * HD + half * HC;
-    auto store8 = [&](uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3, uint32_t o4, uint32_t o5, uint32_t o6, uint32_t o7,
-                      int c) {
-      uint4 w;
-      w.x = pack_op16x2<F16>(__uint_as_float(o0) * inv, __uint_as_float(o1) * inv);
-      w.y = pack_op16x2<F16>(__uint_as_float(o2) * inv, __uint_as_float(o3) * inv);
-      w.z = pack_op16x2<F16>(__uint_as_float(o4) * inv, __uint_as_float(o5) * inv);
-      w.w = pack_op16x2<F16>(__uint_as_float(o6) * inv, __uint_as_float(o7) * inv);
-      *reinterpret_cast<uint4*>(dst + c * 8) = w;
-    };
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(t_o, o);
-    if constexpr (HC > 32) {
-      uint32_t o8[8];
-      tmem_ld_32x32b_x8(t_o + 32, o8);
-      tmem_ld_wait();
-      store8(o8[0], o8[1], o8[2], o8[3], o8[4], o8[5], o8[6], o8[7], 4);
-    } else {
-      tmem_ld_wait();
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      store8(o[c * 8 + 0], o[c * 8 + 1], o[c * 8 + 2], o[c * 8 + 3], o[c * 8 + 4], o[c * 8 + 5], o[c * 8 + 6], o[c * 8 + 7], c);
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem, TC_TMEM_COLS);
   }
@@ -1143,7 +787,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
 #pragma unroll
         for (int j = 0; j < 8; ++j) pm[j] = sv[j];
 #pragma unroll
-        for (int j = 8; j < NK; ++j) pm[j & 7] = fmaxf(pm[j & 7], sv[j]);
+        for (int j = 8; j < NK; j += 2) pm[(j >> 1) & 7] = max3(pm[(j >> 1) & 7], sv[j], sv[j + 1]);
         const float mt_ = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])),
                                 fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
         const float m_new = (mt_ > m_run + LAZY_RESCALE) ? mt_ : m_run;
@@ -1235,13 +879,13 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
   }
 }
 
-// B200SAM_GLOBATTN=row selects the one-thread-per-row global kernel (A/B); the default is two threads per row
-bool global_pair_variant() {
-  static const bool pair = [] {
+// B200SAM_GLOBATTN=smem keeps P in the shared-memory tile (A/B); the default hands P to the PV MMA through TMEM
+bool global_p_in_tmem() {
+  static const bool pt = [] {
     const char* e = std::getenv("B200SAM_GLOBATTN");
-    return !(e && std::strcmp(e, "row") == 0);
+    return !(e && std::strcmp(e, "smem") == 0);
   }();
-  return pair;
+  return pt;
 }
 
 template <int HD, bool F16>
@@ -1279,10 +923,8 @@ int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16_grid4d(&mkv, a.qkv, a.B, 3 * D, 8, 8)) return 1;  // key tiles = 8 x 8 blocks of the token grid
   if (make_tmap_bf16(&mrh, a.rel_h, 127, HD, HD, TQ, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
   if (make_tmap_bf16(&mrw, a.rel_w, 127, HD, HD, TQ, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-  const bool pair = global_pair_variant();
-  auto kernel = pair ? global_attn_pair_kernel<HD, F16> : global_attn_tc_kernel<HD, F16>;
-  const int smem_bytes = L::BYTES + (pair ? 2048 : 0);  // + the row-maximum exchange slots
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem_bytes)) return rc;
+  auto kernel = global_p_in_tmem() ? global_attn_tc_kernel<HD, F16, true> : global_attn_tc_kernel<HD, F16, false>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), L::BYTES)) return rc;
   TcParams p;
   p.out = a.out;
   p.heads = a.heads;
@@ -1290,7 +932,7 @@ int launch_tc(const AttnArgs& a, cudaStream_t stream) {
   dim3 grid(4096 / TQ, a.heads, a.B);
   // algorithmic FLOPs: 4 * heads * T * T * hd * (1 + 64/4096) per image
   TimedLaunch timed(TIMED_GLOBAL_ATTN, 4.0 * a.heads * 4096.0 * 4096.0 * HD * (1.0 + 64.0 / 4096.0) * a.B, a.B, a.heads, HD, stream);
-  B200SAM_CHECK_CUDA(launch_kernel(kernel, grid, dim3(pair ? G2_THREADS : TC_THREADS), smem_bytes, stream, mq, mkv, mrh, mrw, p));
+  B200SAM_CHECK_CUDA(launch_kernel(kernel, grid, dim3(TC_THREADS), L::BYTES, stream, mq, mkv, mrh, mrw, p));
   return 0;
 }
 

@@ -157,3 +157,58 @@ def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor
             torch.zeros((0,) + tuple(segs[0].shape), dtype=torch.uint8, device=dev)
         gathered = sharding.gather_sharded(local, len(segs))
     return results, gathered
+
+
+@torch.no_grad()
+def embed_and_refine(sam, images: Sequence[np.ndarray], segs: Sequence[torch.Tensor], names: Sequence[str],
+                     prompts2use=(("box",), ("pos_points", "neg_points")), batch: int = 8, stage: int = 32,
+                     ccl_selection: str | None = None, gather: bool = False, emb_writer=None, mask_writer=None,
+                     overlap: bool = True):
+    """Both scripts of the reference as ONE software pipeline (the reference runs them one after the other and goes through
+    an h5 file in between): the image set is cut into stages of `stage` images; the encoder of stage s + 1 is enqueued on its
+    own CUDA stream before the refinement of stage s (prompt extraction, two decoder passes, upscale) is issued on a second
+    stream, so the decoder stage's short kernels and host round trips fill under the encoder's long ones.  Results and
+    sharding are those of generate_img_embeddings + refine_segmentations called on every stage.
+    Returns (store, results, gathered embeddings or None, gathered masks or None)."""
+    assert len(images) == len(segs) == len(names)
+    dev = sam.device
+    # the two streams are kept on the model: torch's caching allocator pools blocks per stream, so fresh streams would
+    # send every temporary of every call to cudaMalloc
+    streams = getattr(sam, "_pipeline_streams", None)
+    if streams is None or streams[0].device != torch.device(dev):
+        streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        sam._pipeline_streams = streams
+    enc_stream = streams[0]
+    ref_stream = streams[1] if overlap else enc_stream  # overlap=False: staged, one stream (A/B)
+    start = torch.cuda.current_stream(dev).record_event()
+    store = EmbeddingStore(img_encoder_img_size=sam.image_encoder.img_size)
+    bounds = [(a, min(a + stage, len(images))) for a in range(0, len(images), stage)]
+    encoded, results, emb_parts, seg_parts = [], [], [], []
+
+    def encode(k):
+        a, b = bounds[k]
+        with torch.cuda.stream(enc_stream):
+            if k == 0:
+                enc_stream.wait_event(start)
+            _, g = generate_img_embeddings(sam, images[a:b], names[a:b], batch=batch, store=store, gather=gather,
+                                           writer=emb_writer)
+            emb_parts.append(g)
+            encoded.append(enc_stream.record_event())
+
+    encode(0)
+    for k, (a, b) in enumerate(bounds):
+        if k + 1 < len(bounds):
+            encode(k + 1)
+        with torch.cuda.stream(ref_stream):
+            ref_stream.wait_event(encoded[k])
+            res, g = refine_segmentations(sam, store, segs[a:b], names[a:b], prompts2use=prompts2use, gather=gather,
+                                          batch=batch, ccl_selection=ccl_selection, writer=mask_writer)
+            results.extend((a + i, seg, dice) for i, seg, dice in res)
+            seg_parts.append(g)
+    cur = torch.cuda.current_stream(dev)
+    cur.wait_stream(enc_stream)
+    cur.wait_stream(ref_stream)
+    emb_all = torch.cat(emb_parts) if gather and emb_parts else None
+    seg_all = torch.cat(seg_parts) if gather and seg_parts else None
+    return store, results, emb_all, seg_all
+

@@ -250,6 +250,27 @@ def test_pipeline_drivers_match_single_image_api(vit_b):
     assert min(ds) >= 0.999
 
 
+def test_overlapped_pipeline_equals_two_phase_drivers(vit_b):
+    """embed_and_refine (encoder of stage s+1 and refinement of stage s on two CUDA streams) returns bit-identical
+    embeddings and masks to generate_img_embeddings followed by refine_segmentations."""
+    from samcarriestheburden_b200.scripts.pipelines import embed_and_refine, generate_img_embeddings, refine_segmentations
+    sam, _ = vit_b
+    imgs = [O.synthetic_radiograph(40 + i, *((754, 589) if i % 3 == 1 else (1024, 1024))) for i in range(7)]
+    names = [f"ov{i}" for i in range(len(imgs))]
+    probs = [torch.from_numpy(O.synthetic_unet_probs(i)) for i in range(len(imgs))]
+    store, emb = generate_img_embeddings(sam, imgs, names, batch=2, gather=True)
+    res, seg = refine_segmentations(sam, store, probs, names, gather=True, batch=2, ccl_selection="highest_probability")
+    for _ in range(2):  # twice: the second pass reuses warm engines and exercises stream reuse
+        store2, res2, emb2, seg2 = embed_and_refine(sam, imgs, probs, names, batch=2, stage=3, gather=True,
+                                                    ccl_selection="highest_probability")
+        torch.cuda.synchronize()
+        assert torch.equal(emb, emb2)
+        assert torch.equal(seg, seg2)
+        assert [i for i, _, _ in res2] == [i for i, _, _ in res]
+        for (_, a, da), (_, b, db) in zip(res, res2):
+            assert torch.equal(a, b) and torch.equal(torch.nan_to_num(da, nan=-1.0), torch.nan_to_num(db, nan=-1.0))
+
+
 def test_refine_batch_equals_per_image(vit_b):
     """Multi-image ragged decode (images with different numbers of classes / native sizes in ONE launch sequence)
     is bit-identical to the per-image calls: absent token slots never act as attention keys."""
