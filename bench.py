@@ -543,36 +543,13 @@ def pipeline_set500(sam, dev, world: int, rank: int, n_images: int = 500, batch:
         assert tuple(emb_all.shape) == (n_images, 256, 64, 64) and seg_all.shape[0] == n_images
         return int(n_masks.item()), [float(t) for t in times], emb_all.numel() * 4, seg_all.numel()
 
-    def run_overlapped():
-        # the same work as ONE software pipeline: encoder of stage s+1 and refinement of stage s on two CUDA streams,
-        # embeddings and masks gathered stage by stage (scripts/pipelines.py embed_and_refine)
-        from samcarriestheburden_b200.scripts.pipelines import embed_and_refine
-        sync()
-        t0 = time.perf_counter()
-        _, results, emb_all, seg_all = embed_and_refine(sam, imgs, probs, names, batch=batch, stage=4 * batch * world,
-                                                        ccl_selection="highest_probability", gather=True)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        n_masks = torch.tensor([sum(int((~torch.isnan(r[2])).sum()) for r in results)], device=dev)
-        times = torch.tensor([t1 - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(n_masks)
-            dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        assert tuple(emb_all.shape) == (n_images, 256, 64, 64) and seg_all.shape[0] == n_images
-        return int(n_masks.item()), float(times[0])
-
     run()  # warm-up: lazy engines, allocator, NCCL communicators
     n_masks, (t_all, t_emb, t_ref), emb_bytes, seg_bytes = run()
-    run_overlapped()
-    n_masks_o, t_ovl = run_overlapped()
-    assert n_masks_o == n_masks
     return {"metric": "500-image set: embeddings + refined masks, sharded by image, final NCCL gather of both on every rank",
             "scaling": "strong", "images": n_images, "masks": n_masks, "n_gpus": world,
             "images_per_s": n_images / t_all, "masks_per_s": n_masks / t_all, "seconds": t_all,
             "embed_phase": {"seconds": t_emb, "embeds_per_s": n_images / t_emb, "gathered_bytes": emb_bytes},
-            "refine_phase": {"seconds": t_ref, "masks_per_s": n_masks / t_ref, "gathered_bytes": seg_bytes},
-            "overlapped": {"what": "encoder of stage s+1 || refinement of stage s on two CUDA streams (embed_and_refine)",
-                           "images_per_s": n_images / t_ovl, "masks_per_s": n_masks / t_ovl, "seconds": t_ovl}}
+            "refine_phase": {"seconds": t_ref, "masks_per_s": n_masks / t_ref, "gathered_bytes": seg_bytes}}
 
 
 def e2e_parity(sam, dev, model: str, seed: int = 5, native=(1182, 754)):

@@ -100,10 +100,7 @@ def load(build_if_missing: bool = True):
             raise B200SamError(f"{LIB_PATH} is missing; run `python -m samcarriestheburden_b200.build`")
         from . import build as _build
         _build.build()
-    # PyDLL: the entry points are enqueue-only (microseconds), so the GIL is NOT dropped around them - with CDLL every one
-    # of the ~170 launches of an encoder batch was a hand-over point to background threads (storage.AsyncResultWriter),
-    # and getting the GIL back cost the launch loop up to a switch interval each time.  B200SAM_RELEASE_GIL=1 restores CDLL.
-    lib = (C.CDLL if os.environ.get("B200SAM_RELEASE_GIL", "0") == "1" else C.PyDLL)(str(LIB_PATH))
+    lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in _PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift between header and library
         fn.restype = res

@@ -665,6 +665,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
   } else if (warp >= 4) {
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    const int warp_row0 = quad * 32;
     const int st = threadIdx.x - 128;  // 0..127
     const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     // ---- zero the tails of the query slabs (rows nq..199) so the M=128 tiles only ever see finite values
@@ -742,8 +743,11 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
     uint8_t* prow = smem + L::OFF_P + row * 128;
     int g = 0;
     for (int mt = 0; mt < nmt; ++mt) {
+      // warps whose 32 rows all lie beyond the window's queries (second tile of a 14x14 window: rows 68..127; 8-wide edge
+      // windows) only keep the barriers in phase: no TMEM loads, exponentials or P stores (their P / O rows are never read)
+      const bool active = warp_row0 < nq - mt * TQ;  // warp-uniform
       float bh[WIN], bw[WIN];
-      {
+      if (active) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tl + WCOL_B + mt * 32, v);
         tmem_ld_wait();
@@ -756,6 +760,14 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
         constexpr int NK = KT < 3 ? 64 : 16;
         mbar_wait(s_full, g & 1);
         tcgen05_fence_after();
+        if (!active) {
+          tcgen05_fence_before();
+          mbar_arrive(s_read);
+          if (g > 0) mbar_wait(o_ready, (g - 1) & 1);
+          mbar_arrive(p_full);
+          ++g;
+          return;
+        }
         float sv[NK];
         if constexpr (KT < 3) {
 #pragma unroll
@@ -842,6 +854,11 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
       // ---- epilogue of the M tile
       mbar_wait(o_ready, (g - 1) & 1);
       tcgen05_fence_after();
+      if (!active) {
+        tcgen05_fence_before();
+        mbar_arrive(o_free);
+        continue;
+      }
       const int qi = mt * TQ + row;
       const float inv = 1.0f / l_run;
       const int qr = qi / wcols, qc = qi - qr * wcols;
