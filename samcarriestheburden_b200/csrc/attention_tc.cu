@@ -488,14 +488,21 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 // ================================================================================================
 // 14x14 windowed attention on tcgen05 (image_encoder.py:166-182 window path, :243-289 partition/unpartition)
 //
-// One CTA = one (window, head, image); two CTAs per SM.  The window's 196 key/value tokens (zero-padded tokens
-// included, their K/V = the qkv bias because padding happens after norm1) are resident in shared memory, fetched
-// by ONE 4-D TMA box per 16-dim slab straight out of the raster-order qkv tensor (no window-partition copy; the
-// out-of-grid part of edge windows is zero-filled by TMA and patched with the bias).  Queries are the window's
-// real tokens (196 / 112 / 64 -> two or one M=128 tiles).  Keys are consumed in tiles of 64, 64, 64, 16 with an
-// online softmax; the decomposed rel-pos bias is 14 + 14 fp32 values per query row, produced by a prologue MMA
-// (q . [rel_h ; rel_w]^T), gathered per thread and held in registers (thread = query row, so kh / kw of every
-// score column are compile-time constants).
+// A work item = one (window, head, image); persistent CTAs, two per SM, walk over the items.  The window's 196 key/value
+// tokens (zero-padded tokens included, their K/V = the qkv bias because padding happens after norm1) are resident in
+// shared memory, fetched by ONE 4-D TMA box per 16-dim slab straight out of the raster-order qkv tensor (no window-
+// partition copy; the out-of-grid part of edge windows is zero-filled by TMA and patched with the bias).  Queries are
+// the window's real tokens (196 / 112 / 64 -> two or one M=128 tiles).  Keys are consumed in tiles of 64, 64, 64, 16
+// with an online softmax (lazy rescale); the decomposed rel-pos bias is 14 + 14 fp32 values per query row, produced by a
+// prologue MMA (q . [rel_h ; rel_w]^T), gathered per thread and held in registers (thread = query row, so kh / kw of
+// every score column are compile-time constants).
+//   warp 0 (1 thread)  TMA producer: the rel-pos table once; per item Q + K (as soon as the previous item's last QK^T
+//                      has retired) and V (as soon as the bias gather, which uses the V region as scratch, is done)
+//   warp 1 (1 thread)  tcgen05.mma issuer: T = Q [rel_h ; rel_w]^T, S = Q K^T per key tile, O += P V with P as the A
+//                      operand in TMEM
+//   warp 2             TMEM allocator (256 columns: S | O | bias terms of both tiles | P)
+//   warps 4-7          softmax, one thread per query row; warps whose rows are all beyond the window's queries only
+//                      keep the barriers in phase
 constexpr int WIN = 14;
 constexpr int WTOK = WIN * WIN;
 constexpr uint32_t WCOL_S = 0;
@@ -507,8 +514,7 @@ struct WinLayout {
   static constexpr int NS = HD / 16;
   static constexpr int Q_SLAB = 200 * 32;   // 196 query rows (+4 so slabs stay 256 B aligned)
   static constexpr int KV_SLAB = 208 * 32;  // 196 keys padded to 13 K-steps of 16
-  static constexpr int OFF_P = 0;           // P tile [128 x 64 keys], SWIZZLE_128B; prologue: [rel_h ; rel_w] table, then
-                                            // the fp32 gather scratch [32][128]
+  static constexpr int OFF_P = 0;           // the resident [rel_h ; rel_w] table (10 of 16 KB; P itself lives in TMEM)
   static constexpr int OFF_Q = 16384;
   static constexpr int OFF_K = OFF_Q + NS * Q_SLAB;
   static constexpr int OFF_V = OFF_K + NS * KV_SLAB;
@@ -517,7 +523,8 @@ struct WinLayout {
   static constexpr int BYTES = OFF_BAR + 256;
   static constexpr int BOX_BYTES = WTOK * 32;  // one 14x14 slab
   static_assert(OFF_K % 256 == 0 && OFF_V % 256 == 0, "slabs must be 256 B aligned for SWIZZLE_32B");
-  static_assert(NS * 2048 <= 16384, "rel-pos table must fit in the P tile");
+  static_assert(NS * 2048 <= 16384, "rel-pos table must fit in its 16 KB region");
+  static_assert(32 * TQ * 4 <= NS * KV_SLAB, "the bias gather scratch [32][128] fp32 lives at the head of the V region");
 };
 
 struct WinParams {
@@ -527,58 +534,80 @@ struct WinParams {
   int reverse;  // 1: images last-to-first
 };
 
+// Persistence: barriers and the TMEM allocation are set up once and there is no CTA teardown / relaunch between windows;
+// Q and K of the NEXT window land while the current one's last softmax rounds, PV MMAs and epilogue run; the rel-pos table
+// stays resident.  Every mbarrier completes a fixed number of phases per item (1, or one per step / tile), so each role
+// tracks parities with running counters: `c` items, `gs` softmax steps, `gt` query tiles.  161 us against 172 us for the
+// one-CTA-per-window form (experiments/attention_window_cta.cu.inc), bit-identical output.
+constexpr uint32_t WCOL_P = 224;  // P[128 x 64 keys] as 16-bit pairs: 32 columns
+
+struct WinItem {
+  int head, b, wy, wx, wrows, wcols, nq, nmt;
+};
+B200SAM_DEVINL WinItem win_item(int it, int heads, int batch, int reverse) {
+  WinItem w;
+  const int win = it % 25;
+  const int rest = it / 25;
+  w.head = rest % heads;
+  const int bz = rest / heads;
+  w.b = reverse ? batch - 1 - bz : bz;
+  w.wy = win / 5;
+  w.wx = win % 5;
+  w.wrows = min(WIN, 64 - w.wy * WIN);
+  w.wcols = min(WIN, 64 - w.wx * WIN);
+  w.nq = w.wrows * w.wcols;
+  w.nmt = (w.nq + TQ - 1) / TQ;
+  return w;
+}
+
 template <int HD, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __grid_constant__ CUtensorMap map_q0814,
-                      const __grid_constant__ CUtensorMap map_q1408, const __grid_constant__ CUtensorMap map_q0808,
-                      const __grid_constant__ CUtensorMap map_rh, const __grid_constant__ CUtensorMap map_rw,
-                      WinParams prm) {
+window_attn_persist_kernel(const __grid_constant__ CUtensorMap map_q1414, const __grid_constant__ CUtensorMap map_q0814,
+                           const __grid_constant__ CUtensorMap map_q1408, const __grid_constant__ CUtensorMap map_q0808,
+                           const __grid_constant__ CUtensorMap map_rh, const __grid_constant__ CUtensorMap map_rw,
+                           WinParams prm, int batch) {
   using L = WinLayout<HD>;
   constexpr int NS = L::NS;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* tab_full = bars + 1;
+  uint64_t* tab_full = bars + 0;
+  uint64_t* q_full = bars + 1;
   uint64_t* k_full = bars + 2;
   uint64_t* v_full = bars + 3;
-  uint64_t* qz_done = bars + 4;   // query-slab tails zeroed
-  uint64_t* pre_full = bars + 5;  // prologue MMAs retired
-  uint64_t* pre_done = bars + 6;  // bias gathered into TMEM (P region free again)
-  uint64_t* fix_done = bars + 7;  // pad tokens patched
-  uint64_t* s_full = bars + 8;
-  uint64_t* s_read = bars + 9;
-  uint64_t* p_full = bars + 10;
-  uint64_t* o_ready = bars + 11;
-  uint64_t* o_free = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* qk_free = bars + 4;    // last QK^T of the item retired: Q and K may be overwritten
+  uint64_t* pre_full = bars + 5;   // prologue MMAs retired
+  uint64_t* pre_done = bars + 6;   // bias gathered (V region free for the V load, score columns for QK)
+  uint64_t* kfix_done = bars + 7;  // K pad tokens patched
+  uint64_t* vfix_done = bars + 8;  // V pad tokens patched, V tail rows zeroed
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_read = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_ready = bars + 12;
+  uint64_t* o_free = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int win = blockIdx.x, head = blockIdx.y;
-  const int b = prm.reverse ? static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z) : static_cast<int>(blockIdx.z);
-  const int wy = win / 5, wx = win % 5;
   const int D = prm.heads * HD;
-  const int wrows = min(WIN, 64 - wy * WIN);
-  const int wcols = min(WIN, 64 - wx * WIN);
-  const int nq = wrows * wcols;
-  const int nmt = (nq + TQ - 1) / TQ;
-  const CUtensorMap* map_q = wcols == WIN ? (wrows == WIN ? &map_q1414 : &map_q1408)
-                                          : (wrows == WIN ? &map_q0814 : &map_q0808);
+  const int n_items = 25 * prm.heads * batch;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(map_q);
     tma_prefetch_desc(&map_q1414);
+    tma_prefetch_desc(&map_q0814);
+    tma_prefetch_desc(&map_q1408);
+    tma_prefetch_desc(&map_q0808);
     tma_prefetch_desc(&map_rh);
     tma_prefetch_desc(&map_rw);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
     mbar_init(tab_full, 1);
+    mbar_init(q_full, 1);
     mbar_init(k_full, 1);
     mbar_init(v_full, 1);
-    mbar_init(qz_done, TQ);
+    mbar_init(qk_free, 1);
     mbar_init(pre_full, 1);
     mbar_init(pre_done, TQ);
-    mbar_init(fix_done, TQ);
+    mbar_init(kfix_done, TQ);
+    mbar_init(vfix_done, TQ);
     mbar_init(s_full, 1);
     mbar_init(s_read, TQ);
     mbar_init(p_full, TQ);
@@ -590,6 +619,10 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
     tmem_alloc(tmem_slot, TC_TMEM_COLS);
     tmem_relinquish();
   }
+  // Q, K, V regions start finite (rows the TMA boxes never write are read by the M = 128 / N = 208 MMAs)
+  for (int i = threadIdx.x; i < (L::OFF_BAR - L::OFF_Q) / 16; i += TC_THREADS)
+    reinterpret_cast<uint4*>(smem + L::OFF_Q)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -597,23 +630,42 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
   grid_dependency_wait();    // programmatic dependent launch: the qkv GEMM has completed past this line
   grid_launch_dependents();
 
+  auto q_map = [&](const WinItem& w) {
+    return w.wcols == WIN ? (w.wrows == WIN ? &map_q1414 : &map_q1408) : (w.wrows == WIN ? &map_q0814 : &map_q0808);
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, NS * nq * 32);
-      for (int kk = 0; kk < NS; ++kk)
-        tma_load_4d(smem + L::OFF_Q + kk * L::Q_SLAB, map_q, q_full, head * HD + kk * 16, wx * WIN, wy * WIN, b);
       mbar_arrive_expect_tx(tab_full, NS * 2048);
       for (int kk = 0; kk < NS; ++kk) {
         tma_load_2d(smem + L::OFF_P + kk * 2048, &map_rh, tab_full, kk * 16, 0);         // table rows 0..31
         tma_load_2d(smem + L::OFF_P + kk * 2048 + 1024, &map_rw, tab_full, kk * 16, 0);  // table rows 32..63
       }
-      mbar_arrive_expect_tx(k_full, NS * L::BOX_BYTES);
-      for (int kk = 0; kk < NS; ++kk)
-        tma_load_4d(smem + L::OFF_K + kk * L::KV_SLAB, &map_q1414, k_full, D + head * HD + kk * 16, wx * WIN, wy * WIN, b);
-      mbar_arrive_expect_tx(v_full, NS * L::BOX_BYTES);
-      for (int kk = 0; kk < NS; ++kk)
-        tma_load_4d(smem + L::OFF_V + kk * L::KV_SLAB, &map_q1414, v_full, 2 * D + head * HD + kk * 16, wx * WIN,
-                    wy * WIN, b);
+      auto load_qk = [&](const WinItem& w) {
+        mbar_arrive_expect_tx(q_full, NS * w.nq * 32);
+        for (int kk = 0; kk < NS; ++kk)
+          tma_load_4d(smem + L::OFF_Q + kk * L::Q_SLAB, q_map(w), q_full, w.head * HD + kk * 16, w.wx * WIN, w.wy * WIN, w.b);
+        mbar_arrive_expect_tx(k_full, NS * L::BOX_BYTES);
+        for (int kk = 0; kk < NS; ++kk)
+          tma_load_4d(smem + L::OFF_K + kk * L::KV_SLAB, &map_q1414, k_full, D + w.head * HD + kk * 16, w.wx * WIN,
+                      w.wy * WIN, w.b);
+      };
+      int c = 0;
+      int it = blockIdx.x;
+      if (it < n_items) load_qk(win_item(it, prm.heads, batch, prm.reverse));
+      for (; it < n_items; it += gridDim.x, ++c) {
+        const WinItem w = win_item(it, prm.heads, batch, prm.reverse);
+        mbar_wait(pre_done, c & 1);  // the V region was the gather scratch until here
+        mbar_arrive_expect_tx(v_full, NS * L::BOX_BYTES);
+        for (int kk = 0; kk < NS; ++kk)
+          tma_load_4d(smem + L::OFF_V + kk * L::KV_SLAB, &map_q1414, v_full, 2 * D + w.head * HD + kk * 16, w.wx * WIN,
+                      w.wy * WIN, w.b);
+        const int nxt = it + gridDim.x;
+        if (nxt < n_items) {
+          mbar_wait(qk_free, c & 1);
+          load_qk(win_item(nxt, prm.heads, batch, prm.reverse));
+        }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -621,45 +673,56 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
       const uint32_t sk = smem_u32(smem + L::OFF_K);
       const uint32_t sv = smem_u32(smem + L::OFF_V);
       const uint32_t sp = smem_u32(smem + L::OFF_P);
-      constexpr uint32_t SW32 = 6, SW128 = 2;
-      mbar_wait(q_full, 0);
+      constexpr uint32_t SW32 = 6;
       mbar_wait(tab_full, 0);
-      mbar_wait(qz_done, 0);
-      tcgen05_fence_after();
-      // ---- prologue: T_mt[128 x 64] = Q_mt . [rel_h(27) ; pad ; rel_w(27) ; pad]^T
-      for (int mt = 0; mt < nmt; ++mt)
-        for (int kk = 0; kk < NS; ++kk)
-          umma_bf16_ss(tmem + mt * 64, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
-                       make_smem_desc(sp + kk * 2048, 16, 256, SW32), make_idesc_op16_f32(128, 64, 0, F16), kk > 0);
-      umma_commit(pre_full);
-      mbar_wait(pre_done, 0);
-      mbar_wait(k_full, 0);
-      mbar_wait(fix_done, 0);
-      tcgen05_fence_after();
-      auto issue_qk = [&](int g) {
-        const int mt = g >> 2, kt = g & 3;
-        const uint32_t idesc = kt < 3 ? make_idesc_op16_f32(128, 64, 0, F16) : make_idesc_op16_f32(128, 16, 0, F16);
-        for (int kk = 0; kk < NS; ++kk)
-          umma_bf16_ss(tmem + WCOL_S, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
-                       make_smem_desc(sk + kk * L::KV_SLAB + kt * 2048, 16, 256, SW32), idesc, kk > 0);
-        umma_commit(s_full);
-      };
-      const int nsteps = nmt * 4;
-      issue_qk(0);
-      for (int g = 0; g < nsteps; ++g) {
-        const int mt = g >> 2, kt = g & 3;
-        mbar_wait(s_read, g & 1);
+      int c = 0, gs = 0, gt = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++c) {
+        const WinItem w = win_item(it, prm.heads, batch, prm.reverse);
+        const int nmt = w.nmt;
+        mbar_wait(q_full, c & 1);
+        if (gt > 0) mbar_wait(o_free, (gt - 1) & 1);  // the previous item's last O has been read out (T_1 overlays it)
         tcgen05_fence_after();
-        if (g + 1 < nsteps) issue_qk(g + 1);
-        mbar_wait(p_full, g & 1);
-        if (kt == 0 && mt > 0) mbar_wait(o_free, (mt - 1) & 1);  // previous tile's O has been stored
+        // ---- prologue: T_mt[128 x 64] = Q_mt . [rel_h(27) ; pad ; rel_w(27) ; pad]^T
+        for (int mt = 0; mt < nmt; ++mt)
+          for (int kk = 0; kk < NS; ++kk)
+            umma_bf16_ss(tmem + mt * 64, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
+                         make_smem_desc(sp + kk * 2048, 16, 256, SW32), make_idesc_op16_f32(128, 64, 0, F16), kk > 0);
+        umma_commit(pre_full);
+        mbar_wait(pre_done, c & 1);
+        mbar_wait(k_full, c & 1);
+        mbar_wait(kfix_done, c & 1);
         tcgen05_fence_after();
-        const int nks = kt < 3 ? 4 : 1;
-        for (int ks = 0; ks < nks; ++ks)
-          umma_bf16_ss(tmem + WCOL_O, make_smem_desc(sp + ks * 32, 16, 1024, SW128),
-                       make_smem_desc(sv + kt * 2048 + ks * 512, L::KV_SLAB, 256, SW32),
-                       make_idesc_op16_f32(128, HD, 1, F16), (kt > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(o_ready);
+        const int nsteps = nmt * 4;
+        auto issue_qk = [&](int g) {
+          const int mt = g >> 2, kt = g & 3;
+          const uint32_t idesc = kt < 3 ? make_idesc_op16_f32(128, 64, 0, F16) : make_idesc_op16_f32(128, 16, 0, F16);
+          for (int kk = 0; kk < NS; ++kk)
+            umma_bf16_ss(tmem + WCOL_S, make_smem_desc(sq + kk * L::Q_SLAB + mt * 4096, 16, 256, SW32),
+                         make_smem_desc(sk + kk * L::KV_SLAB + kt * 2048, 16, 256, SW32), idesc, kk > 0);
+          umma_commit(s_full);
+          if (g == nsteps - 1) umma_commit(qk_free);
+        };
+        issue_qk(0);
+        for (int g = 0; g < nsteps; ++g, ++gs) {
+          const int mt = g >> 2, kt = g & 3;
+          mbar_wait(s_read, gs & 1);
+          tcgen05_fence_after();
+          if (g + 1 < nsteps) issue_qk(g + 1);
+          mbar_wait(p_full, gs & 1);
+          if (g == 0) {
+            mbar_wait(v_full, c & 1);
+            mbar_wait(vfix_done, c & 1);
+          }
+          if (kt == 0 && mt > 0) mbar_wait(o_free, (gt + mt - 1) & 1);  // previous tile's O has been stored
+          tcgen05_fence_after();
+          const int nks = kt < 3 ? 4 : 1;
+          for (int ks = 0; ks < nks; ++ks)
+            umma_bf16_ts(tmem + WCOL_O, tmem + WCOL_P + ks * 8,
+                         make_smem_desc(sv + kt * 2048 + ks * 512, L::KV_SLAB, 256, SW32),
+                         make_idesc_op16_f32(128, HD, 1, F16), (kt > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(o_ready);
+        }
+        gt += nmt;
       }
     }
   } else if (warp >= 4) {
@@ -668,208 +731,202 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
     const int warp_row0 = quad * 32;
     const int st = threadIdx.x - 128;  // 0..127
     const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16);
-    // ---- zero the tails of the query slabs (rows nq..199) so the M=128 tiles only ever see finite values
-    for (int i = st; i < NS * (200 - nq) * 2; i += TQ) {
-      const int kk = i / ((200 - nq) * 2), rem = i - kk * (200 - nq) * 2;
-      *reinterpret_cast<uint4*>(smem + L::OFF_Q + kk * L::Q_SLAB + (nq + (rem >> 1)) * 32 + (rem & 1) * 16) =
-          make_uint4(0, 0, 0, 0);
-    }
-    fence_proxy_async_smem();
-    mbar_arrive(qz_done);
-    // ---- prologue: gather the row's 14 + 14 rel-pos terms of every M tile into TMEM (x log2 e)
-    {
-      // scratch = the P tile region: [32][128] fp32, column `row` is private to this thread.  The rel-pos table that
-      // lived there is dead once pre_full fired; T columns 0..31 carry the h-terms, 32..63 the w-terms.
-      float* scratch = reinterpret_cast<float*>(smem + L::OFF_P);
-      mbar_wait(pre_full, 0);
-      tcgen05_fence_after();
-      for (int mt = 0; mt < nmt; ++mt) {
-        const int qi = mt * TQ + row;
-        const int qr = min(qi / wcols, WIN - 1), qc = qi - (qi / wcols) * wcols;
-        uint32_t v[32];
+    const float scale_l2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
+    int c = 0, gs = 0, gt = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++c) {
+      const WinItem w = win_item(it, prm.heads, batch, prm.reverse);
+      const int nq = w.nq, nmt = w.nmt, wcols = w.wcols;
+      const bool edge = w.wrows < WIN || w.wcols < WIN;
+      // ---- prologue: gather the row's 14 + 14 rel-pos terms of every M tile into TMEM (x log2 e)
+      {
+        // scratch = head of the V region ([32][128] fp32, column `row` is private to this thread): the previous item's last
+        // PV retired before this thread left its epilogue, and this item's V is only requested after pre_done
+        float* scratch = reinterpret_cast<float*>(smem + L::OFF_V);
+        mbar_wait(pre_full, c & 1);
+        tcgen05_fence_after();
+        for (int mt = 0; mt < nmt; ++mt) {
+          const int qi = mt * TQ + row;
+          const int qr = min(qi / wcols, WIN - 1), qc = qi - (qi / wcols) * wcols;
+          uint32_t v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t a[32];
-          tmem_ld_32x32b_x32(tl + mt * 64 + c2 * 32, a);
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t a[32];
+            tmem_ld_32x32b_x32(tl + mt * 64 + c2 * 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) scratch[j * TQ + row] = __uint_as_float(a[j]) * LOG2E;
+            if (c2 == 0) {
+#pragma unroll
+              for (int kh = 0; kh < WIN; ++kh) v[kh] = __float_as_uint(scratch[(qr + 13 - kh) * TQ + row]);
+            } else {
+#pragma unroll
+              for (int kw = 0; kw < WIN; ++kw) v[14 + kw] = __float_as_uint(scratch[(qc + 13 - kw) * TQ + row]);
+            }
+          }
+          tmem_st_32x32b_x32(tl + WCOL_B + mt * 32, v);
+        }
+        tmem_st_wait();
+        fence_proxy_async_smem();  // generic writes to the V region before the TMA load that follows pre_done
+        tcgen05_fence_before();
+        mbar_arrive(pre_done);
+      }
+      // ---- pad tokens of edge windows: K now, V (and the V tail rows the scratch dirtied) before the first P is handed over
+      auto patch = [&](int off_region, const __nv_bfloat16* bias, bool tails) {
+        for (int rr = st; rr < 208; rr += TQ) {
+          const int r = rr / WIN, cc = rr - r * WIN;
+          const bool tail = rr >= WTOK;
+          const bool pad = !tail && (w.wy * WIN + r >= 64 || w.wx * WIN + cc >= 64);
+          if (!(pad || (tail && tails))) continue;
+          const int sw = (rr >> 2) & 1;
+          for (int kk = 0; kk < NS; ++kk)
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              uint4 val = make_uint4(0, 0, 0, 0);
+              if (pad) val = *reinterpret_cast<const uint4*>(bias + kk * 16 + ch * 8);
+              *reinterpret_cast<uint4*>(smem + off_region + kk * L::KV_SLAB + rr * 32 + ((ch ^ sw) << 4)) = val;
+            }
+        }
+      };
+      if (edge) {
+        mbar_wait(k_full, c & 1);
+        patch(L::OFF_K, prm.qkv_bias + D + w.head * HD, false);
+        fence_proxy_async_smem();
+      }
+      mbar_arrive(kfix_done);
+
+      for (int mt = 0; mt < nmt; ++mt, ++gt) {
+        const bool active = warp_row0 < nq - mt * TQ;  // warp-uniform: does this warp own any real query row of the tile?
+        float bh[WIN], bw[WIN];
+        if (active) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tl + WCOL_B + mt * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) scratch[j * TQ + row] = __uint_as_float(a[j]) * LOG2E;
-          if (c2 == 0) {
-#pragma unroll
-            for (int kh = 0; kh < WIN; ++kh) v[kh] = __float_as_uint(scratch[(qr + 13 - kh) * TQ + row]);
-          } else {
-#pragma unroll
-            for (int kw = 0; kw < WIN; ++kw) v[14 + kw] = __float_as_uint(scratch[(qc + 13 - kw) * TQ + row]);
-          }
+          for (int i = 0; i < WIN; ++i) { bh[i] = __uint_as_float(v[i]); bw[i] = __uint_as_float(v[14 + i]); }
         }
-        tmem_st_32x32b_x32(tl + WCOL_B + mt * 32, v);
-      }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      mbar_arrive(pre_done);
-    }
-    // ---- patch the zero-filled pad tokens with the qkv bias, zero the key padding rows 196..207
-    {
-      const __nv_bfloat16* bk = prm.qkv_bias + D + head * HD;
-      const __nv_bfloat16* bv = prm.qkv_bias + 2 * D + head * HD;
-      mbar_wait(k_full, 0);
-      mbar_wait(v_full, 0);
-      for (int rr = st; rr < 208; rr += TQ) {
-        const int r = rr / WIN, c = rr - r * WIN;
-        const bool tail = rr >= WTOK;
-        const bool pad = !tail && (wy * WIN + r >= 64 || wx * WIN + c >= 64);
-        if (!tail && !pad) continue;
-        const int sw = (rr >> 2) & 1;
-        for (int kk = 0; kk < NS; ++kk)
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            uint4 kvv = make_uint4(0, 0, 0, 0), vvv = kvv;
-            if (pad) {
-              kvv = *reinterpret_cast<const uint4*>(bk + kk * 16 + ch * 8);
-              vvv = *reinterpret_cast<const uint4*>(bv + kk * 16 + ch * 8);
-            }
-            const int off = kk * L::KV_SLAB + rr * 32 + ((ch ^ sw) << 4);
-            *reinterpret_cast<uint4*>(smem + L::OFF_K + off) = kvv;
-            *reinterpret_cast<uint4*>(smem + L::OFF_V + off) = vvv;
+        float m_run = -INFINITY, l_run = 0.0f;
+        auto step = [&](auto kt_c) {
+          constexpr int KT = decltype(kt_c)::value;
+          constexpr int NK = KT < 3 ? 64 : 16;
+          mbar_wait(s_full, gs & 1);
+          tcgen05_fence_after();
+          if (mt == 0 && KT == 0) {  // first step of the item: V pad tokens + tail rows, before any P is handed to the MMA
+            if (edge) mbar_wait(v_full, c & 1);
+            patch(L::OFF_V, prm.qkv_bias + 2 * D + w.head * HD, true);
+            fence_proxy_async_smem();
+            mbar_arrive(vfix_done);
           }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(fix_done);
-    }
-
-    const float scale_l2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
-    uint8_t* prow = smem + L::OFF_P + row * 128;
-    int g = 0;
-    for (int mt = 0; mt < nmt; ++mt) {
-      // warps whose 32 rows all lie beyond the window's queries (second tile of a 14x14 window: rows 68..127; 8-wide edge
-      // windows) only keep the barriers in phase: no TMEM loads, exponentials or P stores (their P / O rows are never read)
-      const bool active = warp_row0 < nq - mt * TQ;  // warp-uniform
-      float bh[WIN], bw[WIN];
-      if (active) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tl + WCOL_B + mt * 32, v);
-        tmem_ld_wait();
+          if (!active) {
+            tcgen05_fence_before();
+            mbar_arrive(s_read);
+            if (gs > 0) mbar_wait(o_ready, (gs - 1) & 1);
+            mbar_arrive(p_full);
+            ++gs;
+            return;
+          }
+          float sv[NK];
+          if constexpr (KT < 3) {
 #pragma unroll
-        for (int i = 0; i < WIN; ++i) { bh[i] = __uint_as_float(v[i]); bw[i] = __uint_as_float(v[14 + i]); }
-      }
-      float m_run = -INFINITY, l_run = 0.0f;
-      auto step = [&](auto kt_c) {
-        constexpr int KT = decltype(kt_c)::value;
-        constexpr int NK = KT < 3 ? 64 : 16;
-        mbar_wait(s_full, g & 1);
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t a[32];
+              tmem_ld_32x32b_x32(tl + WCOL_S + hf * 32, a);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const int k = KT * 64 + hf * 32 + j;
+                float b0, b1;
+                add2(b0, b1, bh[k / WIN], bh[(k + 1) / WIN], bw[k % WIN], bw[(k + 1) % WIN]);
+                fma2(sv[hf * 32 + j], sv[hf * 32 + j + 1], __uint_as_float(a[j]), __uint_as_float(a[j + 1]), scale_l2, b0, b1);
+              }
+            }
+          } else {
+            uint32_t a[16];
+            tmem_ld_32x32b_x16(tl + WCOL_S, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int k = 192 + j;
+              sv[j] = k < WTOK ? fmaf(__uint_as_float(a[j]), scale_l2, bh[13] + bw[k % WIN]) : -INFINITY;
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(s_read);
+          float pm[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pm[j] = sv[j];
+#pragma unroll
+          for (int j = 8; j < NK; j += 2) pm[(j >> 1) & 7] = max3(pm[(j >> 1) & 7], sv[j], sv[j + 1]);
+          const float mt_ = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])),
+                                  fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
+          const float m_new = (mt_ > m_run + LAZY_RESCALE) ? mt_ : m_run;
+          const float corr = ex2_approx(m_run - m_new);
+#pragma unroll
+          for (int j = 0; j < NK; j += 2) {
+            float x0, x1;
+            add2(x0, x1, sv[j], sv[j + 1], -m_new, -m_new);
+            sv[j] = ex2_approx(x0);
+            sv[j + 1] = ex2_approx(x1);
+          }
+          if (gs > 0) {
+            mbar_wait(o_ready, (gs - 1) & 1);  // previous PV retired: P (and O) are free again
+            tcgen05_fence_after();
+          }
+          if (KT > 0 && __any_sync(0xffffffffu, m_new != m_run)) {
+#pragma unroll
+            for (int cc = 0; cc < HD / 16; ++cc) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(tl + WCOL_O + cc * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
+              tmem_st_32x32b_x16(tl + WCOL_O + cc * 16, o);
+            }
+            tmem_st_wait();
+          }
+          l_run *= corr;
+          m_run = m_new;
+          float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int blk = 0; blk < NK / 16; ++blk) {  // P -> TMEM, 16 keys = 8 columns at a time
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              pk[j >> 1] = pack_op16x2<F16>(sv[blk * 16 + j], sv[blk * 16 + j + 1]);
+              add2(ps[j & 6], ps[(j & 6) + 1], ps[j & 6], ps[(j & 6) + 1], sv[blk * 16 + j], sv[blk * 16 + j + 1]);
+            }
+            tmem_st_32x32b_x8(tl + WCOL_P + blk * 8, pk);
+          }
+          tmem_st_wait();
+          l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+          tcgen05_fence_before();
+          mbar_arrive(p_full);
+          ++gs;
+        };
+        step(std::integral_constant<int, 0>{});
+        step(std::integral_constant<int, 1>{});
+        step(std::integral_constant<int, 2>{});
+        step(std::integral_constant<int, 3>{});
+        // ---- epilogue of the M tile
+        mbar_wait(o_ready, (gs - 1) & 1);
         tcgen05_fence_after();
         if (!active) {
           tcgen05_fence_before();
-          mbar_arrive(s_read);
-          if (g > 0) mbar_wait(o_ready, (g - 1) & 1);
-          mbar_arrive(p_full);
-          ++g;
-          return;
+          mbar_arrive(o_free);
+          continue;
         }
-        float sv[NK];
-        if constexpr (KT < 3) {
+        const int qi = mt * TQ + row;
+        const float inv = 1.0f / l_run;
+        const int qr = qi / wcols, qc = qi - qr * wcols;
+        const int tok = (w.wy * WIN + qr) * 64 + w.wx * WIN + qc;
+        __nv_bfloat16* dst = prm.out + (static_cast<size_t>(w.b) * 4096 + tok) * D + w.head * HD;
+        uint4 outv[HD / 8];
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t a[32];
-            tmem_ld_32x32b_x32(tl + WCOL_S + hf * 32, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int k = KT * 64 + hf * 32 + j;
-              float b0, b1;
-              add2(b0, b1, bh[k / WIN], bh[(k + 1) / WIN], bw[k % WIN], bw[(k + 1) % WIN]);
-              fma2(sv[hf * 32 + j], sv[hf * 32 + j + 1], __uint_as_float(a[j]), __uint_as_float(a[j + 1]), scale_l2, b0, b1);
-            }
-          }
-        } else {
-          uint32_t a[16];
-          tmem_ld_32x32b_x16(tl + WCOL_S, a);
+        for (int cc = 0; cc < HD / 16; ++cc) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(tl + WCOL_O + cc * 16, o);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int k = 192 + j;
-            sv[j] = k < WTOK ? fmaf(__uint_as_float(a[j]), scale_l2, bh[13] + bw[k % WIN]) : -INFINITY;
-          }
-        }
-        tcgen05_fence_before();
-        mbar_arrive(s_read);
-        float pm[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pm[j] = sv[j];
-#pragma unroll
-        for (int j = 8; j < NK; j += 2) pm[(j >> 1) & 7] = max3(pm[(j >> 1) & 7], sv[j], sv[j + 1]);
-        const float mt_ = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])),
-                                fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
-        const float m_new = (mt_ > m_run + LAZY_RESCALE) ? mt_ : m_run;
-        const float corr = ex2_approx(m_run - m_new);
-#pragma unroll
-        for (int j = 0; j < NK; j += 2) {
-          float x0, x1;
-          add2(x0, x1, sv[j], sv[j + 1], -m_new, -m_new);
-          sv[j] = ex2_approx(x0);
-          sv[j + 1] = ex2_approx(x1);
-        }
-        if (g > 0) {
-          mbar_wait(o_ready, (g - 1) & 1);  // previous PV retired: P (and O) are free again
-          tcgen05_fence_after();
-        }
-        if (KT > 0 && __any_sync(0xffffffffu, m_new != m_run)) {
-#pragma unroll
-          for (int c = 0; c < HD / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld_32x32b_x16(tl + WCOL_O + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
-            tmem_st_32x32b_x16(tl + WCOL_O + c * 16, o);
-          }
-          tmem_st_wait();
-        }
-        l_run *= corr;
-        m_run = m_new;
-        float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < NK / 8; ++c) {
-          uint4 pk;
-          pk.x = pack_op16x2<F16>(sv[c * 8 + 0], sv[c * 8 + 1]);
-          pk.y = pack_op16x2<F16>(sv[c * 8 + 2], sv[c * 8 + 3]);
-          pk.z = pack_op16x2<F16>(sv[c * 8 + 4], sv[c * 8 + 5]);
-          pk.w = pack_op16x2<F16>(sv[c * 8 + 6], sv[c * 8 + 7]);
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) add2(ps[j], ps[j + 1], ps[j], ps[j + 1], sv[c * 8 + j], sv[c * 8 + j + 1]);
-          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = pk;
-        }
-        l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        mbar_arrive(p_full);
-        ++g;
-      };
-      step(std::integral_constant<int, 0>{});
-      step(std::integral_constant<int, 1>{});
-      step(std::integral_constant<int, 2>{});
-      step(std::integral_constant<int, 3>{});
-      // ---- epilogue of the M tile
-      mbar_wait(o_ready, (g - 1) & 1);
-      tcgen05_fence_after();
-      if (!active) {
-        tcgen05_fence_before();
-        mbar_arrive(o_free);
-        continue;
-      }
-      const int qi = mt * TQ + row;
-      const float inv = 1.0f / l_run;
-      const int qr = qi / wcols, qc = qi - qr * wcols;
-      const int tok = (wy * WIN + qr) * 64 + wx * WIN + qc;
-      __nv_bfloat16* dst = prm.out + (static_cast<size_t>(b) * 4096 + tok) * D + head * HD;
-#pragma unroll
-      for (int c = 0; c < HD / 16; ++c) {
-        uint32_t o[16];
-        tmem_ld_32x32b_x16(tl + WCOL_O + c * 16, o);
-        tmem_ld_wait();
-        if (qi < nq) {
           uint4 lo, hi4;
           lo.x = pack_op16x2<F16>(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
           lo.y = pack_op16x2<F16>(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
@@ -879,12 +936,16 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q1414, const __gri
           hi4.y = pack_op16x2<F16>(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
           hi4.z = pack_op16x2<F16>(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
           hi4.w = pack_op16x2<F16>(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 16) = lo;
-          *reinterpret_cast<uint4*>(dst + c * 16 + 8) = hi4;
+          outv[2 * cc] = lo;
+          outv[2 * cc + 1] = hi4;
+        }
+        tcgen05_fence_before();
+        mbar_arrive(o_free);  // the accumulator has left TMEM: the MMA warp may move on while the row is stored
+        if (qi < nq) {
+#pragma unroll
+          for (int cc = 0; cc < HD / 8; ++cc) *reinterpret_cast<uint4*>(dst + cc * 8) = outv[cc];
         }
       }
-      tcgen05_fence_before();
-      mbar_arrive(o_free);
     }
   }
 
@@ -916,17 +977,19 @@ int launch_win_tc(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16_grid4d(&m0808, a.qkv, a.B, 3 * D, 8, 8)) return 1;
   if (make_tmap_bf16(&mrh, a.rel_h, 27, HD, HD, 32, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
   if (make_tmap_bf16(&mrw, a.rel_w, 27, HD, HD, 32, 16, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-  auto kernel = window_attn_tc_kernel<HD, F16>;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), L::BYTES)) return rc;
   WinParams p;
   p.out = a.out;
   p.qkv_bias = a.qkv_bias;
   p.heads = a.heads;
   p.reverse = a.reverse;
-  dim3 grid(25, a.heads, a.B);
   // algorithmic FLOPs: 4 * heads * T * 196 * hd * (1 + 14/196) per image
   TimedLaunch timed(TIMED_WINDOW_ATTN, 4.0 * a.heads * 4096.0 * 196.0 * HD * (1.0 + 14.0 / 196.0) * a.B, a.B, a.heads, HD, stream);
-  B200SAM_CHECK_CUDA(launch_kernel(kernel, grid, dim3(TC_THREADS), L::BYTES, stream, m1414, m0814, m1408, m0808, mrh, mrw, p));
+  auto pk = window_attn_persist_kernel<HD, F16>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(pk), L::BYTES)) return rc;
+  const int n_items = 25 * a.heads * a.B;
+  const int ctas = n_items < 2 * num_sms() ? n_items : 2 * num_sms();
+  B200SAM_CHECK_CUDA(launch_kernel(pk, dim3(ctas), dim3(TC_THREADS), L::BYTES, stream, m1414, m0814, m1408, m0808, mrh, mrw, p,
+                                   a.B));
   return 0;
 }
 
