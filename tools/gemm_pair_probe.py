@@ -95,3 +95,22 @@ for name, fn, flop in cases:
           f"({flop / res[1] / 1e9:6.0f} TF/s)   pair/single {res[1] / res[0]:.3f}   pair+direct fp32 epilogue "
           f"{res[2] * 1e3:7.1f} us ({flop / res[2] / 1e9:6.0f} TF/s)", flush=True)
 lib.b200sam_set_gemm_pair(-1)
+
+# the library GEMM (cuBLASLt through torch.matmul, fp16 in / fp16 out, fp32 accumulate) on the same four shapes, same timing:
+# the reference point for "what does a plain GEMM of this shape reach on this board" (no bias, LayerNorm, GELU, residual)
+for name, A, W, flop in (("qkv   [32768 x 1280] x [1280 x 3840]", x16, Wq, 2.0 * M * 3 * D * D),
+                         ("proj  [32768 x 1280] x [1280 x 1280]", att, Wp, 2.0 * M * D * D),
+                         ("lin1  [32768 x 1280] x [1280 x 5120]", x16, W1, 2.0 * M * 4 * D * D),
+                         ("lin2  [32768 x 5120] x [5120 x 1280]", h16, W2, 2.0 * M * D * 4 * D)):
+    Wt = W.t()
+    for _ in range(3):
+        torch.matmul(A, Wt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(A, Wt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"cuBLAS fp16 {name}: {ms * 1e3:7.1f} us ({flop / ms / 1e9:6.0f} TF/s)", flush=True)
