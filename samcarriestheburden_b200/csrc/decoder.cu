@@ -146,6 +146,20 @@ int tc_lin(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* b, con
   return gemm_bf16_tn(g, s);
 }
 
+// several 128-wide projections of the same split operand in ONE launch: Ws = their weights back to back ([n_planes * 128,
+// 3K]), bias = their biases back to back, tables = their per-token (row % 4096) residual tables one `tab_plane` apart,
+// out0 = the first output [M, 128], the others one `out_plane` apart (elements)
+int tc_lin_planes(const __nv_bfloat16* As, const __nv_bfloat16* Ws, const float* bias, const float* tables, size_t tab_plane,
+                  float* out0, size_t out_plane, int n_planes, int M, int K, cudaStream_t s) {
+  GemmArgs g;
+  g.A = As; g.B = Ws; g.out = out0; g.bias = bias; g.residual = tables;
+  g.M = M; g.N = 128 * n_planes; g.K = 3 * K; g.lda = 2 * K; g.ldb = 3 * K; g.ldo = 128; g.ldr = 128; g.res_row_mod = 4096;
+  g.gelu = 0; g.out_kind = 0; g.max_ctas = 0; g.a_wrap = 2 * K;
+  g.out_plane = static_cast<long long>(out_plane);
+  g.res_plane = static_cast<long long>(tab_plane);
+  return gemm_bf16_tn(g, s);
+}
+
 #define TRY(x) do { if (int _rc = (x)) return _rc; } while (0)
 
 }  // namespace
@@ -206,30 +220,47 @@ int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_
     }
     off += static_cast<size_t>(it.N) * 3 * it.K;
   }
-  // pe W^T + b tables of the five projections that take keys + pe (fp32 linear, once)
+  // pe W^T + b tables of the five projections that take keys + pe (fp32 linear, once), interleaved with zero tables so that
+  // the fused k | v | q launch finds them one plane apart (decoder.h)
+  constexpr size_t TAB = static_cast<size_t>(4096) * 128;
   d->pek = nullptr;
-  if (cudaMalloc(&d->pek, 5 * 4096 * 128 * sizeof(float)) != cudaSuccess) {
+  d->bias_kvq = nullptr;
+  if (cudaMalloc(&d->pek, 8 * TAB * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d->bias_kvq, (2 * 384 + 256) * sizeof(float)) != cudaSuccess) {
     set_last_error("decoder_create: cudaMalloc of the positional-encoding tables failed");
+    if (d->pek) cudaFree(d->pek);
     cudaFree(d->wsplit); cudaFree(d->pe_tok); delete d;
     return 1;
   }
   {
     const float* const* Wt = d->w.data();
-    struct PeItem { int w_idx, b_idx; const float** dst; };
+    cudaError_t e = cudaMemsetAsync(d->pek, 0, 8 * TAB * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->bias_kvq, 0, (2 * 384 + 256) * sizeof(float), stream);
+    struct PeItem { int w_idx, b_idx; const float** dst; size_t slot; };
     std::vector<PeItem> pis;
     for (int l = 0; l < 2; ++l) {
       const int L = W_LAYER0 + l * LAYER_STRIDE;
-      pis.push_back({L + L_T2I + 2, L + L_T2I + 3, &d->pek_t2i_k[l]});
-      pis.push_back({L + L_I2T + 0, L + L_I2T + 1, &d->pek_i2t_q[l]});
+      pis.push_back({L + L_T2I + 2, L + L_T2I + 3, &d->pek_t2i_k[l], static_cast<size_t>(3 * l)});
+      pis.push_back({L + L_I2T + 0, L + L_I2T + 1, &d->pek_i2t_q[l], static_cast<size_t>(3 * l + 2)});
+      d->bias_kvq_l[l] = d->bias_kvq + 384 * l;
+      if (e == cudaSuccess)  // v bias into the middle third
+        e = cudaMemcpyAsync(d->bias_kvq + 384 * l + 128, Wt[L + L_T2I + 5], 128 * sizeof(float), cudaMemcpyDeviceToDevice, stream);
     }
-    pis.push_back({W_FINAL + 2, W_FINAL + 3, &d->pek_fin_k});
-    float* dstp = d->pek;
+    pis.push_back({W_FINAL + 2, W_FINAL + 3, &d->pek_fin_k, 6});
+    d->bias_fin_kv = d->bias_kvq + 768;
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d->bias_kvq + 768 + 128, Wt[W_FINAL + 5], 128 * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) {
+      set_last_error("decoder_create: preparing the fused-projection tables failed: %s", cudaGetErrorString(e));
+      cudaFree(d->bias_kvq); cudaFree(d->pek); cudaFree(d->wsplit); cudaFree(d->pe_tok); delete d;
+      return 1;
+    }
     for (const PeItem& it : pis) {
+      float* dstp = d->pek + it.slot * TAB;
       *it.dst = dstp;
       if (int rc = lin(d->pe_tok, nullptr, 0, Wt[it.w_idx], Wt[it.b_idx], nullptr, dstp, 4096, 128, 256, 0, stream)) {
-        cudaFree(d->pek); cudaFree(d->wsplit); cudaFree(d->pe_tok); delete d; return rc;
+        cudaFree(d->bias_kvq); cudaFree(d->pek); cudaFree(d->wsplit); cudaFree(d->pe_tok); delete d; return rc;
       }
-      dstp += 4096 * 128;
     }
   }
   *out = d;
@@ -238,6 +269,7 @@ int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_
 
 void decoder_destroy(Decoder* d) {
   if (d == nullptr) return;
+  if (d->bias_kvq) cudaFree(d->bias_kvq);
   if (d->pek) cudaFree(d->pek);
   if (d->pe_tok) cudaFree(d->pe_tok);
   if (d->wsplit) cudaFree(d->wsplit);
@@ -281,6 +313,7 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
                   "decode: workspace must be non-null and 256-byte aligned");
   Workspace w = carve(reinterpret_cast<uint8_t*>(a.workspace), a.n_images, NB, T);
   B200SAM_REQUIRE(w.total <= a.workspace_bytes, "decode: workspace too small (%zu < %zu)", a.workspace_bytes, w.total);
+  B200SAM_REQUIRE(w.vbuf - w.kbuf == w.qibuf - w.vbuf, "decode: k / v / q output planes must be equally spaced");
   const float* const* W = d->w.data();
   const int Mi = NB * 4096, Mt = NB * T;
   const bool share0 = a.mask_prev == nullptr && a.dense_tok == nullptr && a.image_of != nullptr && a.n_images < NB;
@@ -333,9 +366,9 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
       sbp = w.sa;
     }
     const int* blk_of = shared ? a.image_of : nullptr;
-    TRY(tc_lin(sbp, d->ws_t2i_k[l], nullptr, d->pek_t2i_k[l], w.kbuf, Mp, 128, 256, 0, s, 4096));
-    TRY(tc_lin(sbp, d->ws_t2i_v[l], TI[5], nullptr, w.vbuf, Mp, 128, 256, 0, s));
-    TRY(tc_lin(sbp, d->ws_i2t_q[l], nullptr, d->pek_i2t_q[l], w.qibuf, Mp, 128, 256, 0, s, 4096));
+    // k | v | image-side q in one launch: split(keys) is read from HBM once instead of three times
+    TRY(tc_lin_planes(sbp, d->ws_t2i_k[l], d->bias_kvq_l[l], d->pek_t2i_k[l], static_cast<size_t>(4096) * 128, w.kbuf,
+                      static_cast<size_t>(w.vbuf - w.kbuf), 3, Mp, 256, s));
     TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s, blk_of));
     TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
@@ -354,8 +387,8 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
   {
     const float* const* F = W + W_FINAL;
     TRY(lin(w.queries, w.tokens, 0, F[0], F[1], nullptr, w.tq, Mt, 128, 256, 0, s));
-    TRY(tc_lin(w.sb, d->ws_fin_k, nullptr, d->pek_fin_k, w.kbuf, Mi, 128, 256, 0, s, 4096));
-    TRY(tc_lin(w.sb, d->ws_fin_v, F[5], nullptr, w.vbuf, Mi, 128, 256, 0, s));
+    TRY(tc_lin_planes(w.sb, d->ws_fin_k, d->bias_fin_kv, d->pek_fin_k, static_cast<size_t>(4096) * 128, w.kbuf,
+                      static_cast<size_t>(w.vbuf - w.kbuf), 2, Mi, 256, s));
     TRY(attn_few_queries(w.tq, w.kbuf, w.vbuf, w.ta, NB, T, 4096, 8, 16, w.part, nullptr, s));
     TRY(lin(w.ta, nullptr, 0, F[6], F[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, W[W_NF], W[W_NF + 1], 1e-5f, Mt, 256, w.queries, 0, s));

@@ -22,10 +22,17 @@ struct Decoder {
   // positional-encoding terms of the projections that consume keys + pe, folded into per-token tables (owned):
   // (keys + pe) W^T + b = keys W^T + (pe W^T + b); pek_* = pe W^T + b, fp32 [4096, 128], added by the GEMM epilogue as a
   // residual indexed by row % 4096, so only split(keys) is ever materialised (not split(keys + pe) as well)
-  float* pek;  // 5 tables: t2i k (layer 0, 1), i2t q (layer 0, 1), final k
+  // The k, v and image-side q projections of a layer read the same split(keys): they run as ONE tall-tile GEMM with N = 384
+  // whose three 128-column tiles write three output planes (gemm "planes"); the tables are therefore laid out per layer as
+  // [t2i k | zeros (v has a plain bias) | i2t q], then [final k | zeros], 4096 x 128 floats each, and the biases as
+  // [0 | v bias | 0] per layer, [0 | v bias] for the final attention.
+  float* pek;  // 8 tables
   const float* pek_t2i_k[2];
   const float* pek_i2t_q[2];
   const float* pek_fin_k;
+  float* bias_kvq;  // 2 x 384 + 256 floats (owned)
+  const float* bias_kvq_l[2];
+  const float* bias_fin_kv;
 };
 
 struct DecodeArgs {

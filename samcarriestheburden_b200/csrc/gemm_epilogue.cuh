@@ -14,6 +14,7 @@ struct EpiParams {
   int ldo;
   int ldr;
   int res_row_mod;  // >0: residual row = row % res_row_mod (broadcast table, e.g. pos_embed)
+  long long out_plane = 0, res_plane = 0;  // != 0 (tall tiles only): column tile j writes out + j * out_plane, reads residual + j * res_plane
   int gelu;
   // fused epilogues of the mask decoder's upscaler (mask_decoder.py:53-59,139-145):
   //   mode 1: N = 256 = 4 sub-pixels x 64 channels (ConvT 256->64): + bias, LayerNorm2d(64, eps 1e-6), erf GELU, then

@@ -59,8 +59,10 @@ constexpr uint32_t TMEM_COLS = 512;
 template <int OUT_KIND, int BN_EFF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    EpiParams ep, int M, int N, int K, int a_wrap, int conv_cin, int conv_wp, int reverse_m,
+                    EpiParams ep_in, int M, int N, int K, int a_wrap, int conv_cin, int conv_wp, int reverse_m,
                     int op_f16) {
+  EpiParams ep = ep_in;            // per-tile view (the "planes" mode moves out / residual per column tile)
+  const EpiParams& ep_planes = ep_in;
   // SWIZZLE_128B tiles need 1024 B alignment.  The alignment is requested on the symbol (not by rounding the
   // pointer through an integer): pointer arithmetic through uintptr_t makes the compiler lose the shared
   // state space and emit generic LD/ST (L1TEX path, long-scoreboard latency) for every staging access.
@@ -79,8 +81,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr int BM_T = TALL ? 2 * BM : BM;                 // rows per tile
   constexpr int A_BYTES = TALL ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
   static_assert(A_BYTES + BN_EFF * BK * 2 == STAGE_BYTES, "both tile shapes fill a 48 KiB stage");
+  constexpr int BN_T = TALL ? 128 : BN;                    // columns per tile
   const int num_m = (M + BM_T - 1) / BM_T;
-  const int num_n = (N + BN - 1) / BN;
+  const int num_n = (N + BN_T - 1) / BN_T;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
 
@@ -118,7 +121,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mb = tile / num_n;
         const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM_T;
-        const int n0 = (tile % num_n) * BN;
+        const int n0 = (tile % num_n) * BN_T;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -190,8 +193,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mb = tile / num_n;
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM_T + (TALL ? half * 128 : 0);
-      const int n0 = (tile % num_n) * BN + (TALL ? 0 : half * 128);
+      const int n0 = (tile % num_n) * BN_T + (TALL ? 0 : half * 128);
       const int row_base = m0 + quad * 32;
+      if constexpr (TALL && OUT_KIND == 0) {
+        // "planes": every 128-column tile goes to its own [M, 128] output (and residual table) - several projections of
+        // the same A operand in ONE launch (the n-fastest tile order makes the 2nd and 3rd read of an A block L2 hits)
+        if (ep_planes.out_plane != 0) {
+          const int pl = n0 >> 7;
+          ep.out = reinterpret_cast<float*>(ep_planes.out) + static_cast<ptrdiff_t>(pl) * ep_planes.out_plane - pl * 128;
+          if (ep_planes.residual != nullptr)
+            ep.residual = ep_planes.residual + static_cast<ptrdiff_t>(pl) * ep_planes.res_plane - pl * 128;
+        }
+      }
       float4 rbuf[2][4];
       const RowLN ln = epilogue_prefetch<OUT_KIND>(ep, M, N, row_base, n0, sbias, lane, rbuf);
       mbar_wait(&tmem_full[as], aphase);
@@ -247,7 +260,10 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   B200SAM_REQUIRE(g.out_kind >= 0 && g.out_kind <= 2 && (g.out_kind == 0 || (g.out_kind == 2) == (g.op_f16 != 0)),
                   "gemm: a 16-bit output has the operands' format (out_kind=%d, op_f16=%d)", g.out_kind, g.op_f16);
   if (g.use_pair >= 0 && (g.use_pair == 1 || gemm_pair_enabled()) && gemm_pair_eligible(g)) return gemm_f16_tn_pair(g, stream);
-  const bool narrow = g.N <= 128;
+  B200SAM_REQUIRE(g.out_plane == 0 || (g.N % 128 == 0 && g.out_kind == 0 && g.epi_mode == 0 && g.ldo == 128 &&
+                                       (g.residual == nullptr || g.ldr == 128) && g.xh == nullptr && g.rowstat_out == nullptr),
+                  "gemm: planes need N %% 128 == 0, an fp32 output with ldo = ldr = 128 and the plain epilogue (N=%d)", g.N);
+  const bool narrow = g.N <= 128 || g.out_plane != 0;
   CUtensorMap ta, tb;
   const int a_cols = g.conv_cin > 0 ? 2 * g.conv_cin : (g.a_wrap > 0 ? g.a_wrap : g.K);
   if (make_tmap_bf16(&ta, g.A, g.M, a_cols, g.lda, narrow ? 2 * BM : BM, BK,
@@ -274,12 +290,15 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   ep.ln_inv_d = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.0f;
   ep.ln_eps = g.ln_eps;
   ep.f16 = g.op_f16;
+  ep.out_plane = g.out_plane;
+  ep.res_plane = g.res_plane;
   B200SAM_REQUIRE(g.epi_mode == 0 || (g.epi_mode == 1 && g.N == 256 && g.aux0 && g.aux1) ||
                       (g.epi_mode == 2 && g.N == 128 && g.M % 16384 == 0 && g.aux0 && g.ntok >= 1 && g.ntok <= 3),
                   "gemm: bad fused-epilogue configuration (mode %d, M=%d, N=%d)", g.epi_mode, g.M, g.N);
   B200SAM_REQUIRE(g.epi_mode == 0 || g.op_f16 == 0, "gemm: the fused decoder epilogues are bf16 only");
   const int bm_t = narrow ? 2 * BM : BM;
-  const int tiles = ((g.M + bm_t - 1) / bm_t) * ((g.N + BN - 1) / BN);
+  const int bn_t = narrow ? 128 : BN;
+  const int tiles = ((g.M + bm_t - 1) / bm_t) * ((g.N + bn_t - 1) / bn_t);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int, int, int, int);
