@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round 2, call 36: token-side fp32 linears with 16-row tiles and 32-deep k steps: model tests, refine bench, decode launch list
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_ops_gpu.py -m gpu -x -q --tb=short > gpurun_out/r2c36_pytest.log 2>&1; echo "pytest exit=$?"; tail -3 gpurun_out/r2c36_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2c36_bench.json 2> gpurun_out/r2c36_bench.err; echo "bench exit=$?"
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r2c36_bench.json"))
+print("value", d["value"]); print("refine", d["refine"]["value"], d["refine"]["ms_per_image"], d["refine"]["per_image_api"]); print("set500", d["set500"]["images_per_s"], d["set500"]["refine_phase"]); print("pipeline", d["pipeline"]["images_per_s"]); 
+PY
+timeout 300 python tools/profile_decode_stage.py 8 all > gpurun_out/r2c36_decode_plain.log 2>&1 && \
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2c36_launches_decode_stage.csv python tools/profile_decode_stage.py 8 all > gpurun_out/r2c36_ncu_decode.log 2>&1
+echo "ncu decode exit=$?"
