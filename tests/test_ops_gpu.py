@@ -237,6 +237,29 @@ def test_encoder_attention(heads, hd, glob, fmt):
     assert err.mean().item() < tmean
 
 
+@pytest.mark.parametrize("heads,B", [(1, 1), (2, 3), (16, 1)])
+def test_windowed_attention_persistent_grid_shapes(heads, B):
+    """The windowed kernel is persistent (2 CTAs per SM walk over the 25 * heads * B windows): fewer items than CTAs (25, 150),
+    and a count that is not a multiple of the grid (400 on 296 CTAs: some CTAs take two windows, most one)."""
+    hd, S = 64, 14
+    g = torch.Generator(device="cpu").manual_seed(7 + heads + B)
+    D = heads * hd
+    qkv = torch.randn((B * 4096, 3 * D), generator=g).to(DEV).half()
+    bias = torch.randn((3 * D,), generator=g).to(DEV).half()
+    rel_h = (0.3 * torch.randn((2 * S - 1, hd), generator=g)).to(DEV).half()
+    rel_w = (0.3 * torch.randn((2 * S - 1, hd), generator=g)).to(DEV).half()
+    out = torch.full((B * 4096, D), float("nan"), dtype=torch.float16, device=DEV)
+    lib = _lib.load()
+    for _ in range(2):  # twice: the second launch starts from whatever the first left in shared memory / TMEM
+        _lib.check(lib.b200sam_encoder_attention(qkv.data_ptr(), bias.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(),
+                                                 out.data_ptr(), B, heads, hd, 0, 1, _lib.current_stream()))
+    torch.cuda.synchronize()
+    ref = _attention_reference(qkv, bias, rel_h, rel_w, heads, hd, 14)
+    err = (out.float() - ref).abs()
+    assert not torch.isnan(out).any()
+    assert err.max().item() < 5e-3 and err.mean().item() < 5e-4, (err.max().item(), err.mean().item())
+
+
 def test_encoder_attention_rejects_unknown_modes():
     lib = _lib.load()
     t = torch.zeros((4096, 3 * 64), dtype=torch.float16, device=DEV)
