@@ -198,6 +198,8 @@ int decoder_create(const void* const* weights, int n, Decoder** out, cudaStream_
     items.push_back({L + L_T2I + 4, 128, 256, &d->ws_t2i_v[l]});
     items.push_back({L + L_I2T + 0, 128, 256, &d->ws_i2t_q[l]});
     items.push_back({L + L_I2T + 6, 256, 128, &d->ws_i2t_o[l]});
+    items.push_back({L + L_MLP + 0, 2048, 256, &d->ws_mlp1[l]});
+    items.push_back({L + L_MLP + 2, 256, 2048, &d->ws_mlp2[l]});
   }
   items.push_back({W_FINAL + 2, 128, 256, &d->ws_fin_k});
   items.push_back({W_FINAL + 4, 128, 256, &d->ws_fin_v});
@@ -373,8 +375,17 @@ int decoder_forward(const Decoder* d, const DecodeArgs& a, cudaStream_t s) {
     TRY(lin(w.ta, nullptr, 0, TI[6], TI[7], w.queries, w.queries, Mt, 256, 128, 0, s));
     TRY(layernorm_rows(w.queries, L[L_N2], L[L_N2 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
-    TRY(lin(w.queries, nullptr, 0, L[L_MLP], L[L_MLP + 1], nullptr, w.th, Mt, 2048, 256, 1, s));
-    TRY(lin(w.th, nullptr, 0, L[L_MLP + 2], L[L_MLP + 3], w.queries, w.queries, Mt, 256, 2048, 0, s));
+    // token-side MLP on the tensor cores as well (3-way bf16 split operands like the image side; the scalar fp32 kernel
+    // needed 48 - 140 us per linear for these [prompts x tokens, 256 / 2048] shapes).  The two split operands live at the
+    // head of sa, which is free between the k | v | q projection above and the image->token attention below.
+    {
+      __nv_bfloat16* sq = w.sa;
+      __nv_bfloat16* sth = w.sa + ((static_cast<size_t>(Mt) * 512 + 127) & ~static_cast<size_t>(127));
+      TRY(split3_bf16(w.queries, nullptr, 0, sq, static_cast<size_t>(Mt), 256, 0, s));
+      TRY(tc_lin(sq, d->ws_mlp1[l], L[L_MLP + 1], nullptr, w.th, Mt, 2048, 256, 2, s));   // + ReLU
+      TRY(split3_bf16(w.th, nullptr, 0, sth, static_cast<size_t>(Mt), 2048, 0, s));
+      TRY(tc_lin(sth, d->ws_mlp2[l], L[L_MLP + 3], w.queries, w.queries, Mt, 256, 2048, 0, s));
+    }
     TRY(layernorm_rows(w.queries, L[L_N3], L[L_N3 + 1], 1e-5f, Mt, 256, w.queries, 0, s));
 
     const float* const* IT = L + L_I2T;  // image tokens are the queries here

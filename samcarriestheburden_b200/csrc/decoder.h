@@ -9,12 +9,14 @@ struct Decoder {
   std::vector<const float*> w;  // in decoder_weight_name() order
   float* pe_tok;                // [4096, 256] token-major dense positional encoding (owned)
   // hi/hi/lo bf16 splits ([N, 3K]) of the weights of the image-side linears (owned, one allocation):
-  // per layer l: t2i k, t2i v, i2t q, i2t out; then final k, final v, upscale ConvT1, upscale ConvT2
+  // per layer l: t2i k, t2i v, i2t q, i2t out, mlp 1, mlp 2; then final k, final v, upscale ConvT1, upscale ConvT2
   __nv_bfloat16* wsplit;
   const __nv_bfloat16* ws_t2i_k[2];
   const __nv_bfloat16* ws_t2i_v[2];
   const __nv_bfloat16* ws_i2t_q[2];
   const __nv_bfloat16* ws_i2t_o[2];
+  const __nv_bfloat16* ws_mlp1[2];  // token-side MLP (transformer.py:172-174): 256 -> 2048 (ReLU) -> 256
+  const __nv_bfloat16* ws_mlp2[2];
   const __nv_bfloat16* ws_fin_k;
   const __nv_bfloat16* ws_fin_v;
   const __nv_bfloat16* ws_up1;

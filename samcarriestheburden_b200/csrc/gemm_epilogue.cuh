@@ -15,7 +15,7 @@ struct EpiParams {
   int ldr;
   int res_row_mod;  // >0: residual row = row % res_row_mod (broadcast table, e.g. pos_embed)
   long long out_plane = 0, res_plane = 0;  // != 0 (tall tiles only): column tile j writes out + j * out_plane, reads residual + j * res_plane
-  int gelu;
+  int gelu;  // activation after bias: 0 none, 1 exact erf GELU, 2 ReLU
   // fused epilogues of the mask decoder's upscaler (mask_decoder.py:53-59,139-145):
   //   mode 1: N = 256 = 4 sub-pixels x 64 channels (ConvT 256->64): + bias, LayerNorm2d(64, eps 1e-6), erf GELU, then
   //           the [hi | lo] bf16 split operand of the next ConvT: out = bf16 [M*4, 128]
@@ -230,9 +230,12 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
           v[4] = __uint_as_float(r[8 * j + 4]) + b1.x; v[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
           v[6] = __uint_as_float(r[8 * j + 6]) + b1.z; v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
         }
-        if (ep.gelu) {
+        if (ep.gelu == 1) {
 #pragma unroll
           for (int k = 0; k < 8; k += 2) gelu_erf2(v[k], v[k + 1]);
+        } else if (ep.gelu == 2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.0f);
         }
         uint4 pk;
         pk.x = pack_op16x2<F16>(v[0], v[1]);
@@ -282,7 +285,8 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
           const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 16 + ((rq ^ ((rl >> 1) & 3)) << 2));
           float4 v = make_float4(__uint_as_float(u.x) + b.x, __uint_as_float(u.y) + b.y,
                                  __uint_as_float(u.z) + b.z, __uint_as_float(u.w) + b.w);
-          if (ep.gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+          if (ep.gelu == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+          else if (ep.gelu == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           const float4 rs = rbuf[hf][it];
           v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
           if (row < M && col < N) {

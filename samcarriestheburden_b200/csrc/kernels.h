@@ -41,7 +41,7 @@ struct GemmArgs {
   int res_row_mod;  // >0: residual row index = row % res_row_mod
   long long out_plane = 0;  // != 0: every 128-column tile j writes its own [M, 128] output at out + j * out_plane (fp32, ldo = 128)
   long long res_plane = 0;  //       and reads its residual table at residual + j * res_plane
-  int gelu;         // exact erf GELU after bias
+  int gelu;         // activation after bias: 0 none, 1 exact erf GELU, 2 ReLU
   int out_kind;     // 0: fp32 output, 1: bf16, 2: fp16 (a 16-bit output has the operands' format)
   int max_ctas;     // <= 0: one CTA per SM; > 0 caps the persistent grid
   int a_wrap = 0;   // > 0: A has only a_wrap columns; k >= a_wrap reads column k - a_wrap ([hi|lo|hi] stored as [hi|lo])
