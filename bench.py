@@ -167,7 +167,8 @@ def inrun_kernel_roofline(sam, dev_pool, steps: int, model: str, batch: int, pea
     out = {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
            "frac": tf / peaks["tf_sustained"], "frac_of_burst_peak": tf / peaks["tf_burst"],
            "peak_source": peaks["src"] + " sustained (kernel timed inside a long step; burst: %.1f)" % peaks["tf_burst"],
-           "kernel": "gemm_bf16_tn_kernel (tcgen05 kind::f16, 128x256x64 tiles, TMA ring, TMEM double buffer)",
+           "kernel": "gemm_pair_kernel (tcgen05 cta_group::2 kind::f16, 256x256x64 tiles per CTA pair, 5-stage TMA ring, TMEM double buffer, "
+                      "16 epilogue warps; B200SAM_GEMM_PAIR=0: single-CTA gemm_bf16_tn_kernel)",
            "how": "CUDA events around every GEMM launch of %d instrumented steps (same loop as the timed region)" % steps,
            "launches": n, "launch_ms_mean": ms / max(n, 1), "gemm_ms_per_step": ms / steps,
            "instrumented_ms_per_step": step_ms, "share_of_step": ms / steps / step_ms,
