@@ -240,8 +240,7 @@ B200SAM_API int b200sam_preprocess_patchify(const void* image, int is_u8, int ba
                                 const float* std3_host, void* out16, int operand_format, void* stream);
 /* The encoder's plain linears run on the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles over the two SMs of a TPC)
  * unless B200SAM_GEMM_PAIR=0; b200sam_set_gemm_pair overrides the environment at run time (-1: environment, 0: single-CTA
- * kernel, 1: pair kernel with the shared-memory-staged fp32 epilogue, 2: pair kernel with the direct fp32 epilogue =
- * the default, B200SAM_GEMM_DIRECT=0 selects 1) for A/B measurements and parity tests.  _max_clusters = co-resident CTA pairs on the current
+ * kernel, != 0: pair kernel) for A/B measurements and parity tests.  _max_clusters = co-resident CTA pairs on the current
  * device (SMs whose TPC partner is fused off cannot host one). */
 B200SAM_API int b200sam_set_gemm_pair(int mode);
 B200SAM_API int b200sam_gemm_pair_max_clusters(void);

@@ -326,94 +326,6 @@ B200SAM_DEVINL void epilogue_store(const EpiParams& ep, int M, int N, int row_ba
   }
 }
 
-// ---- fp32 output WITHOUT the shared-memory transpose ("direct"): thread = row, as the accumulator leaves TMEM.  Every thread
-// reads its row's residual and writes its row's result as whole 128-byte lines (8 x 16 B per 32-column chunk), the 16-bit
-// copy as 64-byte half lines, and the row statistics come from its own registers: no staging stores / loads, no
-// __syncwarp, no shuffles.  A warp-wide 16-byte access then touches 32 rows (32 sectors instead of 16), which the LSU has
-// room for; what the staged form could not hide was its serial chain (STS -> sync -> LDS -> add -> STG per 16 columns).
-// res0: the residual values of chunk 0 (raw bits, 8 x uint4 = this row's 32 columns), loaded before the accumulator wait.
-B200SAM_DEVINL void epilogue_load_residual_row(const EpiParams& ep, int M, int N, int row, int col0, uint4 (&buf)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    const int col = col0 + 4 * j;
-    if (ep.residual != nullptr && row < M && col < N) {
-      const int rr = ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row;
-      v = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(rr) * ep.ldr + col);
-    }
-    buf[j] = v;
-  }
-}
-
-template <int COLS>
-B200SAM_DEVINL void epilogue_store_f32_direct(const EpiParams& ep, int M, int N, int row_base, int n0, uint32_t taddr0,
-                                              const float* sbias, int lane, uint4 (&res)[8]) {
-  constexpr int NCH = COLS / 32;
-  const int row = row_base + lane;
-  float* out = reinterpret_cast<float*>(ep.out);
-  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ep.xh);
-  const bool stats = ep.rowstat_out != nullptr;
-  float s1 = 0.0f, s2 = 0.0f;
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(taddr0 + ch * 32, r);
-    tmem_ld_wait();
-    const int col0 = n0 + ch * 32;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = *reinterpret_cast<const float4*>(sbias + ch * 32 + 4 * j);
-      v[4 * j + 0] = (__uint_as_float(r[4 * j + 0]) + b.x) + __uint_as_float(res[j].x);
-      v[4 * j + 1] = (__uint_as_float(r[4 * j + 1]) + b.y) + __uint_as_float(res[j].y);
-      v[4 * j + 2] = (__uint_as_float(r[4 * j + 2]) + b.z) + __uint_as_float(res[j].z);
-      v[4 * j + 3] = (__uint_as_float(r[4 * j + 3]) + b.w) + __uint_as_float(res[j].w);
-    }
-    // the residual registers are free: start the next chunk's loads before this chunk's stores
-    if (ch + 1 < NCH) epilogue_load_residual_row(ep, M, N, row, col0 + 32, res);
-    if (row < M) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (col0 + 4 * j < N)
-          *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ep.ldo + col0 + 4 * j) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      if (xh != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 h;
-          if (ep.f16) {
-            h.x = pack_f16x2(v[8 * j + 0], v[8 * j + 1]); h.y = pack_f16x2(v[8 * j + 2], v[8 * j + 3]);
-            h.z = pack_f16x2(v[8 * j + 4], v[8 * j + 5]); h.w = pack_f16x2(v[8 * j + 6], v[8 * j + 7]);
-          } else {
-            h.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); h.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            h.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); h.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-          }
-          if (col0 + 8 * j < N) *reinterpret_cast<uint4*>(xh + static_cast<size_t>(row) * ep.ldo + col0 + 8 * j) = h;
-        }
-      }
-    }
-    if (stats) {
-      // the same summation tree as the staged epilogue (per 4 columns, then across the 16-column halves in the staged
-      // form's lane order would differ): statistics are defined per producer kernel, consumers only sum the parts
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (col0 + j < N) {
-          s1 += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-          s2 = fmaf(v[j], v[j], fmaf(v[j + 1], v[j + 1], fmaf(v[j + 2], v[j + 2], fmaf(v[j + 3], v[j + 3], s2))));
-        }
-      }
-      if ((ch & 1) == 1) {
-        const int nparts = (N + EPI_STAT_COLS - 1) / EPI_STAT_COLS, part = (n0 + (ch - 1) * 32) / EPI_STAT_COLS;
-        if (row < M && n0 + (ch - 1) * 32 < N)
-          reinterpret_cast<float2*>(ep.rowstat_out)[static_cast<size_t>(row) * nparts + part] = make_float2(s1, s2);
-        s1 = 0.0f;
-        s2 = 0.0f;
-      }
-    }
-  }
-}
-
 // ---- mode 1: LayerNorm2d(64) + exact-erf GELU + [hi | lo] split; one warp = 32 rows x 128 columns = 2 channel groups
 B200SAM_DEVINL void epilogue_ln64_split(const EpiParams& ep, int M, int row_base, int n0, uint32_t taddr0,
                                         const float* sbias, int lane) {

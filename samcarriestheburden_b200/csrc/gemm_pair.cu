@@ -111,11 +111,11 @@ B200SAM_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
       : "memory");
 }
 
-// DIRECT (fp32 output only): the epilogue writes rows straight from the TMEM layout (epilogue_store_f32_direct)
-template <int OUT_KIND, bool DIRECT = false>
+template <int OUT_KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpiParams ep, int M,
-                 int N, int K, int reverse_m, int op_f16) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpiParams ep_in, int M,
+                 int N, int K, int reverse_m, int op_f16, int a_wrap) {
+  EpiParams ep = ep_in;  // per-tile view (the "planes" mode moves out / residual per 128 columns)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_epi = smem + SMEM_TILES2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_TILES2 + SMEM_EPI2);
@@ -175,7 +175,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint8_t* sa = smem + stage * STAGE_BYTES2;
           uint8_t* sb = sa + A_BYTES2;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES2);
-          tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * BK2, m0);
+          int a_col = kb * BK2;
+          if (a_wrap > 0 && a_col >= a_wrap) a_col -= a_wrap;  // [hi | lo | hi] split operand stored as [hi | lo]
+          tma_load_2d_pair(sa, &tma_a, &full_bar[stage], a_col, m0);
           tma_load_2d_pair(sb, &tma_b, &full_bar[stage], kb * BK2, n0);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
@@ -225,12 +227,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m0 = (reverse_m ? num_m - 1 - mb : mb) * BM2 + static_cast<int>(rank) * 128;
       const int n0 = (tile % num_n) * BN2 + cpart * EPI_COLS2;
       const int row_base = m0 + quad * 32;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                              static_cast<uint32_t>(as * BN2 + cpart * EPI_COLS2);
+      if constexpr (OUT_KIND == 0) {
+        if (ep_in.out_plane != 0) {  // "planes": every 128 columns go to their own [M, 128] output / residual table
+          const int pl = n0 >> 7;
+          ep.out = reinterpret_cast<float*>(ep_in.out) + static_cast<ptrdiff_t>(pl) * ep_in.out_plane - pl * 128;
+          if (ep_in.residual != nullptr)
+            ep.residual = ep_in.residual + static_cast<ptrdiff_t>(pl) * ep_in.res_plane - pl * 128;
+        }
+      }
       float4 rbuf[2][4];
       const RowLN ln = epilogue_prefetch<OUT_KIND, EPI_COLS2>(ep, M, N, row_base, n0, sbias, lane, rbuf);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                              static_cast<uint32_t>(as * BN2 + cpart * EPI_COLS2);
       epilogue_store<OUT_KIND, EPI_COLS2, false>(ep, M, N, row_base, n0, taddr0, stg, sbias, lane, ln, rbuf);
       tcgen05_fence_before();
       __syncwarp();
@@ -281,21 +291,8 @@ int max_active_clusters(const void* func) {
 
 namespace {
 std::atomic<int> g_pair_mode{-1};    // -1: B200SAM_GEMM_PAIR decides, 0 / 1: set by b200sam_set_gemm_pair
-std::atomic<int> g_pair_direct{-1};  // fp32 epilogue without the smem transpose: -1 = B200SAM_GEMM_DIRECT decides
 }
-void gemm_pair_set_mode(int mode) {  // -1 env, 0 single-CTA, 1 pair (staged fp32 epilogue), 2 pair + direct fp32 epilogue
-  g_pair_mode.store(mode < 0 ? -1 : (mode ? 1 : 0));
-  g_pair_direct.store(mode < 0 ? -1 : (mode == 2 ? 1 : 0));
-}
-static bool gemm_pair_direct() {
-  const int m = g_pair_direct.load(std::memory_order_relaxed);
-  if (m >= 0) return m == 1;
-  static const bool on = [] {
-    const char* e = std::getenv("B200SAM_GEMM_DIRECT");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
-}
+void gemm_pair_set_mode(int mode) { g_pair_mode.store(mode < 0 ? -1 : (mode ? 1 : 0)); }  // -1 env, 0 single-CTA, 1 pair
 bool gemm_pair_enabled() {
   const int m = g_pair_mode.load(std::memory_order_relaxed);
   if (m >= 0) return m == 1;
@@ -307,13 +304,14 @@ bool gemm_pair_enabled() {
 }
 
 bool gemm_pair_eligible(const GemmArgs& g) {
-  return g.N > 128 && g.a_wrap == 0 && g.conv_cin == 0 && g.epi_mode == 0 && g.max_ctas == 0;
+  return g.N > 128 && (g.a_wrap == 0 || g.a_wrap % BK2 == 0) && g.conv_cin == 0 && g.epi_mode == 0 && g.max_ctas == 0 &&
+         (g.out_plane == 0 || (g.out_kind == 0 && g.xh == nullptr && g.rowstat_out == nullptr));
 }
 
 int gemm_f16_tn_pair(const GemmArgs& g, cudaStream_t stream) {
   B200SAM_REQUIRE(gemm_pair_eligible(g), "gemm_pair: unsupported configuration");
   CUtensorMap ta, tb;
-  if (make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, 128, BK2, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_tmap_bf16(&ta, g.A, g.M, g.a_wrap > 0 ? g.a_wrap : g.K, g.lda, 128, BK2, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   if (make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, 128, BK2, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   EpiParams ep;
   ep.bias = g.bias; ep.residual = g.residual; ep.out = g.out; ep.ldo = g.ldo; ep.ldr = g.ldr;
@@ -322,18 +320,17 @@ int gemm_f16_tn_pair(const GemmArgs& g, cudaStream_t stream) {
   ep.xh = g.xh; ep.rowstat_out = g.rowstat_out; ep.rowstat_in = g.rowstat_in; ep.colsum = g.colsum;
   ep.nparts_in = g.nparts_in; ep.ln_inv_d = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.0f;
   ep.ln_eps = g.ln_eps; ep.f16 = g.op_f16;
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int);
-  static const KernelFn table[4] = {gemm_pair_kernel<0>, gemm_pair_kernel<1>, gemm_pair_kernel<2>, gemm_pair_kernel<0, true>};
-  // the direct fp32 epilogue handles bias + residual (+ 16-bit copy + row statistics); GELU on an fp32 output stays staged
-  const bool direct = g.out_kind == 0 && !g.gelu && gemm_pair_direct() && g.ldo % 4 == 0 && (g.xh == nullptr || g.ldo % 8 == 0);
-  KernelFn kernel = table[direct ? 3 : g.out_kind];
+  ep.out_plane = g.out_plane; ep.res_plane = g.res_plane;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, EpiParams, int, int, int, int, int, int);
+  static const KernelFn table[3] = {gemm_pair_kernel<0>, gemm_pair_kernel<1>, gemm_pair_kernel<2>};
+  KernelFn kernel = table[g.out_kind];
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), SMEM_BYTES2)) return rc;
   const int tiles = ((g.M + BM2 - 1) / BM2) * ((g.N + BN2 - 1) / BN2);
   int clusters = max_active_clusters(reinterpret_cast<const void*>(kernel));
   if (tiles < clusters) clusters = tiles;
   TimedLaunch timed(TIMED_GEMM, 2.0 * g.M * g.N * g.K, g.M, g.N, g.K, stream);
   B200SAM_CHECK_CUDA(launch_kernel(kernel, dim3(2 * clusters), dim3(THREADS2), SMEM_BYTES2, stream, ta, tb, ep, g.M, g.N,
-                                   g.K, g.reverse_m, g.op_f16));
+                                   g.K, g.reverse_m, g.op_f16, g.a_wrap));
   return 0;
 }
 

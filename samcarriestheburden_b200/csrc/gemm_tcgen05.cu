@@ -259,10 +259,10 @@ int gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
                   "gemm: folded LayerNorm needs rowstat_in + colsum + nparts_in + ln_dim and a 16-bit output");
   B200SAM_REQUIRE(g.out_kind >= 0 && g.out_kind <= 2 && (g.out_kind == 0 || (g.out_kind == 2) == (g.op_f16 != 0)),
                   "gemm: a 16-bit output has the operands' format (out_kind=%d, op_f16=%d)", g.out_kind, g.op_f16);
-  if (g.use_pair >= 0 && (g.use_pair == 1 || gemm_pair_enabled()) && gemm_pair_eligible(g)) return gemm_f16_tn_pair(g, stream);
   B200SAM_REQUIRE(g.out_plane == 0 || (g.N % 128 == 0 && g.out_kind == 0 && g.epi_mode == 0 && g.ldo == 128 &&
                                        (g.residual == nullptr || g.ldr == 128) && g.xh == nullptr && g.rowstat_out == nullptr),
                   "gemm: planes need N %% 128 == 0, an fp32 output with ldo = ldr = 128 and the plain epilogue (N=%d)", g.N);
+  if (g.use_pair >= 0 && (g.use_pair == 1 || gemm_pair_enabled()) && gemm_pair_eligible(g)) return gemm_f16_tn_pair(g, stream);
   const bool narrow = g.N <= 128 || g.out_plane != 0;
   CUtensorMap ta, tb;
   const int a_cols = g.conv_cin > 0 ? 2 * g.conv_cin : (g.a_wrap > 0 ? g.a_wrap : g.K);
