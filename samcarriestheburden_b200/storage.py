@@ -21,7 +21,7 @@ after the producing stream by an event) and a background thread waits for that c
 Staging buffers are pinned once per size class (power-of-two bytes) and shared by every writer of the process: native-size
 masks have a different shape per image, and pinning a fresh 4-13 MiB buffer per record (about a millisecond per MiB)
 was what the first version of this writer spent its time on.  Measured (bench.py `pipeline.with_async_writer`, ViT-H, 32
-images host-in -> host-out, one B200): 117 images/s without persistence, 105-110 with it (first version: 78-86); the queue
+images host-in -> host-out, one B200): 125 images/s without persistence, 118 with it (first version: 116 -> 78-86); the queue
 is drained when the pipeline returns.
 """
 from __future__ import annotations
