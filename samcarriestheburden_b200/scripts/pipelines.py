@@ -12,6 +12,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, List, Sequence, Tuple
 
 import numpy as np
@@ -21,6 +22,10 @@ from .. import sharding
 from ..segment_anything.predictor import SamPredictor
 from ..segment_anything.sam_mask_decoder_head import EmbeddingStore, SAMMaskDecoderHead
 from ..utils.seg_refinement import SAMSegRefiner, SegEnhance
+
+
+# B200SAM_UPLOAD_RINGS=0: pageable uploads on the compute stream (A/B of the two uploaders below)
+_UPLOAD_RINGS = os.environ.get("B200SAM_UPLOAD_RINGS", "1") != "0"
 
 
 class _HostBatchUploader:
@@ -55,6 +60,52 @@ class _HostBatchUploader:
         x = self.devbuf[k][:n].permute(0, 3, 1, 2).contiguous()  # [n, 3, H, W] uint8
         self.consumed[k] = cur.record_event()
         return x
+
+
+class _NativeImageUploader:
+    """Native-resolution radiographs (HWC uint8 of any shape, e.g. 2570 x 2040 = 15.7 MB) on their way to the GPU resize:
+    a ring of pinned staging + device buffers and a side stream that carries the H2D (0.6 ms at PCIe rates) AND the resize
+    kernels of image i+1 while the encoder is busy with the previous batch on the compute stream."""
+
+    SLOTS = 4
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.cap = 0
+        self.pinned, self.devbuf = [], []
+        self.copied = [None] * self.SLOTS
+        self.k = 0
+
+    def _grow(self, nbytes: int) -> None:
+        torch.cuda.synchronize(self.device)  # nothing in flight may still reference the old buffers
+        self.cap = 1 << max(20, (nbytes - 1).bit_length())
+        self.pinned = [torch.empty(self.cap, dtype=torch.uint8).pin_memory() for _ in range(self.SLOTS)]
+        self.devbuf = [torch.empty(self.cap, dtype=torch.uint8, device=self.device) for _ in range(self.SLOTS)]
+        self.copied = [None] * self.SLOTS
+
+    def upload_resized(self, img: np.ndarray, transform) -> torch.Tensor:
+        """H2D + `ResizeLongestSide.apply_image_cuda` of one image, both on the uploader's stream (so a ring slot is free
+        again as soon as ITS resize has run, not when the compute stream gets to it behind a whole encoder batch).  Returns
+        the resized [C, h, w] uint8 CUDA tensor; the caller's stream is made to wait for it."""
+        img = np.ascontiguousarray(img)
+        n = img.nbytes
+        if n > self.cap:
+            self._grow(n)
+        k = self.k
+        self.k = (k + 1) % self.SLOTS
+        if self.copied[k] is not None:
+            self.copied[k].synchronize()
+        self.pinned[k][:n].numpy()[...] = img.reshape(-1)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.stream):
+            self.devbuf[k][:n].copy_(self.pinned[k][:n], non_blocking=True)  # (stream order: after the slot's last resize)
+            self.copied[k] = self.stream.record_event()
+            t = transform.apply_image_cuda(self.devbuf[k][:n].view(img.shape), device=self.device, chw=True)
+            ready = self.stream.record_event()
+        t.record_stream(cur)
+        cur.wait_event(ready)
+        return t
 
 
 @torch.no_grad()
@@ -110,10 +161,16 @@ def generate_img_embeddings(sam, images: Sequence[np.ndarray], names: Sequence[s
         target = pred.transform.get_preprocess_shape(img.shape[0], img.shape[1], pred.transform.target_length)
         if target == tuple(img.shape[:2]):  # already at the encoder's size: upload as is (batched, see flush)
             t = np.ascontiguousarray(img)
-            if t.dtype != np.uint8 or t.ndim != 3:
+            if t.dtype != np.uint8 or t.ndim != 3 or not _UPLOAD_RINGS:
                 t = torch.from_numpy(t).permute(2, 0, 1).contiguous()
         else:  # native-resolution radiograph: upload the uint8 pixels once, Pillow-exact resize on the GPU
-            t = pred.transform.apply_image_cuda(img, device=dev, chw=True)
+            if isinstance(img, np.ndarray) and img.dtype == np.uint8 and _UPLOAD_RINGS:
+                nat = uploaders.get(("native", str(dev)))
+                if nat is None:
+                    nat = uploaders[("native", str(dev))] = _NativeImageUploader(dev)
+                t = nat.upload_resized(img, pred.transform)
+            else:
+                t = pred.transform.apply_image_cuda(img, device=dev, chw=True)
         host = isinstance(t, np.ndarray)
         bkey = (host,) + (tuple(t.shape[:2]) if host else tuple(t.shape[-2:]))
         pending.setdefault(bkey, []).append((slot, t, tuple(img.shape[:2])))
