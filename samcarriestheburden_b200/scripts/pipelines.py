@@ -248,9 +248,32 @@ def refine_segmentations(sam, store: EmbeddingStore, segs: Sequence[torch.Tensor
     stage = SegEnhance(refiner, ccl_selection, "dilation", "square", 0, str(dev)) if ccl_selection else None
     mine = sharding.shard_indices(len(segs))
     results = []
-    for j in range(0, len(mine), batch):
-        chunk = mine[j:j + batch]
-        x, nm = torch.stack([segs[i].to(dev) for i in chunk]), [names[i] for i in chunk]
+    # the U-Net maps of batch j+1 (17 x 384 x 224 fp32 = 5.8 MB per image) are uploaded on a copy stream while batch j is
+    # refined (the refinement has host round trips, so the upload must be ISSUED before it starts); sources that are not
+    # pinned simply copy synchronously as before
+    copy_stream = sam.__dict__.setdefault("_seg_upload_stream", None)
+    if copy_stream is None or copy_stream.device != torch.device(dev):
+        copy_stream = sam.__dict__["_seg_upload_stream"] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+
+    def upload(chunk):
+        if not _UPLOAD_RINGS or any(segs[i].is_cuda or segs[i].shape != segs[chunk[0]].shape for i in chunk):
+            return torch.stack([segs[i].to(dev) for i in chunk]), None
+        with torch.cuda.stream(copy_stream):
+            x = torch.empty((len(chunk),) + tuple(segs[chunk[0]].shape), dtype=segs[chunk[0]].dtype, device=dev)
+            for k, i in enumerate(chunk):
+                x[k].copy_(segs[i], non_blocking=True)
+            ev = copy_stream.record_event()
+        x.record_stream(cur)
+        return x, ev
+
+    chunks = [mine[j:j + batch] for j in range(0, len(mine), batch)]
+    nxt = upload(chunks[0]) if chunks else None
+    for ci, chunk in enumerate(chunks):
+        (x, ev), nm = nxt, [names[i] for i in chunk]
+        nxt = upload(chunks[ci + 1]) if ci + 1 < len(chunks) else None
+        if ev is not None:
+            cur.wait_event(ev)
         seg_b, est_b = stage.enhance_batch(x, nm) if stage is not None else refiner.refine_batch(x, nm)
         results.extend((i, seg_b[k], est_b[k]) for k, i in enumerate(chunk))
         if writer is not None:
