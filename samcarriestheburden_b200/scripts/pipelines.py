@@ -9,6 +9,11 @@
       per image: prompt extraction + 2 B=1 decoder calls per class
    -> per BATCH of images: one prompt-extraction launch, two batched decoder passes over all classes of all
       images of the batch, one fused upscale/threshold/nearest-exact launch per distinct native size.
+
+Host -> device traffic never sits in front of compute on the compute stream: image batches, native-resolution radiographs and
+the U-Net maps go through pinned staging buffers and copy / side streams one step ahead of the kernels that consume them
+(_HostBatchUploader, _NativeImageUploader, refine_segmentations.upload; B200SAM_UPLOAD_RINGS=0 restores pageable uploads for
+A/B: set500 123.8 -> 128.6 images/s, native-resolution embedding 136 -> 143-153 images/s, refine phase +6 %).
 """
 from __future__ import annotations
 
