@@ -12,6 +12,7 @@ after the producing stream by an event) and a background thread waits for that c
     embeddings: file attrs `checkpoint`, `img_encoder_img_size`; group `img_embedding/<stem>` with dataset `features`
                 (1 x 256 x 64 x 64 float32, gzip-9) and attrs `original_size`, `input_size`;
     masks:      dataset `segmentation_mask/<stem>` (C x H x W bool, gzip-9) with attr `estimated_dice`; file attrs as given.
+* `path=None` -> the records are collected in host memory (`writer.backend.records`);
 * otherwise (h5py is not part of this image) -> a directory with `attrs.json` and, per record, raw `.npy` files
   `<stem>.<field>.npy` with the same fields (`features`, `original_size`, `input_size` / `segmentation_mask`,
   `estimated_dice`).  Plain `.npy` on purpose: the bytes go to the kernel in one `write` that releases the GIL, whereas
@@ -86,6 +87,21 @@ class _NpyDirBackend(_Backend):
             np.save(self.path / f"{name}.{field}.npy", arr, allow_pickle=False)
 
 
+class _MemoryBackend(_Backend):
+    """path=None: the records are collected in host memory (`writer.backend.records[name][field]` numpy arrays, copied out
+    of the pinned staging buffers by the writer threads) - the "results on the host" hand-over without a blocking
+    `tensor.cpu()` per image on the launch thread."""
+
+    def __init__(self):
+        self.records: Dict[str, Dict[str, np.ndarray]] = {}
+        self._lock = threading.Lock()
+
+    def write(self, kind, name, arrays):
+        rec = {k: np.array(v, copy=True) for k, v in arrays.items()}
+        with self._lock:
+            self.records[name] = rec
+
+
 # pinned staging buffers (uint8, power-of-two size classes) shared by all writers of the process
 _PINNED_POOL: Dict[int, list] = {}
 _PINNED_LOCK = threading.Lock()
@@ -106,8 +122,14 @@ class AsyncResultWriter:
                  device: Optional[torch.device] = None, threads: int = 2):
         assert kind in ("embedding", "mask")
         self.kind = kind
-        path = Path(path)
-        if path.suffix in (".h5", ".hdf5") and _have_h5py():
+        if path is None:
+            self.backend = _MemoryBackend()
+            path = Path(".")
+        else:
+            path = Path(path)
+        if isinstance(getattr(self, "backend", None), _MemoryBackend):
+            pass
+        elif path.suffix in (".h5", ".hdf5") and _have_h5py():
             self.backend: _Backend = _H5Backend(path, file_attrs or {}, gzip)
             threads = 1  # one HDF5 file, one writer
         else:

@@ -50,3 +50,20 @@ def test_h5_layout_matches_reference_when_h5py_exists(tmp_path):
         assert h.attrs["checkpoint"] == "c.pth"
         assert np.array_equal(h["img_embedding/a/features"][:], f.numpy())
         assert h["img_embedding/a"].attrs["input_size"].tolist() == [1024, 512]
+
+
+def test_writer_collects_in_memory_without_a_path():
+    """path=None: records end up as numpy arrays in writer.backend.records (the host hand-over of the pipeline drivers)."""
+    from samcarriestheburden_b200.storage import AsyncResultWriter
+    w = AsyncResultWriter(None, "mask")
+    seg = torch.zeros((3, 5, 7), dtype=torch.bool)
+    seg[1, 2, 3] = True
+    dice = torch.tensor([0.25, float("nan"), 0.75])
+    for i in range(5):
+        w.put_masks(f"m{i}", seg, dice + i)
+    assert w.close() == 5
+    rec = w.backend.records
+    assert sorted(rec) == [f"m{i}" for i in range(5)]
+    assert rec["m3"]["segmentation_mask"].dtype == np.bool_ and rec["m3"]["segmentation_mask"][1, 2, 3]
+    assert np.allclose(rec["m3"]["estimated_dice"], (dice + 3).numpy(), equal_nan=True)
+
