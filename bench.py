@@ -732,11 +732,12 @@ def pipeline_throughput(sam, dev, n_images: int = 32, batch: int = 8):
                 shutil.rmtree(tmp, ignore_errors=True)
         return n_masks, dts, drain
 
-    def embed_native(h=2570, w=2040, n=16):
+    def embed_native(h=2570, w=2040, n=64):
         # the reference's data are native-resolution radiographs: host uint8 [h, w, 3] -> pinned ring + copy stream -> Pillow-exact
         # GPU resize -> encoder (generate_img_embeddings); images/s of the embedding phase alone
         base = O.synthetic_radiograph(300, h, w)
-        nat = [np.roll(base, 37 * i, axis=1) for i in range(n)]
+        distinct = [np.roll(base, 37 * i, axis=1) for i in range(8)]
+        nat = [distinct[i % 8] for i in range(n)]  # 64 uploads of 8 distinct arrays (125 MB of host memory instead of 1 GB)
         nm = [f"n{i}" for i in range(n)]
         generate_img_embeddings(sam, nat, nm, batch=batch)
         torch.cuda.synchronize()
